@@ -1,0 +1,873 @@
+// libdcb200.so: the C ABI of include/dcb200.h -- host orchestration of the sm_100a kernels in kernels.cuh.
+// No CPU fallback: every compute entry point needs a CUDA device and fails loudly otherwise.
+#include "../../include/dcb200.h"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+#include "launch.h"
+
+using namespace dcb;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+extern "C" int dcb200_internal_fail(const char* msg) { return fail(msg); }
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +      \
+                  std::to_string(__LINE__) + ")");                                                   \
+  } while (0)
+#define CKI(call)                     \
+  do {                                \
+    int r__ = (call);                 \
+    if (r__) return r__;              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// small device kernels (layout, free energies, ordering, finalisation)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int CENTRE_SAMPLES = 65536;
+
+// centre[k] = mean of a strided sample of the frames (any centre is valid: it only tightens the
+// error band of the fast path).  One block per dim, fixed-order tree => deterministic.
+__global__ void centre_kernel(const float* __restrict__ coords, size_t n, int d, float* __restrict__ centre) {
+  __shared__ double part[256];
+  const int k = blockIdx.x;
+  const size_t stride = n > CENTRE_SAMPLES ? n / CENTRE_SAMPLES : 1;
+  const size_t m = (n + stride - 1) / stride;
+  double s = 0.0;
+  for (size_t q = threadIdx.x; q < m; q += blockDim.x) s += (double) coords[q * stride * d + k];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int) threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float c = (float) (part[0] / (double) m);
+    centre[k] = (c == c && fabsf(c) < FLT_MAX) ? c : 0.f;
+  }
+}
+
+// row-major coords -> xT [d][ld] (original values) and cT [d+1][ld] (-2*(x-centre), |x-centre|^2);
+// positions >= n are NaN so that padded columns can never pass a '<' filter.
+__global__ void pack_kernel(const float* __restrict__ coords, size_t n, int d, size_t ld, const float* __restrict__ centre,
+                            float* __restrict__ xT, float* __restrict__ cT, unsigned int* __restrict__ maxnorm_bits) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ld) return;
+  const float nan = __int_as_float(0x7fc00000);
+  if (p >= n) {
+    for (int k = 0; k < d; ++k) {
+      xT[(size_t) k * ld + p] = nan;
+      cT[(size_t) k * ld + p] = nan;
+    }
+    cT[(size_t) d * ld + p] = nan;
+    return;
+  }
+  float nrm = 0.f;
+  for (int k = 0; k < d; ++k) {
+    const float x = coords[p * d + k];
+    const float xc = x - centre[k];
+    xT[(size_t) k * ld + p] = x;
+    cT[(size_t) k * ld + p] = -2.0f * xc;
+    nrm = fmaf(xc, xc, nrm);
+  }
+  cT[(size_t) d * ld + p] = nrm;
+  atomicMax(maxnorm_bits, __float_as_uint(nrm));      // nrm >= 0: the bit pattern orders like the value
+}
+
+// permuted copy of a layout: dst[k][p] = src[k][perm[p]]  (free-energy order for the neighbour search)
+__global__ void gather_kernel(const float* __restrict__ sx, const float* __restrict__ sc, size_t ld, size_t n, int d,
+                              const uint32_t* __restrict__ perm, float* __restrict__ dx, float* __restrict__ dc) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ld) return;
+  const float nan = __int_as_float(0x7fc00000);
+  if (p >= n) {
+    for (int k = 0; k < d; ++k) {
+      dx[(size_t) k * ld + p] = nan;
+      dc[(size_t) k * ld + p] = nan;
+    }
+    dc[(size_t) d * ld + p] = nan;
+    return;
+  }
+  const size_t q = perm[p];
+  for (int k = 0; k < d; ++k) {
+    dx[(size_t) k * ld + p] = sx[(size_t) k * ld + q];
+    dc[(size_t) k * ld + p] = sc[(size_t) k * ld + q];
+  }
+  dc[(size_t) d * ld + p] = sc[(size_t) d * ld + q];
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// pops[r][i] = 1 + mult[r] * cnt[bin[r]][i]    (self counted by the initial 1, density_clustering.cpp:133;
+// a radius listed m times is one map entry incremented m times per hit, :131-134,:180)
+struct FinalizeArgs {
+  int n_out;
+  int out_row[MAX_BINS * 4];
+  int bin[MAX_BINS * 4];
+  uint32_t mult[MAX_BINS * 4];
+};
+__global__ void pops_finalize_kernel(const uint32_t* __restrict__ cnt, size_t ld_cnt, size_t rows, uint32_t* __restrict__ pops,
+                                     const FinalizeArgs f) {
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  for (int q = 0; q < f.n_out; ++q)
+    pops[(size_t) f.out_row[q] * rows + i] = 1u + f.mult[q] * cnt[(size_t) f.bin[q] * ld_cnt + i];
+}
+
+__global__ void max_u32_kernel(const uint32_t* __restrict__ v, size_t n, unsigned int* __restrict__ out) {
+  unsigned int m = 0;
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) m = max(m, v[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// calculate_free_energies (density_clustering.cpp:197-212) in its compiled form:
+//   inv = 1.0f / max_pop;  t = (float)pops[i] * inv;  fe = (float)(-log((double) t))
+__global__ void fe_kernel(const uint32_t* __restrict__ pops, size_t n, const unsigned int* __restrict__ max_dev,
+                          uint32_t max_host, float* __restrict__ fe) {
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t mx = max_host ? max_host : *max_dev;
+  const float inv = __fdiv_rn(1.0f, __uint2float_rn(mx));
+  const float t = __fmul_rn(__uint2float_rn(pops[i]), inv);
+  fe[i] = (float) (-log((double) t));
+}
+
+// order-preserving key of a float (-0.0 and +0.0 compare equal, like the reference's '<' on floats)
+__global__ void fe_keys_kernel(const float* __restrict__ fe, size_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ iota) {
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t u = __float_as_uint(fe[i] + 0.0f);
+  keys[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  iota[i] = (uint32_t) i;
+}
+
+// lo[p] = number of frames with a strictly lower free energy = first position of p's run of equal keys
+__global__ void lower_bound_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t* __restrict__ lo) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t k = keys[p];
+  size_t a = 0, b = p;
+  while (a < b) {
+    const size_t mid = (a + b) >> 1;
+    if (keys[mid] < k) a = mid + 1; else b = mid;
+  }
+  lo[p] = (uint32_t) a;
+}
+
+__global__ void nn_finish_kernel(const unsigned long long* __restrict__ knn, const unsigned long long* __restrict__ khd,
+                                 const uint32_t* __restrict__ perm, size_t n, uint32_t* __restrict__ nn_idx,
+                                 float* __restrict__ nn_d2, uint32_t* __restrict__ hd_idx, float* __restrict__ hd_d2) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const size_t o = perm[p];
+  const unsigned long long a = knn[p], b = khd[p];
+  nn_idx[o] = (uint32_t) a;
+  nn_d2[o] = __uint_as_float((uint32_t) (a >> 32));
+  hd_idx[o] = (uint32_t) b;
+  hd_d2[o] = __uint_as_float((uint32_t) (b >> 32));
+}
+
+__global__ void uf_flatten_kernel(uint32_t* parent, size_t m) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m) return;
+  const uint32_t r = uf_find(parent, (uint32_t) p);
+  parent[p] = r;                  // any interleaving leaves a valid forest with the same roots
+}
+
+// merges another forest over the same positions into `parent`
+__global__ void uf_merge_kernel(uint32_t* parent, const uint32_t* __restrict__ other, size_t m) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m) return;
+  const uint32_t q = other[p];
+  if (q != p) uf_union(parent, (uint32_t) p, q);
+}
+
+inline unsigned int blocks_for(size_t n, int bs) { return (unsigned int) ((n + bs - 1) / bs); }
+
+struct Layout {
+  float* xT = nullptr;
+  float* cT = nullptr;
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct dcb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  size_t n = 0, d = 0, ld = 0;
+  DevBuf<float> xT, cT;             // frame order
+  DevBuf<float> xT_s, cT_s;         // free-energy order (neighbour search)
+  DevBuf<uint32_t> perm, lo, keys_a, keys_b, iota;
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<float> stage;              // row-major staging for host uploads
+  DevBuf<float> centre;
+  DevBuf<uint32_t> cnt;
+  DevBuf<unsigned long long> knn, khd;
+  unsigned int* scalars = nullptr;  // [0] work counter, [1] max norm bits, [2] max pop
+  unsigned long long* stats = nullptr;   // [0] slow pairs, [1] exact pairs
+  float maxnorm2 = 0.f;
+  bool nn_ready = false;
+  uint64_t launches = 0;
+};
+
+static float up(double v) {          // smallest float >= v
+  float f = (float) v;
+  if ((double) f < v) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+// Rounding-error bounds of the fast path (u = 2^-24, M = max |x'|^2 over the frames, x' centred):
+//   fast value A = acc + xn (acc: FFMA chain started at the stored |y'|^2, xn the stored |x'|^2)
+//   |A - T'| <= gamma_d (2X + 3Y) <= 5 d u M          (norm sums, FFMA chain; X,Y <= M)
+//   centring (x' = fl(x - c)):  |T' - T| <= 4u sqrt(T M) + 4u^2 M <= 2u (T + M) + ...
+//   exact-order value d2e: |d2e - T| <= (d/4 + 5) u T
+// => |fast - d2e| <= e_abs + e_rel * value with the constants below (safety factor 1.5 on both).
+static void error_bounds(size_t d, float maxnorm2, float* e_abs, float* e_rel) {
+  const double u = ldexp(1.0, -24);
+  *e_abs = up(1.5 * (5.0 * (double) d + 8.0) * u * (double) maxnorm2 + 1e-37);
+  *e_rel = up(1.5 * ((double) d + 8.0) * u);
+}
+
+static int fill_geom(dcb200_ctx* c, bool sorted, size_t row_begin, size_t row_end, int tj, int occupancy, ScanGeom* g, int* grid) {
+  memset(g, 0, sizeof(*g));
+  g->xT = sorted ? c->xT_s.p : c->xT.p;
+  g->cT = sorted ? c->cT_s.p : c->cT.p;
+  g->ld = c->ld;
+  g->d = (int) c->d;
+  g->n = (uint32_t) c->n;
+  g->row_begin = (uint32_t) row_begin;
+  g->row_end = (uint32_t) row_end;
+  g->n_row_blocks = (uint32_t) ((row_end - row_begin + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+  g->n_col_tiles = (uint32_t) (c->ld / tj);
+  if (occupancy < 1) return fail("kernel does not fit on an SM (shared memory / registers)");
+  *grid = c->sm_count * occupancy;
+  // enough work items for dynamic balancing, but at least 8 tiles (>= 512 columns) per item
+  const uint32_t target = (uint32_t) *grid * 24u;
+  uint32_t n_items = (target + g->n_row_blocks - 1) / g->n_row_blocks;
+  n_items = std::max(1u, std::min(n_items, std::max(1u, g->n_col_tiles / 8u)));
+  g->tiles_per_item = (g->n_col_tiles + n_items - 1) / n_items;
+  g->n_col_items = (g->n_col_tiles + g->tiles_per_item - 1) / g->tiles_per_item;
+  *grid = (int) std::min<uint64_t>((uint64_t) *grid, (uint64_t) g->n_row_blocks * g->n_col_items);
+  g->work_counter = c->scalars;
+  g->stats = c->stats;
+  error_bounds(c->d, c->maxnorm2, &g->e_abs, &g->e_rel);
+  return 0;
+}
+
+#define DCB_DISPATCH(D) case D: return FN(D);
+static cudaError_t launch_pops(int d, const PopsArgs& a, int grid, cudaStream_t st) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) launch_pops_d##D(a, grid, st)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return cudaErrorInvalidValue;
+}
+static cudaError_t launch_nn(int d, const NnArgs& a, int grid, cudaStream_t st) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) launch_nn_d##D(a, grid, st)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return cudaErrorInvalidValue;
+}
+static cudaError_t launch_screen(int d, const ScreenArgs& a, int grid, cudaStream_t st) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) launch_screen_d##D(a, grid, st)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return cudaErrorInvalidValue;
+}
+static int occ_pops(int d, int nb) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) occupancy_pops_d##D(nb, d)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return 0;
+}
+static int occ_nn(int d) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) occupancy_nn_d##D(d)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return 0;
+}
+static int occ_screen(int d) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) occupancy_screen_d##D(d)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return 0;
+}
+static int tile_width(size_t d) { return d <= (size_t) MAX_TEMPLATE_D ? TileW<1>::tj : TileW<0>::tj; }
+
+// ------------------------------------------------------------------------------------------------
+// process-wide
+// ------------------------------------------------------------------------------------------------
+static int g_n_gpus = 0;
+
+extern "C" int dcb200_version(void) { return DCB200_VERSION; }
+extern "C" const char* dcb200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int dcb200_device_count(int* n) {
+  if (!n) return fail("dcb200_device_count: null argument");
+  *n = 0;
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) {
+    *n = 0;
+    return fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+extern "C" int dcb200_set_gpus(int n) {
+  if (n < 0) return fail("dcb200_set_gpus: negative count");
+  g_n_gpus = n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// session
+// ------------------------------------------------------------------------------------------------
+extern "C" int dcb200_ctx_create(int device, dcb200_ctx** out) {
+  if (!out) return fail("dcb200_ctx_create: null argument");
+  *out = nullptr;
+  int n = 0;
+  CKI(dcb200_device_count(&n));
+  if (n == 0) return fail("dcb200: no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= n) return fail("dcb200_ctx_create: device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(std::string("dcb200 is built for sm_100a (B200); found ") + prop.name);
+  dcb200_ctx* c = new dcb200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&c->scalars, 4 * sizeof(unsigned int)));
+  CK(cudaMalloc(&c->stats, 2 * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(c->scalars, 0, 4 * sizeof(unsigned int), c->stream));
+  CK(cudaMemsetAsync(c->stats, 0, 2 * sizeof(unsigned long long), c->stream));
+  *out = c;
+  return 0;
+}
+
+extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->xT.release(); c->cT.release(); c->xT_s.release(); c->cT_s.release();
+  c->perm.release(); c->lo.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release();
+  c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
+  cudaFree(c->scalars);
+  cudaFree(c->stats);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+extern "C" void* dcb200_ctx_stream(dcb200_ctx* c) { return c ? (void*) c->stream : nullptr; }
+
+extern "C" int dcb200_ctx_sync(dcb200_ctx* c) {
+  if (!c) return fail("null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int dcb200_ctx_stats(dcb200_ctx* c, uint64_t stats[3]) {
+  if (!c || !stats) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  unsigned long long h[2];
+  CK(cudaMemcpyAsync(h, c->stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  stats[0] = c->launches;
+  stats[1] = h[0];
+  stats[2] = h[1];
+  return 0;
+}
+
+static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t d) {
+  if (n == 0 || d == 0) return fail("dcb200: empty coordinate array");
+  if (n >= 0xfffffff0ull) return fail("dcb200: more than 2^32-16 frames are not supported");
+  const size_t ld = (n + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN;
+  c->n = n; c->d = d; c->ld = ld;
+  c->nn_ready = false;
+  CK(c->xT.reserve(d * ld));
+  CK(c->cT.reserve((d + 1) * ld));
+  CK(c->centre.reserve(d));
+  CK(cudaMemsetAsync(c->scalars + 1, 0, sizeof(unsigned int), c->stream));
+  centre_kernel<<<(unsigned int) d, 256, 0, c->stream>>>(dev_coords, n, (int) d, c->centre.p);
+  pack_kernel<<<blocks_for(ld, 256), 256, 0, c->stream>>>(dev_coords, n, (int) d, ld, c->centre.p, c->xT.p, c->cT.p,
+                                                          c->scalars + 1);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  unsigned int bits = 0;
+  CK(cudaMemcpyAsync(&bits, c->scalars + 1, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(&c->maxnorm2, &bits, 4);
+  if (!(c->maxnorm2 == c->maxnorm2) || c->maxnorm2 > FLT_MAX) return fail("dcb200: coordinates contain NaN or infinite values");
+  return 0;
+}
+
+extern "C" int dcb200_ctx_set_coords_device(dcb200_ctx* c, const float* dev_coords, size_t n, size_t d) {
+  if (!c || !dev_coords) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  return build_layout(c, dev_coords, n, d);
+}
+
+extern "C" int dcb200_ctx_set_coords(dcb200_ctx* c, const float* host_coords, size_t n, size_t d) {
+  if (!c || !host_coords) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  CK(c->stage.reserve(n * d));
+  CK(cudaMemcpyAsync(c->stage.p, host_coords, n * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  return build_layout(c, c->stage.p, n, d);
+}
+
+// ---- populations ----------------------------------------------------------------------------
+extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t n_radii, size_t row_begin, size_t row_end,
+                                      uint32_t* dev_pops) {
+  if (!c || (!radii && n_radii) || !dev_pops) return fail("null argument");
+  if (c->n == 0) return fail("dcb200_ctx_populations: no coordinates set");
+  if (row_begin > row_end || row_end > c->n) return fail("dcb200_ctx_populations: bad row range");
+  if (n_radii == 0 || row_begin == row_end) return 0;
+  CK(cudaSetDevice(c->device));
+  const size_t rows = row_end - row_begin;
+  // squared radii exactly as the reference forms them (float multiply, density_clustering.cpp:139)
+  std::vector<float> rad2(n_radii);
+  for (size_t r = 0; r < n_radii; ++r) rad2[r] = radii[r] * radii[r];
+  std::vector<float> uniq(rad2);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  for (float v : uniq)
+    if (!(v == v)) return fail("dcb200_ctx_populations: NaN radius");
+  const size_t ld_cnt = (rows + 255) / 256 * 256;
+  const int tj = tile_width(c->d);
+  for (size_t b0 = 0; b0 < uniq.size(); b0 += MAX_BINS) {
+    const int nb = (int) std::min<size_t>(MAX_BINS, uniq.size() - b0);
+    PopsArgs a;
+    int grid = 0;
+    CKI(fill_geom(c, false, row_begin, row_end, tj, occ_pops((int) c->d, nb), &a.g, &grid));
+    a.n_bins = nb;
+    for (int q = 0; q < 32; ++q) a.rad2[q] = q < nb ? uniq[b0 + q] : INFINITY;
+    const double rmax2 = (double) uniq[b0 + nb - 1];
+    a.thr_fast = up(rmax2 * (1.0 + (double) a.g.e_rel) + (double) a.g.e_abs);
+    CK(c->cnt.reserve((size_t) nb * ld_cnt));
+    a.cnt = c->cnt.p;
+    a.ld_cnt = ld_cnt;
+    CK(cudaMemsetAsync(c->cnt.p, 0, (size_t) nb * ld_cnt * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+    CK(launch_pops((int) c->d, a, grid, c->stream));
+    c->launches += 1;
+    // input radii served by this pass, in groups the finalize kernel's argument block can hold
+    FinalizeArgs f;
+    f.n_out = 0;
+    auto flush = [&]() -> int {
+      if (f.n_out == 0) return 0;
+      pops_finalize_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->cnt.p, ld_cnt, rows, dev_pops, f);
+      c->launches += 1;
+      f.n_out = 0;
+      CK(cudaGetLastError());
+      return 0;
+    };
+    for (size_t r = 0; r < n_radii; ++r) {
+      const size_t bin = std::lower_bound(uniq.begin(), uniq.end(), rad2[r]) - uniq.begin();
+      if (bin < b0 || bin >= b0 + (size_t) nb) continue;
+      uint32_t mult = 0;
+      for (size_t q = 0; q < n_radii; ++q) mult += (radii[q] == radii[r]);
+      f.out_row[f.n_out] = (int) r;
+      f.bin[f.n_out] = (int) (bin - b0);
+      f.mult[f.n_out] = mult;
+      if (++f.n_out == MAX_BINS * 4) CKI(flush());
+    }
+    CKI(flush());
+  }
+  return 0;
+}
+
+// ---- free energies ----------------------------------------------------------------------------
+extern "C" int dcb200_ctx_free_energies(dcb200_ctx* c, const uint32_t* dev_pops, size_t n, uint32_t max_pop, float* dev_fe) {
+  if (!c || !dev_pops || !dev_fe) return fail("null argument");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  if (max_pop == 0) {
+    CK(cudaMemsetAsync(c->scalars + 2, 0, sizeof(unsigned int), c->stream));
+    max_u32_kernel<<<std::min(blocks_for(n, 256), 1024u), 256, 0, c->stream>>>(dev_pops, n, c->scalars + 2);
+    c->launches += 1;
+  }
+  fe_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(dev_pops, n, c->scalars + 2, max_pop, dev_fe);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- nearest neighbours -----------------------------------------------------------------------
+extern "C" int dcb200_ctx_nn_prepare(dcb200_ctx* c, const float* dev_fe) {
+  if (!c || !dev_fe) return fail("null argument");
+  if (c->n == 0) return fail("dcb200_ctx_nn_prepare: no coordinates set");
+  CK(cudaSetDevice(c->device));
+  const size_t n = c->n;
+  CK(c->keys_a.reserve(n)); CK(c->keys_b.reserve(n)); CK(c->iota.reserve(n)); CK(c->perm.reserve(n)); CK(c->lo.reserve(n));
+  CK(c->xT_s.reserve(c->d * c->ld)); CK(c->cT_s.reserve((c->d + 1) * c->ld));
+  fe_keys_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(dev_fe, n, c->keys_a.p, c->iota.p);
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->keys_a.p, c->keys_b.p, c->iota.p, c->perm.p, (int) n, 0, 32, c->stream));
+  CK(c->cub_tmp.reserve(tmp_bytes));
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->keys_a.p, c->keys_b.p, c->iota.p, c->perm.p, (int) n, 0, 32,
+                                     c->stream));
+  lower_bound_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->keys_b.p, n, c->lo.p);
+  gather_kernel<<<blocks_for(c->ld, 256), 256, 0, c->stream>>>(c->xT.p, c->cT.p, c->ld, n, (int) c->d, c->perm.p, c->xT_s.p,
+                                                               c->cT_s.p);
+  c->launches += 4;
+  CK(cudaGetLastError());
+  c->nn_ready = true;
+  return 0;
+}
+
+extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_end, uint64_t* dev_keys_nn, uint64_t* dev_keys_hd) {
+  if (!c || !dev_keys_nn || !dev_keys_hd) return fail("null argument");
+  if (!c->nn_ready) return fail("dcb200_ctx_nn_scan: call dcb200_ctx_nn_prepare first");
+  if (pos_begin > pos_end || pos_end > c->n) return fail("dcb200_ctx_nn_scan: bad position range");
+  if (pos_begin == pos_end) return 0;
+  CK(cudaSetDevice(c->device));
+  const size_t rows = pos_end - pos_begin;
+  // "no neighbour" = (n_rows + 1, FLT_MAX)  (density_clustering.cpp:257-260)
+  const float fmax = FLT_MAX;
+  uint32_t fbits;
+  memcpy(&fbits, &fmax, 4);
+  const unsigned long long none = ((unsigned long long) fbits << 32) | (unsigned long long) (uint32_t) (c->n + 1);
+  fill_u64_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>((unsigned long long*) dev_keys_nn, rows, none);
+  fill_u64_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>((unsigned long long*) dev_keys_hd, rows, none);
+  NnArgs a;
+  int grid = 0;
+  CKI(fill_geom(c, true, pos_begin, pos_end, tile_width(c->d), occ_nn((int) c->d), &a.g, &grid));
+  a.perm = c->perm.p;
+  a.lo = c->lo.p;
+  a.key_nn = (unsigned long long*) dev_keys_nn;
+  a.key_hd = (unsigned long long*) dev_keys_hd;
+  CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+  CK(launch_nn((int) c->d, a, grid, c->stream));
+  c->launches += 3;
+  return 0;
+}
+
+extern "C" int dcb200_ctx_nn_finish(dcb200_ctx* c, const uint64_t* dev_keys_nn, const uint64_t* dev_keys_hd, uint32_t* dev_nn_idx,
+                                    float* dev_nn_d2, uint32_t* dev_hd_idx, float* dev_hd_d2) {
+  if (!c || !dev_keys_nn || !dev_keys_hd || !dev_nn_idx || !dev_nn_d2 || !dev_hd_idx || !dev_hd_d2) return fail("null argument");
+  if (!c->nn_ready) return fail("dcb200_ctx_nn_finish: call dcb200_ctx_nn_prepare first");
+  CK(cudaSetDevice(c->device));
+  nn_finish_kernel<<<blocks_for(c->n, 256), 256, 0, c->stream>>>((const unsigned long long*) dev_keys_nn,
+                                                                 (const unsigned long long*) dev_keys_hd, c->perm.p, c->n,
+                                                                 dev_nn_idx, dev_nn_d2, dev_hd_idx, dev_hd_d2);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- screening ----------------------------------------------------------------------------------
+extern "C" int dcb200_ctx_screening_scan(dcb200_ctx* c, size_t m_prev, size_t m_new, size_t row_begin, size_t row_end,
+                                         float max_dist2, uint32_t* dev_comp) {
+  if (!c || !dev_comp) return fail("null argument");
+  if (c->n == 0) return fail("dcb200_ctx_screening_scan: no coordinates set");
+  if (m_prev > m_new || m_new > c->n) return fail("dcb200_ctx_screening_scan: bad threshold positions");
+  row_begin = std::max(row_begin, m_prev);
+  row_end = std::min(row_end, m_new);
+  if (row_begin >= row_end) return 0;
+  CK(cudaSetDevice(c->device));
+  ScreenArgs a;
+  int grid = 0;
+  CKI(fill_geom(c, false, row_begin, row_end, tile_width(c->d), occ_screen((int) c->d), &a.g, &grid));
+  a.cut = max_dist2;
+  a.thr_fast = up((double) max_dist2 * (1.0 + (double) a.g.e_rel) + (double) a.g.e_abs);
+  a.parent = dev_comp;
+  CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+  CK(launch_screen((int) c->d, a, grid, c->stream));
+  c->launches += 1;
+  return 0;
+}
+
+extern "C" int dcb200_ctx_screening_flatten(dcb200_ctx* c, size_t m_new, uint32_t* dev_comp) {
+  if (!c || !dev_comp) return fail("null argument");
+  if (m_new == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  uf_flatten_kernel<<<blocks_for(m_new, 256), 256, 0, c->stream>>>(dev_comp, m_new);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dcb200_ctx_screening_merge(dcb200_ctx* c, size_t m_new, uint32_t* dev_comp, const uint32_t* dev_other) {
+  if (!c || !dev_comp || !dev_other) return fail("null argument");
+  if (m_new == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  uf_merge_kernel<<<blocks_for(m_new, 256), 256, 0, c->stream>>>(dev_comp, dev_other, m_new);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (1) host-pointer entry points: one worker thread per GPU, rows sharded, results written straight
+//     into the caller's arrays
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+std::mutex g_pool_mutex;
+std::map<int, dcb200_ctx*> g_pool;     // one cached context per device (buffers are reused across calls)
+
+int pooled_ctx(int device, dcb200_ctx** out) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  auto it = g_pool.find(device);
+  if (it != g_pool.end()) {
+    *out = it->second;
+    return 0;
+  }
+  CKI(dcb200_ctx_create(device, out));
+  g_pool[device] = *out;
+  return 0;
+}
+
+int gpus_to_use(int* n) {
+  CKI(dcb200_device_count(n));
+  if (*n == 0) return fail("dcb200: no CUDA device available (this library has no CPU fallback)");
+  if (g_n_gpus > 0) *n = std::min(*n, g_n_gpus);
+  return 0;
+}
+
+// runs fn(gpu, n_gpus) on one thread per GPU; returns the first failure
+template <class Fn>
+int on_gpus(int n_gpus, Fn&& fn) {
+  std::vector<int> rc(n_gpus, 0);
+  std::vector<std::string> msg(n_gpus);
+  if (n_gpus == 1) {
+    return fn(0, 1);
+  }
+  std::vector<std::thread> th;
+  for (int g = 0; g < n_gpus; ++g)
+    th.emplace_back([&, g]() {
+      rc[g] = fn(g, n_gpus);
+      if (rc[g]) msg[g] = g_err;
+    });
+  for (auto& t : th) t.join();
+  for (int g = 0; g < n_gpus; ++g)
+    if (rc[g]) return fail("GPU " + std::to_string(g) + ": " + msg[g]);
+  return 0;
+}
+
+void shard(size_t n, int g, int n_gpus, size_t* b, size_t* e) {
+  const size_t per = (n + n_gpus - 1) / n_gpus;
+  *b = std::min(n, per * g);
+  *e = std::min(n, per * (g + 1));
+}
+
+}  // namespace
+
+extern "C" int dcb200_populations(const float* coords, size_t n_rows, size_t n_cols, const float* radii, size_t n_radii,
+                                  uint32_t* pops) {
+  if (!coords || !pops || (!radii && n_radii)) return fail("dcb200_populations: null argument");
+  if (n_radii == 0) return 0;
+  int n_gpus = 0;
+  CKI(gpus_to_use(&n_gpus));
+  n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
+  return on_gpus(n_gpus, [&](int g, int G) -> int {
+    dcb200_ctx* c = nullptr;
+    CKI(pooled_ctx(g, &c));
+    size_t b, e;
+    shard(n_rows, g, G, &b, &e);
+    CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
+    if (b == e) return 0;
+    const size_t rows = e - b;
+    uint32_t* dev = nullptr;
+    CK(cudaMalloc(&dev, n_radii * rows * sizeof(uint32_t)));
+    int rc = dcb200_ctx_populations(c, radii, n_radii, b, e, dev);
+    if (!rc) {
+      cudaError_t ce = cudaMemcpy2DAsync(pops + b, n_rows * sizeof(uint32_t), dev, rows * sizeof(uint32_t), rows * sizeof(uint32_t),
+                                         n_radii, cudaMemcpyDeviceToHost, c->stream);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+      if (ce != cudaSuccess) rc = fail(std::string("populations download: ") + cudaGetErrorString(ce));
+    }
+    cudaFree(dev);
+    return rc;
+  });
+}
+
+extern "C" int dcb200_free_energies(const uint32_t* pops, size_t n, float* fe) {
+  if (!pops || !fe) return fail("dcb200_free_energies: null argument");
+  if (n == 0) return 0;
+  int n_gpus = 0;
+  CKI(gpus_to_use(&n_gpus));
+  dcb200_ctx* c = nullptr;
+  CKI(pooled_ctx(0, &c));
+  CK(cudaSetDevice(c->device));
+  uint32_t* dp = nullptr;
+  float* df = nullptr;
+  CK(cudaMalloc(&dp, n * sizeof(uint32_t)));
+  CK(cudaMalloc(&df, n * sizeof(float)));
+  int rc = 0;
+  cudaError_t ce = cudaMemcpyAsync(dp, pops, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (ce == cudaSuccess) rc = dcb200_ctx_free_energies(c, dp, n, 0, df);
+  if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(fe, df, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
+  if (ce != cudaSuccess) rc = fail(std::string("free energies: ") + cudaGetErrorString(ce));
+  cudaFree(dp);
+  cudaFree(df);
+  return rc;
+}
+
+extern "C" int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size_t n_cols, const float* fe, uint32_t* nn_idx,
+                                        float* nn_d2, uint32_t* hd_idx, float* hd_d2) {
+  if (!coords || !fe || !nn_idx || !nn_d2 || !hd_idx || !hd_d2) return fail("dcb200_nearest_neighbors: null argument");
+  int n_gpus = 0;
+  CKI(gpus_to_use(&n_gpus));
+  n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
+  std::vector<unsigned long long> knn(n_rows), khd(n_rows);
+  std::vector<uint32_t> perm(n_rows);
+  CKI(on_gpus(n_gpus, [&](int g, int G) -> int {
+    dcb200_ctx* c = nullptr;
+    CKI(pooled_ctx(g, &c));
+    size_t b, e;
+    shard(n_rows, g, G, &b, &e);
+    CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
+    float* dfe = nullptr;
+    CK(cudaMalloc(&dfe, n_rows * sizeof(float)));
+    int rc = 0;
+    cudaError_t ce = cudaMemcpyAsync(dfe, fe, n_rows * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess) rc = dcb200_ctx_nn_prepare(c, dfe);
+    if (ce == cudaSuccess && !rc && e > b) {
+      ce = c->knn.reserve(e - b);
+      if (ce == cudaSuccess) ce = c->khd.reserve(e - b);
+      if (ce == cudaSuccess) rc = dcb200_ctx_nn_scan(c, b, e, (uint64_t*) c->knn.p, (uint64_t*) c->khd.p);
+      if (ce == cudaSuccess && !rc)
+        ce = cudaMemcpyAsync(knn.data() + b, c->knn.p, (e - b) * 8, cudaMemcpyDeviceToHost, c->stream);
+      if (ce == cudaSuccess && !rc)
+        ce = cudaMemcpyAsync(khd.data() + b, c->khd.p, (e - b) * 8, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (ce == cudaSuccess && !rc && g == 0)
+      ce = cudaMemcpyAsync(perm.data(), c->perm.p, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
+    if (ce != cudaSuccess) rc = fail(std::string("nearest neighbours: ") + cudaGetErrorString(ce));
+    cudaFree(dfe);
+    return rc;
+  }));
+  for (size_t p = 0; p < n_rows; ++p) {
+    const size_t o = perm[p];
+    const uint32_t a = (uint32_t) (knn[p] >> 32), b = (uint32_t) (khd[p] >> 32);
+    nn_idx[o] = (uint32_t) knn[p];
+    memcpy(&nn_d2[o], &a, 4);
+    hd_idx[o] = (uint32_t) khd[p];
+    memcpy(&hd_d2[o], &b, 4);
+  }
+  return 0;
+}
+
+extern "C" int dcb200_screening_step(const float* sorted_coords, size_t n_cols, size_t m_prev, size_t m_new, float max_dist2,
+                                     uint32_t* comp) {
+  if (!sorted_coords || !comp) return fail("dcb200_screening_step: null argument");
+  if (m_prev > m_new) return fail("dcb200_screening_step: m_prev > m_new");
+  if (m_new == m_prev) return 0;
+  int n_gpus = 0;
+  CKI(gpus_to_use(&n_gpus));
+  n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (m_new - m_prev + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
+  for (size_t p = 0; p < m_prev; ++p)
+    if (comp[p] > p) return fail("dcb200_screening_step: comp[p] must be <= p");
+  for (size_t p = m_prev; p < m_new; ++p) comp[p] = (uint32_t) p;
+  std::vector<std::vector<uint32_t>> parts(n_gpus);
+  CKI(on_gpus(n_gpus, [&](int g, int G) -> int {
+    dcb200_ctx* c = nullptr;
+    CKI(pooled_ctx(g, &c));
+    CKI(dcb200_ctx_set_coords(c, sorted_coords, m_new, n_cols));
+    // rows are sharded so that every GPU gets about the same number of pairs (row p has p candidates)
+    auto cut = [&](int q) -> size_t {
+      const double a = (double) m_prev * m_prev, b = (double) m_new * m_new;
+      return q >= G ? m_new : (size_t) sqrt(a + (b - a) * q / G);
+    };
+    const size_t b = std::max(m_prev, cut(g)), e = cut(g + 1);
+    uint32_t* dev = nullptr;
+    CK(cudaMalloc(&dev, m_new * sizeof(uint32_t)));
+    int rc = 0;
+    cudaError_t ce = cudaMemcpyAsync(dev, comp, m_new * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess) rc = dcb200_ctx_screening_scan(c, m_prev, m_new, b, e, max_dist2, dev);
+    if (ce == cudaSuccess && !rc) rc = dcb200_ctx_screening_flatten(c, m_new, dev);
+    parts[g].resize(m_new);
+    if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(parts[g].data(), dev, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
+    if (ce != cudaSuccess) rc = fail(std::string("screening: ") + cudaGetErrorString(ce));
+    cudaFree(dev);
+    return rc;
+  }));
+  if (n_gpus == 1) {
+    memcpy(comp, parts[0].data(), m_new * sizeof(uint32_t));
+    return 0;
+  }
+  // merge the per-GPU forests (roots are the smallest position of a component)
+  std::vector<uint32_t>& par = parts[0];
+  auto find = [&](uint32_t x) {
+    while (par[x] != x) { par[x] = par[par[x]]; x = par[x]; }
+    return x;
+  };
+  for (int g = 1; g < n_gpus; ++g)
+    for (size_t p = 0; p < m_new; ++p) {
+      uint32_t a = find((uint32_t) p), b = find(parts[g][p]);
+      if (a == b) continue;
+      if (a < b) std::swap(a, b);
+      par[a] = b;
+    }
+  for (size_t p = 0; p < m_new; ++p) comp[p] = find((uint32_t) p);
+  return 0;
+}

@@ -1,0 +1,129 @@
+// Shared device-side building blocks of the dcb200 kernels (sm_100a only).
+//
+//  * mbarrier + 1-D bulk TMA (cp.async.bulk, SASS: UBLKCP) wrappers for the column-tile pipeline
+//  * dist2_exact: the squared distance in the rounding order of the reference's CPU build
+//    (reference loops density_clustering.cpp:171-176, :263-268, :315-318)
+//  * tile geometry constants shared by the population / neighbour / screening kernels
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dcb {
+
+// ---------------------------------------------------------------- tile geometry ----------------
+constexpr int RI = 4;                         // rows per thread (register block)
+constexpr int CJ = 4;                         // columns per inner iteration (one LDS.128 per dim)
+constexpr int N_CONSUMER_WARPS = 8;
+constexpr int N_CONSUMERS = N_CONSUMER_WARPS * 32;
+constexpr int CTA_THREADS = N_CONSUMERS + 32; // + one producer warp (TMA issue)
+constexpr int ROWS_PER_CTA = N_CONSUMERS * RI;   // 1024
+constexpr int LD_ALIGN = 256;                 // frame arrays are padded to a multiple of this (covers every tile width)
+constexpr int STAGES = 3;
+constexpr int MAX_BINS = 31;                  // distinct radii per population pass (table of 32 incl. +inf)
+constexpr int MAX_TEMPLATE_D = 16;            // dims held in registers by the specialised kernels
+
+// ---------------------------------------------------------------- PTX wrappers -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16 B aligned)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------- exact distance ---------------
+// Squared Euclidean distance of frames i and j in the rounding order of the reference's CPU build
+// (g++ -O3 -ffast-math, SSE2, no FMA): four lane accumulators over the first 4*floor(D/4) columns
+// (multiply, then add), S = (a0+a2) + (a1+a3); a remainder of >= 2 columns goes into the two lane
+// sums before the final add (lane1 + lane0), a last single column is added to S.
+// xT is the dim-major coordinate array [D][ld].  Intrinsics keep nvcc from contracting to FMA.
+static __device__ __noinline__ float dist2_exact(const float* __restrict__ xT, size_t ld, int D, uint32_t i, uint32_t j) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= D; k += 4) {
+    const float* p = xT + (size_t) k * ld;
+    float c0 = __fsub_rn(__ldg(p + i), __ldg(p + j));
+    float c1 = __fsub_rn(__ldg(p + ld + i), __ldg(p + ld + j));
+    float c2 = __fsub_rn(__ldg(p + 2 * ld + i), __ldg(p + 2 * ld + j));
+    float c3 = __fsub_rn(__ldg(p + 3 * ld + i), __ldg(p + 3 * ld + j));
+    a0 = __fadd_rn(a0, __fmul_rn(c0, c0));
+    a1 = __fadd_rn(a1, __fmul_rn(c1, c1));
+    a2 = __fadd_rn(a2, __fmul_rn(c2, c2));
+    a3 = __fadd_rn(a3, __fmul_rn(c3, c3));
+  }
+  float l0 = __fadd_rn(a0, a2);
+  float l1 = __fadd_rn(a1, a3);
+  float s;
+  if (D - k >= 2) {
+    const float* p = xT + (size_t) k * ld;
+    float c0 = __fsub_rn(__ldg(p + i), __ldg(p + j));
+    float c1 = __fsub_rn(__ldg(p + ld + i), __ldg(p + ld + j));
+    l0 = __fadd_rn(l0, __fmul_rn(c0, c0));
+    l1 = __fadd_rn(l1, __fmul_rn(c1, c1));
+    s = __fadd_rn(l1, l0);
+    k += 2;
+  } else {
+    s = __fadd_rn(l0, l1);
+  }
+  if (k < D) {
+    const float* p = xT + (size_t) k * ld;
+    float c = __fsub_rn(__ldg(p + i), __ldg(p + j));
+    s = __fadd_rn(s, __fmul_rn(c, c));
+  }
+  return s;
+}
+
+// The smallest float strictly greater than x (x finite, any sign); used to round thresholds up.
+__device__ __forceinline__ float next_up(float x) {
+  if (!(x == x) || x == __int_as_float(0x7f800000)) return x;
+  if (x == 0.f) return __int_as_float(1);
+  int b = __float_as_int(x);
+  return __int_as_float(x > 0.f ? b + 1 : b - 1);
+}
+
+// ---------------------------------------------------------------- tile stream ------------------
+// The producer warp streams column tiles through a STAGES-deep ring; each stage carries a small
+// header telling the consumers which work item the tile belongs to.
+struct TileMeta {
+  int32_t row_block;     // -1: end of stream
+  uint32_t col0;         // first column of the tile
+  uint32_t flags;        // bit0: first tile of the item, bit1: last tile of the item
+  uint32_t aux;          // kernel specific (e.g. neighbour search: tile class)
+};
+
+struct Pipe {
+  uint32_t stage = 0, phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+};
+
+}  // namespace dcb

@@ -1,0 +1,118 @@
+// Host-side pieces of the density path that stay on the CPU in the reference as well (they are
+// O(N log N) bookkeeping around the pair scans): the free-energy ordering, sigma^2, and the driver of
+// one screening threshold (which frames are new, which cluster names survive).  The pair scan itself
+// is dcb200_screening_step (CUDA).  All citations are file:line under the reference's src/.
+#include "../../include/dcb200.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <utility>
+#include <vector>
+
+extern "C" int dcb200_internal_fail(const char* msg);
+
+// sorted_free_energies (density_clustering.cpp:214-228): ascending free energy.  The reference uses
+// libstdc++'s unstable std::sort on (frame, fe) pairs and free-energy ties are the norm, so the very
+// same library call on the same element type is made here -- the tie order decides cluster numbers.
+extern "C" int dcb200_sorted_free_energies(const float* fe, size_t n, uint32_t* order) {
+  if (!fe || !order) return dcb200_internal_fail("dcb200_sorted_free_energies: null argument");
+  typedef std::pair<std::size_t, float> FeEntry;
+  std::vector<FeEntry> v(n);
+  for (std::size_t i = 0; i < n; ++i) v[i] = FeEntry(i, fe[i]);
+  std::sort(v.begin(), v.end(), [](const FeEntry& a, const FeEntry& b) -> bool { return a.second < b.second; });
+  for (std::size_t k = 0; k < n; ++k) order[k] = (uint32_t) v[k].first;
+  return 0;
+}
+
+// compute_sigma2 (density_clustering.cpp:334-343): mean squared nearest-neighbour distance,
+// accumulated in double in frame order.
+extern "C" int dcb200_sigma2(const float* nn_d2, size_t n, double* sigma2) {
+  if (!nn_d2 || !sigma2) return dcb200_internal_fail("dcb200_sigma2: null argument");
+  double s = 0.0;
+  for (size_t i = 0; i < n; ++i) s += nn_d2[i];
+  *sigma2 = s / (double) n;
+  return 0;
+}
+
+// One screening threshold = reference screening() (density_clustering_common.cpp:37-134) with
+// prepare_initial_clustering (:382-435), high_density_neighborhood (:292-332), lump_initial_clusters
+// (:506-555) and normalized_cluster_names (:437-456) of density_clustering.cpp.
+//
+// Closed form used here: the clusters are the connected components of
+//   { sorted positions a, b < M : d2(a, b) < (float)(4 sigma2) },   M = #{fe <= threshold},
+// grown from the clusters of `initial` (frames that already carry a name are not expanded again, :98-99);
+// a component keeps the smallest initial name among its members, components without named members
+// are named max(initial)+1, +2, ... in the order of their first sorted member (:527-535), and finally
+// the names are renumbered 1..K in ascending order (:437-456).
+extern "C" int dcb200_screening(const float* fe, const float* nn_d2, float threshold, const float* coords, size_t n_rows,
+                                size_t n_cols, const uint32_t* initial, uint32_t* labels) {
+  if (!fe || !nn_d2 || !coords || !labels) return dcb200_internal_fail("dcb200_screening: null argument");
+  if (n_rows == 0) return 0;
+  std::vector<uint32_t> order(n_rows);
+  int rc = dcb200_sorted_free_energies(fe, n_rows, order.data());
+  if (rc) return rc;
+  // first_frame_above_threshold = upper_bound over the sorted free energies (:403-410)
+  size_t lo = 0, hi = n_rows;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) / 2;
+    if (threshold < fe[order[mid]]) hi = mid; else lo = mid + 1;
+  }
+  const size_t M = lo;
+  double sigma2 = 0.0;
+  dcb200_sigma2(nn_d2, n_rows, &sigma2);
+  const float max_dist2 = (float) (4 * sigma2);
+
+  // frames that already carry a name are "visited" (:417-427); they must be the first m_prev sorted frames
+  size_t m_prev = 0;
+  uint32_t max_name = 0;
+  if (initial) {
+    for (size_t i = 0; i < n_rows; ++i) max_name = std::max(max_name, initial[i]);
+    while (m_prev < M && initial[order[m_prev]] != 0) ++m_prev;
+    for (size_t p = m_prev; p < M; ++p)
+      if (initial[order[p]] != 0)
+        return dcb200_internal_fail(
+            "dcb200_screening: initial clusters are not a prefix of the free-energy order "
+            "(they must come from a screening at a lower threshold of the same data)");
+  }
+  std::vector<uint32_t> comp(M);
+  {
+    // representative of an initial cluster = its first sorted member
+    std::vector<uint32_t> first(max_name + 1, 0xffffffffu);
+    for (size_t p = 0; p < m_prev; ++p) {
+      uint32_t& f = first[initial[order[p]]];
+      if (f == 0xffffffffu) f = (uint32_t) p;
+      comp[p] = f;
+    }
+  }
+  if (M > m_prev) {
+    std::vector<float> sorted((size_t) M * n_cols);
+#pragma omp parallel for schedule(static)
+    for (long long p = 0; p < (long long) M; ++p)
+      memcpy(&sorted[(size_t) p * n_cols], coords + (size_t) order[p] * n_cols, n_cols * sizeof(float));
+    rc = dcb200_screening_step(sorted.data(), n_cols, m_prev, M, max_dist2, comp.data());
+    if (rc) return rc;
+  }
+  // name of a component: smallest initial name among its members, else a fresh name by first member
+  const uint32_t none = 0xffffffffu;
+  std::vector<uint32_t> name_of_rep(M, none);
+  for (size_t p = 0; p < m_prev; ++p) {
+    uint32_t& nm = name_of_rep[comp[p]];
+    nm = std::min(nm, initial[order[p]]);
+  }
+  // ascending order of names: named components by name; fresh ones (all larger) by representative
+  std::vector<std::pair<uint64_t, uint32_t>> keys;
+  for (size_t p = 0; p < M; ++p)
+    if (comp[p] == p) {
+      const uint64_t k = name_of_rep[p] != none ? (uint64_t) name_of_rep[p] : ((uint64_t) 1 << 32) + p;
+      keys.push_back(std::make_pair(k, (uint32_t) p));
+    }
+  std::sort(keys.begin(), keys.end());
+  std::vector<uint32_t> final_name(M, 0);
+  for (size_t q = 0; q < keys.size(); ++q) final_name[keys[q].second] = (uint32_t) (q + 1);
+  memset(labels, 0, n_rows * sizeof(uint32_t));
+  for (size_t p = 0; p < M; ++p) labels[order[p]] = final_name[comp[p]];
+  return 0;
+}

@@ -1,0 +1,60 @@
+// One translation unit per specialised dimension: compiled with -DDCB_D=<n_cols> (0 = run-time D).
+#include "kernels.cuh"
+#include "launch.h"
+
+#ifndef DCB_D
+#error "compile with -DDCB_D=<n>"
+#endif
+#define DCB_CAT2(a, b) a##b
+#define DCB_CAT(a, b) DCB_CAT2(a, b)
+
+namespace dcb {
+
+cudaError_t DCB_CAT(launch_pops_d, DCB_D)(const PopsArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = pops_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d), a.n_bins);
+  cudaError_t e = cudaFuncSetAttribute(pops_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  pops_kernel<DCB_D><<<grid, CTA_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t DCB_CAT(launch_nn_d, DCB_D)(const NnArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = nn_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d));
+  cudaError_t e = cudaFuncSetAttribute(nn_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  nn_kernel<DCB_D><<<grid, CTA_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t DCB_CAT(launch_screen_d, DCB_D)(const ScreenArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = screen_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d));
+  cudaError_t e = cudaFuncSetAttribute(screen_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  screen_kernel<DCB_D><<<grid, CTA_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+int DCB_CAT(occupancy_pops_d, DCB_D)(int n_bins, int d) {
+  int nb = 0;
+  const size_t smem = pops_smem_bytes(SmemRing<DCB_D>::bytes(d), n_bins);
+  cudaFuncSetAttribute(pops_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pops_kernel<DCB_D>, CTA_THREADS, smem);
+  return nb;
+}
+int DCB_CAT(occupancy_nn_d, DCB_D)(int d) {
+  int nb = 0;
+  const size_t smem = nn_smem_bytes(SmemRing<DCB_D>::bytes(d));
+  cudaFuncSetAttribute(nn_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nn_kernel<DCB_D>, CTA_THREADS, smem);
+  return nb;
+}
+
+int DCB_CAT(occupancy_screen_d, DCB_D)(int d) {
+  int nb = 0;
+  const size_t smem = screen_smem_bytes(SmemRing<DCB_D>::bytes(d));
+  cudaFuncSetAttribute(screen_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, screen_kernel<DCB_D>, CTA_THREADS, smem);
+  return nb;
+}
+
+}  // namespace dcb

@@ -1,0 +1,88 @@
+"""Mirror of the reference's density operators on numpy arrays, bound to libdcb200.so.
+
+Same names, argument meaning and result conventions as Clustering::Density (reference
+density_clustering.hpp / density_clustering_cuda.hpp), so that the parity tests read like tests of the
+reference: populations are keyed by radius, neighbourhoods carry (index, squared distance), the
+"no neighbour" entry is (n_rows+1, FLT_MAX), labels are 0 for unassigned frames.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib
+
+
+def _coords(coords):
+    coords = np.ascontiguousarray(coords, dtype=np.float32)
+    if coords.ndim != 2:
+        raise ValueError("coords must be [n_rows][n_cols]")
+    return coords
+
+
+def calculate_populations(coords, radii):
+    """-> uint32 [n_radii][n_rows], row r for radii[r]  (reference: density_clustering.cpp:126-195)."""
+    coords = _coords(coords)
+    radii = np.ascontiguousarray(np.atleast_1d(radii), dtype=np.float32)
+    n, d = coords.shape
+    pops = np.empty((radii.size, n), np.uint32)
+    lib.check(lib.load().dcb200_populations(coords, n, d, radii, radii.size, pops))
+    return pops
+
+
+def calculate_free_energies(pops):
+    """-> float32 [n_rows]  (reference: density_clustering.cpp:197-212)."""
+    pops = np.ascontiguousarray(pops, dtype=np.uint32)
+    fe = np.empty(pops.size, np.float32)
+    lib.check(lib.load().dcb200_free_energies(pops, pops.size, fe))
+    return fe
+
+
+def nearest_neighbors(coords, free_energy):
+    """-> (nn_idx, nn_d2, hd_idx, hd_d2)  (reference: density_clustering.cpp:230-288)."""
+    coords = _coords(coords)
+    fe = np.ascontiguousarray(free_energy, dtype=np.float32)
+    n, d = coords.shape
+    if fe.size != n:
+        raise ValueError("free_energy must have n_rows entries")
+    ni = np.empty(n, np.uint32); nd = np.empty(n, np.float32)
+    hi = np.empty(n, np.uint32); hd = np.empty(n, np.float32)
+    lib.check(lib.load().dcb200_nearest_neighbors(coords, n, d, fe, ni, nd, hi, hd))
+    return ni, nd, hi, hd
+
+
+def sorted_free_energies(free_energy):
+    """-> order[k] = frame at sorted position k  (reference: density_clustering.cpp:214-228)."""
+    fe = np.ascontiguousarray(free_energy, dtype=np.float32)
+    order = np.empty(fe.size, np.uint32)
+    lib.check(lib.load().dcb200_sorted_free_energies(fe, fe.size, order))
+    return order
+
+
+def compute_sigma2(nn_d2):
+    nn_d2 = np.ascontiguousarray(nn_d2, dtype=np.float32)
+    s = C.c_double(0.0)
+    lib.check(lib.load().dcb200_sigma2(nn_d2, nn_d2.size, C.byref(s)))
+    return s.value
+
+
+def screening(free_energy, nn_d2, free_energy_threshold, coords, initial_clusters=None):
+    """One screening threshold -> uint32 labels [n_rows]  (reference: density_clustering_common.cpp:37-134)."""
+    coords = _coords(coords)
+    fe = np.ascontiguousarray(free_energy, dtype=np.float32)
+    nn_d2 = np.ascontiguousarray(nn_d2, dtype=np.float32)
+    n, d = coords.shape
+    labels = np.empty(n, np.uint32)
+    init = None
+    if initial_clusters is not None and len(initial_clusters) == n:
+        init_arr = np.ascontiguousarray(initial_clusters, dtype=np.uint32)
+        init = init_arr.ctypes.data
+    lib.check(lib.load().dcb200_screening(fe, nn_d2, np.float32(free_energy_threshold), coords, n, d, init, labels))
+    return labels
+
+
+def screening_step(sorted_coords, m_prev, m_new, max_dist2, comp):
+    sorted_coords = _coords(sorted_coords)
+    comp = np.ascontiguousarray(comp, dtype=np.uint32)
+    lib.check(lib.load().dcb200_screening_step(sorted_coords, sorted_coords.shape[1], m_prev, m_new,
+                                                np.float32(max_dist2), comp))
+    return comp

@@ -1,0 +1,116 @@
+"""Device-resident session over libdcb200.so's dcb200_ctx_* API.  torch is used only as the owner of
+device memory (raw pointers are passed through the C ABI); all compute is in the library's CUDA kernels."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class Session:
+    def __init__(self, device=0):
+        self.L = lib.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        lib.check(self.L.dcb200_ctx_create(self.device, C.byref(h)))
+        self.h = h
+        self.dev = torch.device("cuda", self.device)
+        self.n = self.d = 0
+
+    def close(self):
+        if self.h:
+            self.L.dcb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream_handle(self):
+        return self.L.dcb200_ctx_stream(self.h)
+
+    def torch_stream(self):
+        return torch.cuda.ExternalStream(self.stream_handle, device=self.dev)
+
+    def sync(self):
+        lib.check(self.L.dcb200_ctx_sync(self.h))
+
+    def stats(self):
+        s = (C.c_uint64 * 3)()
+        lib.check(self.L.dcb200_ctx_stats(self.h, s))
+        return dict(launches=int(s[0]), slow_pairs=int(s[1]), exact_pairs=int(s[2]))
+
+    # ---- coordinates
+    def set_coords(self, coords):
+        """coords: numpy [n][d] (host upload) or a CUDA torch tensor [n][d] (adopted from device memory)."""
+        if isinstance(coords, torch.Tensor):
+            assert coords.is_cuda and coords.dtype == torch.float32 and coords.is_contiguous()
+            self.n, self.d = coords.shape
+            torch.cuda.current_stream(self.dev).synchronize()
+            lib.check(self.L.dcb200_ctx_set_coords_device(self.h, _ptr(coords), self.n, self.d))
+        else:
+            coords = np.ascontiguousarray(coords, np.float32)
+            self.n, self.d = coords.shape
+            lib.check(self.L.dcb200_ctx_set_coords(self.h, C.c_void_p(coords.ctypes.data), self.n, self.d))
+
+    # ---- populations / free energies
+    def populations(self, radii, row_begin=0, row_end=None, out=None):
+        radii = np.ascontiguousarray(np.atleast_1d(radii), np.float32)
+        row_end = self.n if row_end is None else row_end
+        if out is None:
+            out = torch.empty((radii.size, row_end - row_begin), dtype=torch.int32, device=self.dev)
+        lib.check(self.L.dcb200_ctx_populations(self.h, radii, radii.size, row_begin, row_end, _ptr(out)))
+        return out
+
+    def free_energies(self, pops, max_pop=0, out=None):
+        assert pops.is_cuda and pops.dtype == torch.int32 and pops.is_contiguous()
+        if out is None:
+            out = torch.empty(pops.numel(), dtype=torch.float32, device=self.dev)
+        lib.check(self.L.dcb200_ctx_free_energies(self.h, _ptr(pops), pops.numel(), int(max_pop), _ptr(out)))
+        return out
+
+    # ---- nearest neighbours
+    def nn_prepare(self, fe):
+        assert fe.is_cuda and fe.dtype == torch.float32 and fe.is_contiguous() and fe.numel() == self.n
+        lib.check(self.L.dcb200_ctx_nn_prepare(self.h, _ptr(fe)))
+
+    def nn_scan(self, pos_begin=0, pos_end=None, out=None):
+        pos_end = self.n if pos_end is None else pos_end
+        if out is None:
+            out = torch.empty((2, pos_end - pos_begin), dtype=torch.int64, device=self.dev)
+        lib.check(self.L.dcb200_ctx_nn_scan(self.h, pos_begin, pos_end, _ptr(out[0]), _ptr(out[1])))
+        return out
+
+    def nn_finish(self, keys, out=None):
+        """keys: int64 [2][n] in sorted-position order -> (nn_idx, nn_d2, hd_idx, hd_d2) in frame order."""
+        assert keys.shape == (2, self.n) and keys.is_contiguous()
+        if out is None:
+            out = (torch.empty(self.n, dtype=torch.int32, device=self.dev), torch.empty(self.n, dtype=torch.float32, device=self.dev),
+                   torch.empty(self.n, dtype=torch.int32, device=self.dev), torch.empty(self.n, dtype=torch.float32, device=self.dev))
+        lib.check(self.L.dcb200_ctx_nn_finish(self.h, _ptr(keys[0]), _ptr(keys[1]), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                              _ptr(out[3])))
+        return out
+
+    def nearest_neighbors(self, fe):
+        self.nn_prepare(fe)
+        return self.nn_finish(self.nn_scan())
+
+    # ---- screening (coords must be the free-energy-sorted frames)
+    def screening_scan(self, m_prev, m_new, max_dist2, comp, row_begin=0, row_end=None):
+        row_end = m_new if row_end is None else row_end
+        assert comp.is_cuda and comp.dtype == torch.int32 and comp.numel() >= m_new
+        lib.check(self.L.dcb200_ctx_screening_scan(self.h, m_prev, m_new, row_begin, row_end, float(max_dist2), _ptr(comp)))
+
+    def screening_flatten(self, m_new, comp):
+        lib.check(self.L.dcb200_ctx_screening_flatten(self.h, m_new, _ptr(comp)))
+
+    def screening_merge(self, m_new, comp, other):
+        lib.check(self.L.dcb200_ctx_screening_merge(self.h, m_new, _ptr(comp), _ptr(other)))

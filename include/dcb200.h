@@ -1,0 +1,130 @@
+/* dcb200 -- C ABI of the B200-native `clustering density` hot path (libdcb200.so).
+ *
+ * Drop-in boundary for moldyn/Clustering (citations are file:line under the reference's src/):
+ * these are the entry points the reference's Clustering::Density::CUDA functions
+ * (density_clustering_cuda.hpp:13-54, called from density_clustering.cpp:113-118, :616-621, :659-663,
+ * :716-720, :746-750, :808-814 and clustering.cpp:110-113) bind to.  The C++ shim with the reference's own
+ * signatures lives in clustering_b200/csrc/density_cuda.hpp.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success, non-zero on failure
+ *     (dcb200_last_error() gives the message of the calling thread's last failure);
+ *   - coords is the reference's row-major float[n_rows][n_cols] array (tools.hxx:39-111);
+ *   - results are bit-identical to the reference's CPU/OpenMP build (CPU semantics,
+ *     CPU rounding order): strict '<' radius test, self counted once, nearest-neighbour ties -> smallest
+ *     frame index, "no neighbour" = (n_rows+1, FLT_MAX), squared distances stored;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Two layers:
+ *   (1) host-pointer entry points (dcb200_populations, ...): allocate/upload/compute/download per call on
+ *       all selected GPUs (rows sharded across devices), exactly like the reference's CUDA path;
+ *   (2) a device-resident session (dcb200_ctx_*): coordinates stay in HBM, outputs are device pointers,
+ *       row shards are explicit -- used by the benchmark, by one-process-per-GPU drivers
+ *       (torch.distributed / NCCL) and by the host-pointer layer itself.
+ */
+#ifndef DCB200_H
+#define DCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCB200_VERSION 100
+
+/* ---- process-wide ------------------------------------------------------------------------- */
+/* replaces Clustering::Density::CUDA::get_num_gpus (density_clustering_cuda.cu:32-43) */
+int dcb200_device_count(int* n_devices);
+/* number of GPUs the host-pointer entry points shard over (default: all visible); 0 restores the default */
+int dcb200_set_gpus(int n_gpus);
+const char* dcb200_last_error(void);
+int dcb200_version(void);
+
+/* ---- (1) host-pointer entry points -------------------------------------------------------- */
+/* replaces CUDA::calculate_populations (density_clustering_cuda.cu:139-182; CPU: density_clustering.cpp:126-195)
+ * pops: uint32 [n_radii][n_rows]; row r belongs to radii[r] (input order, duplicates allowed). */
+int dcb200_populations(const float* coords, size_t n_rows, size_t n_cols, const float* radii, size_t n_radii,
+                       uint32_t* pops);
+/* replaces calculate_free_energies (density_clustering.cpp:197-212): fe[i] = -log(pops[i] / max(pops)) */
+int dcb200_free_energies(const uint32_t* pops, size_t n_rows, float* fe);
+/* replaces CUDA::nearest_neighbors (density_clustering_cuda.cu:286-328; CPU: density_clustering.cpp:230-288)
+ * nn_*: nearest neighbour; hd_*: nearest neighbour with strictly lower free energy; *_d2 are SQUARED distances */
+int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size_t n_cols, const float* fe, uint32_t* nn_idx,
+                             float* nn_d2, uint32_t* hd_idx, float* hd_d2);
+/* replaces the pair scan + cluster merging of CUDA::screening (density_clustering_cuda.cu:396-594;
+ * CPU: density_clustering_common.cpp:37-134, density_clustering.cpp:292-332, :506-555).
+ *   sorted_coords: frames in ascending free-energy order (the order of sorted_free_energies, :214-228),
+ *                  row-major [n_sorted][n_cols], at least m_new rows
+ *   m_prev / m_new: number of sorted frames below the previous / the current free-energy threshold
+ *   max_dist2:     (float)(4 * sigma2)
+ *   comp:          uint32 [m_new], in/out.  In: for p < m_prev the component representative of the previous
+ *                  threshold (smallest sorted position of p's cluster; pass p itself when m_prev == 0).
+ *                  Out: for every p < m_new the smallest sorted position of the cluster p belongs to.
+ * The caller maps representatives to the reference's cluster numbers (1..K by ascending representative). */
+int dcb200_screening_step(const float* sorted_coords, size_t n_cols, size_t m_prev, size_t m_new, float max_dist2,
+                          uint32_t* comp);
+
+/* host-side bookkeeping of the screening (no pair work; kept bit-compatible with the reference's libstdc++ calls)
+ *   dcb200_sorted_free_energies: order[k] = frame at sorted position k   (sorted_free_energies, density_clustering.cpp:214-228)
+ *   dcb200_sigma2:               mean squared nearest-neighbour distance  (compute_sigma2, :334-343)
+ *   dcb200_screening:            one free-energy threshold, = reference screening() (density_clustering_common.cpp:37-134);
+ *                                initial: NULL or the labels of the previous (lower) threshold; labels: uint32 [n_rows], 0 = unassigned.
+ *                                The pair scan inside runs on the GPU(s) through dcb200_screening_step. */
+int dcb200_sorted_free_energies(const float* fe, size_t n_rows, uint32_t* order);
+int dcb200_sigma2(const float* nn_d2, size_t n_rows, double* sigma2);
+int dcb200_screening(const float* fe, const float* nn_d2, float threshold, const float* coords, size_t n_rows,
+                     size_t n_cols, const uint32_t* initial, uint32_t* labels);
+
+/* ---- (2) device-resident session ---------------------------------------------------------- */
+typedef struct dcb200_ctx dcb200_ctx;
+
+int dcb200_ctx_create(int device, dcb200_ctx** ctx);
+int dcb200_ctx_destroy(dcb200_ctx* ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
+void* dcb200_ctx_stream(dcb200_ctx* ctx);
+int dcb200_ctx_sync(dcb200_ctx* ctx);
+
+/* upload (host pointer) or adopt (device pointer, row-major) the coordinates; builds the dim-major
+ * tile layout in HBM.  The source array is not retained. */
+int dcb200_ctx_set_coords(dcb200_ctx* ctx, const float* host_coords, size_t n_rows, size_t n_cols);
+int dcb200_ctx_set_coords_device(dcb200_ctx* ctx, const float* dev_coords, size_t n_rows, size_t n_cols);
+
+/* populations of rows [row_begin,row_end) against all frames.
+ * dev_pops: device uint32 [n_radii][row_end-row_begin].  Asynchronous on the context stream. */
+int dcb200_ctx_populations(dcb200_ctx* ctx, const float* radii, size_t n_radii, size_t row_begin, size_t row_end,
+                           uint32_t* dev_pops);
+/* free energies from device populations (all n_rows); max_pop == 0: computed on the device. */
+int dcb200_ctx_free_energies(dcb200_ctx* ctx, const uint32_t* dev_pops, size_t n_rows, uint32_t max_pop,
+                             float* dev_fe);
+
+/* neighbour search, three steps so that row shards can be exchanged between devices in between:
+ *   prepare : orders the frames by free energy on the device (dev_fe: device float [n_rows])
+ *   scan    : rows = sorted positions [pos_begin,pos_end) against all frames; dev_keys_*: device
+ *             uint64 [pos_end-pos_begin] = (d2 bits << 32 | frame index), ready for concatenation
+ *   finish  : full key arrays [n_rows] in sorted-position order -> outputs in frame order (device arrays) */
+int dcb200_ctx_nn_prepare(dcb200_ctx* ctx, const float* dev_fe);
+int dcb200_ctx_nn_scan(dcb200_ctx* ctx, size_t pos_begin, size_t pos_end, uint64_t* dev_keys_nn,
+                       uint64_t* dev_keys_hd);
+int dcb200_ctx_nn_finish(dcb200_ctx* ctx, const uint64_t* dev_keys_nn, const uint64_t* dev_keys_hd,
+                         uint32_t* dev_nn_idx, float* dev_nn_d2, uint32_t* dev_hd_idx, float* dev_hd_d2);
+
+/* screening on the device: the context's coordinates must be the free-energy-sorted frames.
+ * New rows [m_prev,m_new) restricted to [row_begin,row_end) are scanned against all lower positions;
+ * dev_comp: device uint32 [m_new] union-find parents (in/out, see dcb200_screening_step).
+ * dcb200_ctx_screening_flatten replaces every entry by its representative. */
+int dcb200_ctx_screening_scan(dcb200_ctx* ctx, size_t m_prev, size_t m_new, size_t row_begin, size_t row_end,
+                              float max_dist2, uint32_t* dev_comp);
+int dcb200_ctx_screening_flatten(dcb200_ctx* ctx, size_t m_new, uint32_t* dev_comp);
+/* unions another forest over the same positions (e.g. a peer GPU's result) into dev_comp */
+int dcb200_ctx_screening_merge(dcb200_ctx* ctx, size_t m_new, uint32_t* dev_comp, const uint32_t* dev_other);
+
+/* counters of the last scan on this context (for the benchmark / tests):
+ * [0] kernels launched, [1] pairs handed to the slow path, [2] pairs re-evaluated in exact arithmetic */
+int dcb200_ctx_stats(dcb200_ctx* ctx, uint64_t stats[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCB200_H */

@@ -1,0 +1,181 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every result of libdcb200.so (through the C ABI)
+is compared bit-for-bit with the golden fixtures produced by the compiled reference and with the CPU
+oracle on fresh seeded inputs.  No reference sources are needed at run time."""
+import numpy as np
+import pytest
+
+from clustering_b200 import density
+from clustering_b200.synth import gaussian_mixture, contact_like
+from conftest import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+# ---------------------------------------------------------------- golden fixtures ----------------
+@pytest.mark.parametrize("name", golden_cases())
+def test_populations_free_energies_match_golden(golden, name):
+    g = golden(name)
+    pops = density.calculate_populations(g["coords"], g["radii"])
+    assert np.array_equal(pops, g["pops"])
+    for r in range(len(g["radii"])):
+        assert np.array_equal(bits(density.calculate_free_energies(pops[r])), bits(g["fe"][r]))
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_nearest_neighbors_match_golden(golden, name):
+    g = golden(name)
+    fe = g["fe"][int(g["r_scr"])]
+    ni, nd, hi, hd = density.nearest_neighbors(g["coords"], fe)
+    assert np.array_equal(ni, g["nn_idx"]) and np.array_equal(hi, g["hd_idx"])
+    assert np.array_equal(bits(nd), bits(g["nn_d2"])) and np.array_equal(bits(hd), bits(g["hd_d2"]))
+    assert density.compute_sigma2(nd) == float(g["sigma2"])
+    assert np.array_equal(density.sorted_free_energies(fe), g["order"])
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_screening_matches_golden(golden, name):
+    g = golden(name)
+    fe = g["fe"][int(g["r_scr"])]
+    prev = None
+    for k, t in enumerate(g["thresholds"]):          # incremental, exactly like Density::main (:806-816)
+        lab = density.screening(fe, g["nn_d2"], t, g["coords"], prev)
+        assert np.array_equal(lab, g["labels"][k]), (name, k)
+        prev = lab
+    # from scratch at a late threshold: same labels (numbering by first sorted member)
+    k = len(g["thresholds"]) - 1
+    lab = density.screening(fe, g["nn_d2"], g["thresholds"][k], g["coords"], None)
+    assert np.array_equal(lab, g["labels"][k])
+
+
+# ---------------------------------------------------------------- oracle, fresh inputs -----------
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 33])
+def test_vs_oracle_all_dims(oracle, d):
+    n = 3000 if d <= 16 else 1200
+    x = gaussian_mixture(n, d, seed=2000 + d)
+    x[17] = x[3]
+    x[n - 1] = x[3]                                 # exact duplicates: d2 = 0 neighbours are legal
+    radii = np.array([0.3, 0.55, 0.15, 0.3], np.float32) * np.float32(np.sqrt(d))   # unsorted, one duplicate
+    po = oracle.populations(x, radii)
+    pg = density.calculate_populations(x, radii)
+    assert np.array_equal(po, pg)
+    fe = oracle.free_energies(po[0])
+    assert np.array_equal(bits(fe), bits(density.calculate_free_energies(pg[0])))
+    a, b = oracle.nearest_neighbors(x, fe), density.nearest_neighbors(x, fe)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(bits(a[1]), bits(b[1])) and np.array_equal(bits(a[3]), bits(b[3]))
+
+
+def test_offset_data_and_many_radii(oracle):
+    # far from the origin (the centring of the fast path must not change a single count) and > 31 radii (two passes)
+    x = gaussian_mixture(2500, 4, seed=77) + np.float32(1000.0)
+    radii = np.linspace(0.05, 1.5, 40).astype(np.float32)
+    assert np.array_equal(oracle.populations(x, radii), density.calculate_populations(x, radii))
+
+
+def test_boundary_pairs_lattice(oracle):
+    # integer lattice: many pairs sit exactly ON the radius (d2 == r2 must not count: strict '<')
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(12), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    radii = np.array([1.0, np.sqrt(2.0), 2.0, 3.0, 2.5], np.float32)
+    po, pg = oracle.populations(g, radii), density.calculate_populations(g, radii)
+    assert np.array_equal(po, pg)
+    assert pg[0].max() == 1                          # d == 1.0 exactly is not inside
+    fe = oracle.free_energies(po[3])
+    a, b = oracle.nearest_neighbors(g, fe), density.nearest_neighbors(g, fe)      # massive ties: smallest index wins
+    for u, v in zip(a, b):
+        assert np.array_equal(bits(u) if u.dtype == np.float32 else u, bits(v) if v.dtype == np.float32 else v)
+
+
+def test_kat_small_cases():
+    x = np.arange(10, dtype=np.float32).reshape(-1, 1)
+    p = density.calculate_populations(x, [1.5, 1.0, 2.0])
+    assert p[0].tolist() == [2, 3, 3, 3, 3, 3, 3, 3, 3, 2]
+    assert p[1].tolist() == [1] * 10
+    assert p[2].tolist() == [2, 3, 3, 3, 3, 3, 3, 3, 3, 2]
+    x = np.array([[0, 0], [1, 0], [-1, 0], [0, 0], [5, 5]], np.float32)
+    fe = np.array([0.5, 0.1, 0.1, 0.5, 0.0], np.float32)
+    ni, nd, hi, hd = density.nearest_neighbors(x, fe)
+    assert ni.tolist() == [3, 0, 0, 0, 1] and nd.tolist() == [0, 1, 1, 0, 41]
+    assert hi.tolist() == [1, 4, 4, 1, 6]
+    assert hd[4] == np.finfo(np.float32).max and hd[1] == 41
+    one = np.array([[1.0, 2.0, 3.0]], np.float32)
+    assert density.calculate_populations(one, [0.5]).tolist() == [[1]]
+    ni, nd, hi, hd = density.nearest_neighbors(one, np.zeros(1, np.float32))
+    assert ni[0] == 2 and hi[0] == 2 and nd[0] == np.finfo(np.float32).max
+    fe = density.calculate_free_energies(np.array([5, 7, 7, 1], np.uint32))
+    assert bits(fe)[1] == 0x80000000
+
+
+def test_free_energy_formula_all_pops(oracle):
+    for mx in (1000, 16390, 123457, 1000000, 4999999):
+        p = np.arange(1, mx + 1, dtype=np.uint32)
+        assert np.array_equal(bits(density.calculate_free_energies(p)), bits(oracle.free_energies(p))), mx
+
+
+def test_screening_vs_oracle_fresh(oracle):
+    x = gaussian_mixture(1500, 4, k=6, seed=78)
+    x[10] = x[2]
+    fe = oracle.free_energies(oracle.populations(x, [0.35])[0])
+    _, nd, _, _ = oracle.nearest_neighbors(x, fe)
+    prev_o = prev_g = None
+    t = np.float32(0.1)
+    while t < fe.max() + 0.1:
+        lo = oracle.screening(fe, nd, t, x, prev_o)
+        lg = density.screening(fe, nd, t, x, prev_g)
+        assert np.array_equal(lo.astype(np.uint32), lg), float(t)
+        prev_o, prev_g = lo, lg
+        t = np.float32(t + np.float32(0.3))
+
+
+def test_high_dim_contact_like(oracle):
+    x = contact_like(900, 128, k=6, seed=21)
+    radii = np.array([1.0, 0.8], np.float32)
+    po = oracle.populations(x, radii)
+    assert np.array_equal(po, density.calculate_populations(x, radii))
+    fe = oracle.free_energies(po[0])
+    a, b = oracle.nearest_neighbors(x, fe), density.nearest_neighbors(x, fe)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(bits(a[1]), bits(b[1])) and np.array_equal(bits(a[3]), bits(b[3]))
+
+
+# ---------------------------------------------------------------- size-independent properties ----
+def test_medium_size_properties(oracle):
+    """60k x 5 (several row blocks, column items and tiles): sampled rows against the oracle's scalar
+    distance, symmetry of the counts, and NN consistency."""
+    n, d = 60000, 5
+    x = gaussian_mixture(n, d, seed=5)
+    radii = np.array([0.1, 0.2, 0.3, 0.4, 0.5], np.float32)
+    pops = density.calculate_populations(x, radii)
+    rng = np.random.default_rng(0)
+    rows = rng.choice(n, 24, replace=False)
+    r2 = (radii * radii).astype(np.float32)
+    for i in rows:
+        diff = (x - x[i]).astype(np.float32)
+        approx = (diff * diff).sum(1)
+        cand = np.nonzero(approx < r2.max() * 1.001 + 1e-6)[0]
+        exact = np.array([oracle.dist2(x[i], x[j]) for j in cand], np.float32)
+        for r in range(len(radii)):
+            assert pops[r, i] == 1 + int(np.count_nonzero((exact < r2[r]) & (cand != i))), (i, r)
+    assert int(pops[:, :].astype(np.int64).sum() - pops.size) % 2 == 0     # every pair is counted from both ends
+    fe = density.calculate_free_energies(pops[2])
+    ni, nd, hi, hd = density.nearest_neighbors(x, fe)
+    for i in rows:
+        diff = (x - x[i]).astype(np.float32)
+        approx = (diff * diff).sum(1)
+        approx[i] = np.inf
+        cand = np.nonzero(approx <= approx.min() * 1.001 + 1e-7)[0]
+        exact = np.array([oracle.dist2(x[i], x[j]) for j in cand], np.float32)
+        j = cand[np.flatnonzero(exact == exact.min())[0]]
+        assert ni[i] == j and bits(nd[i]) == bits(exact.min())
+        lower = np.nonzero(fe < fe[i])[0]
+        if lower.size:
+            a2 = approx[lower]
+            c2 = lower[np.nonzero(a2 <= a2.min() * 1.001 + 1e-7)[0]]
+            e2 = np.array([oracle.dist2(x[i], x[j]) for j in c2], np.float32)
+            assert hi[i] == c2[np.flatnonzero(e2 == e2.min())[0]] and bits(hd[i]) == bits(e2.min())
+        else:
+            assert hi[i] == n + 1
+    assert np.all(hd >= nd)
