@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the `clustering density` hot path (BASELINE.json metric: density run wall-time & Gpair.dim/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C1|C3|C4|C5] [--impl ours|reference]
+
+One step = one full density pass over the workload: coordinate layout build, populations, free energies,
+nearest neighbours (+ nearest neighbour with lower free energy).  Default workload = BASELINE.json
+configs[1] (C2: 1M frames x 5 dims, radius 0.3, seed 2; synthetic "HP35-like" Gaussian mixture).
+
+  value  whole-job Gpair.dim/s with the coordinates resident in HBM when the timed region starts
+         (pair.dim = one (x_ik - x_jk)^2 term of the ordered N x N pair matrix; two pair scans per step)
+  e2e    same metric through the C ABI with HOST buffers (H2D/D2H inside the timed region)
+  N > 1  one process per GPU (torchrun), rows sharded, per-shard results assembled with NCCL all-gather
+         on the device; fixed total work => "strong" scaling
+  --impl reference   the reference's own OpenMP CPU implementation (oracle/_ref/libdcref.so, compiled from
+         the unmodified reference sources; else the C port in oracle/) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "density_run_throughput"
+UNIT = "Gpair.dim/s"
+FLOP_PER_PAIR_DIM = 3.0          # one (x-y)^2 accumulate = FSUB + FFMA = 3 flop
+FLOP_EXECUTED_PER_PAIR_DIM = 2.0  # what the kernels issue: one FFMA per pair.dim (|y|^2 - 2x.y form)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=None, help="override the frame count (debugging only; invalid as a bench line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(name, n=None):
+    from clustering_b200.synth import CONFIGS, config_data
+    c = dict(CONFIGS[name])
+    if n is not None:
+        c["n"] = n
+    x = config_data(name, c["n"])
+    return c, x
+
+
+def pair_dims_per_step(n, d):
+    return 2.0 * float(n) * float(n) * float(d)      # populations scan + neighbour scan, ordered N x N pairs each
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [s for s in sm if s >= 0.5 * max(sm)] or sm          # samples under load
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own OpenMP implementation (oracle/_ref) or the C port (oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_impl():
+    from _oracle import Oracle, REF_SO
+    if os.path.exists(REF_SO):
+        from _oracle import Ref
+        r = Ref()
+        return "reference", r, r.max_threads()
+    o = Oracle()
+    return "port", o, os.cpu_count()
+
+
+def cpu_step(kind, impl, x, radius):
+    """pops + FE + NN on the CPU; returns seconds."""
+    t0 = time.perf_counter()
+    pops = impl.populations(x, np.array([radius], np.float32))
+    fe = impl.free_energies(pops[0])
+    impl.nearest_neighbors(x, fe)
+    return time.perf_counter() - t0
+
+
+def cpu_sample_size(kind, impl, x_full, radius, target_s):
+    """frames of the workload whose CPU step takes about target_s (brute-force NN is exactly quadratic)."""
+    n0 = min(8000, len(x_full))
+    t = cpu_step(kind, impl, x_full[:n0], radius)
+    n = int(n0 * (target_s / max(t, 1e-3)) ** 0.5)
+    return max(2000, min(len(x_full), n))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, x = workload(args.workload, args.n)
+    d = cfg["d"]
+    kind, impl, cores = cpu_impl()
+    total = args.steps + args.warmup
+    target = min(4.0, 150.0 / max(total, 1))
+    ns = cpu_sample_size(kind, impl, x, cfg["radii"][0], target)
+    xs = np.ascontiguousarray(x[:ns])
+    for _ in range(args.warmup):
+        cpu_step(kind, impl, xs, cfg["radii"][0])
+    t = [cpu_step(kind, impl, xs, cfg["radii"][0]) for _ in range(args.steps)]
+    sec = float(np.mean(t))
+    val = pair_dims_per_step(ns, d) / sec / 1e9
+    sample = f"first {ns} frames of {args.workload} ({cfg['n']}x{d}), pops(r={cfg['radii'][0]})+FE+NN per step; pops is box-pruned on the CPU, pair.dims counted as the full N x N matrix"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: clustering density, {cfg['n']} frames x {d} dims, radius {cfg['radii'][0]}: populations + free energies + nearest neighbours",
+                   "sample_frames": ns},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from clustering_b200 import density, lib
+    from clustering_b200.session import Session
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, x = workload(args.workload, args.n)
+    n, d = x.shape
+    radii = np.asarray(cfg["radii"], np.float32)
+    r_fe = 0                                            # free energies / neighbours from the first radius
+    sess = Session(local)
+    stream = sess.torch_stream()
+
+    per = ((n + 1023) // 1024 + world - 1) // world * 1024        # position shards are whole row blocks
+    b, e = min(n, rank * per), min(n, (rank + 1) * per)
+
+    x_dev = torch.from_numpy(x).to(dev)                # resident in HBM before the timed region
+    x_pin = torch.from_numpy(x).pin_memory()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > L2 (126 MB)
+    pops_shard = torch.zeros((radii.size, per), dtype=torch.int32, device=dev)
+    pops_all = torch.empty((world, radii.size, per), dtype=torch.int32, device=dev)
+    pops_loc = torch.zeros((radii.size, e - b), dtype=torch.int32, device=dev)
+    keys_loc = torch.zeros((2, e - b), dtype=torch.int64, device=dev)
+    pops_frame = torch.empty((radii.size, n), dtype=torch.int32, device=dev)
+    keys_shard = torch.zeros((2, per), dtype=torch.int64, device=dev)
+    keys_all = torch.empty((world, 2, per), dtype=torch.int64, device=dev)
+    out_host = [torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory(),
+                torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory()]
+    pops_host = torch.empty((radii.size, n), dtype=torch.int32).pin_memory()
+    fe_host = torch.empty(n, dtype=torch.float32).pin_memory()
+
+    def step(coords):
+        """one density pass; coords: device tensor (resident) or pinned host tensor (e2e)."""
+        with torch.cuda.stream(stream):
+            if coords.is_cuda:
+                sess.set_coords(coords)
+            else:
+                sess.set_coords(coords.numpy())
+            sess.populations(radii, b, e, out=pops_loc)
+            if world > 1:
+                pops_shard[:, :e - b].copy_(pops_loc)
+            if world > 1:
+                dist.all_gather_into_tensor(pops_all, pops_shard)
+                pops_pos = pops_all.permute(1, 0, 2).reshape(radii.size, world * per)[:, :n].contiguous()
+            else:
+                pops_pos = pops_loc
+            pops = sess.to_frame_order(pops_pos, out=pops_frame)
+            fe = sess.free_energies(pops[r_fe])
+            sess.nn_prepare(fe)
+            sess.nn_scan(b, e, out=keys_loc)
+            if world > 1:
+                keys_shard[:, :e - b].copy_(keys_loc)
+            if world > 1:
+                dist.all_gather_into_tensor(keys_all, keys_shard)
+                keys = keys_all.permute(1, 0, 2).reshape(2, world * per)[:, :n].contiguous()
+            else:
+                keys = keys_loc
+            nn = sess.nn_finish(keys)
+            if not coords.is_cuda:                       # e2e: results back in host memory
+                pops_host.copy_(pops, non_blocking=True)
+                fe_host.copy_(fe, non_blocking=True)
+                for h, t in zip(out_host, nn):
+                    h.copy_(t, non_blocking=True)
+        return pops, fe, nn
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(coords, steps):
+        """per-step CUDA events on the session stream, L2 flushed between steps (outside the events)."""
+        tot = 0.0
+        for _ in range(steps):
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step(coords)
+            e1.record(stream)
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps                   # ms per step, max over ranks
+
+    # ---- warm-up, FFMA peak, timed region --------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                 # nvidia-smi needs ~1 s to deliver its first sample
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    barrier()
+    peak_tflops = sess.ffma_peak(300.0)
+    s0 = sess.stats(reset=True)
+    barrier()
+    ms = timed(x_dev, args.steps)
+    barrier()
+    s1 = sess.stats()
+    # keep the load on until the sampler has seen it (short timed regions), then stop it
+    t_end = time.time() + 1.5
+    while time.time() < t_end:
+        step(x_dev)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    counts = torch.tensor([s1["launches"] - s0["launches"], s1["pairs_evaluated"], s1["pairs_scheduled"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    launches = counts[0]
+    evaluated_frac = float(counts[1].item()) / max(1.0, float(counts[2].item()))
+    pd = pair_dims_per_step(n, d)
+    value = pd / (ms * 1e-3) / 1e9
+
+    # ---- dominant kernel (neighbour scan) alone, for the roofline ---------------------------------
+    with torch.cuda.stream(stream):
+        fe_dev = sess.free_energies(sess.to_frame_order(sess.populations(radii[:1], 0, n))[0]) if world == 1 else None
+    kms = None
+    if world == 1:
+        sess.nn_prepare(fe_dev)
+        kt = []
+        sess.nn_scan(0, n, out=keys_loc)
+        sess.stats(reset=True)
+        for _ in range(5):
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sess.nn_scan(0, n, out=keys_loc)           # 2 fills + the scan kernel; the fills are < 0.1 % of the time
+            e1.record(stream)
+            e1.synchronize()
+            kt.append(e0.elapsed_time(e1))
+        kms = float(np.mean(kt))
+        kstat = sess.stats()
+        k_pairs = kstat["pairs_evaluated"] / 5.0          # pairs the kernel evaluated per launch (tiles streamed x tile size)
+
+    # ---- end to end: host buffers through the C ABI ----------------------------------------------
+    if world == 1:
+        def e2e_step():
+            pops = density.calculate_populations(x, radii)
+            fe = density.calculate_free_energies(pops[r_fe])
+            density.nearest_neighbors(x, fe)
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        h2d = 2 * x.nbytes + 4 * n + 4 * n                # coords for each of the two scans, pops, fe
+        d2h = radii.size * 4 * n + 4 * n + 2 * 8 * n + 4 * n   # pops, fe, neighbour keys, frame order
+        e2e_api = "host-pointer C ABI: dcb200_populations + dcb200_free_energies + dcb200_nearest_neighbors (wall clock)"
+    else:
+        step(x_pin)
+        e2e_ms = timed(x_pin, args.steps)
+        h2d = x.nbytes
+        d2h = radii.size * 4 * n + 4 * n + 16 * n
+        e2e_api = "session C ABI per rank with pinned host buffers: H2D coords, sharded scans, NCCL all-gather, D2H results (CUDA events, max over ranks)"
+    e2e_value = pd / (e2e_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: clustering density, {n} frames x {d} dims, radii {[float(r) for r in radii]}: layout build + populations + free energies + nearest neighbours (+ lower-free-energy neighbour)",
+                       "pair_dims_per_step": pd, "parallelism": f"rows sharded over {world} GPU(s), coords replicated, NCCL all-gather of populations and neighbour keys",
+                       "l2": "flushed between timed steps (256 MiB write)", "seed": cfg["seed"],
+                       "pairs_evaluated_frac": evaluated_frac},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "api": e2e_api},
+            "gpu_launches": int(launches.item()),
+        }
+        if kms is not None:
+            pairs = float(n) * float(n)
+            achieved = FLOP_EXECUTED_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12
+            line["roofline"] = {
+                "bound": "fp32", "kernel": "nn_kernel (neighbour scan, one launch over all rows)",
+                "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                "kernel_ms": kms,
+                "pairs_evaluated_per_launch": k_pairs, "pairs_evaluated_frac": k_pairs / pairs,
+                "evaluated_gpair_dim_per_s": k_pairs * d / (kms * 1e-3) / 1e9,
+                "effective_gpair_dim_per_s": pairs * d / (kms * 1e-3) / 1e9,
+                "algorithmic_3flop_tflops_on_evaluated_pairs": FLOP_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12,
+                "peak_source": "FFMA-only microbenchmark in this run (dcb200_ctx_ffma_peak); MEASURED_PEAKS.json has no FP32 entry",
+                "traffic": None,
+                "note": "achieved = 2 flop (one FFMA) per pair.dim x the pairs of the column tiles the kernel actually streamed "
+                        "(tiles out of reach of a row block are pruned and not counted); the headline value counts the full N x N matrix",
+            }
+        if not args.no_cpu_baseline:
+            try:
+                kind, impl, cores = cpu_impl()
+                ns = cpu_sample_size(kind, impl, x, float(radii[0]), 12.0)
+                sec = cpu_step(kind, impl, np.ascontiguousarray(x[:ns]), float(radii[0]))
+                line["cpu_baseline"] = {
+                    "value": pair_dims_per_step(ns, d) / sec / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                    "sample": f"first {ns} frames of the workload, one pops+FE+NN step in {sec:.1f} s (brute-force NN is quadratic; pops is box-pruned, counted as full N x N)"}
+            except Exception as ex:                       # the baseline must never take the bench line down
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,31 +50,68 @@ namespace {
 
 constexpr int CENTRE_SAMPLES = 65536;
 
-// centre[k] = mean of a strided sample of the frames (any centre is valid: it only tightens the
-// error band of the fast path).  One block per dim, fixed-order tree => deterministic.
-__global__ void centre_kernel(const float* __restrict__ coords, size_t n, int d, float* __restrict__ centre) {
-  __shared__ double part[256];
+// centre[k] / spread[k] = mean and standard deviation of a strided sample of the frames (any centre is
+// valid: it only tightens the error band of the fast path; the spread only scales the ordering key).
+// One block per dim, fixed-order tree => deterministic.
+__global__ void centre_kernel(const float* __restrict__ coords, size_t n, int d, float* __restrict__ centre,
+                              float* __restrict__ spread) {
+  __shared__ double part[256], part2[256];
   const int k = blockIdx.x;
   const size_t stride = n > CENTRE_SAMPLES ? n / CENTRE_SAMPLES : 1;
   const size_t m = (n + stride - 1) / stride;
-  double s = 0.0;
-  for (size_t q = threadIdx.x; q < m; q += blockDim.x) s += (double) coords[q * stride * d + k];
+  double s = 0.0, s2 = 0.0;
+  for (size_t q = threadIdx.x; q < m; q += blockDim.x) {
+    const double v = (double) coords[q * stride * d + k];
+    s += v;
+    s2 += v * v;
+  }
   part[threadIdx.x] = s;
+  part2[threadIdx.x] = s2;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if ((int) threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    if ((int) threadIdx.x < o) {
+      part[threadIdx.x] += part[threadIdx.x + o];
+      part2[threadIdx.x] += part2[threadIdx.x + o];
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float c = (float) (part[0] / (double) m);
+    const double mean = part[0] / (double) m;
+    const double var = fmax(part2[0] / (double) m - mean * mean, 0.0);
+    const float c = (float) mean, sd = (float) sqrt(var);
     centre[k] = (c == c && fabsf(c) < FLT_MAX) ? c : 0.f;
+    spread[k] = (sd == sd && sd > 0.f && sd < FLT_MAX) ? sd : 1.f;
   }
 }
 
-// row-major coords -> xT [d][ld] (original values) and cT [d+1][ld] (-2*(x-centre), |x-centre|^2);
-// positions >= n are NaN so that padded columns can never pass a '<' filter.
+// Spatial ordering key: Morton code of the first m = min(d, 6) dims, each quantised to `bits` bits over
+// centre +- 4 spread.  Frames that are close in space end up close in the array, so that the column
+// tiles (and the row blocks) have small bounding boxes and whole tiles can be skipped.
+__global__ void morton_keys_kernel(const float* __restrict__ coords, size_t n, int d, const float* __restrict__ centre,
+                                   const float* __restrict__ spread, int m, int bits, uint32_t* __restrict__ keys,
+                                   uint32_t* __restrict__ iota) {
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t q[6];
+  const float cells = (float) (1u << bits);
+  for (int k = 0; k < m; ++k) {
+    const float u = (coords[i * d + k] - centre[k]) / (8.0f * spread[k]) + 0.5f;
+    const float v = fminf(fmaxf(u * cells, 0.0f), cells - 1.0f);
+    q[k] = (v == v) ? (uint32_t) v : 0u;
+  }
+  uint32_t key = 0;
+  for (int b = bits - 1; b >= 0; --b)
+    for (int k = 0; k < m; ++k) key = (key << 1) | ((q[k] >> b) & 1u);
+  keys[i] = key;
+  iota[i] = (uint32_t) i;
+}
+
+// row-major coords -> xT [d][ld] (original values) and cT [d+1][ld] (-2*(x-centre), |x-centre|^2) in the
+// order given by perm (position -> frame; nullptr = frame order); positions >= n are NaN so that
+// padded columns can never pass a '<' filter.
 __global__ void pack_kernel(const float* __restrict__ coords, size_t n, int d, size_t ld, const float* __restrict__ centre,
-                            float* __restrict__ xT, float* __restrict__ cT, unsigned int* __restrict__ maxnorm_bits) {
+                            const uint32_t* __restrict__ perm, float* __restrict__ xT, float* __restrict__ cT,
+                            unsigned int* __restrict__ maxnorm_bits) {
   const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ld) return;
   const float nan = __int_as_float(0x7fc00000);
@@ -86,9 +123,10 @@ __global__ void pack_kernel(const float* __restrict__ coords, size_t n, int d, s
     cT[(size_t) d * ld + p] = nan;
     return;
   }
+  const size_t src = perm ? perm[p] : p;
   float nrm = 0.f;
   for (int k = 0; k < d; ++k) {
-    const float x = coords[p * d + k];
+    const float x = coords[src * d + k];
     const float xc = x - centre[k];
     xT[(size_t) k * ld + p] = x;
     cT[(size_t) k * ld + p] = -2.0f * xc;
@@ -98,26 +136,56 @@ __global__ void pack_kernel(const float* __restrict__ coords, size_t n, int d, s
   atomicMax(maxnorm_bits, __float_as_uint(nrm));      // nrm >= 0: the bit pattern orders like the value
 }
 
-// permuted copy of a layout: dst[k][p] = src[k][perm[p]]  (free-energy order for the neighbour search)
-__global__ void gather_kernel(const float* __restrict__ sx, const float* __restrict__ sc, size_t ld, size_t n, int d,
-                              const uint32_t* __restrict__ perm, float* __restrict__ dx, float* __restrict__ dc) {
-  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= ld) return;
-  const float nan = __int_as_float(0x7fc00000);
-  if (p >= n) {
-    for (int k = 0; k < d; ++k) {
-      dx[(size_t) k * ld + p] = nan;
-      dc[(size_t) k * ld + p] = nan;
-    }
-    dc[(size_t) d * ld + p] = nan;
-    return;
-  }
-  const size_t q = perm[p];
+// bounding boxes of 64-frame groups in centred coordinates: bbox[g][0..d) = lo, [d..2d) = hi.
+// One warp per group; padded positions are ignored (an all-padding group gets lo=+inf, hi=-inf).
+__global__ void bbox_kernel(const float* __restrict__ cT, size_t ld, size_t n, int d, float* __restrict__ bbox) {
+  const size_t grp = (size_t) blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (grp * 64 >= ld) return;
   for (int k = 0; k < d; ++k) {
-    dx[(size_t) k * ld + p] = sx[(size_t) k * ld + q];
-    dc[(size_t) k * ld + p] = sc[(size_t) k * ld + q];
+    float lo = INFINITY, hi = -INFINITY;
+    for (int q = 0; q < 2; ++q) {
+      const size_t p = grp * 64 + q * 32 + lane;
+      if (p < n) {
+        const float x = -0.5f * cT[(size_t) k * ld + p];
+        lo = fminf(lo, x);
+        hi = fmaxf(hi, x);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      bbox[grp * 2 * d + k] = lo;
+      bbox[grp * 2 * d + d + k] = hi;
+    }
   }
-  dc[(size_t) d * ld + p] = sc[(size_t) d * ld + q];
+}
+
+// dst[a][perm[p]] = src[a][p]: position order -> frame order
+__global__ void to_frame_order_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ perm,
+                                      size_t n, size_t n_arrays) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const size_t o = perm[p];
+  for (size_t a = 0; a < n_arrays; ++a) dst[a * n + o] = src[a * n + p];
+}
+
+// lo_pos[p] = lo_frame[perm[p]] after lo_frame[fe_perm[q]] = lo_sorted[q]
+__global__ void scatter_by_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ index, size_t n,
+                                  uint32_t* __restrict__ dst) {
+  const size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) dst[index[q]] = src[q];
+}
+__global__ void gather_by_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ index, size_t n,
+                                 uint32_t* __restrict__ dst) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = src[index[p]];
+}
+__global__ void iota_kernel(uint32_t* p, size_t n) {
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t) i;
 }
 
 __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
@@ -125,7 +193,7 @@ __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long l
   if (i < n) p[i] = v;
 }
 
-// pops[r][i] = 1 + mult[r] * cnt[bin[r]][i]    (self counted by the initial 1, density_clustering.cpp:133;
+// pops[r][i] = 1 + mult[r] * sum_{b <= bin[r]} cnt[b][i]    (self counted by the initial 1, density_clustering.cpp:133;
 // a radius listed m times is one map entry incremented m times per hit, :131-134,:180)
 struct FinalizeArgs {
   int n_out;
@@ -137,8 +205,11 @@ __global__ void pops_finalize_kernel(const uint32_t* __restrict__ cnt, size_t ld
                                      const FinalizeArgs f) {
   const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
-  for (int q = 0; q < f.n_out; ++q)
-    pops[(size_t) f.out_row[q] * rows + i] = 1u + f.mult[q] * cnt[(size_t) f.bin[q] * ld_cnt + i];
+  for (int q = 0; q < f.n_out; ++q) {
+    uint32_t c = 0;
+    for (int b = 0; b <= f.bin[q]; ++b) c += cnt[(size_t) b * ld_cnt + i];     // d2 < rad2[bin] = all bins up to it
+    pops[(size_t) f.out_row[q] * rows + i] = 1u + f.mult[q] * c;
+  }
 }
 
 __global__ void max_u32_kernel(const uint32_t* __restrict__ v, size_t n, unsigned int* __restrict__ out) {
@@ -210,6 +281,21 @@ __global__ void uf_merge_kernel(uint32_t* parent, const uint32_t* __restrict__ o
   if (q != p) uf_union(parent, (uint32_t) p, q);
 }
 
+// FFMA-only loop: the denominator of the FP32 roofline (16 independent chains per thread)
+__global__ void ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = (float) (threadIdx.x + q);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = fmaf(v[q], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) s += v[q];
+  if (s == 123.456f) out[0] = s;
+}
+
 inline unsigned int blocks_for(size_t n, int bs) { return (unsigned int) ((n + bs - 1) / bs); }
 
 struct Layout {
@@ -247,19 +333,23 @@ struct dcb200_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   size_t n = 0, d = 0, ld = 0;
-  DevBuf<float> xT, cT;             // frame order
-  DevBuf<float> xT_s, cT_s;         // free-energy order (neighbour search)
-  DevBuf<uint32_t> perm, lo, keys_a, keys_b, iota;
+  bool spatial = false;             // frames are held in spatial (Morton) order; perm maps position -> frame
+  DevBuf<float> xT, cT;             // [d][ld] original coords, [d+1][ld] column pack (context order)
+  DevBuf<float> bbox;               // [ld/64][2d]
+  DevBuf<uint32_t> perm;            // [n] position -> frame (identity when !spatial)
+  DevBuf<uint32_t> lo;              // [n] per position: number of frames with strictly lower free energy
+  DevBuf<uint32_t> keys_a, keys_b, iota, tmp_u32, tmp2_u32;
   DevBuf<unsigned char> cub_tmp;
   DevBuf<float> stage;              // row-major staging for host uploads
-  DevBuf<float> centre;
+  DevBuf<float> centre;             // [2d] centre, spread
   DevBuf<uint32_t> cnt;
   DevBuf<unsigned long long> knn, khd;
   unsigned int* scalars = nullptr;  // [0] work counter, [1] max norm bits, [2] max pop
-  unsigned long long* stats = nullptr;   // [0] slow pairs, [1] exact pairs
+  unsigned long long* stats = nullptr;   // [0] slow pairs, [1] exact pairs, [2] tiles streamed
   float maxnorm2 = 0.f;
   bool nn_ready = false;
   uint64_t launches = 0;
+  uint64_t pairs_scheduled = 0;     // pairs of the full row x column ranges of the scans since the last reset
 };
 
 static float up(double v) {          // smallest float >= v
@@ -280,10 +370,13 @@ static void error_bounds(size_t d, float maxnorm2, float* e_abs, float* e_rel) {
   *e_rel = up(1.5 * ((double) d + 8.0) * u);
 }
 
-static int fill_geom(dcb200_ctx* c, bool sorted, size_t row_begin, size_t row_end, int tj, int occupancy, ScanGeom* g, int* grid) {
+static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, int occupancy, uint32_t tiles_per_item, ScanGeom* g,
+                     int* grid) {
   memset(g, 0, sizeof(*g));
-  g->xT = sorted ? c->xT_s.p : c->xT.p;
-  g->cT = sorted ? c->cT_s.p : c->cT.p;
+  g->xT = c->xT.p;
+  g->cT = c->cT.p;
+  g->bbox = c->bbox.p;
+  g->prune_thr = INFINITY;
   g->ld = c->ld;
   g->d = (int) c->d;
   g->n = (uint32_t) c->n;
@@ -293,16 +386,14 @@ static int fill_geom(dcb200_ctx* c, bool sorted, size_t row_begin, size_t row_en
   g->n_col_tiles = (uint32_t) (c->ld / tj);
   if (occupancy < 1) return fail("kernel does not fit on an SM (shared memory / registers)");
   *grid = c->sm_count * occupancy;
-  // enough work items for dynamic balancing, but at least 8 tiles (>= 512 columns) per item
-  const uint32_t target = (uint32_t) *grid * 24u;
-  uint32_t n_items = (target + g->n_row_blocks - 1) / g->n_row_blocks;
-  n_items = std::max(1u, std::min(n_items, std::max(1u, g->n_col_tiles / 8u)));
-  g->tiles_per_item = (g->n_col_tiles + n_items - 1) / n_items;
+  g->tiles_per_item = std::max(1u, std::min(tiles_per_item, g->n_col_tiles));
   g->n_col_items = (g->n_col_tiles + g->tiles_per_item - 1) / g->tiles_per_item;
+  if ((uint64_t) g->n_row_blocks * g->n_col_items >= 0x7fffffffull) return fail("too many work items");
   *grid = (int) std::min<uint64_t>((uint64_t) *grid, (uint64_t) g->n_row_blocks * g->n_col_items);
   g->work_counter = c->scalars;
   g->stats = c->stats;
   error_bounds(c->d, c->maxnorm2, &g->e_abs, &g->e_rel);
+  c->pairs_scheduled += (uint64_t) (row_end - row_begin) * (uint64_t) c->n;
   return 0;
 }
 
@@ -401,9 +492,9 @@ extern "C" int dcb200_ctx_create(int device, dcb200_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&c->scalars, 4 * sizeof(unsigned int)));
-  CK(cudaMalloc(&c->stats, 2 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->stats, 4 * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(c->scalars, 0, 4 * sizeof(unsigned int), c->stream));
-  CK(cudaMemsetAsync(c->stats, 0, 2 * sizeof(unsigned long long), c->stream));
+  CK(cudaMemsetAsync(c->stats, 0, 4 * sizeof(unsigned long long), c->stream));
   *out = c;
   return 0;
 }
@@ -412,8 +503,9 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->xT.release(); c->cT.release(); c->xT_s.release(); c->cT_s.release();
+  c->xT.release(); c->cT.release(); c->bbox.release();
   c->perm.release(); c->lo.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release();
+  c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
   cudaFree(c->scalars);
   cudaFree(c->stats);
@@ -431,31 +523,65 @@ extern "C" int dcb200_ctx_sync(dcb200_ctx* c) {
   return 0;
 }
 
-extern "C" int dcb200_ctx_stats(dcb200_ctx* c, uint64_t stats[3]) {
+extern "C" int dcb200_ctx_stats(dcb200_ctx* c, uint64_t stats[6], int reset) {
   if (!c || !stats) return fail("null argument");
   CK(cudaSetDevice(c->device));
-  unsigned long long h[2];
+  unsigned long long h[3];
   CK(cudaMemcpyAsync(h, c->stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   stats[0] = c->launches;
   stats[1] = h[0];
   stats[2] = h[1];
+  stats[3] = h[2];
+  stats[4] = c->pairs_scheduled;
+  stats[5] = (uint64_t) tile_width(c->d) * ROWS_PER_CTA;
+  if (reset) {
+    CK(cudaMemsetAsync(c->stats, 0, 4 * sizeof(unsigned long long), c->stream));
+    c->pairs_scheduled = 0;
+  }
   return 0;
 }
 
-static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t d) {
+static int sort_pairs_u32(dcb200_ctx* c, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                          size_t n, int end_bit) {
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int) n, 0, end_bit, c->stream));
+  CK(c->cub_tmp.reserve(tmp_bytes));
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int) n, 0, end_bit, c->stream));
+  c->launches += 4;
+  return 0;
+}
+
+static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t d, bool keep_order) {
   if (n == 0 || d == 0) return fail("dcb200: empty coordinate array");
-  if (n >= 0xfffffff0ull) return fail("dcb200: more than 2^32-16 frames are not supported");
+  if (n >= 0x7ffffff0ull) return fail("dcb200: more than 2^31-16 frames are not supported");
   const size_t ld = (n + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN;
   c->n = n; c->d = d; c->ld = ld;
   c->nn_ready = false;
+  c->spatial = !keep_order;
   CK(c->xT.reserve(d * ld));
   CK(c->cT.reserve((d + 1) * ld));
-  CK(c->centre.reserve(d));
+  CK(c->bbox.reserve(ld / 64 * 2 * d));
+  CK(c->centre.reserve(2 * d));
+  CK(c->perm.reserve(n));
   CK(cudaMemsetAsync(c->scalars + 1, 0, sizeof(unsigned int), c->stream));
-  centre_kernel<<<(unsigned int) d, 256, 0, c->stream>>>(dev_coords, n, (int) d, c->centre.p);
-  pack_kernel<<<blocks_for(ld, 256), 256, 0, c->stream>>>(dev_coords, n, (int) d, ld, c->centre.p, c->xT.p, c->cT.p,
-                                                          c->scalars + 1);
+  centre_kernel<<<(unsigned int) d, 256, 0, c->stream>>>(dev_coords, n, (int) d, c->centre.p, c->centre.p + d);
+  c->launches += 1;
+  if (c->spatial) {
+    const int m = (int) std::min<size_t>(d, 6);
+    const int bits = std::min(10, 30 / m);
+    CK(c->keys_a.reserve(n)); CK(c->keys_b.reserve(n)); CK(c->iota.reserve(n));
+    morton_keys_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(dev_coords, n, (int) d, c->centre.p, c->centre.p + d, m, bits,
+                                                                   c->keys_a.p, c->iota.p);
+    c->launches += 1;
+    CKI(sort_pairs_u32(c, c->keys_a.p, c->keys_b.p, c->iota.p, c->perm.p, n, m * bits));
+  } else {
+    iota_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->perm.p, n);
+    c->launches += 1;
+  }
+  pack_kernel<<<blocks_for(ld, 256), 256, 0, c->stream>>>(dev_coords, n, (int) d, ld, c->centre.p, c->spatial ? c->perm.p : nullptr,
+                                                          c->xT.p, c->cT.p, c->scalars + 1);
+  bbox_kernel<<<blocks_for(ld / 64, 8), 256, 0, c->stream>>>(c->cT.p, ld, n, (int) d, c->bbox.p);
   c->launches += 2;
   CK(cudaGetLastError());
   unsigned int bits = 0;
@@ -466,18 +592,38 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
   return 0;
 }
 
-extern "C" int dcb200_ctx_set_coords_device(dcb200_ctx* c, const float* dev_coords, size_t n, size_t d) {
-  if (!c || !dev_coords) return fail("null argument");
+extern "C" int dcb200_ctx_set_coords_ex(dcb200_ctx* c, const float* coords, size_t n, size_t d, int on_device, int keep_order) {
+  if (!c || !coords) return fail("null argument");
   CK(cudaSetDevice(c->device));
-  return build_layout(c, dev_coords, n, d);
+  if (on_device) return build_layout(c, coords, n, d, keep_order != 0);
+  CK(c->stage.reserve(n * d));
+  CK(cudaMemcpyAsync(c->stage.p, coords, n * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  return build_layout(c, c->stage.p, n, d, keep_order != 0);
+}
+extern "C" int dcb200_ctx_set_coords_device(dcb200_ctx* c, const float* dev_coords, size_t n, size_t d) {
+  return dcb200_ctx_set_coords_ex(c, dev_coords, n, d, 1, 0);
+}
+extern "C" int dcb200_ctx_set_coords(dcb200_ctx* c, const float* host_coords, size_t n, size_t d) {
+  return dcb200_ctx_set_coords_ex(c, host_coords, n, d, 0, 0);
 }
 
-extern "C" int dcb200_ctx_set_coords(dcb200_ctx* c, const float* host_coords, size_t n, size_t d) {
-  if (!c || !host_coords) return fail("null argument");
+extern "C" int dcb200_ctx_order(dcb200_ctx* c, uint32_t* dev_perm) {
+  if (!c || !dev_perm) return fail("null argument");
+  if (c->n == 0) return fail("dcb200_ctx_order: no coordinates set");
   CK(cudaSetDevice(c->device));
-  CK(c->stage.reserve(n * d));
-  CK(cudaMemcpyAsync(c->stage.p, host_coords, n * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  return build_layout(c, c->stage.p, n, d);
+  CK(cudaMemcpyAsync(dev_perm, c->perm.p, c->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+extern "C" int dcb200_ctx_to_frame_order(dcb200_ctx* c, const uint32_t* dev_src, size_t n_arrays, uint32_t* dev_dst) {
+  if (!c || !dev_src || !dev_dst) return fail("null argument");
+  if (c->n == 0) return fail("dcb200_ctx_to_frame_order: no coordinates set");
+  if (n_arrays == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  to_frame_order_kernel<<<blocks_for(c->n, 256), 256, 0, c->stream>>>(dev_src, dev_dst, c->perm.p, c->n, n_arrays);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
 }
 
 // ---- populations ----------------------------------------------------------------------------
@@ -485,7 +631,7 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
                                       uint32_t* dev_pops) {
   if (!c || (!radii && n_radii) || !dev_pops) return fail("null argument");
   if (c->n == 0) return fail("dcb200_ctx_populations: no coordinates set");
-  if (row_begin > row_end || row_end > c->n) return fail("dcb200_ctx_populations: bad row range");
+  if (row_begin > row_end || row_end > c->n) return fail("dcb200_ctx_populations: bad position range");
   if (n_radii == 0 || row_begin == row_end) return 0;
   CK(cudaSetDevice(c->device));
   const size_t rows = row_end - row_begin;
@@ -503,11 +649,13 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     const int nb = (int) std::min<size_t>(MAX_BINS, uniq.size() - b0);
     PopsArgs a;
     int grid = 0;
-    CKI(fill_geom(c, false, row_begin, row_end, tj, occ_pops((int) c->d, nb), &a.g, &grid));
+    CKI(fill_geom(c, row_begin, row_end, tj, occ_pops((int) c->d, nb), nb > 4 ? 64u : 32u, &a.g, &grid));
     a.n_bins = nb;
     for (int q = 0; q < 32; ++q) a.rad2[q] = q < nb ? uniq[b0 + q] : INFINITY;
     const double rmax2 = (double) uniq[b0 + nb - 1];
     a.thr_fast = up(rmax2 * (1.0 + (double) a.g.e_rel) + (double) a.g.e_abs);
+    // a tile whose bounding-box distance exceeds this cannot contain a pair that passes the filter
+    a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.e_abs);
     CK(c->cnt.reserve((size_t) nb * ld_cnt));
     a.cnt = c->cnt.p;
     a.ld_cnt = ld_cnt;
@@ -558,22 +706,19 @@ extern "C" int dcb200_ctx_free_energies(dcb200_ctx* c, const uint32_t* dev_pops,
 }
 
 // ---- nearest neighbours -----------------------------------------------------------------------
+// dev_fe: free energies in FRAME order.  Builds lo[p] = #{frames with fe < fe[frame at position p]}.
 extern "C" int dcb200_ctx_nn_prepare(dcb200_ctx* c, const float* dev_fe) {
   if (!c || !dev_fe) return fail("null argument");
   if (c->n == 0) return fail("dcb200_ctx_nn_prepare: no coordinates set");
   CK(cudaSetDevice(c->device));
   const size_t n = c->n;
-  CK(c->keys_a.reserve(n)); CK(c->keys_b.reserve(n)); CK(c->iota.reserve(n)); CK(c->perm.reserve(n)); CK(c->lo.reserve(n));
-  CK(c->xT_s.reserve(c->d * c->ld)); CK(c->cT_s.reserve((c->d + 1) * c->ld));
+  CK(c->keys_a.reserve(n)); CK(c->keys_b.reserve(n)); CK(c->iota.reserve(n)); CK(c->tmp_u32.reserve(n));
+  CK(c->tmp2_u32.reserve(n)); CK(c->lo.reserve(n));
   fe_keys_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(dev_fe, n, c->keys_a.p, c->iota.p);
-  size_t tmp_bytes = 0;
-  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->keys_a.p, c->keys_b.p, c->iota.p, c->perm.p, (int) n, 0, 32, c->stream));
-  CK(c->cub_tmp.reserve(tmp_bytes));
-  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->keys_a.p, c->keys_b.p, c->iota.p, c->perm.p, (int) n, 0, 32,
-                                     c->stream));
-  lower_bound_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->keys_b.p, n, c->lo.p);
-  gather_kernel<<<blocks_for(c->ld, 256), 256, 0, c->stream>>>(c->xT.p, c->cT.p, c->ld, n, (int) c->d, c->perm.p, c->xT_s.p,
-                                                               c->cT_s.p);
+  CKI(sort_pairs_u32(c, c->keys_a.p, c->keys_b.p, c->iota.p, c->tmp_u32.p, n, 32));              // tmp_u32: fe position -> frame
+  lower_bound_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->keys_b.p, n, c->keys_a.p);    // keys_a: lo by fe position
+  scatter_by_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->keys_a.p, c->tmp_u32.p, n, c->tmp2_u32.p);   // lo by frame
+  gather_by_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->tmp2_u32.p, c->perm.p, n, c->lo.p);           // lo by position
   c->launches += 4;
   CK(cudaGetLastError());
   c->nn_ready = true;
@@ -596,7 +741,7 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
   fill_u64_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>((unsigned long long*) dev_keys_hd, rows, none);
   NnArgs a;
   int grid = 0;
-  CKI(fill_geom(c, true, pos_begin, pos_end, tile_width(c->d), occ_nn((int) c->d), &a.g, &grid));
+  CKI(fill_geom(c, pos_begin, pos_end, tile_width(c->d), occ_nn((int) c->d), 32u, &a.g, &grid));
   a.perm = c->perm.p;
   a.lo = c->lo.p;
   a.key_nn = (unsigned long long*) dev_keys_nn;
@@ -610,7 +755,7 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
 extern "C" int dcb200_ctx_nn_finish(dcb200_ctx* c, const uint64_t* dev_keys_nn, const uint64_t* dev_keys_hd, uint32_t* dev_nn_idx,
                                     float* dev_nn_d2, uint32_t* dev_hd_idx, float* dev_hd_d2) {
   if (!c || !dev_keys_nn || !dev_keys_hd || !dev_nn_idx || !dev_nn_d2 || !dev_hd_idx || !dev_hd_d2) return fail("null argument");
-  if (!c->nn_ready) return fail("dcb200_ctx_nn_finish: call dcb200_ctx_nn_prepare first");
+  if (c->n == 0) return fail("dcb200_ctx_nn_finish: no coordinates set");
   CK(cudaSetDevice(c->device));
   nn_finish_kernel<<<blocks_for(c->n, 256), 256, 0, c->stream>>>((const unsigned long long*) dev_keys_nn,
                                                                  (const unsigned long long*) dev_keys_hd, c->perm.p, c->n,
@@ -625,6 +770,7 @@ extern "C" int dcb200_ctx_screening_scan(dcb200_ctx* c, size_t m_prev, size_t m_
                                          float max_dist2, uint32_t* dev_comp) {
   if (!c || !dev_comp) return fail("null argument");
   if (c->n == 0) return fail("dcb200_ctx_screening_scan: no coordinates set");
+  if (c->spatial) return fail("dcb200_ctx_screening_scan: the coordinates must be set with keep_order (free-energy-sorted frames)");
   if (m_prev > m_new || m_new > c->n) return fail("dcb200_ctx_screening_scan: bad threshold positions");
   row_begin = std::max(row_begin, m_prev);
   row_end = std::min(row_end, m_new);
@@ -632,9 +778,10 @@ extern "C" int dcb200_ctx_screening_scan(dcb200_ctx* c, size_t m_prev, size_t m_
   CK(cudaSetDevice(c->device));
   ScreenArgs a;
   int grid = 0;
-  CKI(fill_geom(c, false, row_begin, row_end, tile_width(c->d), occ_screen((int) c->d), &a.g, &grid));
+  CKI(fill_geom(c, row_begin, row_end, tile_width(c->d), occ_screen((int) c->d), 32u, &a.g, &grid));
   a.cut = max_dist2;
   a.thr_fast = up((double) max_dist2 * (1.0 + (double) a.g.e_rel) + (double) a.g.e_abs);
+  a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.e_abs);
   a.parent = dev_comp;
   CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
   CK(launch_screen((int) c->d, a, grid, c->stream));
@@ -662,9 +809,44 @@ extern "C" int dcb200_ctx_screening_merge(dcb200_ctx* c, size_t m_new, uint32_t*
   return 0;
 }
 
+// Diagnostics: sustained FFMA throughput of the device (TFLOP/s, 2 flop per FFMA), measured with CUDA
+// events over `ms_target` milliseconds of back-to-back launches.  Used by bench.py as the FP32 roofline peak.
+extern "C" int dcb200_ctx_ffma_peak(dcb200_ctx* c, double ms_target, double* tflops) {
+  if (!c || !tflops) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  float* out = nullptr;
+  CK(cudaMalloc(&out, 4));
+  const int iters = 8192, bs = 256, grid = c->sm_count * 8;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  ffma_peak_kernel<<<grid, bs, 0, c->stream>>>(out, iters, 1.0001f, 0.5f);     // warm-up
+  CK(cudaStreamSynchronize(c->stream));
+  double best = 0.0, spent = 0.0;
+  int launches = 1;
+  while (spent < ms_target) {
+    CK(cudaEventRecord(e0, c->stream));
+    for (int q = 0; q < 4; ++q) ffma_peak_kernel<<<grid, bs, 0, c->stream>>>(out, iters, 1.0001f, 0.5f);
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    spent += ms;
+    launches += 4;
+    const double fl = 4.0 * 2.0 * 16.0 * (double) iters * (double) grid * bs;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  c->launches += launches;
+  *tflops = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
-// (1) host-pointer entry points: one worker thread per GPU, rows sharded, results written straight
-//     into the caller's arrays
+// (1) host-pointer entry points: one worker thread per GPU, positions sharded, results scattered
+//     into the caller's arrays in frame order
 // ------------------------------------------------------------------------------------------------
 namespace {
 
@@ -693,11 +875,9 @@ int gpus_to_use(int* n) {
 // runs fn(gpu, n_gpus) on one thread per GPU; returns the first failure
 template <class Fn>
 int on_gpus(int n_gpus, Fn&& fn) {
+  if (n_gpus == 1) return fn(0, 1);
   std::vector<int> rc(n_gpus, 0);
   std::vector<std::string> msg(n_gpus);
-  if (n_gpus == 1) {
-    return fn(0, 1);
-  }
   std::vector<std::thread> th;
   for (int g = 0; g < n_gpus; ++g)
     th.emplace_back([&, g]() {
@@ -710,8 +890,10 @@ int on_gpus(int n_gpus, Fn&& fn) {
   return 0;
 }
 
+// shards are multiples of the row block so that no CTA straddles two devices
 void shard(size_t n, int g, int n_gpus, size_t* b, size_t* e) {
-  const size_t per = (n + n_gpus - 1) / n_gpus;
+  const size_t blocks = (n + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  const size_t per = (blocks + n_gpus - 1) / n_gpus * ROWS_PER_CTA;
   *b = std::min(n, per * g);
   *e = std::min(n, per * (g + 1));
 }
@@ -725,26 +907,51 @@ extern "C" int dcb200_populations(const float* coords, size_t n_rows, size_t n_c
   int n_gpus = 0;
   CKI(gpus_to_use(&n_gpus));
   n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
-  return on_gpus(n_gpus, [&](int g, int G) -> int {
+  if (n_gpus == 1) {                         // everything on the device, results land in frame order
     dcb200_ctx* c = nullptr;
-    CKI(pooled_ctx(g, &c));
-    size_t b, e;
-    shard(n_rows, g, G, &b, &e);
+    CKI(pooled_ctx(0, &c));
     CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
-    if (b == e) return 0;
-    const size_t rows = e - b;
-    uint32_t* dev = nullptr;
-    CK(cudaMalloc(&dev, n_radii * rows * sizeof(uint32_t)));
-    int rc = dcb200_ctx_populations(c, radii, n_radii, b, e, dev);
+    uint32_t *dev = nullptr, *dev2 = nullptr;
+    CK(cudaMalloc(&dev, 2 * n_radii * n_rows * sizeof(uint32_t)));
+    dev2 = dev + n_radii * n_rows;
+    int rc = dcb200_ctx_populations(c, radii, n_radii, 0, n_rows, dev);
+    if (!rc) rc = dcb200_ctx_to_frame_order(c, dev, n_radii, dev2);
     if (!rc) {
-      cudaError_t ce = cudaMemcpy2DAsync(pops + b, n_rows * sizeof(uint32_t), dev, rows * sizeof(uint32_t), rows * sizeof(uint32_t),
-                                         n_radii, cudaMemcpyDeviceToHost, c->stream);
+      cudaError_t ce = cudaMemcpyAsync(pops, dev2, n_radii * n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
       if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
       if (ce != cudaSuccess) rc = fail(std::string("populations download: ") + cudaGetErrorString(ce));
     }
     cudaFree(dev);
     return rc;
-  });
+  }
+  std::vector<uint32_t> tmp(n_radii * n_rows), perm(n_rows);
+  CKI(on_gpus(n_gpus, [&](int g, int G) -> int {
+    dcb200_ctx* c = nullptr;
+    CKI(pooled_ctx(g, &c));
+    size_t b, e;
+    shard(n_rows, g, G, &b, &e);
+    CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));     // same deterministic order on every device
+    int rc = 0;
+    cudaError_t ce = cudaSuccess;
+    uint32_t* dev = nullptr;
+    if (e > b) {
+      const size_t rows = e - b;
+      CK(cudaMalloc(&dev, n_radii * rows * sizeof(uint32_t)));
+      rc = dcb200_ctx_populations(c, radii, n_radii, b, e, dev);
+      if (!rc)
+        ce = cudaMemcpy2DAsync(tmp.data() + b, n_rows * sizeof(uint32_t), dev, rows * sizeof(uint32_t), rows * sizeof(uint32_t),
+                               n_radii, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (!rc && ce == cudaSuccess && g == 0)
+      ce = cudaMemcpyAsync(perm.data(), c->perm.p, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    if (ce != cudaSuccess) rc = fail(std::string("populations download: ") + cudaGetErrorString(ce));
+    if (dev) cudaFree(dev);
+    return rc;
+  }));
+  for (size_t r = 0; r < n_radii; ++r)
+    for (size_t p = 0; p < n_rows; ++p) pops[r * n_rows + perm[p]] = tmp[r * n_rows + p];
+  return 0;
 }
 
 extern "C" int dcb200_free_energies(const uint32_t* pops, size_t n, float* fe) {
@@ -831,7 +1038,7 @@ extern "C" int dcb200_screening_step(const float* sorted_coords, size_t n_cols, 
   CKI(on_gpus(n_gpus, [&](int g, int G) -> int {
     dcb200_ctx* c = nullptr;
     CKI(pooled_ctx(g, &c));
-    CKI(dcb200_ctx_set_coords(c, sorted_coords, m_new, n_cols));
+    CKI(dcb200_ctx_set_coords_ex(c, sorted_coords, m_new, n_cols, 0, 1));
     // rows are sharded so that every GPU gets about the same number of pairs (row p has p candidates)
     auto cut = [&](int q) -> size_t {
       const double a = (double) m_prev * m_prev, b = (double) m_new * m_new;

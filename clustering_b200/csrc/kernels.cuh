@@ -41,7 +41,10 @@ struct ScanGeom {
   uint32_t n_col_items;             // ceil(n_col_tiles / tiles_per_item)
   unsigned int* work_counter;       // zero-initialised before the launch
   float e_abs, e_rel;               // |fast - exact| <= e_abs + e_rel * value   (api.cu: error_bounds)
-  unsigned long long* stats;        // [0] pairs handed to the slow path, [1] pairs re-evaluated exactly
+  unsigned long long* stats;        // [0] pairs handed to the slow path, [1] pairs re-evaluated exactly,
+                                    // [2] column tiles streamed (x ROWS_PER_CTA x tile width = pairs evaluated)
+  const float* bbox;                // [ld/64][2*d] bounding boxes (lo[d], hi[d]) of 64-frame groups, centred coords
+  float prune_thr;                  // static pruning threshold (fast-value units); +inf disables pruning
 };
 
 // per-thread slow-path counters, added to g.stats once per kernel
@@ -73,9 +76,12 @@ struct SmemRing {
   uint64_t* full;          // STAGES
   uint64_t* empty;         // STAGES
   TileMeta* meta;          // STAGES
+  unsigned long long* wthr;   // N_CONSUMER_WARPS: (item << 32 | float bits) pruning threshold published per warp
+  float* rbb;              // 2*d: bounding box of the current row block (producer scratch)
   size_t tile_floats;
   __host__ __device__ static size_t bytes(int d) {
-    return (size_t) STAGES * (d + 1) * TJ * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta);
+    return (size_t) STAGES * (d + 1) * TJ * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta) + N_CONSUMER_WARPS * 8 +
+           (size_t) 2 * d * 4;
   }
   __device__ SmemRing(unsigned char* base, int d) {
     tile_floats = (size_t) (d + 1) * TJ;
@@ -83,6 +89,8 @@ struct SmemRing {
     full = reinterpret_cast<uint64_t*>(base + STAGES * tile_floats * 4);
     empty = full + STAGES;
     meta = reinterpret_cast<TileMeta*>(empty + STAGES);
+    wthr = reinterpret_cast<unsigned long long*>(meta + STAGES);
+    rbb = reinterpret_cast<float*>(wthr + N_CONSUMER_WARPS);
   }
   __device__ void init() {
     if (threadIdx.x == 0) {
@@ -90,62 +98,160 @@ struct SmemRing {
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], N_CONSUMER_WARPS);
       }
+      for (int w = 0; w < N_CONSUMER_WARPS; ++w) wthr[w] = ~0ull;
       fence_mbar_init();
     }
   }
 };
 
-// Producer: one elected lane walks the work items and streams their column tiles.
-// range(rb, lim0, lim1) lets a kernel restrict the column tiles per row block (screening only
-// needs the columns below its rows).
-template <int D, class TileRange>
-__device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, TileRange&& range) {
+// Work item -> (row block, column range).  Items are ordered column-step-major: at step 0 every row
+// block scans the column range that contains its own frames (spatial order: its near neighbourhood),
+// then ranges at growing distance, alternating sides.  Concurrently running items therefore belong
+// to different row blocks, and a row block's later items start from what its earlier ones found.
+__device__ __forceinline__ void item_coords(const ScanGeom& g, uint32_t item, uint32_t TJ, uint32_t* rb, uint32_t* ci) {
+  const uint32_t step = item / g.n_row_blocks;
+  *rb = item % g.n_row_blocks;
+  const uint32_t diag = min((g.row_begin + *rb * ROWS_PER_CTA) / (g.tiles_per_item * TJ), g.n_col_items - 1);
+  // offsets 0, +1, -1, +2, -2, ... folded into [0, n_col_items)
+  const uint32_t k = (step + 1) >> 1;
+  const uint32_t n = g.n_col_items;
+  uint32_t c;
+  if (step & 1) c = (diag + k) % n; else c = (diag + n - (k % n)) % n;
+  // the alternating walk visits every range exactly once only if it is made a permutation:
+  // walk positions p = 0..n-1 are mapped through the cyclic order starting at diag
+  *ci = c;
+}
+
+// Producer warp: walks the work items, drops the column tiles whose bounding box is provably out of
+// reach of every row of the block (dynamic threshold published by the consumers, or the static one),
+// and streams the others with 1-D bulk TMA.  An item that streamed at least one tile is closed by a
+// data-less end marker (flags 2|4) on which the consumers write their results back.
+// item_thr(rb, lane): warp-collective, returns the (uniform) pruning threshold the item starts with.
+template <int D, class TileRange, class ItemThr>
+__device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bool dynamic_thr, TileRange&& range, ItemThr&& item_thr) {
   constexpr int TJ = TileW<D>::tj;
+  constexpr int GPT = TJ / 64;                      // 64-frame bounding-box groups per tile
+  const int lane = threadIdx.x & 31;
   Pipe pp;
   const int d = D ? D : g.d;
   const uint32_t total = g.n_row_blocks * g.n_col_items;
+  unsigned long long streamed = 0;
   for (;;) {
-    const uint32_t item = atomicAdd(g.work_counter, 1u);
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(g.work_counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total) break;
-    const uint32_t rb = item / g.n_col_items, ci = item % g.n_col_items;
+    uint32_t rb, ci;
+    item_coords(g, item, TJ, &rb, &ci);
     uint32_t t0 = ci * g.tiles_per_item;
     uint32_t t1 = min(t0 + g.tiles_per_item, g.n_col_tiles);
     uint32_t lim0 = 0, lim1 = g.n_col_tiles;
     range(rb, lim0, lim1);
     t0 = max(t0, lim0);
     t1 = min(t1, lim1);
-    for (uint32_t t = t0; t < t1; ++t) {
+    if (t0 >= t1) continue;
+    // bounding box of the row block = union of its 64-frame groups
+    {
+      const uint32_t r0 = g.row_begin + rb * ROWS_PER_CTA;
+      const uint32_t r1 = min(r0 + ROWS_PER_CTA, g.row_end);
+      const uint32_t g0 = r0 / 64, g1 = (r1 - 1) / 64;
+      for (int k = lane; k < d; k += 32) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (uint32_t q = g0; q <= g1; ++q) {
+          lo = fminf(lo, __ldg(g.bbox + (size_t) q * 2 * d + k));
+          hi = fmaxf(hi, __ldg(g.bbox + (size_t) q * 2 * d + d + k));
+        }
+        ring.rbb[k] = lo;
+        ring.rbb[d + k] = hi;
+      }
+      __syncwarp();
+    }
+    bool first = true;
+    // pruning threshold: the largest filter threshold of any row of the block (fast-value units)
+    const float thr0 = item_thr(rb, lane);
+    for (uint32_t base = t0; base < t1; base += 32) {
+      const uint32_t t = base + lane;
+      float lb = INFINITY;                          // lower bound of the fast value over (row block) x (tile t)
+      if (t < t1) {
+        for (int q = 0; q < GPT; ++q) {
+          const float* bb = g.bbox + (size_t) (t * GPT + q) * 2 * d;
+          float s = 0.f;
+          for (int k = 0; k < d; ++k) {
+            const float gap = fmaxf(fmaxf(ring.rbb[k] - __ldg(bb + d + k), __ldg(bb + k) - ring.rbb[d + k]), 0.f);
+            s = fmaf(gap, gap, s);
+          }
+          lb = q == 0 ? s : fminf(lb, s);
+        }
+        lb *= 0.999f;
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, t < t1 && !(lb > thr0));     // NaN keeps
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        const uint32_t tt = base + (uint32_t) src;
+        mask &= mask - 1;
+        if (dynamic_thr) {
+          // the consumers tighten the threshold while they work: look again right before streaming
+          float thr = 0.f;
+          for (int w = 0; w < N_CONSUMER_WARPS; ++w) {
+            const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(ring.wthr + w);
+            // a value published for another item says nothing about this one
+            thr = fmaxf(thr, (uint32_t) (v >> 32) == item ? __uint_as_float((uint32_t) v) : INFINITY);
+          }
+          if (__shfl_sync(0xffffffffu, lb, src) > thr) continue;
+        }
+        if (lane == 0) {
+          mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+          TileMeta m;
+          m.row_block = (int32_t) rb;
+          m.col0 = tt * TJ;
+          m.flags = first ? 1u : 0u;
+          m.aux = item;
+          ring.meta[pp.stage] = m;
+          mbar_arrive_expect_tx(&ring.full[pp.stage], (uint32_t) (ring.tile_floats * 4));
+        }
+        __syncwarp();
+        {
+          float* dst = ring.tiles + pp.stage * ring.tile_floats;
+          const float* src = g.cT + (size_t) tt * TJ;
+          for (int k = lane; k <= d; k += 32) tma_load_1d(dst + k * TJ, src + (size_t) k * g.ld, TJ * 4, &ring.full[pp.stage]);
+        }
+        first = false;
+        ++streamed;
+        pp.advance();
+      }
+    }
+    if (!first && lane == 0) {                    // end-of-item marker
       mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
       TileMeta m;
       m.row_block = (int32_t) rb;
-      m.col0 = t * TJ;
-      m.flags = (t == t0 ? 1u : 0u) | (t + 1 == t1 ? 2u : 0u);
-      m.aux = 0;
+      m.col0 = 0;
+      m.flags = 2u | 4u;
+      m.aux = item;
       ring.meta[pp.stage] = m;
-      mbar_arrive_expect_tx(&ring.full[pp.stage], (uint32_t) (ring.tile_floats * 4));
-      float* dst = ring.tiles + pp.stage * ring.tile_floats;
-      const float* src = g.cT + m.col0;
-#pragma unroll 1
-      for (int k = 0; k <= d; ++k) tma_load_1d(dst + k * TJ, src + (size_t) k * g.ld, TJ * 4, &ring.full[pp.stage]);
-      pp.advance();
+      mbar_arrive(&ring.full[pp.stage]);
     }
+    if (!first) pp.advance();
   }
-  mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
-  ring.meta[pp.stage].row_block = -1;
-  mbar_arrive(&ring.full[pp.stage]);
+  if (lane == 0) {
+    mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+    ring.meta[pp.stage].row_block = -1;
+    mbar_arrive(&ring.full[pp.stage]);
+    if (g.stats && streamed) atomicAdd(g.stats + 2, streamed);
+  }
 }
 
-// Row operands of a consumer thread.
+// Row operands of a consumer thread: rows row0 + r * N_CONSUMERS, r = 0..RI-1.
 template <int D>
 struct Rows {
   float x[RI][D];           // centred coordinates x'
   float xn[RI];             // |x'|^2
-  uint32_t row[RI];
+  uint32_t row0;
+  __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * N_CONSUMERS; }
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid) {
+    row0 = g.row_begin + rb * ROWS_PER_CTA + tid;
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
-      row[r] = g.row_begin + rb * ROWS_PER_CTA + r * N_CONSUMERS + tid;
-      const size_t p = min((size_t) row[r], g.ld - 1);     // rows past the end: clamped, results discarded
+      const size_t p = min((size_t) row(r), g.ld - 1);     // rows past the end: clamped, results discarded
 #pragma unroll
       for (int k = 0; k < D; ++k) x[r][k] = -0.5f * __ldg(g.cT + (size_t) k * g.ld + p);
       xn[r] = __ldg(g.cT + (size_t) D * g.ld + p);
@@ -155,25 +261,60 @@ struct Rows {
 template <>
 struct Rows<0> {
   float xn[RI];
-  uint32_t row[RI];
+  uint32_t row0;
   size_t p[RI];
+  __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * N_CONSUMERS; }
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid) {
+    row0 = g.row_begin + rb * ROWS_PER_CTA + tid;
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
-      row[r] = g.row_begin + rb * ROWS_PER_CTA + r * N_CONSUMERS + tid;
-      p[r] = min((size_t) row[r], g.ld - 1);
+      p[r] = min((size_t) row(r), g.ld - 1);
       xn[r] = __ldg(g.cT + (size_t) g.d * g.ld + p[r]);
     }
   }
 };
 
+// register arrays must not be indexed dynamically (that would spill them to local memory)
+__device__ __forceinline__ float sel4(const float (&v)[RI], int r) {
+  return r == 0 ? v[0] : r == 1 ? v[1] : r == 2 ? v[2] : v[3];
+}
+__device__ __forceinline__ void put4(float (&v)[RI], int r, float x) {
+  if (r == 0) v[0] = x; else if (r == 1) v[1] = x; else if (r == 2) v[2] = x; else v[3] = x;
+}
+
+constexpr size_t SCRATCH_BYTES = (size_t) RI * CJ * N_CONSUMERS * 4;     // per-thread spill of one 4x4 block
+
+// Slow path entry: the 4x4 block of one step has at least one pair below its row threshold somewhere
+// in the warp.  The block is parked in shared memory (slot-private column => no bank conflicts) and
+// the hits of this lane are walked with ONE compact copy of the handler, so the instruction footprint
+// of the kernel stays small (the hot loop must live in the instruction cache).
+template <class Hit>
+__device__ __forceinline__ void walk_hits(float* __restrict__ scratch, const float (&acc)[RI][CJ], float (&t)[RI], int jt0, Hit& hit) {
+  uint32_t mask = 0;
+#pragma unroll
+  for (int r = 0; r < RI; ++r)
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) {
+      scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c];
+      mask |= (acc[r][c] < t[r]) ? (1u << (r * CJ + c)) : 0u;
+    }
+#pragma unroll 1
+  while (mask) {
+    const int p = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int r = p / CJ;
+    const float a = scratch[p * N_CONSUMERS];
+    if (a < sel4(t, r)) hit(r, jt0 + (p % CJ), a);        // re-checked: the handler may have tightened t[r]
+  }
+}
+
 // Consumer inner loop over one tile: acc[r][c] = |y_c|^2 - 2 x_r.y_c for an RI x CJ block per step;
 // hit(r, j_in_tile, acc) is called for every pair with acc < t[r].
 template <int D, class Hit>
 __device__ __forceinline__ void scan_tile(const ScanGeom&, const float* __restrict__ tl, const Rows<D>& R, float (&t)[RI],
-                                          Hit&& hit) {
+                                          float* __restrict__ scratch, Hit& hit) {
   constexpr int TJ = TileW<D>::tj;
-#pragma unroll 2
+#pragma unroll 1
   for (int g = 0; g < TJ; g += CJ) {
     float acc[RI][CJ];
     {
@@ -204,30 +345,26 @@ __device__ __forceinline__ void scan_tile(const ScanGeom&, const float* __restri
       const float m = fminf(fminf(acc[r][0], acc[r][1]), fminf(acc[r][2], acc[r][3]));
       any |= (m < t[r]);
     }
-    if (any) {
-#pragma unroll
-      for (int r = 0; r < RI; ++r)
-#pragma unroll
-        for (int c = 0; c < CJ; ++c)
-          if (acc[r][c] < t[r]) hit(r, g + c, acc[r][c]);
-    }
+    if (any) walk_hits(scratch, acc, t, g, hit);
   }
 }
 
 // run-time-D variant: 4 rows x 16 columns per step, row operands from L1/L2
 template <class Hit>
 __device__ __forceinline__ void scan_tile(const ScanGeom& gm, const float* __restrict__ tl, const Rows<0>& R, float (&t)[RI],
-                                          Hit&& hit) {
+                                          float* __restrict__ scratch, Hit& hit) {
   constexpr int TJ = TileW<0>::tj, CG = TileW<0>::cj;
   const int d = gm.d;
 #pragma unroll 1
   for (int g = 0; g < TJ; g += CG) {
-    float acc[RI][CG];
+    float acc[CG / CJ][RI][CJ];
 #pragma unroll
-    for (int c = 0; c < CG; ++c) {
-      const float nrm = tl[d * TJ + g + c];
+    for (int c4 = 0; c4 < CG / CJ; ++c4) {
+      const float4 n4 = *reinterpret_cast<const float4*>(tl + d * TJ + g + c4 * CJ);
 #pragma unroll
-      for (int r = 0; r < RI; ++r) acc[r][c] = nrm;
+      for (int r = 0; r < RI; ++r) {
+        acc[c4][r][0] = n4.x; acc[c4][r][1] = n4.y; acc[c4][r][2] = n4.z; acc[c4][r][3] = n4.w;
+      }
     }
 #pragma unroll 2
     for (int k = 0; k < d; ++k) {
@@ -235,31 +372,26 @@ __device__ __forceinline__ void scan_tile(const ScanGeom& gm, const float* __res
 #pragma unroll
       for (int r = 0; r < RI; ++r) xr[r] = -0.5f * __ldg(gm.cT + (size_t) k * gm.ld + R.p[r]);
 #pragma unroll
-      for (int c4 = 0; c4 < CG; c4 += 4) {
-        const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + g + c4);
+      for (int c4 = 0; c4 < CG / CJ; ++c4) {
+        const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + g + c4 * CJ);
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-          acc[r][c4 + 0] = fmaf(xr[r], y4.x, acc[r][c4 + 0]);
-          acc[r][c4 + 1] = fmaf(xr[r], y4.y, acc[r][c4 + 1]);
-          acc[r][c4 + 2] = fmaf(xr[r], y4.z, acc[r][c4 + 2]);
-          acc[r][c4 + 3] = fmaf(xr[r], y4.w, acc[r][c4 + 3]);
+          acc[c4][r][0] = fmaf(xr[r], y4.x, acc[c4][r][0]);
+          acc[c4][r][1] = fmaf(xr[r], y4.y, acc[c4][r][1]);
+          acc[c4][r][2] = fmaf(xr[r], y4.z, acc[c4][r][2]);
+          acc[c4][r][3] = fmaf(xr[r], y4.w, acc[c4][r][3]);
         }
       }
     }
-    bool any = false;
 #pragma unroll
-    for (int r = 0; r < RI; ++r) {
-      float m = acc[r][0];
+    for (int c4 = 0; c4 < CG / CJ; ++c4) {
+      bool any = false;
 #pragma unroll
-      for (int c = 1; c < CG; ++c) m = fminf(m, acc[r][c]);
-      any |= (m < t[r]);
-    }
-    if (any) {
-#pragma unroll
-      for (int r = 0; r < RI; ++r)
-#pragma unroll
-        for (int c = 0; c < CG; ++c)
-          if (acc[r][c] < t[r]) hit(r, g + c, acc[r][c]);
+      for (int r = 0; r < RI; ++r) {
+        const float m = fminf(fminf(acc[c4][r][0], acc[c4][r][1]), fminf(acc[c4][r][2], acc[c4][r][3]));
+        any |= (m < t[r]);
+      }
+      if (any) walk_hits(scratch, acc[c4], t, g + c4 * CJ, hit);
     }
   }
 }
@@ -274,12 +406,26 @@ struct PopsArgs {
   int n_bins;               // distinct radii in this pass (<= MAX_BINS)
   float rad2[32];           // ascending squared radii, padded with +inf
   float thr_fast;           // rad2[n_bins-1] + error margin
-  uint32_t* cnt;            // [n_bins][ld_cnt]: #{j != i : d2(i,j) < rad2[b]}, rows relative to row_begin
+  uint32_t* cnt;            // [n_bins][ld_cnt]: #{j != i : rad2[b-1] <= d2(i,j) < rad2[b]}, rows relative to row_begin
   size_t ld_cnt;
 };
 
 __host__ __device__ inline size_t pops_smem_bytes(size_t ring_bytes, int n_bins) {
-  return ((ring_bytes + 15) & ~size_t(15)) + 32 * 4 + (size_t) n_bins * ROWS_PER_CTA * 4;
+  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + 32 * 4 + (size_t) n_bins * ROWS_PER_CTA * 4;
+}
+
+// number of table entries <= s (table ascending, padded with +inf up to 32 entries)
+__device__ __forceinline__ int bin_of(const float* __restrict__ rad2s, int nb, float s) {
+  int b = 0;
+  if (nb <= 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b += (rad2s[q] <= s) ? 1 : 0;
+  } else {
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1)
+      if (rad2s[b + step - 1] <= s) b += step;
+  }
+  return b;
 }
 
 template <int D>
@@ -288,15 +434,17 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
   const ScanGeom& g = a.g;
   const int d = D ? D : g.d;
   SmemRing<D> ring(smem, d);
-  float* rad2s = reinterpret_cast<float*>(smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15)));
-  uint32_t* hist = reinterpret_cast<uint32_t*>(rad2s + 32);       // [n_bins][ROWS_PER_CTA], slot-private counters
+  unsigned char* extra = smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15));
+  float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
+  float* rad2s = reinterpret_cast<float*>(extra + SCRATCH_BYTES);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(rad2s + 32) + threadIdx.x;   // [n_bins][ROWS_PER_CTA], slot-private counters
   ring.init();
   if (threadIdx.x < 32) rad2s[threadIdx.x] = a.rad2[threadIdx.x];
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == N_CONSUMER_WARPS) {
-    if (lane == 0) produce<D>(g, ring, [](uint32_t, uint32_t&, uint32_t&) {});
+    produce<D>(g, ring, false, [](uint32_t, uint32_t&, uint32_t&) {}, [&](uint32_t, int) { return g.prune_thr; });
     return;
   }
   const int tid = threadIdx.x;
@@ -305,6 +453,23 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
   float t[RI];
   Pipe cp;
   SlowStats st;
+  uint32_t col0 = 0;
+  auto hit = [&](int r, int jt, float accv) {
+    const uint32_t j = col0 + jt;
+    const uint32_t i = R.row(r);
+    float s = accv + sel4(R.xn, r);
+    ++st.slow;
+    int b = bin_of(rad2s, nb, s);
+    const float lo = b > 0 ? rad2s[b - 1] : -INFINITY;
+    const float hi = rad2s[b];
+    const float e = fmaf(g.e_rel, fabsf(s), g.e_abs);
+    if ((s - lo < e) || (hi - s <= e)) {       // within the error band of a radius: decide exactly
+      s = dist2_exact(g.xT, g.ld, d, i, j);
+      ++st.exact;
+      b = bin_of(rad2s, nb, s);
+    }
+    if (j != i && b < nb) hist[b * ROWS_PER_CTA + r * N_CONSUMERS] += 1;
+  };
   for (;;) {
     mbar_wait(&ring.full[cp.stage], cp.phase);
     const TileMeta m = ring.meta[cp.stage];
@@ -315,40 +480,22 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
       for (int r = 0; r < RI; ++r) t[r] = next_up(a.thr_fast - R.xn[r]);
       for (int b = 0; b < nb; ++b)
 #pragma unroll
-        for (int r = 0; r < RI; ++r) hist[b * ROWS_PER_CTA + r * N_CONSUMERS + tid] = 0;
+        for (int r = 0; r < RI; ++r) hist[b * ROWS_PER_CTA + r * N_CONSUMERS] = 0;
     }
-    const float* tl = ring.tiles + cp.stage * ring.tile_floats;
-    scan_tile(g, tl, R, t, [&](int r, int jt, float accv) {
-      const uint32_t j = m.col0 + jt;
-      float s = accv + R.xn[r];
-      ++st.slow;
-      int b = 0;
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1)
-        if (rad2s[b + step - 1] <= s) b += step;
-      const float lo = b > 0 ? rad2s[b - 1] : -INFINITY;
-      const float hi = rad2s[b];
-      const float e = fmaf(g.e_rel, fabsf(s), g.e_abs);
-      if ((s - lo < e) || (hi - s <= e)) {       // within the error band of a radius: decide exactly
-        s = dist2_exact(g.xT, g.ld, d, R.row[r], j);
-        ++st.exact;
-        b = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1)
-          if (rad2s[b + step - 1] <= s) b += step;
-      }
-      if (j != R.row[r] && b < nb) hist[b * ROWS_PER_CTA + r * N_CONSUMERS + tid] += 1;
-    });
+    col0 = m.col0;
+    if (!(m.flags & 4u)) {
+      const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      scan_tile(g, tl, R, t, scratch, hit);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
     if (m.flags & 2u) {
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
-        if (R.row[r] < g.row_end) {
-          uint32_t run = 0;
+        if (R.row(r) < g.row_end) {
           for (int b = 0; b < nb; ++b) {
-            run += hist[b * ROWS_PER_CTA + r * N_CONSUMERS + tid];
-            if (run) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + (R.row[r] - g.row_begin), run);
+            const uint32_t h = hist[b * ROWS_PER_CTA + r * N_CONSUMERS];
+            if (h) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + (R.row(r) - g.row_begin), h);
           }
         }
       }
@@ -359,20 +506,21 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
 }
 
 // ================================================================================================
-// nearest neighbours (rows and columns in free-energy-sorted order)
+// nearest neighbours (rows and columns in the context's spatial order)
 // ================================================================================================
 struct NnArgs {
   ScanGeom g;
-  const uint32_t* perm;         // [n] sorted position -> original frame
-  const uint32_t* lo;           // [n] number of frames with strictly lower free energy than position p
+  const uint32_t* perm;         // [n] position -> original frame
+  const uint32_t* lo;           // [n] per position: number of frames with a strictly lower free energy
+                                //     (fe[j] < fe[i]  <=>  lo[j] < lo[i])
   unsigned long long* key_nn;   // [row_end-row_begin] (d2 bits << 32 | original index), atomicMin'ed
   unsigned long long* key_hd;
 };
 
-__host__ __device__ inline size_t screen_smem_bytes(size_t ring_bytes) { return (ring_bytes + 15) & ~size_t(15); }
+__host__ __device__ inline size_t screen_smem_bytes(size_t ring_bytes) { return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES; }
 
 __host__ __device__ inline size_t nn_smem_bytes(size_t ring_bytes) {
-  return ((ring_bytes + 15) & ~size_t(15)) + (size_t) 2 * ROWS_PER_CTA * 8;
+  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + (size_t) 2 * ROWS_PER_CTA * 8 + (size_t) ROWS_PER_CTA * 4;
 }
 
 __device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as_float((uint32_t) (k >> 32)); }
@@ -383,24 +531,69 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
   const ScanGeom& g = a.g;
   const int d = D ? D : g.d;
   SmemRing<D> ring(smem, d);
+  unsigned char* extra = smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15));
+  float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
   // best[0][slot] = nearest-neighbour key, best[1][slot] = nearest neighbour with lower free energy
-  unsigned long long* best = reinterpret_cast<unsigned long long*>(smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15)));
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(extra + SCRATCH_BYTES) + threadIdx.x;
+  uint32_t* lo_s = reinterpret_cast<uint32_t*>(extra + SCRATCH_BYTES + (size_t) 2 * ROWS_PER_CTA * 8) + threadIdx.x;
   ring.init();
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == N_CONSUMER_WARPS) {
-    if (lane == 0) produce<D>(g, ring, [](uint32_t, uint32_t&, uint32_t&) {});
+    // initial pruning threshold of an item: what earlier items already found for the rows of the block
+    produce<D>(g, ring, true, [](uint32_t, uint32_t&, uint32_t&) {}, [&](uint32_t rb, int ln) {
+      const uint32_t r0 = g.row_begin + rb * ROWS_PER_CTA;
+      const uint32_t r1 = min(r0 + ROWS_PER_CTA, g.row_end);
+      float v = 0.f;
+      for (uint32_t i = r0 + ln; i < r1; i += 32) {
+        const float dn = key_d2(a.key_nn[i - g.row_begin]);
+        const float dh = __ldg(a.lo + i) == 0 ? dn : key_d2(a.key_hd[i - g.row_begin]);
+        v = fmaxf(v, fmaxf(dn, dh));                     // NaN-free: keys hold real distances or FLT_MAX
+      }
+      v = (fmaf(g.e_rel, v, v) + g.e_abs) * 1.00001f;    // the rows' filter thresholds in fast-value units
+      if (!(v < INFINITY)) v = INFINITY;
+      return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+    });
     return;
   }
   const int tid = threadIdx.x;
   Rows<D> R;
   float t[RI], t_nn[RI], t_hd[RI];
-  uint32_t lo_max = 0;
+  uint32_t col0 = 0;
   Pipe cp;
   SlowStats st;
   // every column whose exact d2 is <= `d2` satisfies acc < thr(d2) (api.cu: error_bounds)
   auto thr = [&](float d2, float xnr) { return next_up(next_up(fmaf(g.e_rel, d2, d2) + g.e_abs - xnr)); };
+  auto hit = [&](int r, int jt, float accv) {
+    const uint32_t j = col0 + jt;
+    const uint32_t i = R.row(r);
+    ++st.slow;
+    if (j == i || j >= g.n || i >= g.row_end) return;
+    float tn = sel4(t_nn, r), th = sel4(t_hd, r);
+    const bool hd_cand = __ldg(a.lo + j) < lo_s[r * N_CONSUMERS];
+    if (!hd_cand && !(accv < tn)) return;     // passed only the (weaker) lower-free-energy filter, but is no candidate for it
+    const float d2 = dist2_exact(g.xT, g.ld, d, i, j);
+    ++st.exact;
+    if (!(d2 < FLT_MAX)) return;
+    const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | __ldg(a.perm + j);
+    unsigned long long* b0 = best + r * N_CONSUMERS;
+    unsigned long long* b1 = b0 + ROWS_PER_CTA;
+    const float xnr = sel4(R.xn, r);
+    if (key < *b0) { *b0 = key; tn = thr(d2, xnr); put4(t_nn, r, tn); }
+    if (hd_cand && key < *b1) { *b1 = key; th = thr(d2, xnr); put4(t_hd, r, th); }
+    put4(t, r, fmaxf(tn, th));
+  };
+  // pruning threshold of this warp's rows in fast-value units (acc + xn), published for the producer
+  auto publish = [&](uint32_t item) {
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < RI; ++r)
+      if (R.row(r) < g.row_end) v = fmaxf(v, (t[r] + R.xn[r]) * 1.000001f);     // fmaxf drops NaN
+    if (!(v < INFINITY)) v = INFINITY;
+    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));   // v >= 0: bits order like values
+    if (lane == 0) ring.wthr[warp] = ((unsigned long long) item << 32) | m;
+  };
   for (;;) {
     mbar_wait(&ring.full[cp.stage], cp.phase);
     const TileMeta m = ring.meta[cp.stage];
@@ -410,47 +603,36 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
         unsigned long long k0 = ~0ull, k1 = ~0ull;
-        if (R.row[r] < g.row_end) {                     // warm start from what other items already found
-          k0 = a.key_nn[R.row[r] - g.row_begin];
-          k1 = a.key_hd[R.row[r] - g.row_begin];
+        uint32_t lo_i = 0;
+        if (R.row(r) < g.row_end) {                     // warm start from what earlier items already found
+          k0 = a.key_nn[R.row(r) - g.row_begin];
+          k1 = a.key_hd[R.row(r) - g.row_begin];
+          lo_i = __ldg(a.lo + R.row(r));
         }
-        best[r * N_CONSUMERS + tid] = k0;
-        best[ROWS_PER_CTA + r * N_CONSUMERS + tid] = k1;
+        best[r * N_CONSUMERS] = k0;
+        best[ROWS_PER_CTA + r * N_CONSUMERS] = k1;
+        lo_s[r * N_CONSUMERS] = lo_i;
         t_nn[r] = thr(key_d2(k0), R.xn[r]);
-        t_hd[r] = thr(key_d2(k1), R.xn[r]);
+        // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
+        t_hd[r] = lo_i == 0 ? t_nn[r] : thr(key_d2(k1), R.xn[r]);
+        t[r] = fmaxf(t_nn[r], t_hd[r]);
       }
-      const uint32_t rb0 = g.row_begin + (uint32_t) m.row_block * ROWS_PER_CTA;
-      lo_max = __ldg(a.lo + min(rb0 + ROWS_PER_CTA - 1, min(g.row_end, g.n) - 1));
+      publish(m.aux);
     }
-    // Tile class (free energies ascend with the position): no column of the tile has a lower free
-    // energy than any row of the block -> the plain nearest-neighbour threshold filters; otherwise
-    // the weaker of the two thresholds does, and the slow path sorts the pair out.
-    const bool none_hd = m.col0 >= lo_max;
-#pragma unroll
-    for (int r = 0; r < RI; ++r) t[r] = none_hd ? t_nn[r] : fmaxf(t_nn[r], t_hd[r]);
-    const float* tl = ring.tiles + cp.stage * ring.tile_floats;
-    scan_tile(g, tl, R, t, [&](int r, int jt, float) {
-      const uint32_t j = m.col0 + jt;
-      ++st.slow;
-      if (j == R.row[r] || j >= g.n || R.row[r] >= g.row_end) return;
-      const float d2 = dist2_exact(g.xT, g.ld, d, R.row[r], j);
-      ++st.exact;
-      if (!(d2 < FLT_MAX)) return;
-      const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | __ldg(a.perm + j);
-      unsigned long long* b0 = best + r * N_CONSUMERS + tid;
-      unsigned long long* b1 = b0 + ROWS_PER_CTA;
-      if (key < *b0) { *b0 = key; t_nn[r] = thr(d2, R.xn[r]); }
-      if (j < __ldg(a.lo + R.row[r]) && key < *b1) { *b1 = key; t_hd[r] = thr(d2, R.xn[r]); }
-      t[r] = none_hd ? t_nn[r] : fmaxf(t_nn[r], t_hd[r]);
-    });
+    col0 = m.col0;
+    if (!(m.flags & 4u)) {
+      const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      scan_tile(g, tl, R, t, scratch, hit);
+      publish(m.aux);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
     if (m.flags & 2u) {
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
-        if (R.row[r] < g.row_end) {
-          atomicMin(a.key_nn + (R.row[r] - g.row_begin), best[r * N_CONSUMERS + tid]);
-          atomicMin(a.key_hd + (R.row[r] - g.row_begin), best[ROWS_PER_CTA + r * N_CONSUMERS + tid]);
+        if (R.row(r) < g.row_end) {
+          atomicMin(a.key_nn + (R.row(r) - g.row_begin), best[r * N_CONSUMERS]);
+          atomicMin(a.key_hd + (R.row(r) - g.row_begin), best[ROWS_PER_CTA + r * N_CONSUMERS]);
         }
       }
     }
@@ -500,19 +682,33 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == N_CONSUMER_WARPS) {
-    if (lane == 0)
-      produce<D>(g, ring, [&](uint32_t rb, uint32_t&, uint32_t& lim1) {
-        // only columns below the last row of the block can form an edge (j < i)
-        const uint32_t last_row = min(g.row_begin + (rb + 1) * ROWS_PER_CTA, g.row_end) - 1;
-        lim1 = min(lim1, last_row / TJ + 1);
-      });
+    produce<D>(g, ring, false, [&](uint32_t rb, uint32_t&, uint32_t& lim1) {
+      // only columns below the last row of the block can form an edge (j < i)
+      const uint32_t last_row = min(g.row_begin + (rb + 1) * ROWS_PER_CTA, g.row_end) - 1;
+      lim1 = min(lim1, last_row / TJ + 1);
+    }, [&](uint32_t, int) { return g.prune_thr; });
     return;
   }
   const int tid = threadIdx.x;
+  float* scratch = reinterpret_cast<float*>(smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15))) + threadIdx.x;
   Rows<D> R;
   float t[RI];
   Pipe cp;
   SlowStats st;
+  uint32_t col0 = 0;
+  auto hit = [&](int r, int jt, float accv) {
+    const uint32_t j = col0 + jt;
+    const uint32_t i = R.row(r);
+    if (j >= i || i >= g.row_end) return;
+    ++st.slow;
+    float s = accv + sel4(R.xn, r);
+    const float e = fmaf(g.e_rel, fabsf(s), g.e_abs);
+    if (fabsf(s - a.cut) <= e) {
+      s = dist2_exact(g.xT, g.ld, d, i, j);
+      ++st.exact;
+    }
+    if (s < a.cut) uf_union(a.parent, i, j);
+  };
   for (;;) {
     mbar_wait(&ring.full[cp.stage], cp.phase);
     const TileMeta m = ring.meta[cp.stage];
@@ -522,20 +718,11 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
 #pragma unroll
       for (int r = 0; r < RI; ++r) t[r] = next_up(a.thr_fast - R.xn[r]);
     }
-    const float* tl = ring.tiles + cp.stage * ring.tile_floats;
-    scan_tile(g, tl, R, t, [&](int r, int jt, float accv) {
-      const uint32_t j = m.col0 + jt;
-      const uint32_t i = R.row[r];
-      if (j >= i || i >= g.row_end) return;
-      ++st.slow;
-      float s = accv + R.xn[r];
-      const float e = fmaf(g.e_rel, fabsf(s), g.e_abs);
-      if (fabsf(s - a.cut) <= e) {
-        s = dist2_exact(g.xT, g.ld, d, i, j);
-        ++st.exact;
-      }
-      if (s < a.cut) uf_union(a.parent, i, j);
-    });
+    col0 = m.col0;
+    if (!(m.flags & 4u)) {
+      const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      scan_tile(g, tl, R, t, scratch, hit);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
     cp.advance();

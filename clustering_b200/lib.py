@@ -13,9 +13,10 @@ SYMBOLS = [
     "dcb200_populations", "dcb200_free_energies", "dcb200_nearest_neighbors", "dcb200_screening_step",
     "dcb200_sorted_free_energies", "dcb200_sigma2", "dcb200_screening",
     "dcb200_ctx_create", "dcb200_ctx_destroy", "dcb200_ctx_stream", "dcb200_ctx_sync",
-    "dcb200_ctx_set_coords", "dcb200_ctx_set_coords_device", "dcb200_ctx_populations",
+    "dcb200_ctx_set_coords", "dcb200_ctx_set_coords_device", "dcb200_ctx_set_coords_ex", "dcb200_ctx_order",
+    "dcb200_ctx_to_frame_order", "dcb200_ctx_populations",
     "dcb200_ctx_free_energies", "dcb200_ctx_nn_prepare", "dcb200_ctx_nn_scan", "dcb200_ctx_nn_finish",
-    "dcb200_ctx_screening_scan", "dcb200_ctx_screening_flatten", "dcb200_ctx_screening_merge", "dcb200_ctx_stats",
+    "dcb200_ctx_screening_scan", "dcb200_ctx_screening_flatten", "dcb200_ctx_screening_merge", "dcb200_ctx_stats", "dcb200_ctx_ffma_peak",
 ]
 
 _f = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
@@ -64,7 +65,11 @@ def load():
     L.dcb200_ctx_screening_scan.argtypes = [_p, _sz, _sz, _sz, _sz, C.c_float, _p]
     L.dcb200_ctx_screening_flatten.argtypes = [_p, _sz, _p]
     L.dcb200_ctx_screening_merge.argtypes = [_p, _sz, _p, _p]
-    L.dcb200_ctx_stats.argtypes = [_p, C.POINTER(C.c_uint64)]
+    L.dcb200_ctx_stats.argtypes = [_p, C.POINTER(C.c_uint64), C.c_int]
+    L.dcb200_ctx_set_coords_ex.argtypes = [_p, _p, _sz, _sz, C.c_int, C.c_int]
+    L.dcb200_ctx_order.argtypes = [_p, _p]
+    L.dcb200_ctx_to_frame_order.argtypes = [_p, _p, _sz, _p]
+    L.dcb200_ctx_ffma_peak.argtypes = [_p, C.c_double, C.POINTER(C.c_double)]
     _lib = L
     return L
 

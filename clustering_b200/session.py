@@ -43,26 +43,48 @@ class Session:
     def sync(self):
         lib.check(self.L.dcb200_ctx_sync(self.h))
 
-    def stats(self):
-        s = (C.c_uint64 * 3)()
-        lib.check(self.L.dcb200_ctx_stats(self.h, s))
-        return dict(launches=int(s[0]), slow_pairs=int(s[1]), exact_pairs=int(s[2]))
+    def stats(self, reset=False):
+        s = (C.c_uint64 * 6)()
+        lib.check(self.L.dcb200_ctx_stats(self.h, s, 1 if reset else 0))
+        return dict(launches=int(s[0]), slow_pairs=int(s[1]), exact_pairs=int(s[2]), tiles_streamed=int(s[3]),
+                    pairs_scheduled=int(s[4]), pairs_evaluated=int(s[3]) * int(s[5]))
+
+    def ffma_peak(self, ms_target=200.0):
+        t = C.c_double(0.0)
+        lib.check(self.L.dcb200_ctx_ffma_peak(self.h, float(ms_target), C.byref(t)))
+        return t.value
 
     # ---- coordinates
-    def set_coords(self, coords):
-        """coords: numpy [n][d] (host upload) or a CUDA torch tensor [n][d] (adopted from device memory)."""
+    def set_coords(self, coords, keep_order=False):
+        """coords: numpy [n][d] (host upload) or a CUDA torch tensor [n][d] (adopted from device memory).
+        keep_order: positions = frame order (screening input); default: spatial order chosen by the library."""
         if isinstance(coords, torch.Tensor):
             assert coords.is_cuda and coords.dtype == torch.float32 and coords.is_contiguous()
             self.n, self.d = coords.shape
             torch.cuda.current_stream(self.dev).synchronize()
-            lib.check(self.L.dcb200_ctx_set_coords_device(self.h, _ptr(coords), self.n, self.d))
+            lib.check(self.L.dcb200_ctx_set_coords_ex(self.h, _ptr(coords), self.n, self.d, 1, int(keep_order)))
         else:
             coords = np.ascontiguousarray(coords, np.float32)
             self.n, self.d = coords.shape
-            lib.check(self.L.dcb200_ctx_set_coords(self.h, C.c_void_p(coords.ctypes.data), self.n, self.d))
+            lib.check(self.L.dcb200_ctx_set_coords_ex(self.h, C.c_void_p(coords.ctypes.data), self.n, self.d, 0, int(keep_order)))
+
+    def order(self):
+        """int32 [n]: frame index at every position."""
+        out = torch.empty(self.n, dtype=torch.int32, device=self.dev)
+        lib.check(self.L.dcb200_ctx_order(self.h, _ptr(out)))
+        return out
+
+    def to_frame_order(self, src, out=None):
+        """src: 32-bit device tensor [k][n] in position order -> same shape in frame order."""
+        assert src.is_cuda and src.is_contiguous() and src.element_size() == 4 and src.shape[-1] == self.n
+        if out is None:
+            out = torch.empty_like(src)
+        lib.check(self.L.dcb200_ctx_to_frame_order(self.h, _ptr(src), src.numel() // self.n, _ptr(out)))
+        return out
 
     # ---- populations / free energies
     def populations(self, radii, row_begin=0, row_end=None, out=None):
+        """positions [row_begin,row_end) -> int32 [n_radii][rows] in POSITION order (see to_frame_order)."""
         radii = np.ascontiguousarray(np.atleast_1d(radii), np.float32)
         row_end = self.n if row_end is None else row_end
         if out is None:
@@ -100,6 +122,7 @@ class Session:
         return out
 
     def nearest_neighbors(self, fe):
+        """fe: frame order -> (nn_idx, nn_d2, hd_idx, hd_d2) in frame order."""
         self.nn_prepare(fe)
         return self.nn_finish(self.nn_scan())
 

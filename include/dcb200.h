@@ -78,6 +78,11 @@ int dcb200_screening(const float* fe, const float* nn_d2, float threshold, const
                      size_t n_cols, const uint32_t* initial, uint32_t* labels);
 
 /* ---- (2) device-resident session ---------------------------------------------------------- */
+/* A context holds the frames in HBM in its own order ("positions"): by default a spatial (Morton) order, so
+ * that column tiles have small bounding boxes and tiles out of reach of a row block are never scanned.
+ * Scans take ranges of POSITIONS (any partition of [0, n_rows) may be spread over devices -- every device
+ * builds the same deterministic order) and return results in position order; dcb200_ctx_to_frame_order /
+ * dcb200_ctx_nn_finish bring complete arrays back to the frame order of the input. */
 typedef struct dcb200_ctx dcb200_ctx;
 
 int dcb200_ctx_create(int device, dcb200_ctx** ctx);
@@ -87,30 +92,37 @@ void* dcb200_ctx_stream(dcb200_ctx* ctx);
 int dcb200_ctx_sync(dcb200_ctx* ctx);
 
 /* upload (host pointer) or adopt (device pointer, row-major) the coordinates; builds the dim-major
- * tile layout in HBM.  The source array is not retained. */
+ * tile layout in HBM.  The source array is not retained.
+ * _ex: on_device: coords is a device pointer; keep_order: positions = frame order (needed by the screening,
+ * whose input is already sorted by free energy). */
 int dcb200_ctx_set_coords(dcb200_ctx* ctx, const float* host_coords, size_t n_rows, size_t n_cols);
 int dcb200_ctx_set_coords_device(dcb200_ctx* ctx, const float* dev_coords, size_t n_rows, size_t n_cols);
+int dcb200_ctx_set_coords_ex(dcb200_ctx* ctx, const float* coords, size_t n_rows, size_t n_cols, int on_device, int keep_order);
+/* dev_perm: device uint32 [n_rows], frame index at every position */
+int dcb200_ctx_order(dcb200_ctx* ctx, uint32_t* dev_perm);
+/* dev_dst[a][frame] = dev_src[a][position] for n_arrays arrays of n_rows 32-bit values (device pointers) */
+int dcb200_ctx_to_frame_order(dcb200_ctx* ctx, const uint32_t* dev_src, size_t n_arrays, uint32_t* dev_dst);
 
-/* populations of rows [row_begin,row_end) against all frames.
- * dev_pops: device uint32 [n_radii][row_end-row_begin].  Asynchronous on the context stream. */
-int dcb200_ctx_populations(dcb200_ctx* ctx, const float* radii, size_t n_radii, size_t row_begin, size_t row_end,
+/* populations of positions [pos_begin,pos_end) against all frames.
+ * dev_pops: device uint32 [n_radii][pos_end-pos_begin], position order.  Asynchronous on the context stream. */
+int dcb200_ctx_populations(dcb200_ctx* ctx, const float* radii, size_t n_radii, size_t pos_begin, size_t pos_end,
                            uint32_t* dev_pops);
-/* free energies from device populations (all n_rows); max_pop == 0: computed on the device. */
+/* free energies from device populations (all n_rows, any order); max_pop == 0: computed on the device. */
 int dcb200_ctx_free_energies(dcb200_ctx* ctx, const uint32_t* dev_pops, size_t n_rows, uint32_t max_pop,
                              float* dev_fe);
 
-/* neighbour search, three steps so that row shards can be exchanged between devices in between:
- *   prepare : orders the frames by free energy on the device (dev_fe: device float [n_rows])
- *   scan    : rows = sorted positions [pos_begin,pos_end) against all frames; dev_keys_*: device
- *             uint64 [pos_end-pos_begin] = (d2 bits << 32 | frame index), ready for concatenation
- *   finish  : full key arrays [n_rows] in sorted-position order -> outputs in frame order (device arrays) */
+/* neighbour search, three steps so that shards can be exchanged between devices in between:
+ *   prepare : ranks the frames by free energy on the device (dev_fe: device float [n_rows], FRAME order)
+ *   scan    : positions [pos_begin,pos_end) against all frames; dev_keys_*: device uint64
+ *             [pos_end-pos_begin] = (d2 bits << 32 | frame index), position order, ready for concatenation
+ *   finish  : full key arrays [n_rows] in position order -> outputs in frame order (device arrays) */
 int dcb200_ctx_nn_prepare(dcb200_ctx* ctx, const float* dev_fe);
 int dcb200_ctx_nn_scan(dcb200_ctx* ctx, size_t pos_begin, size_t pos_end, uint64_t* dev_keys_nn,
                        uint64_t* dev_keys_hd);
 int dcb200_ctx_nn_finish(dcb200_ctx* ctx, const uint64_t* dev_keys_nn, const uint64_t* dev_keys_hd,
                          uint32_t* dev_nn_idx, float* dev_nn_d2, uint32_t* dev_hd_idx, float* dev_hd_d2);
 
-/* screening on the device: the context's coordinates must be the free-energy-sorted frames.
+/* screening on the device: the context's coordinates must be the free-energy-sorted frames, set with keep_order.
  * New rows [m_prev,m_new) restricted to [row_begin,row_end) are scanned against all lower positions;
  * dev_comp: device uint32 [m_new] union-find parents (in/out, see dcb200_screening_step).
  * dcb200_ctx_screening_flatten replaces every entry by its representative. */
@@ -120,9 +132,13 @@ int dcb200_ctx_screening_flatten(dcb200_ctx* ctx, size_t m_new, uint32_t* dev_co
 /* unions another forest over the same positions (e.g. a peer GPU's result) into dev_comp */
 int dcb200_ctx_screening_merge(dcb200_ctx* ctx, size_t m_new, uint32_t* dev_comp, const uint32_t* dev_other);
 
-/* counters of the last scan on this context (for the benchmark / tests):
- * [0] kernels launched, [1] pairs handed to the slow path, [2] pairs re-evaluated in exact arithmetic */
-int dcb200_ctx_stats(dcb200_ctx* ctx, uint64_t stats[3]);
+/* counters of the scans on this context since the last reset (for the benchmark / tests):
+ * [0] kernels launched, [1] pairs handed to the slow path, [2] pairs re-evaluated in exact arithmetic,
+ * [3] column tiles streamed, [4] pairs of the full row x column ranges requested, [5] pairs per streamed tile */
+int dcb200_ctx_stats(dcb200_ctx* ctx, uint64_t stats[6], int reset);
+
+/* diagnostics: FFMA-only throughput of the device in TFLOP/s (2 flop per FFMA), the FP32 roofline denominator */
+int dcb200_ctx_ffma_peak(dcb200_ctx* ctx, double ms_target, double* tflops);
 
 #ifdef __cplusplus
 }
