@@ -120,6 +120,7 @@ def cpu_impl():
     if os.path.exists(REF_SO):
         from _oracle import Ref
         r = Ref()
+        r.set_threads(os.cpu_count() or 1)              # torchrun pins OMP_NUM_THREADS=1; the baseline uses every core
         return "reference", r, r.max_threads()
     o = Oracle()
     return "port", o, os.cpu_count()
@@ -196,19 +197,14 @@ def run_ours(args):
     sess = Session(local)
     stream = sess.torch_stream()
 
-    per = ((n + 1023) // 1024 + world - 1) // world * 1024        # position shards are whole row blocks
-    b, e = min(n, rank * per), min(n, (rank + 1) * per)
+    from clustering_b200.dist import DensityPass, shard_bounds
+    b, e = shard_bounds(n, world, rank)
+    dpass = DensityPass(sess, n, radii)
 
     x_dev = torch.from_numpy(x).to(dev)                # resident in HBM before the timed region
     x_pin = torch.from_numpy(x).pin_memory()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > L2 (126 MB)
-    pops_shard = torch.zeros((radii.size, per), dtype=torch.int32, device=dev)
-    pops_all = torch.empty((world, radii.size, per), dtype=torch.int32, device=dev)
-    pops_loc = torch.zeros((radii.size, e - b), dtype=torch.int32, device=dev)
-    keys_loc = torch.zeros((2, e - b), dtype=torch.int64, device=dev)
-    pops_frame = torch.empty((radii.size, n), dtype=torch.int32, device=dev)
-    keys_shard = torch.zeros((2, per), dtype=torch.int64, device=dev)
-    keys_all = torch.empty((world, 2, per), dtype=torch.int64, device=dev)
+    keys_loc = torch.zeros((2, n), dtype=torch.int64, device=dev) if world == 1 else None
     out_host = [torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory(),
                 torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory()]
     pops_host = torch.empty((radii.size, n), dtype=torch.int32).pin_memory()
@@ -217,30 +213,7 @@ def run_ours(args):
     def step(coords):
         """one density pass; coords: device tensor (resident) or pinned host tensor (e2e)."""
         with torch.cuda.stream(stream):
-            if coords.is_cuda:
-                sess.set_coords(coords)
-            else:
-                sess.set_coords(coords.numpy())
-            sess.populations(radii, b, e, out=pops_loc)
-            if world > 1:
-                pops_shard[:, :e - b].copy_(pops_loc)
-            if world > 1:
-                dist.all_gather_into_tensor(pops_all, pops_shard)
-                pops_pos = pops_all.permute(1, 0, 2).reshape(radii.size, world * per)[:, :n].contiguous()
-            else:
-                pops_pos = pops_loc
-            pops = sess.to_frame_order(pops_pos, out=pops_frame)
-            fe = sess.free_energies(pops[r_fe])
-            sess.nn_prepare(fe)
-            sess.nn_scan(b, e, out=keys_loc)
-            if world > 1:
-                keys_shard[:, :e - b].copy_(keys_loc)
-            if world > 1:
-                dist.all_gather_into_tensor(keys_all, keys_shard)
-                keys = keys_all.permute(1, 0, 2).reshape(2, world * per)[:, :n].contiguous()
-            else:
-                keys = keys_loc
-            nn = sess.nn_finish(keys)
+            pops, fe, nn = dpass.run(coords if coords.is_cuda else coords.numpy(), r_fe)
             if not coords.is_cuda:                       # e2e: results back in host memory
                 pops_host.copy_(pops, non_blocking=True)
                 fe_host.copy_(fe, non_blocking=True)
