@@ -7,6 +7,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -42,6 +43,30 @@ extern "C" int dcb200_internal_fail(const char* msg) { return fail(msg); }
     int r__ = (call);                 \
     if (r__) return r__;              \
   } while (0)
+
+// DCB200_TRACE=1: wall-clock phases of the host-pointer entry points on stderr (diagnostics only)
+#include <chrono>
+namespace {
+struct Trace {
+  bool on;
+  const char* what;
+  std::chrono::steady_clock::time_point t0, last;
+  explicit Trace(const char* w) : what(w) {
+    static const bool enabled = getenv("DCB200_TRACE") != nullptr;
+    on = enabled;
+    t0 = last = std::chrono::steady_clock::now();
+  }
+  void lap(const char* phase) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dcb200] %s: %-18s %8.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  }
+  ~Trace() {
+    if (on) fprintf(stderr, "[dcb200] %s: total %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // small device kernels (layout, free energies, ordering, finalisation)
@@ -116,11 +141,13 @@ __global__ void pack_kernel(const float* __restrict__ coords, size_t n, int d, s
   if (p >= ld) return;
   const float nan = __int_as_float(0x7fc00000);
   if (p >= n) {
+    // padded columns: exact coordinates NaN (no '<' ever passes), fast-path pack (0, ..., 0, +inf) so that the
+    // accumulator is +inf for every row: never below a threshold, sign bit clear, outside every error band
     for (int k = 0; k < d; ++k) {
       xT[(size_t) k * ld + p] = nan;
-      cT[(size_t) k * ld + p] = nan;
+      cT[(size_t) k * ld + p] = 0.f;
     }
-    cT[(size_t) d * ld + p] = nan;
+    cT[(size_t) d * ld + p] = INFINITY;
     return;
   }
   const size_t src = perm ? perm[p] : p;
@@ -195,8 +222,11 @@ __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long l
 
 // pops[r][i] = 1 + mult[r] * sum_{b <= bin[r]} cnt[b][i]    (self counted by the initial 1, density_clustering.cpp:133;
 // a radius listed m times is one map entry incremented m times per hit, :131-134,:180)
+// cumulative (count mode): cnt[b] already holds #{d2 < rad2[b]}, including the frame itself iff self[q]
 struct FinalizeArgs {
   int n_out;
+  int cumulative;
+  uint32_t self[MAX_BINS * 4];
   int out_row[MAX_BINS * 4];
   int bin[MAX_BINS * 4];
   uint32_t mult[MAX_BINS * 4];
@@ -207,7 +237,11 @@ __global__ void pops_finalize_kernel(const uint32_t* __restrict__ cnt, size_t ld
   if (i >= rows) return;
   for (int q = 0; q < f.n_out; ++q) {
     uint32_t c = 0;
-    for (int b = 0; b <= f.bin[q]; ++b) c += cnt[(size_t) b * ld_cnt + i];     // d2 < rad2[bin] = all bins up to it
+    if (f.cumulative) {
+      c = cnt[(size_t) f.bin[q] * ld_cnt + i] - f.self[q];
+    } else {
+      for (int b = 0; b <= f.bin[q]; ++b) c += cnt[(size_t) b * ld_cnt + i];     // d2 < rad2[bin] = all bins up to it
+    }
     pops[(size_t) f.out_row[q] * rows + i] = 1u + f.mult[q] * c;
   }
 }
@@ -344,6 +378,8 @@ struct dcb200_ctx {
   DevBuf<float> centre;             // [2d] centre, spread
   DevBuf<uint32_t> cnt;
   DevBuf<unsigned long long> knn, khd;
+  DevBuf<uint32_t> io_u32;          // host-pointer entry points: device-side staging of inputs / outputs
+  DevBuf<float> io_f32;
   unsigned int* scalars = nullptr;  // [0] work counter, [1] max norm bits, [2] max pop
   unsigned long long* stats = nullptr;   // [0] slow pairs, [1] exact pairs, [2] tiles streamed
   float maxnorm2 = 0.f;
@@ -430,6 +466,22 @@ static int occ_pops(int d, int nb) {
   }
   return 0;
 }
+static cudaError_t launch_pops_count(int d, const PopsArgs& a, int grid, cudaStream_t st) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) launch_pops_count_d##D(a, grid, st)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return cudaErrorInvalidValue;
+}
+static int occ_pops_count(int d, int nb) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) occupancy_pops_count_d##D(nb, d)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return 0;
+}
 static int occ_nn(int d) {
   switch (d <= MAX_TEMPLATE_D ? d : 0) {
 #define FN(D) occupancy_nn_d##D(d)
@@ -507,6 +559,7 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   c->perm.release(); c->lo.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release();
   c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
+  c->io_u32.release(); c->io_f32.release();
   cudaFree(c->scalars);
   cudaFree(c->stats);
   cudaStreamDestroy(c->stream);
@@ -645,12 +698,24 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     if (!(v == v)) return fail("dcb200_ctx_populations: NaN radius");
   const size_t ld_cnt = (rows + 255) / 256 * 256;
   const int tj = tile_width(c->d);
+  // one or two distinct radii: branch-free count mode (pops_count_kernel)
+  const bool count_mode = uniq.size() <= 2 && c->d <= (size_t) MAX_TEMPLATE_D;
   for (size_t b0 = 0; b0 < uniq.size(); b0 += MAX_BINS) {
     const int nb = (int) std::min<size_t>(MAX_BINS, uniq.size() - b0);
     PopsArgs a;
     int grid = 0;
-    CKI(fill_geom(c, row_begin, row_end, tj, occ_pops((int) c->d, nb), nb > 4 ? 64u : 32u, &a.g, &grid));
+    CKI(fill_geom(c, row_begin, row_end, tj, count_mode ? occ_pops_count((int) c->d, nb) : occ_pops((int) c->d, nb),
+                  nb > 4 ? 64u : 32u, &a.g, &grid));
     a.n_bins = nb;
+    a.band[0] = a.band[1] = 0.f;
+    if (count_mode) {
+      // |v - (d2_exact - r^2)| <= e_abs + e_rel*value (fast path) + roundings of r^2 - |x'|^2 and of the subtraction
+      const double u = ldexp(1.0, -24);
+      for (int q = 0; q < nb; ++q) {
+        const double r2 = (double) uniq[b0 + q];
+        a.band[q] = up(1.01 * ((double) a.g.e_abs + (double) a.g.e_rel * r2 * 1.001) + 4.0 * u * ((double) c->maxnorm2 + r2) + 1e-37);
+      }
+    }
     for (int q = 0; q < 32; ++q) a.rad2[q] = q < nb ? uniq[b0 + q] : INFINITY;
     const double rmax2 = (double) uniq[b0 + nb - 1];
     a.thr_fast = up(rmax2 * (1.0 + (double) a.g.e_rel) + (double) a.g.e_abs);
@@ -661,11 +726,12 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     a.ld_cnt = ld_cnt;
     CK(cudaMemsetAsync(c->cnt.p, 0, (size_t) nb * ld_cnt * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
-    CK(launch_pops((int) c->d, a, grid, c->stream));
+    CK(count_mode ? launch_pops_count((int) c->d, a, grid, c->stream) : launch_pops((int) c->d, a, grid, c->stream));
     c->launches += 1;
     // input radii served by this pass, in groups the finalize kernel's argument block can hold
     FinalizeArgs f;
     f.n_out = 0;
+    f.cumulative = count_mode ? 1 : 0;
     auto flush = [&]() -> int {
       if (f.n_out == 0) return 0;
       pops_finalize_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->cnt.p, ld_cnt, rows, dev_pops, f);
@@ -682,6 +748,7 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
       f.out_row[f.n_out] = (int) r;
       f.bin[f.n_out] = (int) (bin - b0);
       f.mult[f.n_out] = mult;
+      f.self[f.n_out] = rad2[r] > 0.f ? 1u : 0u;      // d2(i,i) = 0 < r^2
       if (++f.n_out == MAX_BINS * 4) CKI(flush());
     }
     CKI(flush());
@@ -907,21 +974,25 @@ extern "C" int dcb200_populations(const float* coords, size_t n_rows, size_t n_c
   int n_gpus = 0;
   CKI(gpus_to_use(&n_gpus));
   n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
+  Trace tr("populations");
   if (n_gpus == 1) {                         // everything on the device, results land in frame order
     dcb200_ctx* c = nullptr;
     CKI(pooled_ctx(0, &c));
+    tr.lap("context");
     CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
-    uint32_t *dev = nullptr, *dev2 = nullptr;
-    CK(cudaMalloc(&dev, 2 * n_radii * n_rows * sizeof(uint32_t)));
-    dev2 = dev + n_radii * n_rows;
+    tr.lap("upload+layout");
+    CK(c->io_u32.reserve(2 * n_radii * n_rows));
+    uint32_t *dev = c->io_u32.p, *dev2 = dev + n_radii * n_rows;
+    tr.lap("buffers");
     int rc = dcb200_ctx_populations(c, radii, n_radii, 0, n_rows, dev);
     if (!rc) rc = dcb200_ctx_to_frame_order(c, dev, n_radii, dev2);
+    if (tr.on) { cudaStreamSynchronize(c->stream); tr.lap("scan"); }
     if (!rc) {
       cudaError_t ce = cudaMemcpyAsync(pops, dev2, n_radii * n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
       if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
       if (ce != cudaSuccess) rc = fail(std::string("populations download: ") + cudaGetErrorString(ce));
     }
-    cudaFree(dev);
+    tr.lap("download");
     return rc;
   }
   std::vector<uint32_t> tmp(n_radii * n_rows), perm(n_rows);
@@ -933,10 +1004,10 @@ extern "C" int dcb200_populations(const float* coords, size_t n_rows, size_t n_c
     CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));     // same deterministic order on every device
     int rc = 0;
     cudaError_t ce = cudaSuccess;
-    uint32_t* dev = nullptr;
     if (e > b) {
       const size_t rows = e - b;
-      CK(cudaMalloc(&dev, n_radii * rows * sizeof(uint32_t)));
+      CK(c->io_u32.reserve(n_radii * rows));
+      uint32_t* dev = c->io_u32.p;
       rc = dcb200_ctx_populations(c, radii, n_radii, b, e, dev);
       if (!rc)
         ce = cudaMemcpy2DAsync(tmp.data() + b, n_rows * sizeof(uint32_t), dev, rows * sizeof(uint32_t), rows * sizeof(uint32_t),
@@ -946,7 +1017,6 @@ extern "C" int dcb200_populations(const float* coords, size_t n_rows, size_t n_c
       ce = cudaMemcpyAsync(perm.data(), c->perm.p, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
     if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
     if (ce != cudaSuccess) rc = fail(std::string("populations download: ") + cudaGetErrorString(ce));
-    if (dev) cudaFree(dev);
     return rc;
   }));
   for (size_t r = 0; r < n_radii; ++r)
@@ -962,18 +1032,16 @@ extern "C" int dcb200_free_energies(const uint32_t* pops, size_t n, float* fe) {
   dcb200_ctx* c = nullptr;
   CKI(pooled_ctx(0, &c));
   CK(cudaSetDevice(c->device));
-  uint32_t* dp = nullptr;
-  float* df = nullptr;
-  CK(cudaMalloc(&dp, n * sizeof(uint32_t)));
-  CK(cudaMalloc(&df, n * sizeof(float)));
+  CK(c->io_u32.reserve(n));
+  CK(c->io_f32.reserve(n));
+  uint32_t* dp = c->io_u32.p;
+  float* df = c->io_f32.p;
   int rc = 0;
   cudaError_t ce = cudaMemcpyAsync(dp, pops, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (ce == cudaSuccess) rc = dcb200_ctx_free_energies(c, dp, n, 0, df);
   if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(fe, df, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
   if (ce != cudaSuccess) rc = fail(std::string("free energies: ") + cudaGetErrorString(ce));
-  cudaFree(dp);
-  cudaFree(df);
   return rc;
 }
 
@@ -983,6 +1051,32 @@ extern "C" int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size
   int n_gpus = 0;
   CKI(gpus_to_use(&n_gpus));
   n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
+  Trace tr("nearest_neighbors");
+  if (n_gpus == 1) {                         // everything on the device: scan, frame-order scatter, four downloads
+    dcb200_ctx* c = nullptr;
+    CKI(pooled_ctx(0, &c));
+    CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
+    tr.lap("upload+layout");
+    CK(c->io_f32.reserve(3 * n_rows));
+    CK(c->io_u32.reserve(2 * n_rows));
+    CK(c->knn.reserve(n_rows));
+    CK(c->khd.reserve(n_rows));
+    float *dfe = c->io_f32.p, *d_nd = dfe + n_rows, *d_hd = d_nd + n_rows;
+    uint32_t *d_ni = c->io_u32.p, *d_hi = d_ni + n_rows;
+    CK(cudaMemcpyAsync(dfe, fe, n_rows * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CKI(dcb200_ctx_nn_prepare(c, dfe));
+    if (tr.on) { cudaStreamSynchronize(c->stream); tr.lap("fe upload+ranks"); }
+    CKI(dcb200_ctx_nn_scan(c, 0, n_rows, (uint64_t*) c->knn.p, (uint64_t*) c->khd.p));
+    CKI(dcb200_ctx_nn_finish(c, (const uint64_t*) c->knn.p, (const uint64_t*) c->khd.p, d_ni, d_nd, d_hi, d_hd));
+    if (tr.on) { cudaStreamSynchronize(c->stream); tr.lap("scan"); }
+    CK(cudaMemcpyAsync(nn_idx, d_ni, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(nn_d2, d_nd, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hd_idx, d_hi, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hd_d2, d_hd, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    tr.lap("download");
+    return 0;
+  }
   std::vector<unsigned long long> knn(n_rows), khd(n_rows);
   std::vector<uint32_t> perm(n_rows);
   CKI(on_gpus(n_gpus, [&](int g, int G) -> int {
@@ -991,8 +1085,8 @@ extern "C" int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size
     size_t b, e;
     shard(n_rows, g, G, &b, &e);
     CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
-    float* dfe = nullptr;
-    CK(cudaMalloc(&dfe, n_rows * sizeof(float)));
+    CK(c->io_f32.reserve(n_rows));
+    float* dfe = c->io_f32.p;
     int rc = 0;
     cudaError_t ce = cudaMemcpyAsync(dfe, fe, n_rows * sizeof(float), cudaMemcpyHostToDevice, c->stream);
     if (ce == cudaSuccess) rc = dcb200_ctx_nn_prepare(c, dfe);
@@ -1009,7 +1103,6 @@ extern "C" int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size
       ce = cudaMemcpyAsync(perm.data(), c->perm.p, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
     if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
     if (ce != cudaSuccess) rc = fail(std::string("nearest neighbours: ") + cudaGetErrorString(ce));
-    cudaFree(dfe);
     return rc;
   }));
   for (size_t p = 0; p < n_rows; ++p) {
@@ -1045,8 +1138,8 @@ extern "C" int dcb200_screening_step(const float* sorted_coords, size_t n_cols, 
       return q >= G ? m_new : (size_t) sqrt(a + (b - a) * q / G);
     };
     const size_t b = std::max(m_prev, cut(g)), e = cut(g + 1);
-    uint32_t* dev = nullptr;
-    CK(cudaMalloc(&dev, m_new * sizeof(uint32_t)));
+    CK(c->io_u32.reserve(m_new));
+    uint32_t* dev = c->io_u32.p;
     int rc = 0;
     cudaError_t ce = cudaMemcpyAsync(dev, comp, m_new * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
     if (ce == cudaSuccess) rc = dcb200_ctx_screening_scan(c, m_prev, m_new, b, e, max_dist2, dev);
@@ -1055,7 +1148,6 @@ extern "C" int dcb200_screening_step(const float* sorted_coords, size_t n_cols, 
     if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(parts[g].data(), dev, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
     if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
     if (ce != cudaSuccess) rc = fail(std::string("screening: ") + cudaGetErrorString(ce));
-    cudaFree(dev);
     return rc;
   }));
   if (n_gpus == 1) {

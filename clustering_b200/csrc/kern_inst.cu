@@ -18,6 +18,39 @@ cudaError_t DCB_CAT(launch_pops_d, DCB_D)(const PopsArgs& a, int grid, cudaStrea
   return cudaGetLastError();
 }
 
+#if DCB_D >= 1
+// count mode: one or two distinct radii
+cudaError_t DCB_CAT(launch_pops_count_d, DCB_D)(const PopsArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = pops_count_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d));
+  cudaError_t e;
+  if (a.n_bins == 1) {
+    e = cudaFuncSetAttribute(pops_count_kernel<DCB_D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    pops_count_kernel<DCB_D, 1><<<grid, CTA_THREADS, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(pops_count_kernel<DCB_D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    pops_count_kernel<DCB_D, 2><<<grid, CTA_THREADS, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+int DCB_CAT(occupancy_pops_count_d, DCB_D)(int n_bins, int d) {
+  int nb = 0;
+  const size_t smem = pops_count_smem_bytes(SmemRing<DCB_D>::bytes(d));
+  if (n_bins == 1) {
+    cudaFuncSetAttribute(pops_count_kernel<DCB_D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pops_count_kernel<DCB_D, 1>, CTA_THREADS, smem);
+  } else {
+    cudaFuncSetAttribute(pops_count_kernel<DCB_D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pops_count_kernel<DCB_D, 2>, CTA_THREADS, smem);
+  }
+  return nb;
+}
+#else
+cudaError_t DCB_CAT(launch_pops_count_d, DCB_D)(const PopsArgs&, int, cudaStream_t) { return cudaErrorInvalidValue; }
+int DCB_CAT(occupancy_pops_count_d, DCB_D)(int, int) { return 0; }
+#endif
+
 cudaError_t DCB_CAT(launch_nn_d, DCB_D)(const NnArgs& a, int grid, cudaStream_t st) {
   const size_t smem = nn_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d));
   cudaError_t e = cudaFuncSetAttribute(nn_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

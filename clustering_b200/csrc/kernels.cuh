@@ -406,6 +406,7 @@ struct PopsArgs {
   int n_bins;               // distinct radii in this pass (<= MAX_BINS)
   float rad2[32];           // ascending squared radii, padded with +inf
   float thr_fast;           // rad2[n_bins-1] + error margin
+  float band[2];            // count mode: half width of the error band around rad2[0], rad2[1]
   uint32_t* cnt;            // [n_bins][ld_cnt]: #{j != i : rad2[b-1] <= d2(i,j) < rad2[b]}, rows relative to row_begin
   size_t ld_cnt;
 };
@@ -458,6 +459,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
     const uint32_t j = col0 + jt;
     const uint32_t i = R.row(r);
     float s = accv + sel4(R.xn, r);
+    if (i >= g.row_end) return;                // clamped rows past the shard: results are discarded anyway
     ++st.slow;
     int b = bin_of(rad2s, nb, s);
     const float lo = b > 0 ? rad2s[b - 1] : -INFINITY;
@@ -499,6 +501,148 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
           }
         }
       }
+    }
+    cp.advance();
+  }
+  st.flush(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// populations, count mode (one or two distinct radii, D <= MAX_TEMPLATE_D): no filter and no slow path
+// for ordinary hits.  Per pair and radius: v = acc - (r^2 - |x'|^2) (one FADD), the count takes the sign
+// bit of v (one integer op), and a running min of |v| per row tells whether any pair of the step lies
+// inside the rounding-error band of the radius; only those (rare) pairs are re-decided with dist2_exact.
+// Cost per pair: D FFMA + ~2.75 instructions per radius, independent of the hit rate -- the tiles that
+// survive the bounding-box pruning have hit rates of 5-20 %, where a per-hit handler costs far more.
+// cnt[b][row] receives #{j : d2(i,j) < rad2[b]} INCLUDING the frame itself when rad2[b] > 0
+// (pops_finalize removes it again).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t pops_count_smem_bytes(size_t ring_bytes) { return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES; }
+
+__device__ __forceinline__ uint32_t sel4u(const uint32_t (&v)[RI], int r) {
+  return r == 0 ? v[0] : r == 1 ? v[1] : r == 2 ? v[2] : v[3];
+}
+__device__ __forceinline__ void add4u(uint32_t (&v)[RI], int r, uint32_t x) {
+  if (r == 0) v[0] += x; else if (r == 1) v[1] += x; else if (r == 2) v[2] += x; else v[3] += x;
+}
+
+template <int D, int NB>
+__global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ PopsArgs a) {
+  static_assert(D >= 1 && NB >= 1 && NB <= 2, "count mode: specialised dims, one or two radii");
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int TJ = TileW<D>::tj;
+  const ScanGeom& g = a.g;
+  SmemRing<D> ring(smem, D);
+  float* scratch = reinterpret_cast<float*>(smem + ((SmemRing<D>::bytes(D) + 15) & ~size_t(15))) + threadIdx.x;
+  ring.init();
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == N_CONSUMER_WARPS) {
+    produce<D>(g, ring, false, [](uint32_t, uint32_t&, uint32_t&) {}, [&](uint32_t, int) { return g.prune_thr; });
+    return;
+  }
+  const int tid = threadIdx.x;
+  Rows<D> R;
+  float tm[NB][RI];           // decision boundary of radius b for row r in accumulator units: rad2[b] - |x'_r|^2
+  float w[NB];                // half width of the rounding-error band around it
+  uint32_t cnt[NB][RI];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) w[b] = a.band[b];
+  Pipe cp;
+  SlowStats st;
+  for (;;) {
+    mbar_wait(&ring.full[cp.stage], cp.phase);
+    const TileMeta m = ring.meta[cp.stage];
+    if (m.row_block < 0) break;
+    if (m.flags & 1u) {
+      R.load(g, (uint32_t) m.row_block, tid);
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+          tm[b][r] = a.rad2[b] - R.xn[r];
+          cnt[b][r] = 0;
+        }
+    }
+    if (!(m.flags & 4u)) {
+      const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+#pragma unroll 1
+      for (int gcol = 0; gcol < TJ; gcol += CJ) {
+        float acc[RI][CJ];
+        {
+          const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + gcol);
+          const float4 y4 = *reinterpret_cast<const float4*>(tl + gcol);
+#pragma unroll
+          for (int r = 0; r < RI; ++r) {
+            acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
+            acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
+            acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
+            acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
+          }
+        }
+#pragma unroll
+        for (int k = 1; k < D; ++k) {
+          const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + gcol);
+#pragma unroll
+          for (int r = 0; r < RI; ++r) {
+            acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
+            acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
+            acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
+            acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
+          }
+        }
+        bool band = false;
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int r = 0; r < RI; ++r) {
+            const float v0 = acc[r][0] - tm[b][r], v1 = acc[r][1] - tm[b][r];
+            const float v2 = acc[r][2] - tm[b][r], v3 = acc[r][3] - tm[b][r];
+            cnt[b][r] += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
+            cnt[b][r] += (__float_as_uint(v2) >> 31) + (__float_as_uint(v3) >> 31);
+            const float mn = fminf(fminf(fabsf(v0), fabsf(v1)), fminf(fabsf(v2), fabsf(v3)));
+            band |= mn < w[b];
+          }
+        if (band) {
+          // rare: some pair of this 4x4 block is within the error band of a radius.  One compact loop
+          // (block parked in shared memory) replaces the sign-bit decision of those pairs by the exact one.
+#pragma unroll
+          for (int r = 0; r < RI; ++r)
+#pragma unroll
+            for (int c = 0; c < CJ; ++c) scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c];
+#pragma unroll 1
+          for (int p = 0; p < RI * CJ; ++p) {
+            const int r = p / CJ;
+            const float av = scratch[p * N_CONSUMERS];
+            float d2 = 0.f;
+            bool have = false;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const float v = av - sel4(tm[b], r);
+              if (fabsf(v) < w[b] && R.row(r) < g.row_end) {
+                ++st.slow;
+                if (!have) {
+                  d2 = dist2_exact(g.xT, g.ld, D, R.row(r), m.col0 + gcol + (p % CJ));
+                  have = true;
+                  ++st.exact;
+                }
+                const uint32_t inside = d2 < a.rad2[b] ? 1u : 0u;      // NaN (padding) -> outside
+                add4u(cnt[b], r, inside - (__float_as_uint(v) >> 31));
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    if (m.flags & 2u) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < RI; ++r)
+          if (R.row(r) < g.row_end && cnt[b][r]) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + (R.row(r) - g.row_begin), cnt[b][r]);
     }
     cp.advance();
   }

@@ -13,6 +13,8 @@ struct ScreenArgs;
   cudaError_t launch_pops_d##D(const PopsArgs&, int grid, cudaStream_t st);  \
   cudaError_t launch_nn_d##D(const NnArgs&, int grid, cudaStream_t st);      \
   int occupancy_pops_d##D(int n_bins, int d);                                \
+  cudaError_t launch_pops_count_d##D(const PopsArgs&, int grid, cudaStream_t st);  \
+  int occupancy_pops_count_d##D(int n_bins, int d);                          \
   int occupancy_nn_d##D(int d);                                              \
   cudaError_t launch_screen_d##D(const ScreenArgs&, int grid, cudaStream_t st); \
   int occupancy_screen_d##D(int d);

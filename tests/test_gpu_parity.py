@@ -69,6 +69,41 @@ def test_vs_oracle_all_dims(oracle, d):
     assert np.array_equal(bits(a[1]), bits(b[1])) and np.array_equal(bits(a[3]), bits(b[3]))
 
 
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16])
+def test_count_mode_one_and_two_radii(oracle, d):
+    # <= 2 distinct radii run the branch-free count kernel (pops_count_kernel): decisions by sign bit + exact band recheck
+    n = 5000
+    x = gaussian_mixture(n, d, seed=3100 + d)
+    x[100] = x[7]
+    x[n - 2] = x[7]
+    s = np.float32(np.sqrt(d))
+    for radii in ([0.3 * s], [0.25 * s, 0.5 * s], [0.4 * s, 0.4 * s, 0.2 * s], [0.0], [0.0, 0.3 * s]):
+        radii = np.array(radii, np.float32)
+        assert np.array_equal(oracle.populations(x, radii), density.calculate_populations(x, radii)), (d, radii)
+
+
+def test_count_mode_boundary_lattice_and_offset(oracle):
+    g = np.stack(np.meshgrid(np.arange(14), np.arange(14), np.arange(14), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    for radii in ([1.0], [np.sqrt(2.0)], [2.0, 3.0], [np.sqrt(5.0), 1.0]):
+        radii = np.array(radii, np.float32)
+        po, pg = oracle.populations(g, radii), density.calculate_populations(g, radii)
+        assert np.array_equal(po, pg), radii
+    assert density.calculate_populations(g, [1.0]).max() == 1
+    x = gaussian_mixture(4000, 3, seed=99) + np.float32(500.0)          # far from the origin: wide error band, many rechecks
+    for radii in ([0.2], [0.1, 0.3]):
+        assert np.array_equal(oracle.populations(x, np.array(radii, np.float32)), density.calculate_populations(x, radii))
+
+
+def test_count_mode_medium_vs_oracle(oracle):
+    # several row blocks / work items / pruned tiles; n not a multiple of the padding
+    x = gaussian_mixture(30011, 5, seed=41)
+    for radii in ([0.3], [0.2, 0.45]):
+        radii = np.array(radii, np.float32)
+        assert np.array_equal(oracle.populations(x, radii), density.calculate_populations(x, radii))
+    x = gaussian_mixture(4096, 3, k=3, seed=42)                        # n == padded size: clamped rows are real rows
+    assert np.array_equal(oracle.populations(x, np.array([0.15], np.float32)), density.calculate_populations(x, [0.15]))
+
+
 def test_offset_data_and_many_radii(oracle):
     # far from the origin (the centring of the fast path must not change a single count) and > 31 radii (two passes)
     x = gaussian_mixture(2500, 4, seed=77) + np.float32(1000.0)
