@@ -131,63 +131,71 @@ __global__ void morton_keys_kernel(const float* __restrict__ coords, size_t n, i
   iota[i] = (uint32_t) i;
 }
 
-// row-major coords -> xT [d][ld] (original values) and cT [d+1][ld] (-2*(x-centre), |x-centre|^2) in the
-// order given by perm (position -> frame; nullptr = frame order); positions >= n are NaN so that
-// padded columns can never pass a '<' filter.
-__global__ void pack_kernel(const float* __restrict__ coords, size_t n, int d, size_t ld, const float* __restrict__ centre,
-                            const uint32_t* __restrict__ perm, float* __restrict__ xT, float* __restrict__ cT,
-                            unsigned int* __restrict__ maxnorm_bits) {
-  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= ld) return;
+// One block per column tile (tj = 128 or 64 frames, one thread per frame).  Row-major coords ->
+//   xT   [d][ld]     original values (padding: NaN, so that no exact '<' ever passes)
+//   cT   [d+1][ld]   tile-local column pack: y' = x - c_t with c_t = mean of the tile's frames (any point near the
+//                    tile works; the mean keeps |y'| smallest): rows 0..d-1 = -2 y', row d = |y'|^2
+//                    (padding: 0, ..., 0, +inf: the accumulator of a padded column is +inf for every row)
+//   tcen [tiles][dp] c_t[0..d-1], then max |y'|^2 over the tile's real frames
+//   bbox [ld/64][2d] bounding boxes of 64-frame groups in globally centred coordinates (tile pruning)
+// in the order given by perm (position -> frame; nullptr = frame order).  Fixed-order reductions => the same
+// bits on every GPU.
+__global__ void pack_tiles_kernel(const float* __restrict__ coords, size_t n, int d, size_t ld, int dp,
+                                  const float* __restrict__ centre, const uint32_t* __restrict__ perm, float* __restrict__ xT,
+                                  float* __restrict__ cT, float* __restrict__ tcen, float* __restrict__ bbox,
+                                  unsigned int* __restrict__ maxnorm_bits) {
+  __shared__ float sh_sum[4], sh_lo[4], sh_hi[4];
+  const int tj = blockDim.x;                      // 128 or 64
+  const int nw = tj / 32;
+  const size_t tile = blockIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const size_t p = tile * tj + t;
+  const bool real = p < n;
+  const size_t src = real ? (perm ? (size_t) perm[p] : p) : 0;
+  const size_t first = tile * tj;
+  const float cnt = first < n ? (float) (n - first < (size_t) tj ? n - first : (size_t) tj) : 0.f;
   const float nan = __int_as_float(0x7fc00000);
-  if (p >= n) {
-    // padded columns: exact coordinates NaN (no '<' ever passes), fast-path pack (0, ..., 0, +inf) so that the
-    // accumulator is +inf for every row: never below a threshold, sign bit clear, outside every error band
-    for (int k = 0; k < d; ++k) {
-      xT[(size_t) k * ld + p] = nan;
-      cT[(size_t) k * ld + p] = 0.f;
-    }
-    cT[(size_t) d * ld + p] = INFINITY;
-    return;
-  }
-  const size_t src = perm ? perm[p] : p;
-  float nrm = 0.f;
+  float nrm_local = 0.f, nrm_global = 0.f;
   for (int k = 0; k < d; ++k) {
-    const float x = coords[src * d + k];
-    const float xc = x - centre[k];
-    xT[(size_t) k * ld + p] = x;
-    cT[(size_t) k * ld + p] = -2.0f * xc;
-    nrm = fmaf(xc, xc, nrm);
-  }
-  cT[(size_t) d * ld + p] = nrm;
-  atomicMax(maxnorm_bits, __float_as_uint(nrm));      // nrm >= 0: the bit pattern orders like the value
-}
-
-// bounding boxes of 64-frame groups in centred coordinates: bbox[g][0..d) = lo, [d..2d) = hi.
-// One warp per group; padded positions are ignored (an all-padding group gets lo=+inf, hi=-inf).
-__global__ void bbox_kernel(const float* __restrict__ cT, size_t ld, size_t n, int d, float* __restrict__ bbox) {
-  const size_t grp = (size_t) blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (grp * 64 >= ld) return;
-  for (int k = 0; k < d; ++k) {
-    float lo = INFINITY, hi = -INFINITY;
-    for (int q = 0; q < 2; ++q) {
-      const size_t p = grp * 64 + q * 32 + lane;
-      if (p < n) {
-        const float x = -0.5f * cT[(size_t) k * ld + p];
-        lo = fminf(lo, x);
-        hi = fmaxf(hi, x);
-      }
-    }
+    const float x = real ? coords[src * d + k] : 0.f;
+    const float xg = x - centre[k];
+    float sum = real ? x : 0.f, lo = real ? xg : INFINITY, hi = real ? xg : -INFINITY;
     for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
       lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) {
-      bbox[grp * 2 * d + k] = lo;
-      bbox[grp * 2 * d + d + k] = hi;
+    if (lane == 0) { sh_sum[warp] = sum; sh_lo[warp] = lo; sh_hi[warp] = hi; }
+    __syncthreads();
+    float tot = 0.f;
+    for (int q = 0; q < nw; ++q) tot += sh_sum[q];
+    float c = cnt > 0.f ? tot / cnt : 0.f;
+    if (!(fabsf(c) < FLT_MAX)) c = 0.f;
+    if (lane == 0 && (warp & 1) == 0) {           // 64-frame group = two consecutive warps
+      const size_t grp = p / 64;
+      bbox[grp * 2 * d + k] = fminf(sh_lo[warp], sh_lo[warp + 1]);
+      bbox[grp * 2 * d + d + k] = fmaxf(sh_hi[warp], sh_hi[warp + 1]);
     }
+    __syncthreads();
+    const float yl = x - c;
+    xT[(size_t) k * ld + p] = real ? x : nan;
+    cT[(size_t) k * ld + p] = real ? -2.0f * yl : 0.f;
+    nrm_local = fmaf(yl, yl, nrm_local);
+    nrm_global = fmaf(xg, xg, nrm_global);
+    if (t == 0) tcen[tile * dp + k] = c;
   }
+  cT[(size_t) d * ld + p] = real ? nrm_local : INFINITY;
+  float mx = real ? nrm_local : 0.f;
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) sh_sum[warp] = mx;
+  __syncthreads();
+  if (t == 0) {
+    float m = 0.f;
+    for (int q = 0; q < nw; ++q) m = fmaxf(m, sh_sum[q]);
+    tcen[tile * dp + d] = m;
+    for (int k = d + 1; k < dp; ++k) tcen[tile * dp + k] = 0.f;
+  }
+  if (real) atomicMax(maxnorm_bits, __float_as_uint(nrm_global));      // >= 0: the bit pattern orders like the value
 }
 
 // dst[a][perm[p]] = src[a][p]: position order -> frame order
@@ -370,6 +378,7 @@ struct dcb200_ctx {
   bool spatial = false;             // frames are held in spatial (Morton) order; perm maps position -> frame
   DevBuf<float> xT, cT;             // [d][ld] original coords, [d+1][ld] column pack (context order)
   DevBuf<float> bbox;               // [ld/64][2d]
+  DevBuf<float> tcen;               // [ld/tile][dp] tile centres + max local norm
   DevBuf<uint32_t> perm;            // [n] position -> frame (identity when !spatial)
   DevBuf<uint32_t> lo;              // [n] per position: number of frames with strictly lower free energy
   DevBuf<uint32_t> keys_a, keys_b, iota, tmp_u32, tmp2_u32;
@@ -394,16 +403,21 @@ static float up(double v) {          // smallest float >= v
   return f;
 }
 
-// Rounding-error bounds of the fast path (u = 2^-24, M = max |x'|^2 over the frames, x' centred):
-//   fast value A = acc + xn (acc: FFMA chain started at the stored |y'|^2, xn the stored |x'|^2)
-//   |A - T'| <= gamma_d (2X + 3Y) <= 5 d u M          (norm sums, FFMA chain; X,Y <= M)
-//   centring (x' = fl(x - c)):  |T' - T| <= 4u sqrt(T M) + 4u^2 M <= 2u (T + M) + ...
-//   exact-order value d2e: |d2e - T| <= (d/4 + 5) u T
-// => |fast - d2e| <= e_abs + e_rel * value with the constants below (safety factor 1.5 on both).
-static void error_bounds(size_t d, float maxnorm2, float* e_abs, float* e_rel) {
+// Rounding-error bounds of the fast path (u = 2^-24).  Per tile the columns are y' = fl(y - c_t) and the rows
+// x' = fl(x - c_t); X = |x'|^2, Y = |y'|^2, T = true squared distance, S = acc + xn in real arithmetic with
+//   acc = FFMA chain started at the stored |y'|^2 over x'_k * (-2 y'_k),  xn = FFMA chain of x'_k^2:
+//   |S - T''| <= D u (2X + 3Y)            (T'' = X + Y - 2 x'.y' in real arithmetic; D roundings per chain,
+//                                          partial sums bounded by X + 2Y resp. X resp. Y)
+//   |T'' - T| <= u (T + 2 (X + Y))         (roundings of the two subtractions of c_t)
+//   |d2e - T| <= (D/4 + 8) u T             (reference order: sub, mul, <= ceil(D/4)+4 adds of non-negative terms)
+// => |S - d2e| <= c_loc (X + Y) + e_rel T with the constants below (safety factor 1.5 on both).
+// prune_slack bounds the rounding of the bounding-box arithmetic, done in globally centred coordinates
+// (M = max |x - centre|^2).
+static void error_bounds(size_t d, float maxnorm2, float* c_loc, float* e_rel, float* prune_slack) {
   const double u = ldexp(1.0, -24);
-  *e_abs = up(1.5 * (5.0 * (double) d + 8.0) * u * (double) maxnorm2 + 1e-37);
-  *e_rel = up(1.5 * ((double) d + 8.0) * u);
+  *c_loc = up(1.5 * (3.0 * (double) d + 2.0) * u);
+  *e_rel = up(1.5 * ((double) d / 4.0 + 9.0) * u);
+  *prune_slack = up(1.5 * (5.0 * (double) d + 8.0) * u * (double) maxnorm2 + 1e-37);
 }
 
 static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, int occupancy, uint32_t tiles_per_item, ScanGeom* g,
@@ -412,6 +426,8 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, in
   g->xT = c->xT.p;
   g->cT = c->cT.p;
   g->bbox = c->bbox.p;
+  g->tcen = c->tcen.p;
+  g->dp = (int) ((c->d + 1 + 3) / 4 * 4);
   g->prune_thr = INFINITY;
   g->ld = c->ld;
   g->d = (int) c->d;
@@ -428,7 +444,7 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, in
   *grid = (int) std::min<uint64_t>((uint64_t) *grid, (uint64_t) g->n_row_blocks * g->n_col_items);
   g->work_counter = c->scalars;
   g->stats = c->stats;
-  error_bounds(c->d, c->maxnorm2, &g->e_abs, &g->e_rel);
+  error_bounds(c->d, c->maxnorm2, &g->c_loc, &g->e_rel, &g->prune_slack);
   c->pairs_scheduled += (uint64_t) (row_end - row_begin) * (uint64_t) c->n;
   return 0;
 }
@@ -555,7 +571,7 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->xT.release(); c->cT.release(); c->bbox.release();
+  c->xT.release(); c->cT.release(); c->bbox.release(); c->tcen.release();
   c->perm.release(); c->lo.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release();
   c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
@@ -615,6 +631,9 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
   CK(c->xT.reserve(d * ld));
   CK(c->cT.reserve((d + 1) * ld));
   CK(c->bbox.reserve(ld / 64 * 2 * d));
+  const int tj = d <= (size_t) MAX_TEMPLATE_D ? TileW<1>::tj : TileW<0>::tj;
+  const int dp = (int) ((d + 1 + 3) / 4 * 4);
+  CK(c->tcen.reserve(ld / tj * dp));
   CK(c->centre.reserve(2 * d));
   CK(c->perm.reserve(n));
   CK(cudaMemsetAsync(c->scalars + 1, 0, sizeof(unsigned int), c->stream));
@@ -632,10 +651,10 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
     iota_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->perm.p, n);
     c->launches += 1;
   }
-  pack_kernel<<<blocks_for(ld, 256), 256, 0, c->stream>>>(dev_coords, n, (int) d, ld, c->centre.p, c->spatial ? c->perm.p : nullptr,
-                                                          c->xT.p, c->cT.p, c->scalars + 1);
-  bbox_kernel<<<blocks_for(ld / 64, 8), 256, 0, c->stream>>>(c->cT.p, ld, n, (int) d, c->bbox.p);
-  c->launches += 2;
+  pack_tiles_kernel<<<(unsigned int) (ld / tj), tj, 0, c->stream>>>(dev_coords, n, (int) d, ld, dp, c->centre.p,
+                                                                    c->spatial ? c->perm.p : nullptr, c->xT.p, c->cT.p, c->tcen.p,
+                                                                    c->bbox.p, c->scalars + 1);
+  c->launches += 1;
   CK(cudaGetLastError());
   unsigned int bits = 0;
   CK(cudaMemcpyAsync(&bits, c->scalars + 1, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
@@ -709,18 +728,18 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     a.n_bins = nb;
     a.band[0] = a.band[1] = 0.f;
     if (count_mode) {
-      // |v - (d2_exact - r^2)| <= e_abs + e_rel*value (fast path) + roundings of r^2 - |x'|^2 and of the subtraction
+      // radius-dependent part of the band: e_rel * r^2 (fast path) + roundings of r^2 - |x'|^2 and of the subtraction
       const double u = ldexp(1.0, -24);
       for (int q = 0; q < nb; ++q) {
         const double r2 = (double) uniq[b0 + q];
-        a.band[q] = up(1.01 * ((double) a.g.e_abs + (double) a.g.e_rel * r2 * 1.001) + 4.0 * u * ((double) c->maxnorm2 + r2) + 1e-37);
+        a.band[q] = up((1.02 * (double) a.g.e_rel + 4.0 * u) * r2 + 1e-37);
       }
     }
     for (int q = 0; q < 32; ++q) a.rad2[q] = q < nb ? uniq[b0 + q] : INFINITY;
     const double rmax2 = (double) uniq[b0 + nb - 1];
-    a.thr_fast = up(rmax2 * (1.0 + (double) a.g.e_rel) + (double) a.g.e_abs);
-    // a tile whose bounding-box distance exceeds this cannot contain a pair that passes the filter
-    a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.e_abs);
+    a.thr_fast = up(rmax2 * (1.0 + 1.01 * (double) a.g.e_rel));
+    // a tile whose bounding-box distance exceeds this cannot contain a pair with exact d2 < r_max^2
+    a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.prune_slack);
     CK(c->cnt.reserve((size_t) nb * ld_cnt));
     a.cnt = c->cnt.p;
     a.ld_cnt = ld_cnt;
@@ -847,8 +866,8 @@ extern "C" int dcb200_ctx_screening_scan(dcb200_ctx* c, size_t m_prev, size_t m_
   int grid = 0;
   CKI(fill_geom(c, row_begin, row_end, tile_width(c->d), occ_screen((int) c->d), 32u, &a.g, &grid));
   a.cut = max_dist2;
-  a.thr_fast = up((double) max_dist2 * (1.0 + (double) a.g.e_rel) + (double) a.g.e_abs);
-  a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.e_abs);
+  a.thr_fast = up((double) max_dist2 * (1.0 + 1.01 * (double) a.g.e_rel));
+  a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.prune_slack);
   a.parent = dev_comp;
   CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
   CK(launch_screen((int) c->d, a, grid, c->stream));

@@ -14,7 +14,9 @@
 //     memory ring with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx); no __syncthreads in steady state;
 //   * every consumer thread keeps RI=4 rows in registers and sweeps CJ=4 columns per step with one
 //     broadcast LDS.128 per dim and RI*CJ FFMAs: acc = |y|^2 - 2 x.y (the column pack holds -2y and |y|^2
-//     of the centred coordinates), so the common path costs D FFMA + ~1 compare per pair;
+//     of coordinates taken relative to the TILE's own centre; the rows are re-centred on that point at
+//     every tile, so operands are as small as the tile's neighbourhood and the rounding error of the
+//     expanded form stays ~1e-6 relative at the decision boundary), D FFMA + ~1 compare per pair;
 //   * that fast value only *filters*: a pair is handed to the slow path when acc < t_row, where t_row
 //     carries a proven rounding-error margin.  The slow path decides with the squared distance
 //     evaluated in the exact rounding order of the reference's CPU build (dist2_exact) whenever the fast
@@ -29,8 +31,10 @@ namespace dcb {
 
 struct ScanGeom {
   const float* xT;          // [D][ld]   original coordinates, dim-major, NaN padded
-  const float* cT;          // [D+1][ld] column pack of the centred coordinates x' = x - centre:
-                            //           rows 0..D-1 = -2*x', row D = |x'|^2 (NaN padded)
+  const float* cT;          // [D+1][ld] column pack, tile-local: with c_t the centre of the tile a column belongs to and
+                            //           y' = y - c_t: rows 0..D-1 = -2*y', row D = |y'|^2 (padding: 0, ..., 0, +inf)
+  const float* tcen;        // [n_col_tiles][dp] per tile: centre c_t[0..D-1], then max |y'|^2 over the tile
+  int dp;                   // floats per tcen entry (multiple of 4, >= D+1)
   size_t ld;                // padded frame count (multiple of 256)
   int d;                    // n_cols (== D for the specialised kernels)
   uint32_t n;               // real frame count
@@ -40,7 +44,8 @@ struct ScanGeom {
   uint32_t tiles_per_item;          // column tiles per work item
   uint32_t n_col_items;             // ceil(n_col_tiles / tiles_per_item)
   unsigned int* work_counter;       // zero-initialised before the launch
-  float e_abs, e_rel;               // |fast - exact| <= e_abs + e_rel * value   (api.cu: error_bounds)
+  float c_loc, e_rel;               // |fast - exact| <= c_loc * (|x'|^2 + max|y'|^2) + e_rel * value   (api.cu: error_bounds)
+  float prune_slack;                // absolute slack of the bounding-box arithmetic (globally centred coordinates)
   unsigned long long* stats;        // [0] pairs handed to the slow path, [1] pairs re-evaluated exactly,
                                     // [2] column tiles streamed (x ROWS_PER_CTA x tile width = pairs evaluated)
   const float* bbox;                // [ld/64][2*d] bounding boxes (lo[d], hi[d]) of 64-frame groups, centred coords
@@ -72,19 +77,20 @@ template <> struct TileW<0> { static constexpr int tj = 64; static constexpr int
 template <int D>
 struct SmemRing {
   static constexpr int TJ = TileW<D>::tj;
-  float* tiles;            // STAGES * (d+1) * TJ
+  float* tiles;            // STAGES * ((d+1) * TJ + dp): column pack of the tile, then its centre entry (tcen)
   uint64_t* full;          // STAGES
   uint64_t* empty;         // STAGES
   TileMeta* meta;          // STAGES
   unsigned long long* wthr;   // N_CONSUMER_WARPS: (item << 32 | float bits) pruning threshold published per warp
   float* rbb;              // 2*d: bounding box of the current row block (producer scratch)
   size_t tile_floats;
+  __host__ __device__ static int dp_of(int d) { return (d + 1 + 3) / 4 * 4; }
   __host__ __device__ static size_t bytes(int d) {
-    return (size_t) STAGES * (d + 1) * TJ * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta) + N_CONSUMER_WARPS * 8 +
+    return (size_t) STAGES * ((d + 1) * TJ + dp_of(d)) * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta) + N_CONSUMER_WARPS * 8 +
            (size_t) 2 * d * 4;
   }
   __device__ SmemRing(unsigned char* base, int d) {
-    tile_floats = (size_t) (d + 1) * TJ;
+    tile_floats = (size_t) (d + 1) * TJ + dp_of(d);
     tiles = reinterpret_cast<float*>(base);
     full = reinterpret_cast<uint64_t*>(base + STAGES * tile_floats * 4);
     empty = full + STAGES;
@@ -214,6 +220,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
           float* dst = ring.tiles + pp.stage * ring.tile_floats;
           const float* src = g.cT + (size_t) tt * TJ;
           for (int k = lane; k <= d; k += 32) tma_load_1d(dst + k * TJ, src + (size_t) k * g.ld, TJ * 4, &ring.full[pp.stage]);
+          if (lane == 31) tma_load_1d(dst + (d + 1) * TJ, g.tcen + (size_t) tt * g.dp, (uint32_t) g.dp * 4, &ring.full[pp.stage]);
         }
         first = false;
         ++streamed;
@@ -240,36 +247,71 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
   }
 }
 
-// Row operands of a consumer thread: rows row0 + r * N_CONSUMERS, r = 0..RI-1.
+// Row operands of a consumer thread: rows row0 + r * N_CONSUMERS, r = 0..RI-1.  retarget() re-centres them
+// on the centre of the tile about to be scanned (cen: the tile's tcen entry in shared memory):
+//   x[r][k] = x_original - c_t[k],  xn[r] = |x'|^2,  eabs[r] = c_loc * (xn[r] + max|y'|^2 of the tile),
+// the absolute part of the fast path's rounding-error bound for this row against this tile.
+// The original coordinates are re-read from xT (coalesced, L1 resident after the first tile of an item).
 template <int D>
 struct Rows {
-  float x[RI][D];           // centred coordinates x'
+  float x[RI][D];           // tile-local coordinates x'
   float xn[RI];             // |x'|^2
+  float eabs[RI];
   uint32_t row0;
+  uint32_t p[RI];           // clamped positions
   __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * N_CONSUMERS; }
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid) {
     row0 = g.row_begin + rb * ROWS_PER_CTA + tid;
 #pragma unroll
-    for (int r = 0; r < RI; ++r) {
-      const size_t p = min((size_t) row(r), g.ld - 1);     // rows past the end: clamped, results discarded
+    for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);     // rows past the end: clamped, results discarded
+  }
+  __device__ __forceinline__ void retarget(const ScanGeom& g, const float* __restrict__ cen) {
+    float c[D];
 #pragma unroll
-      for (int k = 0; k < D; ++k) x[r][k] = -0.5f * __ldg(g.cT + (size_t) k * g.ld + p);
-      xn[r] = __ldg(g.cT + (size_t) D * g.ld + p);
+    for (int k = 0; k < D; ++k) c[k] = cen[k];
+    const float ymax = cen[D];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        x[r][k] = __ldg(g.xT + (size_t) k * g.ld + p[r]) - c[k];
+        s = fmaf(x[r][k], x[r][k], s);
+      }
+      xn[r] = s;
+      eabs[r] = g.c_loc * (s + ymax);
     }
   }
 };
 template <>
 struct Rows<0> {
   float xn[RI];
+  float eabs[RI];
   uint32_t row0;
-  size_t p[RI];
+  uint32_t p[RI];
   __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * N_CONSUMERS; }
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid) {
     row0 = g.row_begin + rb * ROWS_PER_CTA + tid;
 #pragma unroll
+    for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
+  }
+  __device__ __forceinline__ void retarget(const ScanGeom& g, const float* __restrict__ cen) {
+    float s[RI];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) s[r] = 0.f;
+    for (int k = 0; k < g.d; ++k) {
+      const float c = cen[k];
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        const float v = __ldg(g.xT + (size_t) k * g.ld + p[r]) - c;
+        s[r] = fmaf(v, v, s[r]);
+      }
+    }
+    const float ymax = cen[g.d];
+#pragma unroll
     for (int r = 0; r < RI; ++r) {
-      p[r] = min((size_t) row(r), g.ld - 1);
-      xn[r] = __ldg(g.cT + (size_t) g.d * g.ld + p[r]);
+      xn[r] = s[r];
+      eabs[r] = g.c_loc * (s[r] + ymax);
     }
   }
 };
@@ -355,6 +397,7 @@ __device__ __forceinline__ void scan_tile(const ScanGeom& gm, const float* __res
                                           float* __restrict__ scratch, Hit& hit) {
   constexpr int TJ = TileW<0>::tj, CG = TileW<0>::cj;
   const int d = gm.d;
+  const float* __restrict__ cen = tl + (d + 1) * TJ;
 #pragma unroll 1
   for (int g = 0; g < TJ; g += CG) {
     float acc[CG / CJ][RI][CJ];
@@ -369,8 +412,9 @@ __device__ __forceinline__ void scan_tile(const ScanGeom& gm, const float* __res
 #pragma unroll 2
     for (int k = 0; k < d; ++k) {
       float xr[RI];
+      const float ck = cen[k];
 #pragma unroll
-      for (int r = 0; r < RI; ++r) xr[r] = -0.5f * __ldg(gm.cT + (size_t) k * gm.ld + R.p[r]);
+      for (int r = 0; r < RI; ++r) xr[r] = __ldg(gm.xT + (size_t) k * gm.ld + R.p[r]) - ck;
 #pragma unroll
       for (int c4 = 0; c4 < CG / CJ; ++c4) {
         const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + g + c4 * CJ);
@@ -405,8 +449,8 @@ struct PopsArgs {
   ScanGeom g;
   int n_bins;               // distinct radii in this pass (<= MAX_BINS)
   float rad2[32];           // ascending squared radii, padded with +inf
-  float thr_fast;           // rad2[n_bins-1] + error margin
-  float band[2];            // count mode: half width of the error band around rad2[0], rad2[1]
+  float thr_fast;           // rad2[n_bins-1] (1 + e_rel): relative part of the filter margin (absolute part: Rows::eabs)
+  float band[2];            // count mode: the part of the error band around rad2[b] that depends on the radius only
   uint32_t* cnt;            // [n_bins][ld_cnt]: #{j != i : rad2[b-1] <= d2(i,j) < rad2[b]}, rows relative to row_begin
   size_t ld_cnt;
 };
@@ -464,7 +508,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
     int b = bin_of(rad2s, nb, s);
     const float lo = b > 0 ? rad2s[b - 1] : -INFINITY;
     const float hi = rad2s[b];
-    const float e = fmaf(g.e_rel, fabsf(s), g.e_abs);
+    const float e = fmaf(g.e_rel, fabsf(s), sel4(R.eabs, r)) * 1.0001f;
     if ((s - lo < e) || (hi - s <= e)) {       // within the error band of a radius: decide exactly
       s = dist2_exact(g.xT, g.ld, d, i, j);
       ++st.exact;
@@ -478,8 +522,6 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
     if (m.row_block < 0) break;
     if (m.flags & 1u) {
       R.load(g, (uint32_t) m.row_block, tid);
-#pragma unroll
-      for (int r = 0; r < RI; ++r) t[r] = next_up(a.thr_fast - R.xn[r]);
       for (int b = 0; b < nb; ++b)
 #pragma unroll
         for (int r = 0; r < RI; ++r) hist[b * ROWS_PER_CTA + r * N_CONSUMERS] = 0;
@@ -487,6 +529,10 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
     col0 = m.col0;
     if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      R.retarget(g, tl + (d + 1) * TileW<D>::tj);
+      // every pair with exact d2 < r_max^2 has acc < t[r]  (thr_fast = r_max^2 (1 + e_rel), eabs: absolute error part)
+#pragma unroll
+      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));
       scan_tile(g, tl, R, t, scratch, hit);
     }
     __syncwarp();
@@ -545,10 +591,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
   const int tid = threadIdx.x;
   Rows<D> R;
   float tm[NB][RI];           // decision boundary of radius b for row r in accumulator units: rad2[b] - |x'_r|^2
-  float w[NB];                // half width of the rounding-error band around it
+  float w[NB][RI];            // half width of the rounding-error band around it (depends on the row and the tile)
   uint32_t cnt[NB][RI];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) w[b] = a.band[b];
   Pipe cp;
   SlowStats st;
   for (;;) {
@@ -560,13 +604,19 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
 #pragma unroll
       for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int r = 0; r < RI; ++r) {
-          tm[b][r] = a.rad2[b] - R.xn[r];
-          cnt[b][r] = 0;
-        }
+        for (int r = 0; r < RI; ++r) cnt[b][r] = 0;
     }
     if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      R.retarget(g, tl + (D + 1) * TJ);
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+          tm[b][r] = a.rad2[b] - R.xn[r];
+          // |v - (d2_exact - r^2)| < w: fast-path error (eabs + e_rel r^2) + roundings of tm and of v
+          w[b][r] = fmaf(1.01f, R.eabs[r], a.band[b]) + 2.4e-7f * R.xn[r];
+        }
 #pragma unroll 1
       for (int gcol = 0; gcol < TJ; gcol += CJ) {
         float acc[RI][CJ];
@@ -602,7 +652,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
             cnt[b][r] += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
             cnt[b][r] += (__float_as_uint(v2) >> 31) + (__float_as_uint(v3) >> 31);
             const float mn = fminf(fminf(fabsf(v0), fabsf(v1)), fminf(fabsf(v2), fabsf(v3)));
-            band |= mn < w[b];
+            band |= mn < w[b][r];
           }
         if (band) {
           // rare: some pair of this 4x4 block is within the error band of a radius.  One compact loop
@@ -620,7 +670,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
               const float v = av - sel4(tm[b], r);
-              if (fabsf(v) < w[b] && R.row(r) < g.row_end) {
+              if (fabsf(v) < sel4(w[b], r) && R.row(r) < g.row_end) {
                 ++st.slow;
                 if (!have) {
                   d2 = dist2_exact(g.xT, g.ld, D, R.row(r), m.col0 + gcol + (p % CJ));
@@ -695,7 +745,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
         const float dh = __ldg(a.lo + i) == 0 ? dn : key_d2(a.key_hd[i - g.row_begin]);
         v = fmaxf(v, fmaxf(dn, dh));                     // NaN-free: keys hold real distances or FLT_MAX
       }
-      v = (fmaf(g.e_rel, v, v) + g.e_abs) * 1.00001f;    // the rows' filter thresholds in fast-value units
+      v = (fmaf(g.e_rel, v, v) + g.prune_slack) * 1.00001f;    // what the bounding-box lower bound is compared with
       if (!(v < INFINITY)) v = INFINITY;
       return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
     });
@@ -708,7 +758,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
   Pipe cp;
   SlowStats st;
   // every column whose exact d2 is <= `d2` satisfies acc < thr(d2) (api.cu: error_bounds)
-  auto thr = [&](float d2, float xnr) { return next_up(next_up(fmaf(g.e_rel, d2, d2) + g.e_abs - xnr)); };
+  auto thr = [&](float d2, float eabs, float xnr) { return next_up(next_up(fmaf(g.e_rel, d2, d2) + eabs - xnr)); };
   auto hit = [&](int r, int jt, float accv) {
     const uint32_t j = col0 + jt;
     const uint32_t i = R.row(r);
@@ -723,9 +773,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | __ldg(a.perm + j);
     unsigned long long* b0 = best + r * N_CONSUMERS;
     unsigned long long* b1 = b0 + ROWS_PER_CTA;
-    const float xnr = sel4(R.xn, r);
-    if (key < *b0) { *b0 = key; tn = thr(d2, xnr); put4(t_nn, r, tn); }
-    if (hd_cand && key < *b1) { *b1 = key; th = thr(d2, xnr); put4(t_hd, r, th); }
+    const float xnr = sel4(R.xn, r), ear = sel4(R.eabs, r);
+    if (key < *b0) { *b0 = key; tn = thr(d2, ear, xnr); put4(t_nn, r, tn); }
+    if (hd_cand && key < *b1) { *b1 = key; th = thr(d2, ear, xnr); put4(t_hd, r, th); }
     put4(t, r, fmaxf(tn, th));
   };
   // pruning threshold of this warp's rows in fast-value units (acc + xn), published for the producer
@@ -733,7 +783,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     float v = 0.f;
 #pragma unroll
     for (int r = 0; r < RI; ++r)
-      if (R.row(r) < g.row_end) v = fmaxf(v, (t[r] + R.xn[r]) * 1.000001f);     // fmaxf drops NaN
+      if (R.row(r) < g.row_end) v = fmaxf(v, (t[r] + R.xn[r]) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
     if (!(v < INFINITY)) v = INFINITY;
     const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));   // v >= 0: bits order like values
     if (lane == 0) ring.wthr[warp] = ((unsigned long long) item << 32) | m;
@@ -756,16 +806,20 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
         best[r * N_CONSUMERS] = k0;
         best[ROWS_PER_CTA + r * N_CONSUMERS] = k1;
         lo_s[r * N_CONSUMERS] = lo_i;
-        t_nn[r] = thr(key_d2(k0), R.xn[r]);
-        // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
-        t_hd[r] = lo_i == 0 ? t_nn[r] : thr(key_d2(k1), R.xn[r]);
-        t[r] = fmaxf(t_nn[r], t_hd[r]);
       }
-      publish(m.aux);
     }
     col0 = m.col0;
     if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      R.retarget(g, tl + (d + 1) * TileW<D>::tj);
+      // filter thresholds of this tile from the best keys so far (the error margin depends on the tile)
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        t_nn[r] = thr(key_d2(best[r * N_CONSUMERS]), R.eabs[r], R.xn[r]);
+        // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
+        t_hd[r] = lo_s[r * N_CONSUMERS] == 0 ? t_nn[r] : thr(key_d2(best[ROWS_PER_CTA + r * N_CONSUMERS]), R.eabs[r], R.xn[r]);
+        t[r] = fmaxf(t_nn[r], t_hd[r]);
+      }
       scan_tile(g, tl, R, t, scratch, hit);
       publish(m.aux);
     }
@@ -791,7 +845,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
 struct ScreenArgs {
   ScanGeom g;               // rows [row_begin,row_end) = the new sorted positions of this shard
   float cut;                // (float)(4*sigma2); an edge needs d2 < cut (density_clustering.cpp:319)
-  float thr_fast;           // cut + error margin
+  float thr_fast;           // cut (1 + e_rel)
   uint32_t* parent;         // [m_new] union-find forest, parent[p] <= p, roots are the smallest position
 };
 
@@ -846,7 +900,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
     if (j >= i || i >= g.row_end) return;
     ++st.slow;
     float s = accv + sel4(R.xn, r);
-    const float e = fmaf(g.e_rel, fabsf(s), g.e_abs);
+    const float e = fmaf(g.e_rel, fabsf(s), sel4(R.eabs, r)) * 1.0001f;
     if (fabsf(s - a.cut) <= e) {
       s = dist2_exact(g.xT, g.ld, d, i, j);
       ++st.exact;
@@ -857,14 +911,13 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
     mbar_wait(&ring.full[cp.stage], cp.phase);
     const TileMeta m = ring.meta[cp.stage];
     if (m.row_block < 0) break;
-    if (m.flags & 1u) {
-      R.load(g, (uint32_t) m.row_block, tid);
-#pragma unroll
-      for (int r = 0; r < RI; ++r) t[r] = next_up(a.thr_fast - R.xn[r]);
-    }
+    if (m.flags & 1u) R.load(g, (uint32_t) m.row_block, tid);
     col0 = m.col0;
     if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      R.retarget(g, tl + (d + 1) * TJ);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));
       scan_tile(g, tl, R, t, scratch, hit);
     }
     __syncwarp();
