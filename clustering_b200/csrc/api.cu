@@ -218,14 +218,20 @@ __global__ void gather_by_kernel(const uint32_t* __restrict__ src, const uint32_
   const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (p < n) dst[p] = src[index[p]];
 }
+// lo by position (gathered through perm) and the same ranks as floats for the neighbour filter: (float)(lo >> shift),
+// exact for shift == 0 (n <= 2^24); +inf in the padding so that a padded column is never a candidate
+__global__ void lo_by_position_kernel(const uint32_t* __restrict__ lo_frame, const uint32_t* __restrict__ perm, size_t n, size_t ld,
+                                      int shift, uint32_t* __restrict__ lo, float* __restrict__ lof) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ld) return;
+  if (p >= n) { lof[p] = INFINITY; return; }
+  const uint32_t v = lo_frame[perm[p]];
+  lo[p] = v;
+  lof[p] = (float) (v >> shift);
+}
 __global__ void iota_kernel(uint32_t* p, size_t n) {
   const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = (uint32_t) i;
-}
-
-__global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
-  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
 }
 
 // pops[r][i] = 1 + mult[r] * sum_{b <= bin[r]} cnt[b][i]    (self counted by the initial 1, density_clustering.cpp:133;
@@ -293,6 +299,73 @@ __global__ void lower_bound_kernel(const uint32_t* __restrict__ keys, size_t n, 
     if (keys[mid] < k) a = mid + 1; else b = mid;
   }
   lo[p] = (uint32_t) a;
+}
+
+// Seeds the neighbour keys of positions [row_begin,row_end) with the best of the 2*W frames next to them in the
+// context's spatial order (exact arithmetic, real candidates): the pair scan then starts from tight thresholds,
+// prunes far tiles from its first item on and re-evaluates only the few columns that really improve on the seed.
+__global__ void nn_seed_kernel(const float* __restrict__ xT, size_t ld, int d, uint32_t n, const uint32_t* __restrict__ perm,
+                               const uint32_t* __restrict__ lo, uint32_t row_begin, uint32_t row_end, int W,
+                               unsigned long long none, unsigned long long* __restrict__ key_nn, unsigned long long* __restrict__ key_hd) {
+  const uint32_t p = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= row_end) return;
+  unsigned long long knn = none, khd = none;
+  const uint32_t lo_p = lo[p];
+  for (int o = 1; o <= W; ++o) {
+    for (int side = 0; side < 2; ++side) {
+      const long long jj = side ? (long long) p + o : (long long) p - o;
+      if (jj < 0 || jj >= (long long) n) continue;
+      const uint32_t j = (uint32_t) jj;
+      const float d2 = dist2_exact(xT, ld, d, p, j);
+      if (!(d2 < FLT_MAX)) continue;
+      const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | perm[j];
+      knn = min(knn, key);
+      if (lo[j] < lo_p) khd = min(khd, key);
+    }
+  }
+  key_nn[p - row_begin] = knn;
+  key_hd[p - row_begin] = khd;
+}
+
+// bounding boxes of the row blocks of one launch = union of the 64-frame group boxes they touch (one warp per block)
+__global__ void row_bbox_kernel(const float* __restrict__ bbox, int d, uint32_t row_begin, uint32_t row_end, uint32_t n_row_blocks,
+                                float* __restrict__ rbbox) {
+  const uint32_t rb = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (rb >= n_row_blocks) return;
+  const uint32_t r0 = row_begin + rb * ROWS_PER_CTA;
+  const uint32_t r1 = min(r0 + (uint32_t) ROWS_PER_CTA, row_end);
+  const uint32_t g0 = r0 / 64, g1 = (r1 - 1) / 64;
+  for (int k = lane; k < d; k += 32) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (uint32_t q = g0; q <= g1; ++q) {
+      lo = fminf(lo, bbox[(size_t) q * 2 * d + k]);
+      hi = fmaxf(hi, bbox[(size_t) q * 2 * d + d + k]);
+    }
+    rbbox[(size_t) rb * 2 * d + k] = lo;
+    rbbox[(size_t) rb * 2 * d + d + k] = hi;
+  }
+}
+
+// blk_thr[rb][w] = bound (d2 units, with the pruning margins) of what the rows of block rb owned by consumer warp w
+// still accept after seeding: max over its rows of the seeded d2 (nearest / nearest with lower free energy)
+__global__ void nn_block_thr_kernel(const unsigned long long* __restrict__ key_nn, const unsigned long long* __restrict__ key_hd,
+                                    const uint32_t* __restrict__ lo, uint32_t row_begin, uint32_t row_end, uint32_t n_row_blocks,
+                                    float e_rel, float slack, float* __restrict__ blk_thr) {
+  const uint32_t rb = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;      // blockDim = N_CONSUMERS: thread = consumer slot
+  float v = 0.f;
+  for (int r = 0; r < RI; ++r) {
+    const uint32_t i = row_begin + rb * ROWS_PER_CTA + threadIdx.x + (uint32_t) r * N_CONSUMERS;
+    if (i >= row_end) continue;
+    const float dn = __uint_as_float((uint32_t) (key_nn[i - row_begin] >> 32));
+    const float dh = lo[i] == 0 ? dn : __uint_as_float((uint32_t) (key_hd[i - row_begin] >> 32));
+    v = fmaxf(v, fmaxf(dn, dh));
+  }
+  v = (fmaf(e_rel, v, v) + slack) * 1.00001f;
+  if (!(v < INFINITY)) v = INFINITY;
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) blk_thr[(size_t) rb * N_CONSUMER_WARPS + w] = v;
 }
 
 __global__ void nn_finish_kernel(const unsigned long long* __restrict__ knn, const unsigned long long* __restrict__ khd,
@@ -379,8 +452,12 @@ struct dcb200_ctx {
   DevBuf<float> xT, cT;             // [d][ld] original coords, [d+1][ld] column pack (context order)
   DevBuf<float> bbox;               // [ld/64][2d]
   DevBuf<float> tcen;               // [ld/tile][dp] tile centres + max local norm
+  DevBuf<float> rbbox;              // [row blocks of the current launch][2d]
+  DevBuf<float> blk_thr;            // [row blocks][N_CONSUMER_WARPS] neighbour search pruning bounds
   DevBuf<uint32_t> perm;            // [n] position -> frame (identity when !spatial)
   DevBuf<uint32_t> lo;              // [n] per position: number of frames with strictly lower free energy
+  DevBuf<float> lof;                // [ld] the same ranks as floats (>> lo_shift), +inf padded
+  int lo_shift = 0;
   DevBuf<uint32_t> keys_a, keys_b, iota, tmp_u32, tmp2_u32;
   DevBuf<unsigned char> cub_tmp;
   DevBuf<float> stage;              // row-major staging for host uploads
@@ -438,6 +515,9 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, in
   g->n_col_tiles = (uint32_t) (c->ld / tj);
   if (occupancy < 1) return fail("kernel does not fit on an SM (shared memory / registers)");
   *grid = c->sm_count * occupancy;
+  // about 16 column items per row block: enough for load balance and for the column-step-major order
+  // (own neighbourhood first), few enough that the producers' per-item work stays negligible
+  tiles_per_item = std::max(tiles_per_item, (g->n_col_tiles + 15) / 16);
   g->tiles_per_item = std::max(1u, std::min(tiles_per_item, g->n_col_tiles));
   g->n_col_items = (g->n_col_tiles + g->tiles_per_item - 1) / g->tiles_per_item;
   if ((uint64_t) g->n_row_blocks * g->n_col_items >= 0x7fffffffull) return fail("too many work items");
@@ -445,6 +525,11 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, in
   g->work_counter = c->scalars;
   g->stats = c->stats;
   error_bounds(c->d, c->maxnorm2, &g->c_loc, &g->e_rel, &g->prune_slack);
+  CK(c->rbbox.reserve((size_t) g->n_row_blocks * 2 * c->d));
+  g->rbbox = c->rbbox.p;
+  row_bbox_kernel<<<blocks_for(g->n_row_blocks, 8), 256, 0, c->stream>>>(c->bbox.p, (int) c->d, g->row_begin, g->row_end, g->n_row_blocks,
+                                                                         c->rbbox.p);
+  c->launches += 1;
   c->pairs_scheduled += (uint64_t) (row_end - row_begin) * (uint64_t) c->n;
   return 0;
 }
@@ -571,8 +656,8 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->xT.release(); c->cT.release(); c->bbox.release(); c->tcen.release();
-  c->perm.release(); c->lo.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release();
+  c->xT.release(); c->cT.release(); c->bbox.release(); c->tcen.release(); c->rbbox.release(); c->blk_thr.release();
+  c->perm.release(); c->lo.release(); c->lof.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release();
   c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
   c->io_u32.release(); c->io_f32.release();
@@ -799,12 +884,15 @@ extern "C" int dcb200_ctx_nn_prepare(dcb200_ctx* c, const float* dev_fe) {
   CK(cudaSetDevice(c->device));
   const size_t n = c->n;
   CK(c->keys_a.reserve(n)); CK(c->keys_b.reserve(n)); CK(c->iota.reserve(n)); CK(c->tmp_u32.reserve(n));
-  CK(c->tmp2_u32.reserve(n)); CK(c->lo.reserve(n));
+  CK(c->tmp2_u32.reserve(n)); CK(c->lo.reserve(n)); CK(c->lof.reserve(c->ld));
+  c->lo_shift = 0;
+  while ((n >> c->lo_shift) > (size_t(1) << 24)) ++c->lo_shift;
   fe_keys_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(dev_fe, n, c->keys_a.p, c->iota.p);
   CKI(sort_pairs_u32(c, c->keys_a.p, c->keys_b.p, c->iota.p, c->tmp_u32.p, n, 32));              // tmp_u32: fe position -> frame
   lower_bound_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->keys_b.p, n, c->keys_a.p);    // keys_a: lo by fe position
   scatter_by_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->keys_a.p, c->tmp_u32.p, n, c->tmp2_u32.p);   // lo by frame
-  gather_by_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->tmp2_u32.p, c->perm.p, n, c->lo.p);           // lo by position
+  lo_by_position_kernel<<<blocks_for(c->ld, 256), 256, 0, c->stream>>>(c->tmp2_u32.p, c->perm.p, n, c->ld, c->lo_shift, c->lo.p,
+                                                                       c->lof.p);                                    // lo by position
   c->launches += 4;
   CK(cudaGetLastError());
   c->nn_ready = true;
@@ -823,17 +911,43 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
   uint32_t fbits;
   memcpy(&fbits, &fmax, 4);
   const unsigned long long none = ((unsigned long long) fbits << 32) | (unsigned long long) (uint32_t) (c->n + 1);
-  fill_u64_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>((unsigned long long*) dev_keys_nn, rows, none);
-  fill_u64_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>((unsigned long long*) dev_keys_hd, rows, none);
+  nn_seed_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->xT.p, c->ld, (int) c->d, (uint32_t) c->n, c->perm.p, c->lo.p,
+                                                               (uint32_t) pos_begin, (uint32_t) pos_end, 8, none,
+                                                               (unsigned long long*) dev_keys_nn, (unsigned long long*) dev_keys_hd);
   NnArgs a;
   int grid = 0;
   CKI(fill_geom(c, pos_begin, pos_end, tile_width(c->d), occ_nn((int) c->d), 32u, &a.g, &grid));
   a.perm = c->perm.p;
   a.lo = c->lo.p;
+  a.lof = c->lof.p;
+  a.lo_bias = c->lo_shift ? 1.f : 0.f;
+  a.g.xrow = c->lof.p;
+  CK(c->blk_thr.reserve((size_t) a.g.n_row_blocks * N_CONSUMER_WARPS));
+  a.g.blk_thr = c->blk_thr.p;
+  nn_block_thr_kernel<<<a.g.n_row_blocks, N_CONSUMERS, 0, c->stream>>>((const unsigned long long*) dev_keys_nn,
+                                                                       (const unsigned long long*) dev_keys_hd, c->lo.p, (uint32_t) pos_begin,
+                                                                       (uint32_t) pos_end, a.g.n_row_blocks, a.g.e_rel, a.g.prune_slack,
+                                                                       c->blk_thr.p);
   a.key_nn = (unsigned long long*) dev_keys_nn;
   a.key_hd = (unsigned long long*) dev_keys_hd;
+  // pass 1: every row block against its own neighbourhood in the spatial order (one item per block): the nearest
+  // neighbours are almost always there, so pass 2 (all tiles, large items) starts from final-quality thresholds
+  const uint32_t full_tpi = a.g.tiles_per_item, full_items = a.g.n_col_items;
+  const int full_grid = grid;
+  if (c->spatial && a.g.n_col_tiles > 96) {
+    a.window = 16;
+    a.g.tiles_per_item = a.g.n_col_tiles;
+    a.g.n_col_items = 1;
+    grid = (int) std::min<uint64_t>((uint64_t) full_grid, a.g.n_row_blocks);
+    CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+    CK(launch_nn((int) c->d, a, grid, c->stream));
+    c->launches += 1;
+  }
+  a.window = 0;
+  a.g.tiles_per_item = full_tpi;
+  a.g.n_col_items = full_items;
   CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
-  CK(launch_nn((int) c->d, a, grid, c->stream));
+  CK(launch_nn((int) c->d, a, grid = full_grid, c->stream));
   c->launches += 3;
   return 0;
 }

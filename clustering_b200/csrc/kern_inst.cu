@@ -52,7 +52,7 @@ int DCB_CAT(occupancy_pops_count_d, DCB_D)(int, int) { return 0; }
 #endif
 
 cudaError_t DCB_CAT(launch_nn_d, DCB_D)(const NnArgs& a, int grid, cudaStream_t st) {
-  const size_t smem = nn_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d));
+  const size_t smem = nn_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d, 1));
   cudaError_t e = cudaFuncSetAttribute(nn_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
   nn_kernel<DCB_D><<<grid, CTA_THREADS, smem, st>>>(a);
@@ -76,7 +76,7 @@ int DCB_CAT(occupancy_pops_d, DCB_D)(int n_bins, int d) {
 }
 int DCB_CAT(occupancy_nn_d, DCB_D)(int d) {
   int nb = 0;
-  const size_t smem = nn_smem_bytes(SmemRing<DCB_D>::bytes(d));
+  const size_t smem = nn_smem_bytes(SmemRing<DCB_D>::bytes(d, 1));
   cudaFuncSetAttribute(nn_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nn_kernel<DCB_D>, CTA_THREADS, smem);
   return nb;

@@ -33,6 +33,8 @@ struct ScanGeom {
   const float* xT;          // [D][ld]   original coordinates, dim-major, NaN padded
   const float* cT;          // [D+1][ld] column pack, tile-local: with c_t the centre of the tile a column belongs to and
                             //           y' = y - c_t: rows 0..D-1 = -2*y', row D = |y'|^2 (padding: 0, ..., 0, +inf)
+  const float* xrow;        // optional extra per-column row [ld] streamed with every tile (neighbour search: free-energy
+                            // ranks as floats), nullptr = none; the kernel's SmemRing must be built with xrows = 1
   const float* tcen;        // [n_col_tiles][dp] per tile: centre c_t[0..D-1], then max |y'|^2 over the tile
   int dp;                   // floats per tcen entry (multiple of 4, >= D+1)
   size_t ld;                // padded frame count (multiple of 256)
@@ -49,6 +51,9 @@ struct ScanGeom {
   unsigned long long* stats;        // [0] pairs handed to the slow path, [1] pairs re-evaluated exactly,
                                     // [2] column tiles streamed (x ROWS_PER_CTA x tile width = pairs evaluated)
   const float* bbox;                // [ld/64][2*d] bounding boxes (lo[d], hi[d]) of 64-frame groups, centred coords
+  const float* rbbox;               // [n_row_blocks][2*d] bounding boxes of this launch's row blocks (api.cu: row_bbox_kernel)
+  float* blk_thr;                   // neighbour search only: [n_row_blocks][N_CONSUMER_WARPS] upper bounds (d2 units) of what the
+                                    // rows of a block owned by one consumer warp still accept; lowered by atomicMin as items finish
   float prune_thr;                  // static pruning threshold (fast-value units); +inf disables pruning
 };
 
@@ -77,7 +82,8 @@ template <> struct TileW<0> { static constexpr int tj = 64; static constexpr int
 template <int D>
 struct SmemRing {
   static constexpr int TJ = TileW<D>::tj;
-  float* tiles;            // STAGES * ((d+1) * TJ + dp): column pack of the tile, then its centre entry (tcen)
+  float* tiles;            // STAGES * ((d+1) * TJ + dp + xrows * TJ): column pack of the tile, its centre entry (tcen),
+                           // then the optional extra row
   uint64_t* full;          // STAGES
   uint64_t* empty;         // STAGES
   TileMeta* meta;          // STAGES
@@ -85,12 +91,12 @@ struct SmemRing {
   float* rbb;              // 2*d: bounding box of the current row block (producer scratch)
   size_t tile_floats;
   __host__ __device__ static int dp_of(int d) { return (d + 1 + 3) / 4 * 4; }
-  __host__ __device__ static size_t bytes(int d) {
-    return (size_t) STAGES * ((d + 1) * TJ + dp_of(d)) * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta) + N_CONSUMER_WARPS * 8 +
+  __host__ __device__ static size_t bytes(int d, int xrows = 0) {
+    return (size_t) STAGES * ((d + 1 + xrows) * TJ + dp_of(d)) * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta) + N_CONSUMER_WARPS * 8 +
            (size_t) 2 * d * 4;
   }
-  __device__ SmemRing(unsigned char* base, int d) {
-    tile_floats = (size_t) (d + 1) * TJ + dp_of(d);
+  __device__ SmemRing(unsigned char* base, int d, int xrows = 0) {
+    tile_floats = (size_t) (d + 1 + xrows) * TJ + dp_of(d);
     tiles = reinterpret_cast<float*>(base);
     full = reinterpret_cast<uint64_t*>(base + STAGES * tile_floats * 4);
     empty = full + STAGES;
@@ -156,25 +162,11 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
     t0 = max(t0, lim0);
     t1 = min(t1, lim1);
     if (t0 >= t1) continue;
-    // bounding box of the row block = union of its 64-frame groups
-    {
-      const uint32_t r0 = g.row_begin + rb * ROWS_PER_CTA;
-      const uint32_t r1 = min(r0 + ROWS_PER_CTA, g.row_end);
-      const uint32_t g0 = r0 / 64, g1 = (r1 - 1) / 64;
-      for (int k = lane; k < d; k += 32) {
-        float lo = INFINITY, hi = -INFINITY;
-        for (uint32_t q = g0; q <= g1; ++q) {
-          lo = fminf(lo, __ldg(g.bbox + (size_t) q * 2 * d + k));
-          hi = fmaxf(hi, __ldg(g.bbox + (size_t) q * 2 * d + d + k));
-        }
-        ring.rbb[k] = lo;
-        ring.rbb[d + k] = hi;
-      }
-      __syncwarp();
-    }
-    bool first = true;
-    // pruning threshold: the largest filter threshold of any row of the block (fast-value units)
+    // bounding box of the row block (precomputed per launch) and the pruning threshold the item starts with
+    for (int k = lane; k < 2 * d; k += 32) ring.rbb[k] = __ldg(g.rbbox + (size_t) rb * 2 * d + k);
     const float thr0 = item_thr(rb, lane);
+    __syncwarp();
+    bool first = true;
     for (uint32_t base = t0; base < t1; base += 32) {
       const uint32_t t = base + lane;
       float lb = INFINITY;                          // lower bound of the fast value over (row block) x (tile t)
@@ -221,6 +213,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
           const float* src = g.cT + (size_t) tt * TJ;
           for (int k = lane; k <= d; k += 32) tma_load_1d(dst + k * TJ, src + (size_t) k * g.ld, TJ * 4, &ring.full[pp.stage]);
           if (lane == 31) tma_load_1d(dst + (d + 1) * TJ, g.tcen + (size_t) tt * g.dp, (uint32_t) g.dp * 4, &ring.full[pp.stage]);
+          if (lane == 30 && g.xrow) tma_load_1d(dst + (d + 1) * TJ + g.dp, g.xrow + (size_t) tt * TJ, TJ * 4, &ring.full[pp.stage]);
         }
         first = false;
         ++streamed;
@@ -703,10 +696,14 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
 // nearest neighbours (rows and columns in the context's spatial order)
 // ================================================================================================
 struct NnArgs {
-  ScanGeom g;
+  ScanGeom g;                   // g.xrow = lof
   const uint32_t* perm;         // [n] position -> original frame
   const uint32_t* lo;           // [n] per position: number of frames with a strictly lower free energy
                                 //     (fe[j] < fe[i]  <=>  lo[j] < lo[i])
+  const float* lof;             // [ld] (float)(lo >> lo_shift), +inf in the padding: the same ranks for the fast filter
+  float lo_bias;                // 0 when the float ranks are exact (lo_shift == 0), else 1 (equal coarse ranks stay candidates)
+  uint32_t window;              // > 0: scan only the column tiles within `window` tiles of the row block's own position
+                                // (first pass: settles tight thresholds before the full scan); 0: all tiles
   unsigned long long* key_nn;   // [row_end-row_begin] (d2 bits << 32 | original index), atomicMin'ed
   unsigned long long* key_hd;
 };
@@ -719,13 +716,148 @@ __host__ __device__ inline size_t nn_smem_bytes(size_t ring_bytes) {
 
 __device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as_float((uint32_t) (k >> 32)); }
 
+// Filter state of the neighbour search.  A pair (row r, column c) is worth the exact evaluation iff
+//   acc < t_nn[r]                      (could beat or tie the nearest neighbour found so far), or
+//   acc < t_hd[r] and lo[c] < lo[r]    (could beat the nearest neighbour with lower free energy).
+// Both in one comparison with a per-pair threshold  te = t_nn[r] + cand * dl[r],  cand = sat(lor[r] - lo_c) in {0,1}
+// (one FADD.SAT + one FFMA + one FSETP per pair): frames that are close but have no lower free energy never
+// reach the slow path, however far the lower-free-energy neighbour of a density peak is.
+struct NnFilter {
+  float t_nn[RI], t_hd[RI];
+  float dl[RI];                 // min(t_hd - t_nn, 1e37), rounded up; 0 where t_nn is +inf
+  float lor[RI];                // (float rank of the row) + lo_bias
+  __device__ __forceinline__ void set_dl(int r) {
+    const float tn = sel4(t_nn, r), th = sel4(t_hd, r);
+    float v = 0.f;
+    if (tn < INFINITY) v = th < INFINITY ? fminf(next_up((th - tn) * 1.000001f), 1e37f) : 1e37f;
+    put4(dl, r, fmaxf(v, 0.f));
+  }
+};
+
+// hits of one RI x CJ block under the per-pair thresholds; one compact copy of the handler (see walk_hits)
+template <class Hit>
+__device__ __forceinline__ void walk_hits_nn(float* __restrict__ scratch, const float (&acc)[RI][CJ], const float4 l4, NnFilter& F, int jt0,
+                                             Hit& hit) {
+  uint32_t mask = 0;
+  const float lc[CJ] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+  for (int r = 0; r < RI; ++r)
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) {
+      scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c];
+      const float te = fmaf(__saturatef(F.lor[r] - lc[c]), F.dl[r], F.t_nn[r]);
+      mask |= (acc[r][c] < te) ? (1u << (r * CJ + c)) : 0u;
+    }
+#pragma unroll 1
+  while (mask) {
+    const int p = __ffs(mask) - 1;
+    mask &= mask - 1;
+    hit(p / CJ, jt0 + (p % CJ), scratch[p * N_CONSUMERS]);     // hit() re-checks against the thresholds of the moment
+  }
+}
+
+template <int D, class Hit>
+__device__ __forceinline__ void scan_tile_nn(const ScanGeom&, const float* __restrict__ tl, const float* __restrict__ lrow, const Rows<D>& R,
+                                             NnFilter& F, float* __restrict__ scratch, Hit& hit) {
+  constexpr int TJ = TileW<D>::tj;
+#pragma unroll 1
+  for (int g = 0; g < TJ; g += CJ) {
+    float acc[RI][CJ];
+    {
+      const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + g);
+      const float4 y4 = *reinterpret_cast<const float4*>(tl + g);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
+        acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
+        acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
+        acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
+      }
+    }
+#pragma unroll
+    for (int k = 1; k < D; ++k) {
+      const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + g);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
+        acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
+        acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
+        acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
+      }
+    }
+    const float4 l4 = *reinterpret_cast<const float4*>(lrow + g);
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      any |= acc[r][0] < fmaf(__saturatef(F.lor[r] - l4.x), F.dl[r], F.t_nn[r]);
+      any |= acc[r][1] < fmaf(__saturatef(F.lor[r] - l4.y), F.dl[r], F.t_nn[r]);
+      any |= acc[r][2] < fmaf(__saturatef(F.lor[r] - l4.z), F.dl[r], F.t_nn[r]);
+      any |= acc[r][3] < fmaf(__saturatef(F.lor[r] - l4.w), F.dl[r], F.t_nn[r]);
+    }
+    if (any) walk_hits_nn(scratch, acc, l4, F, g, hit);
+  }
+}
+
+// run-time-D variant
+template <class Hit>
+__device__ __forceinline__ void scan_tile_nn(const ScanGeom& gm, const float* __restrict__ tl, const float* __restrict__ lrow, const Rows<0>& R,
+                                             NnFilter& F, float* __restrict__ scratch, Hit& hit) {
+  constexpr int TJ = TileW<0>::tj, CG = TileW<0>::cj;
+  const int d = gm.d;
+  const float* __restrict__ cen = tl + (d + 1) * TJ;
+#pragma unroll 1
+  for (int g = 0; g < TJ; g += CG) {
+    float acc[CG / CJ][RI][CJ];
+#pragma unroll
+    for (int c4 = 0; c4 < CG / CJ; ++c4) {
+      const float4 n4 = *reinterpret_cast<const float4*>(tl + d * TJ + g + c4 * CJ);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        acc[c4][r][0] = n4.x; acc[c4][r][1] = n4.y; acc[c4][r][2] = n4.z; acc[c4][r][3] = n4.w;
+      }
+    }
+#pragma unroll 2
+    for (int k = 0; k < d; ++k) {
+      float xr[RI];
+      const float ck = cen[k];
+#pragma unroll
+      for (int r = 0; r < RI; ++r) xr[r] = __ldg(gm.xT + (size_t) k * gm.ld + R.p[r]) - ck;
+#pragma unroll
+      for (int c4 = 0; c4 < CG / CJ; ++c4) {
+        const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + g + c4 * CJ);
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+          acc[c4][r][0] = fmaf(xr[r], y4.x, acc[c4][r][0]);
+          acc[c4][r][1] = fmaf(xr[r], y4.y, acc[c4][r][1]);
+          acc[c4][r][2] = fmaf(xr[r], y4.z, acc[c4][r][2]);
+          acc[c4][r][3] = fmaf(xr[r], y4.w, acc[c4][r][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c4 = 0; c4 < CG / CJ; ++c4) {
+      const float4 l4 = *reinterpret_cast<const float4*>(lrow + g + c4 * CJ);
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        any |= acc[c4][r][0] < fmaf(__saturatef(F.lor[r] - l4.x), F.dl[r], F.t_nn[r]);
+        any |= acc[c4][r][1] < fmaf(__saturatef(F.lor[r] - l4.y), F.dl[r], F.t_nn[r]);
+        any |= acc[c4][r][2] < fmaf(__saturatef(F.lor[r] - l4.z), F.dl[r], F.t_nn[r]);
+        any |= acc[c4][r][3] < fmaf(__saturatef(F.lor[r] - l4.w), F.dl[r], F.t_nn[r]);
+      }
+      if (any) walk_hits_nn(scratch, acc[c4], l4, F, g + c4 * CJ, hit);
+    }
+  }
+}
+
 template <int D>
 __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int TJ = TileW<D>::tj;
   const ScanGeom& g = a.g;
   const int d = D ? D : g.d;
-  SmemRing<D> ring(smem, d);
-  unsigned char* extra = smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15));
+  SmemRing<D> ring(smem, d, 1);
+  unsigned char* extra = smem + ((SmemRing<D>::bytes(d, 1) + 15) & ~size_t(15));
   float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
   // best[0][slot] = nearest-neighbour key, best[1][slot] = nearest neighbour with lower free energy
   unsigned long long* best = reinterpret_cast<unsigned long long*>(extra + SCRATCH_BYTES) + threadIdx.x;
@@ -735,25 +867,24 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == N_CONSUMER_WARPS) {
-    // initial pruning threshold of an item: what earlier items already found for the rows of the block
-    produce<D>(g, ring, true, [](uint32_t, uint32_t&, uint32_t&) {}, [&](uint32_t rb, int ln) {
-      const uint32_t r0 = g.row_begin + rb * ROWS_PER_CTA;
-      const uint32_t r1 = min(r0 + ROWS_PER_CTA, g.row_end);
-      float v = 0.f;
-      for (uint32_t i = r0 + ln; i < r1; i += 32) {
-        const float dn = key_d2(a.key_nn[i - g.row_begin]);
-        const float dh = __ldg(a.lo + i) == 0 ? dn : key_d2(a.key_hd[i - g.row_begin]);
-        v = fmaxf(v, fmaxf(dn, dh));                     // NaN-free: keys hold real distances or FLT_MAX
+    // initial pruning threshold of an item: what the seeds and earlier items already found for the rows of the block
+    produce<D>(g, ring, true, [&](uint32_t rb, uint32_t& lim0, uint32_t& lim1) {
+      if (a.window) {
+        const uint32_t t_first = (g.row_begin + rb * ROWS_PER_CTA) / TJ;
+        const uint32_t t_last = (min(g.row_begin + (rb + 1) * ROWS_PER_CTA, g.row_end) - 1) / TJ;
+        lim0 = t_first > a.window ? t_first - a.window : 0u;
+        lim1 = min(lim1, t_last + a.window + 1);
       }
-      v = (fmaf(g.e_rel, v, v) + g.prune_slack) * 1.00001f;    // what the bounding-box lower bound is compared with
+    }, [&](uint32_t rb, int ln) {
+      float v = ln < N_CONSUMER_WARPS ? *reinterpret_cast<volatile float*>(g.blk_thr + (size_t) rb * N_CONSUMER_WARPS + ln) : 0.f;
       if (!(v < INFINITY)) v = INFINITY;
-      return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+      return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f))));
     });
     return;
   }
   const int tid = threadIdx.x;
   Rows<D> R;
-  float t[RI], t_nn[RI], t_hd[RI];
+  NnFilter F;
   uint32_t col0 = 0;
   Pipe cp;
   SlowStats st;
@@ -764,9 +895,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     const uint32_t i = R.row(r);
     ++st.slow;
     if (j == i || j >= g.n || i >= g.row_end) return;
-    float tn = sel4(t_nn, r), th = sel4(t_hd, r);
+    const float tn = sel4(F.t_nn, r), th = sel4(F.t_hd, r);
     const bool hd_cand = __ldg(a.lo + j) < lo_s[r * N_CONSUMERS];
-    if (!hd_cand && !(accv < tn)) return;     // passed only the (weaker) lower-free-energy filter, but is no candidate for it
+    if (!(accv < tn) && !(hd_cand && accv < th)) return;      // thresholds may have tightened since the block was filtered
     const float d2 = dist2_exact(g.xT, g.ld, d, i, j);
     ++st.exact;
     if (!(d2 < FLT_MAX)) return;
@@ -774,19 +905,28 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     unsigned long long* b0 = best + r * N_CONSUMERS;
     unsigned long long* b1 = b0 + ROWS_PER_CTA;
     const float xnr = sel4(R.xn, r), ear = sel4(R.eabs, r);
-    if (key < *b0) { *b0 = key; tn = thr(d2, ear, xnr); put4(t_nn, r, tn); }
-    if (hd_cand && key < *b1) { *b1 = key; th = thr(d2, ear, xnr); put4(t_hd, r, th); }
-    put4(t, r, fmaxf(tn, th));
+    bool changed = false;
+    if (key < *b0) {
+      *b0 = key;
+      const float v = thr(d2, ear, xnr);
+      put4(F.t_nn, r, v);
+      if (lo_s[r * N_CONSUMERS] == 0) put4(F.t_hd, r, v);
+      changed = true;
+    }
+    if (hd_cand && key < *b1) { *b1 = key; put4(F.t_hd, r, thr(d2, ear, xnr)); changed = true; }
+    if (changed) F.set_dl(r);
   };
   // pruning threshold of this warp's rows in fast-value units (acc + xn), published for the producer
+  uint32_t last_pub = 0x7f800000u;        // what this warp published last (float bits, +inf = nothing yet)
   auto publish = [&](uint32_t item) {
     float v = 0.f;
 #pragma unroll
     for (int r = 0; r < RI; ++r)
-      if (R.row(r) < g.row_end) v = fmaxf(v, (t[r] + R.xn[r]) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
+      if (R.row(r) < g.row_end) v = fmaxf(v, (fmaxf(F.t_nn[r], F.t_hd[r]) + R.xn[r]) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
     if (!(v < INFINITY)) v = INFINITY;
     const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));   // v >= 0: bits order like values
     if (lane == 0) ring.wthr[warp] = ((unsigned long long) item << 32) | m;
+    last_pub = m;
   };
   for (;;) {
     mbar_wait(&ring.full[cp.stage], cp.phase);
@@ -798,29 +938,32 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
       for (int r = 0; r < RI; ++r) {
         unsigned long long k0 = ~0ull, k1 = ~0ull;
         uint32_t lo_i = 0;
+        float lf = 0.f;
         if (R.row(r) < g.row_end) {                     // warm start from what earlier items already found
           k0 = a.key_nn[R.row(r) - g.row_begin];
           k1 = a.key_hd[R.row(r) - g.row_begin];
           lo_i = __ldg(a.lo + R.row(r));
+          lf = __ldg(a.lof + R.row(r));
         }
         best[r * N_CONSUMERS] = k0;
         best[ROWS_PER_CTA + r * N_CONSUMERS] = k1;
         lo_s[r * N_CONSUMERS] = lo_i;
+        F.lor[r] = lf + a.lo_bias;
       }
     }
     col0 = m.col0;
     if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
-      R.retarget(g, tl + (d + 1) * TileW<D>::tj);
+      R.retarget(g, tl + (d + 1) * TJ);
       // filter thresholds of this tile from the best keys so far (the error margin depends on the tile)
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
-        t_nn[r] = thr(key_d2(best[r * N_CONSUMERS]), R.eabs[r], R.xn[r]);
+        F.t_nn[r] = thr(key_d2(best[r * N_CONSUMERS]), R.eabs[r], R.xn[r]);
         // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
-        t_hd[r] = lo_s[r * N_CONSUMERS] == 0 ? t_nn[r] : thr(key_d2(best[ROWS_PER_CTA + r * N_CONSUMERS]), R.eabs[r], R.xn[r]);
-        t[r] = fmaxf(t_nn[r], t_hd[r]);
+        F.t_hd[r] = lo_s[r * N_CONSUMERS] == 0 ? F.t_nn[r] : thr(key_d2(best[ROWS_PER_CTA + r * N_CONSUMERS]), R.eabs[r], R.xn[r]);
+        F.set_dl(r);
       }
-      scan_tile(g, tl, R, t, scratch, hit);
+      scan_tile_nn(g, tl, tl + (d + 1) * TJ + g.dp, R, F, scratch, hit);
       publish(m.aux);
     }
     __syncwarp();
@@ -833,6 +976,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
           atomicMin(a.key_hd + (R.row(r) - g.row_begin), best[ROWS_PER_CTA + r * N_CONSUMERS]);
         }
       }
+      // what this warp's rows still accept bounds every later item of the row block (positive floats order like their bits)
+      if (lane == 0) atomicMin(reinterpret_cast<unsigned int*>(g.blk_thr) + (size_t) m.row_block * N_CONSUMER_WARPS + warp, last_pub);
     }
     cp.advance();
   }
