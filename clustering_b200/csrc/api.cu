@@ -136,7 +136,8 @@ __global__ void morton_keys_kernel(const float* __restrict__ coords, size_t n, i
 //   cT   [d+1][ld]   tile-local column pack: y' = x - c_t with c_t = mean of the tile's frames (any point near the
 //                    tile works; the mean keeps |y'| smallest): rows 0..d-1 = -2 y', row d = |y'|^2
 //                    (padding: 0, ..., 0, +inf: the accumulator of a padded column is +inf for every row)
-//   tcen [tiles][dp] c_t[0..d-1], then max |y'|^2 over the tile's real frames
+//   tcen [tiles][dp] c_t[0..d-1], max |y'|^2 over the tile's real frames, then the tile's bounding box lo[d], hi[d]
+//                    in globally centred coordinates
 //   bbox [ld/64][2d] bounding boxes of 64-frame groups in globally centred coordinates (tile pruning)
 // in the order given by perm (position -> frame; nullptr = frame order).  Fixed-order reductions => the same
 // bits on every GPU.
@@ -176,6 +177,12 @@ __global__ void pack_tiles_kernel(const float* __restrict__ coords, size_t n, in
       bbox[grp * 2 * d + k] = fminf(sh_lo[warp], sh_lo[warp + 1]);
       bbox[grp * 2 * d + d + k] = fmaxf(sh_hi[warp], sh_hi[warp + 1]);
     }
+    if (t == 0) {                                 // box of the whole tile, for the consumers' warp-level pruning
+      float tlo = INFINITY, thi = -INFINITY;
+      for (int q = 0; q < nw; ++q) { tlo = fminf(tlo, sh_lo[q]); thi = fmaxf(thi, sh_hi[q]); }
+      tcen[tile * dp + d + 1 + k] = tlo;
+      tcen[tile * dp + 2 * d + 1 + k] = thi;
+    }
     __syncthreads();
     const float yl = x - c;
     xT[(size_t) k * ld + p] = real ? x : nan;
@@ -193,7 +200,7 @@ __global__ void pack_tiles_kernel(const float* __restrict__ coords, size_t n, in
     float m = 0.f;
     for (int q = 0; q < nw; ++q) m = fmaxf(m, sh_sum[q]);
     tcen[tile * dp + d] = m;
-    for (int k = d + 1; k < dp; ++k) tcen[tile * dp + k] = 0.f;
+    for (int k = 3 * d + 1; k < dp; ++k) tcen[tile * dp + k] = 0.f;
   }
   if (real) atomicMax(maxnorm_bits, __float_as_uint(nrm_global));      // >= 0: the bit pattern orders like the value
 }
@@ -356,7 +363,7 @@ __global__ void nn_block_thr_kernel(const unsigned long long* __restrict__ key_n
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;      // blockDim = N_CONSUMERS: thread = consumer slot
   float v = 0.f;
   for (int r = 0; r < RI; ++r) {
-    const uint32_t i = row_begin + rb * ROWS_PER_CTA + threadIdx.x + (uint32_t) r * N_CONSUMERS;
+    const uint32_t i = row_begin + rb * ROWS_PER_CTA + (uint32_t) w * (32u * RI) + (uint32_t) r * 32u + (uint32_t) lane;   // Rows::row
     if (i >= row_end) continue;
     const float dn = __uint_as_float((uint32_t) (key_nn[i - row_begin] >> 32));
     const float dh = lo[i] == 0 ? dn : __uint_as_float((uint32_t) (key_hd[i - row_begin] >> 32));
@@ -498,13 +505,14 @@ static void error_bounds(size_t d, float maxnorm2, float* c_loc, float* e_rel, f
 }
 
 static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, int occupancy, uint32_t tiles_per_item, ScanGeom* g,
-                     int* grid) {
+                     int* grid, uint32_t max_tiles_per_item = 0xffffffffu) {
   memset(g, 0, sizeof(*g));
   g->xT = c->xT.p;
   g->cT = c->cT.p;
   g->bbox = c->bbox.p;
   g->tcen = c->tcen.p;
-  g->dp = (int) ((c->d + 1 + 3) / 4 * 4);
+  g->dp = (int) ((3 * c->d + 1 + 3) / 4 * 4);
+  g->centre = c->centre.p;
   g->prune_thr = INFINITY;
   g->ld = c->ld;
   g->d = (int) c->d;
@@ -517,7 +525,7 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, in
   *grid = c->sm_count * occupancy;
   // about 16 column items per row block: enough for load balance and for the column-step-major order
   // (own neighbourhood first), few enough that the producers' per-item work stays negligible
-  tiles_per_item = std::max(tiles_per_item, (g->n_col_tiles + 15) / 16);
+  tiles_per_item = std::min(std::max(tiles_per_item, (g->n_col_tiles + 15) / 16), max_tiles_per_item);
   g->tiles_per_item = std::max(1u, std::min(tiles_per_item, g->n_col_tiles));
   g->n_col_items = (g->n_col_tiles + g->tiles_per_item - 1) / g->tiles_per_item;
   if ((uint64_t) g->n_row_blocks * g->n_col_items >= 0x7fffffffull) return fail("too many work items");
@@ -680,15 +688,15 @@ extern "C" int dcb200_ctx_sync(dcb200_ctx* c) {
 extern "C" int dcb200_ctx_stats(dcb200_ctx* c, uint64_t stats[6], int reset) {
   if (!c || !stats) return fail("null argument");
   CK(cudaSetDevice(c->device));
-  unsigned long long h[3];
+  unsigned long long h[4];
   CK(cudaMemcpyAsync(h, c->stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   stats[0] = c->launches;
   stats[1] = h[0];
   stats[2] = h[1];
-  stats[3] = h[2];
+  stats[3] = h[3];                                       // (warp, tile) scans: a warp owns 32*RI rows
   stats[4] = c->pairs_scheduled;
-  stats[5] = (uint64_t) tile_width(c->d) * ROWS_PER_CTA;
+  stats[5] = (uint64_t) tile_width(c->d) * 32 * RI;
   if (reset) {
     CK(cudaMemsetAsync(c->stats, 0, 4 * sizeof(unsigned long long), c->stream));
     c->pairs_scheduled = 0;
@@ -717,7 +725,7 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
   CK(c->cT.reserve((d + 1) * ld));
   CK(c->bbox.reserve(ld / 64 * 2 * d));
   const int tj = d <= (size_t) MAX_TEMPLATE_D ? TileW<1>::tj : TileW<0>::tj;
-  const int dp = (int) ((d + 1 + 3) / 4 * 4);
+  const int dp = (int) ((3 * d + 1 + 3) / 4 * 4);
   CK(c->tcen.reserve(ld / tj * dp));
   CK(c->centre.reserve(2 * d));
   CK(c->perm.reserve(n));
@@ -809,7 +817,7 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     PopsArgs a;
     int grid = 0;
     CKI(fill_geom(c, row_begin, row_end, tj, count_mode ? occ_pops_count((int) c->d, nb) : occ_pops((int) c->d, nb),
-                  nb > 4 ? 64u : 32u, &a.g, &grid));
+                  nb > 4 ? 64u : 32u, &a.g, &grid, count_mode ? 0xffffffffu : (uint32_t) (57344 / tj)));
     a.n_bins = nb;
     a.band[0] = a.band[1] = 0.f;
     if (count_mode) {

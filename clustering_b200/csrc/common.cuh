@@ -18,7 +18,9 @@ constexpr int N_CONSUMERS = N_CONSUMER_WARPS * 32;
 constexpr int CTA_THREADS = N_CONSUMERS + 32; // + one producer warp (TMA issue)
 constexpr int ROWS_PER_CTA = N_CONSUMERS * RI;   // 1024
 constexpr int LD_ALIGN = 256;                 // frame arrays are padded to a multiple of this (covers every tile width)
-constexpr int STAGES = 3;
+// depth of the tile ring: deep for the register kernels (consumer warps that skip or finish a tile early run ahead
+// instead of idling), shallow for the run-time-D kernels whose tiles are large
+template <int D> struct StagesOf { static constexpr int n = D == 0 ? 3 : 6; };
 constexpr int MAX_BINS = 31;                  // distinct radii per population pass (table of 32 incl. +inf)
 constexpr int MAX_TEMPLATE_D = 16;            // dims held in registers by the specialised kernels
 
@@ -110,7 +112,7 @@ __device__ __forceinline__ float next_up(float x) {
 }
 
 // ---------------------------------------------------------------- tile stream ------------------
-// The producer warp streams column tiles through a STAGES-deep ring; each stage carries a small
+// The producer warp streams column tiles through a StagesOf<D>::n-deep ring; each stage carries a small
 // header telling the consumers which work item the tile belongs to.
 struct TileMeta {
   int32_t row_block;     // -1: end of stream
@@ -119,10 +121,11 @@ struct TileMeta {
   uint32_t aux;          // kernel specific (e.g. neighbour search: tile class)
 };
 
+template <int NSTAGES>
 struct Pipe {
   uint32_t stage = 0, phase = 0;
   __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
   }
 };
 

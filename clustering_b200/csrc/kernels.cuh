@@ -35,8 +35,10 @@ struct ScanGeom {
                             //           y' = y - c_t: rows 0..D-1 = -2*y', row D = |y'|^2 (padding: 0, ..., 0, +inf)
   const float* xrow;        // optional extra per-column row [ld] streamed with every tile (neighbour search: free-energy
                             // ranks as floats), nullptr = none; the kernel's SmemRing must be built with xrows = 1
-  const float* tcen;        // [n_col_tiles][dp] per tile: centre c_t[0..D-1], then max |y'|^2 over the tile
-  int dp;                   // floats per tcen entry (multiple of 4, >= D+1)
+  const float* tcen;        // [n_col_tiles][dp] per tile: centre c_t[0..D-1], max |y'|^2 over the tile, then the tile's bounding
+                            // box lo[0..D-1], hi[0..D-1] in globally centred coordinates (x - centre)
+  int dp;                   // floats per tcen entry (multiple of 4, >= 3D+1)
+  const float* centre;      // [D] global centre the bounding boxes refer to
   size_t ld;                // padded frame count (multiple of 256)
   int d;                    // n_cols (== D for the specialised kernels)
   uint32_t n;               // real frame count
@@ -49,7 +51,7 @@ struct ScanGeom {
   float c_loc, e_rel;               // |fast - exact| <= c_loc * (|x'|^2 + max|y'|^2) + e_rel * value   (api.cu: error_bounds)
   float prune_slack;                // absolute slack of the bounding-box arithmetic (globally centred coordinates)
   unsigned long long* stats;        // [0] pairs handed to the slow path, [1] pairs re-evaluated exactly,
-                                    // [2] column tiles streamed (x ROWS_PER_CTA x tile width = pairs evaluated)
+                                    // [2] column tiles streamed, [3] (warp, tile) scans (x 32*RI rows x tile width = pairs evaluated)
   const float* bbox;                // [ld/64][2*d] bounding boxes (lo[d], hi[d]) of 64-frame groups, centred coords
   const float* rbbox;               // [n_row_blocks][2*d] bounding boxes of this launch's row blocks (api.cu: row_bbox_kernel)
   float* blk_thr;                   // neighbour search only: [n_row_blocks][N_CONSUMER_WARPS] upper bounds (d2 units) of what the
@@ -60,6 +62,7 @@ struct ScanGeom {
 // per-thread slow-path counters, added to g.stats once per kernel
 struct SlowStats {
   uint32_t slow = 0, exact = 0;
+  uint32_t wtiles = 0;          // tiles this warp really scanned (warp-uniform)
   __device__ __forceinline__ void flush(const ScanGeom& g) {
     for (int o = 16; o > 0; o >>= 1) {
       slow += __shfl_xor_sync(0xffffffffu, slow, o);
@@ -68,6 +71,7 @@ struct SlowStats {
     if ((threadIdx.x & 31) == 0 && g.stats) {
       if (slow) atomicAdd(g.stats, (unsigned long long) slow);
       if (exact) atomicAdd(g.stats + 1, (unsigned long long) exact);
+      if (wtiles) atomicAdd(g.stats + 3, (unsigned long long) wtiles);
     }
   }
 };
@@ -82,6 +86,7 @@ template <> struct TileW<0> { static constexpr int tj = 64; static constexpr int
 template <int D>
 struct SmemRing {
   static constexpr int TJ = TileW<D>::tj;
+  static constexpr int STAGES = StagesOf<D>::n;
   float* tiles;            // STAGES * ((d+1) * TJ + dp + xrows * TJ): column pack of the tile, its centre entry (tcen),
                            // then the optional extra row
   uint64_t* full;          // STAGES
@@ -90,7 +95,7 @@ struct SmemRing {
   unsigned long long* wthr;   // N_CONSUMER_WARPS: (item << 32 | float bits) pruning threshold published per warp
   float* rbb;              // 2*d: bounding box of the current row block (producer scratch)
   size_t tile_floats;
-  __host__ __device__ static int dp_of(int d) { return (d + 1 + 3) / 4 * 4; }
+  __host__ __device__ static int dp_of(int d) { return (3 * d + 1 + 3) / 4 * 4; }
   __host__ __device__ static size_t bytes(int d, int xrows = 0) {
     return (size_t) STAGES * ((d + 1 + xrows) * TJ + dp_of(d)) * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta) + N_CONSUMER_WARPS * 8 +
            (size_t) 2 * d * 4;
@@ -144,7 +149,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
   constexpr int TJ = TileW<D>::tj;
   constexpr int GPT = TJ / 64;                      // 64-frame bounding-box groups per tile
   const int lane = threadIdx.x & 31;
-  Pipe pp;
+  Pipe<StagesOf<D>::n> pp;
   const int d = D ? D : g.d;
   const uint32_t total = g.n_row_blocks * g.n_col_items;
   unsigned long long streamed = 0;
@@ -240,7 +245,8 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
   }
 }
 
-// Row operands of a consumer thread: rows row0 + r * N_CONSUMERS, r = 0..RI-1.  retarget() re-centres them
+// Row operands of a consumer thread: rows row0 + 32 r, r = 0..RI-1, so that a warp owns 32*RI = 128 CONSECUTIVE rows of the
+// block (a compact piece of the spatial order: WarpBox below skips whole tiles for it).  retarget() re-centres them
 // on the centre of the tile about to be scanned (cen: the tile's tcen entry in shared memory):
 //   x[r][k] = x_original - c_t[k],  xn[r] = |x'|^2,  eabs[r] = c_loc * (xn[r] + max|y'|^2 of the tile),
 // the absolute part of the fast path's rounding-error bound for this row against this tile.
@@ -252,9 +258,11 @@ struct Rows {
   float eabs[RI];
   uint32_t row0;
   uint32_t p[RI];           // clamped positions
-  __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * N_CONSUMERS; }
-  __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid) {
-    row0 = g.row_begin + rb * ROWS_PER_CTA + tid;
+  uint32_t stride;          // 32: the warp owns 128 consecutive rows; N_CONSUMERS: rows interleaved over the whole block
+  __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * stride; }
+  __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid, bool coherent = true) {
+    stride = coherent ? 32u : (uint32_t) N_CONSUMERS;
+    row0 = g.row_begin + rb * ROWS_PER_CTA + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
 #pragma unroll
     for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);     // rows past the end: clamped, results discarded
   }
@@ -282,9 +290,11 @@ struct Rows<0> {
   float eabs[RI];
   uint32_t row0;
   uint32_t p[RI];
-  __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * N_CONSUMERS; }
-  __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid) {
-    row0 = g.row_begin + rb * ROWS_PER_CTA + tid;
+  uint32_t stride;
+  __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * stride; }
+  __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid, bool coherent = true) {
+    stride = coherent ? 32u : (uint32_t) N_CONSUMERS;
+    row0 = g.row_begin + rb * ROWS_PER_CTA + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
 #pragma unroll
     for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
   }
@@ -307,6 +317,54 @@ struct Rows<0> {
       eabs[r] = g.c_loc * (s[r] + ymax);
     }
   }
+};
+
+// Bounding box of the 128 rows a consumer warp owns (globally centred coordinates, the same arithmetic as the tile
+// boxes of api.cu: pack_tiles_kernel); lane k holds dimension k.  reach() is the warp-level version of the producer's
+// tile pruning: a streamed tile is scanned by a warp only if its box comes within the warp's own threshold.
+// Specialised kernels only (D <= 16 <= 32 lanes); the run-time-D kernels scan every streamed tile.
+template <int D>
+struct WarpBox {
+  float wlo, whi;
+  __device__ __forceinline__ void compute(const ScanGeom& g, const Rows<D>& R, int lane) {
+    wlo = INFINITY;
+    whi = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const float ck = __ldg(g.centre + k);
+      float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        if (R.row(r) < g.row_end) {
+          const float v = __ldg(g.xT + (size_t) k * g.ld + R.p[r]) - ck;
+          lo = fminf(lo, v);
+          hi = fmaxf(hi, v);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      if (lane == k) { wlo = lo; whi = hi; }
+    }
+  }
+  // cen: the tile's header in shared memory.  false => no pair of (this warp's rows) x (tile) is closer than thr (d2 units)
+  __device__ __forceinline__ bool reach(const float* __restrict__ cen, int lane, float thr) const {
+    float s = 0.f;
+    if (lane < D) {
+      const float gap = fmaxf(fmaxf(wlo - cen[2 * D + 1 + lane], cen[D + 1 + lane] - whi), 0.f);
+      s = gap * gap;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return !(s * 0.999f > thr);          // NaN keeps
+  }
+};
+template <>
+struct WarpBox<0> {
+  __device__ __forceinline__ void compute(const ScanGeom&, const Rows<0>&, int) {}
+  __device__ __forceinline__ bool reach(const float*, int, float) const { return true; }
 };
 
 // register arrays must not be indexed dynamically (that would spill them to local memory)
@@ -449,7 +507,7 @@ struct PopsArgs {
 };
 
 __host__ __device__ inline size_t pops_smem_bytes(size_t ring_bytes, int n_bins) {
-  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + 32 * 4 + (size_t) n_bins * ROWS_PER_CTA * 4;
+  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + 32 * 4 + (size_t) n_bins * ROWS_PER_CTA * 2;
 }
 
 // number of table entries <= s (table ascending, padded with +inf up to 32 entries)
@@ -475,7 +533,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
   unsigned char* extra = smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15));
   float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
   float* rad2s = reinterpret_cast<float*>(extra + SCRATCH_BYTES);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(rad2s + 32) + threadIdx.x;   // [n_bins][ROWS_PER_CTA], slot-private counters
+  // [n_bins][ROWS_PER_CTA] slot-private 16-bit counters, flushed per work item (api.cu keeps an item below 65536 columns)
+  uint16_t* hist = reinterpret_cast<uint16_t*>(rad2s + 32) + threadIdx.x;
   ring.init();
   if (threadIdx.x < 32) rad2s[threadIdx.x] = a.rad2[threadIdx.x];
   __syncthreads();
@@ -489,7 +548,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
   const int nb = a.n_bins;
   Rows<D> R;
   float t[RI];
-  Pipe cp;
+  Pipe<StagesOf<D>::n> cp;
   SlowStats st;
   uint32_t col0 = 0;
   auto hit = [&](int r, int jt, float accv) {
@@ -514,7 +573,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
     const TileMeta m = ring.meta[cp.stage];
     if (m.row_block < 0) break;
     if (m.flags & 1u) {
-      R.load(g, (uint32_t) m.row_block, tid);
+      // rows interleaved over the block and no warp-level tile skipping here: this kernel's cost is the per-hit handler,
+      // and near tiles must spread their hits over all eight warps instead of piling them onto the one warp next to them
+      R.load(g, (uint32_t) m.row_block, tid, false);
       for (int b = 0; b < nb; ++b)
 #pragma unroll
         for (int r = 0; r < RI; ++r) hist[b * ROWS_PER_CTA + r * N_CONSUMERS] = 0;
@@ -522,6 +583,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
     col0 = m.col0;
     if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      ++st.wtiles;
       R.retarget(g, tl + (d + 1) * TileW<D>::tj);
       // every pair with exact d2 < r_max^2 has acc < t[r]  (thr_fast = r_max^2 (1 + e_rel), eabs: absolute error part)
 #pragma unroll
@@ -583,10 +645,11 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
   }
   const int tid = threadIdx.x;
   Rows<D> R;
+  WarpBox<D> wb;
   float tm[NB][RI];           // decision boundary of radius b for row r in accumulator units: rad2[b] - |x'_r|^2
   float w[NB][RI];            // half width of the rounding-error band around it (depends on the row and the tile)
   uint32_t cnt[NB][RI];
-  Pipe cp;
+  Pipe<StagesOf<D>::n> cp;
   SlowStats st;
   for (;;) {
     mbar_wait(&ring.full[cp.stage], cp.phase);
@@ -594,13 +657,15 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
     if (m.row_block < 0) break;
     if (m.flags & 1u) {
       R.load(g, (uint32_t) m.row_block, tid);
+      wb.compute(g, R, lane);
 #pragma unroll
       for (int b = 0; b < NB; ++b)
 #pragma unroll
         for (int r = 0; r < RI; ++r) cnt[b][r] = 0;
     }
-    if (!(m.flags & 4u)) {
+    if (!(m.flags & 4u) && wb.reach(ring.tiles + cp.stage * ring.tile_floats + (D + 1) * TJ, lane, g.prune_thr)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      ++st.wtiles;
       R.retarget(g, tl + (D + 1) * TJ);
 #pragma unroll
       for (int b = 0; b < NB; ++b)
@@ -884,9 +949,10 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
   }
   const int tid = threadIdx.x;
   Rows<D> R;
+  WarpBox<D> wb;
   NnFilter F;
   uint32_t col0 = 0;
-  Pipe cp;
+  Pipe<StagesOf<D>::n> cp;
   SlowStats st;
   // every column whose exact d2 is <= `d2` satisfies acc < thr(d2) (api.cu: error_bounds)
   auto thr = [&](float d2, float eabs, float xnr) { return next_up(next_up(fmaf(g.e_rel, d2, d2) + eabs - xnr)); };
@@ -950,10 +1016,26 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
         lo_s[r * N_CONSUMERS] = lo_i;
         F.lor[r] = lf + a.lo_bias;
       }
+      wb.compute(g, R, lane);
+      // what this warp's rows accept at the start of the item (d2 units, pruning margins included)
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        if (R.row(r) < g.row_end) {
+          const float dn = key_d2(best[r * N_CONSUMERS]);
+          const float dh = lo_s[r * N_CONSUMERS] == 0 ? dn : key_d2(best[ROWS_PER_CTA + r * N_CONSUMERS]);
+          v = fmaxf(v, fmaxf(dn, dh));
+        }
+      }
+      v = (fmaf(g.e_rel, v, v) + g.prune_slack) * 1.00001f;
+      if (!(v < INFINITY)) v = INFINITY;
+      last_pub = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));
+      if (lane == 0) ring.wthr[warp] = ((unsigned long long) m.aux << 32) | last_pub;
     }
     col0 = m.col0;
-    if (!(m.flags & 4u)) {
+    if (!(m.flags & 4u) && wb.reach(ring.tiles + cp.stage * ring.tile_floats + (d + 1) * TJ, lane, __uint_as_float(last_pub))) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      ++st.wtiles;
       R.retarget(g, tl + (d + 1) * TJ);
       // filter thresholds of this tile from the best keys so far (the error margin depends on the tile)
 #pragma unroll
@@ -1035,8 +1117,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
   const int tid = threadIdx.x;
   float* scratch = reinterpret_cast<float*>(smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15))) + threadIdx.x;
   Rows<D> R;
+  WarpBox<D> wb;
   float t[RI];
-  Pipe cp;
+  Pipe<StagesOf<D>::n> cp;
   SlowStats st;
   uint32_t col0 = 0;
   auto hit = [&](int r, int jt, float accv) {
@@ -1056,10 +1139,14 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
     mbar_wait(&ring.full[cp.stage], cp.phase);
     const TileMeta m = ring.meta[cp.stage];
     if (m.row_block < 0) break;
-    if (m.flags & 1u) R.load(g, (uint32_t) m.row_block, tid);
+    if (m.flags & 1u) {
+      R.load(g, (uint32_t) m.row_block, tid);
+      wb.compute(g, R, lane);
+    }
     col0 = m.col0;
-    if (!(m.flags & 4u)) {
+    if (!(m.flags & 4u) && wb.reach(ring.tiles + cp.stage * ring.tile_floats + (d + 1) * TJ, lane, g.prune_thr)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      ++st.wtiles;
       R.retarget(g, tl + (d + 1) * TJ);
 #pragma unroll
       for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));

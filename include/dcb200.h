@@ -134,7 +134,7 @@ int dcb200_ctx_screening_merge(dcb200_ctx* ctx, size_t m_new, uint32_t* dev_comp
 
 /* counters of the scans on this context since the last reset (for the benchmark / tests):
  * [0] kernels launched, [1] pairs handed to the slow path, [2] pairs re-evaluated in exact arithmetic,
- * [3] column tiles streamed, [4] pairs of the full row x column ranges requested, [5] pairs per streamed tile */
+ * [3] (warp, tile) scans (a consumer warp owns 128 rows), [4] pairs of the full row x column ranges requested, [5] pairs per (warp, tile) scan */
 int dcb200_ctx_stats(dcb200_ctx* ctx, uint64_t stats[6], int reset);
 
 /* diagnostics: FFMA-only throughput of the device in TFLOP/s (2 flop per FFMA), the FP32 roofline denominator */

@@ -1,0 +1,5 @@
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for w in C2 C4 C1 C3; do timeout 300 python scripts/profile_kernels.py $w >> gpurun_out/r17_prof.jsonl 2>&1; done
+timeout 300 python scripts/profile_kernels.py C5 100000 1 >> gpurun_out/r17_prof.jsonl 2>&1
+cat gpurun_out/r17_prof.jsonl
