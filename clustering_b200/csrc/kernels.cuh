@@ -1033,7 +1033,38 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
       if (lane == 0) ring.wthr[warp] = ((unsigned long long) m.aux << 32) | last_pub;
     }
     col0 = m.col0;
-    if (!(m.flags & 4u) && wb.reach(ring.tiles + cp.stage * ring.tile_floats + (d + 1) * TJ, lane, __uint_as_float(last_pub))) {
+    bool scan = !(m.flags & 4u);
+    if (scan) {
+      // Does this warp need the tile?  Row r accepts columns within its nearest-neighbour bound, and within its (usually
+      // much larger, for density peaks inter-cluster sized) lower-free-energy bound only if the tile holds a frame with a
+      // lower free energy than r at all: the smallest rank of the tile decides that.
+      const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      const float* lrow = tl + (d + 1) * TJ + g.dp;
+      float lomin;
+      if (TJ == 128) {
+        const float4 q = *reinterpret_cast<const float4*>(lrow + 4 * lane);
+        lomin = fminf(fminf(q.x, q.y), fminf(q.z, q.w));
+      } else {
+        const float2 q = *reinterpret_cast<const float2*>(lrow + 2 * lane);
+        lomin = fminf(q.x, q.y);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lomin = fminf(lomin, __shfl_xor_sync(0xffffffffu, lomin, o));
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        if (R.row(r) < g.row_end) {
+          const float dn = key_d2(best[r * N_CONSUMERS]);
+          const bool hd_here = lo_s[r * N_CONSUMERS] != 0 && lomin < F.lor[r];
+          v = fmaxf(v, hd_here ? fmaxf(dn, key_d2(best[ROWS_PER_CTA + r * N_CONSUMERS])) : dn);
+        }
+      }
+      v = (fmaf(g.e_rel, v, v) + g.prune_slack) * 1.00001f;
+      if (!(v < INFINITY)) v = INFINITY;
+      const uint32_t vb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));
+      scan = wb.reach(tl + (d + 1) * TJ, lane, __uint_as_float(vb));
+    }
+    if (scan) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
       ++st.wtiles;
       R.retarget(g, tl + (d + 1) * TJ);
