@@ -56,6 +56,20 @@ def workload(name, n=None):
     return c, x
 
 
+def ncu_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, from profiles/ncu_traffic.json
+    (written by scripts/ncu_summary.py from an `ncu --set full` capture of this workload); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        for key, val in t.items():
+            if key in kernel_name:
+                return val
+    except Exception:
+        pass
+    return None
+
+
 def pair_dims_per_step(n, d):
     return 2.0 * float(n) * float(n) * float(d)      # populations scan + neighbour scan, ordered N x N pairs each
 
@@ -271,27 +285,34 @@ def run_ours(args):
     pd = pair_dims_per_step(n, d)
     value = pd / (ms * 1e-3) / 1e9
 
-    # ---- dominant kernel (neighbour scan) alone, for the roofline ---------------------------------
-    with torch.cuda.stream(stream):
-        fe_dev = sess.free_energies(sess.to_frame_order(sess.populations(radii[:1], 0, n))[0]) if world == 1 else None
+    # ---- the two pair scans alone, for the roofline (the slower one is the dominant kernel) ---------
     kms = None
     if world == 1:
+        def time_scan(fn, reps=5):
+            fn()
+            sess.stats(reset=True)
+            kt = []
+            for _ in range(reps):
+                with torch.cuda.stream(stream):
+                    flush_buf.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                e1.synchronize()
+                kt.append(e0.elapsed_time(e1))
+            return float(np.mean(kt)), sess.stats()["pairs_evaluated"] / float(reps)
+
+        pops_loc = torch.zeros((radii.size, n), dtype=torch.int32, device=dev)
+        with torch.cuda.stream(stream):
+            fe_dev = sess.free_energies(sess.to_frame_order(sess.populations(radii, 0, n))[r_fe].contiguous())
         sess.nn_prepare(fe_dev)
-        kt = []
-        sess.nn_scan(0, n, out=keys_loc)
-        sess.stats(reset=True)
-        for _ in range(5):
-            with torch.cuda.stream(stream):
-                flush_buf.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            sess.nn_scan(0, n, out=keys_loc)           # 2 fills + the scan kernel; the fills are < 0.1 % of the time
-            e1.record(stream)
-            e1.synchronize()
-            kt.append(e0.elapsed_time(e1))
-        kms = float(np.mean(kt))
-        kstat = sess.stats()
-        k_pairs = kstat["pairs_evaluated"] / 5.0          # pairs the kernel evaluated per launch (tiles streamed x tile size)
+        # nn_scan = seed kernel + block bounds + neighbourhood pass + full pass of nn_kernel (the last one is > 90 % of it)
+        nn_ms, nn_pairs = time_scan(lambda: sess.nn_scan(0, n, out=keys_loc))
+        pops_ms, pops_pairs = time_scan(lambda: sess.populations(radii, 0, n, out=pops_loc))
+        scans = {"nn_kernel (neighbour scan)": (nn_ms, nn_pairs), "pops kernel (population scan)": (pops_ms, pops_pairs)}
+        kname = max(scans, key=lambda k: scans[k][0])
+        kms, k_pairs = scans[kname]
 
     # ---- end to end: host buffers through the C ABI ----------------------------------------------
     if world == 1:
@@ -335,7 +356,7 @@ def run_ours(args):
             pairs = float(n) * float(n)
             achieved = FLOP_EXECUTED_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12
             line["roofline"] = {
-                "bound": "fp32", "kernel": "nn_kernel (neighbour scan, one launch over all rows)",
+                "bound": "fp32", "kernel": kname,
                 "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                 "kernel_ms": kms,
                 "pairs_evaluated_per_launch": k_pairs, "pairs_evaluated_frac": k_pairs / pairs,
@@ -343,9 +364,14 @@ def run_ours(args):
                 "effective_gpair_dim_per_s": pairs * d / (kms * 1e-3) / 1e9,
                 "algorithmic_3flop_tflops_on_evaluated_pairs": FLOP_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12,
                 "peak_source": "FFMA-only microbenchmark in this run (dcb200_ctx_ffma_peak); MEASURED_PEAKS.json has no FP32 entry",
-                "traffic": None,
-                "note": "achieved = 2 flop (one FFMA) per pair.dim x the pairs of the column tiles the kernel actually streamed "
-                        "(tiles out of reach of a row block are pruned and not counted); the headline value counts the full N x N matrix",
+                "traffic": ncu_traffic(kname),
+                "other_scans": {k: {"kernel_ms": v[0], "pairs_evaluated_frac": v[1] / pairs,
+                                    "achieved_tflops": FLOP_EXECUTED_PER_PAIR_DIM * v[1] * d / (v[0] * 1e-3) / 1e12}
+                                for k, v in scans.items() if k != kname},
+                "note": "compute-bound path (SURVEY.md 8d): the roofline is the FP32 FFMA pipe, not HBM. achieved = 2 flop (one FFMA) per "
+                        "pair.dim x the pairs the kernel really evaluated = (warp, tile) scans x 128 rows x 128 columns; tiles out of reach "
+                        "of a row block / of a warp's rows are pruned and not counted; the headline value counts the full N x N matrix. "
+                        "traffic = dram bytes per launch from the committed ncu capture (profiles/), null if none",
             }
         if not args.no_cpu_baseline:
             try:

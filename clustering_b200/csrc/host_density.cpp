@@ -37,6 +37,44 @@ extern "C" int dcb200_sigma2(const float* nn_d2, size_t n, double* sigma2) {
   return 0;
 }
 
+// assign_low_density_frames (density_clustering.cpp:345-360): in ascending free-energy order every frame without a
+// state takes the state of its nearest neighbour with lower free energy (which, coming earlier in that order, is
+// settled already).  A frame whose neighbour entry is the "none" sentinel keeps state 0 (the reference would index
+// out of bounds there).
+extern "C" int dcb200_assign_low_density_frames(const uint32_t* initial, const uint32_t* hd_idx, const float* fe, size_t n,
+                                                uint32_t* states) {
+  if (!initial || !hd_idx || !fe || !states) return dcb200_internal_fail("dcb200_assign_low_density_frames: null argument");
+  std::vector<uint32_t> order(n);
+  const int rc = dcb200_sorted_free_energies(fe, n, order.data());
+  if (rc) return rc;
+  memmove(states, initial, n * sizeof(uint32_t));
+  for (size_t k = 0; k < n; ++k) {
+    const size_t id = order[k];
+    if (states[id] == 0 && hd_idx[id] < n) states[id] = states[hd_idx[id]];
+  }
+  return 0;
+}
+
+// sorted_cluster_names (density_clustering.cpp:458-493): states renamed 1..K by DEcreasing population.  Populations
+// tie often; the order of equal counts is whatever libstdc++'s unstable std::sort makes of the (state, count) vector,
+// so the same call on the same element type is made here.
+extern "C" int dcb200_sorted_cluster_names(const uint32_t* states, size_t n, uint32_t* renamed) {
+  if (!states || !renamed) return dcb200_internal_fail("dcb200_sorted_cluster_names: null argument");
+  uint32_t mx = 0;
+  for (size_t i = 0; i < n; ++i) mx = std::max(mx, states[i]);
+  std::vector<std::size_t> count((size_t) mx + 1, 0);
+  for (size_t i = 0; i < n; ++i) ++count[states[i]];
+  typedef std::pair<std::size_t, std::size_t> Entry;                 // (state, population), ascending state like the map
+  std::vector<Entry> v;
+  for (size_t s = 0; s <= mx; ++s)
+    if (count[s]) v.push_back(Entry(s, count[s]));
+  std::sort(v.begin(), v.end(), [](const Entry& a, const Entry& b) -> bool { return a.second < b.second; });
+  std::vector<uint32_t> name((size_t) mx + 1, 0);
+  for (size_t i = 0; i < v.size(); ++i) name[v[i].first] = (uint32_t) (v.size() - i);
+  for (size_t i = 0; i < n; ++i) renamed[i] = name[states[i]];
+  return 0;
+}
+
 // One screening threshold = reference screening() (density_clustering_common.cpp:37-134) with
 // prepare_initial_clustering (:382-435), high_density_neighborhood (:292-332), lump_initial_clusters
 // (:506-555) and normalized_cluster_names (:437-456) of density_clustering.cpp.

@@ -80,6 +80,24 @@ def screening(free_energy, nn_d2, free_energy_threshold, coords, initial_cluster
     return labels
 
 
+def assign_low_density_frames(initial_clustering, hd_idx, free_energy):
+    """-> uint32 states [n_rows]  (reference: density_clustering.cpp:345-360)."""
+    init = np.ascontiguousarray(initial_clustering, dtype=np.uint32)
+    hd = np.ascontiguousarray(hd_idx, dtype=np.uint32)
+    fe = np.ascontiguousarray(free_energy, dtype=np.float32)
+    out = np.empty(init.size, np.uint32)
+    lib.check(lib.load().dcb200_assign_low_density_frames(init, hd, fe, init.size, out))
+    return out
+
+
+def sorted_cluster_names(clustering):
+    """-> uint32 [n_rows], states renamed 1..K by decreasing population  (reference: density_clustering.cpp:458-493)."""
+    st = np.ascontiguousarray(clustering, dtype=np.uint32)
+    out = np.empty(st.size, np.uint32)
+    lib.check(lib.load().dcb200_sorted_cluster_names(st, st.size, out))
+    return out
+
+
 def screening_step(sorted_coords, m_prev, m_new, max_dist2, comp):
     sorted_coords = _coords(sorted_coords)
     comp = np.ascontiguousarray(comp, dtype=np.uint32)

@@ -12,6 +12,10 @@ SYMBOLS = [
     "dcb200_device_count", "dcb200_set_gpus", "dcb200_last_error", "dcb200_version",
     "dcb200_populations", "dcb200_free_energies", "dcb200_nearest_neighbors", "dcb200_screening_step",
     "dcb200_sorted_free_energies", "dcb200_sigma2", "dcb200_screening",
+    "dcb200_assign_low_density_frames", "dcb200_sorted_cluster_names",
+    "dcb200_io_write_pops", "dcb200_io_write_fes", "dcb200_io_write_states", "dcb200_io_write_neighborhood",
+    "dcb200_io_read_coords", "dcb200_io_read_column_float", "dcb200_io_read_column_uint", "dcb200_io_read_neighborhood",
+    "dcb200_io_read_comment",
     "dcb200_ctx_create", "dcb200_ctx_destroy", "dcb200_ctx_stream", "dcb200_ctx_sync",
     "dcb200_ctx_set_coords", "dcb200_ctx_set_coords_device", "dcb200_ctx_set_coords_ex", "dcb200_ctx_order",
     "dcb200_ctx_to_frame_order", "dcb200_ctx_populations",
@@ -50,6 +54,8 @@ def load():
     L.dcb200_sorted_free_energies.argtypes = [_f, _sz, _u32]
     L.dcb200_sigma2.argtypes = [_f, _sz, C.POINTER(C.c_double)]
     L.dcb200_screening.argtypes = [_f, _f, C.c_float, _f, _sz, _sz, _p, _u32]
+    L.dcb200_assign_low_density_frames.argtypes = [_u32, _u32, _f, _sz, _u32]
+    L.dcb200_sorted_cluster_names.argtypes = [_u32, _sz, _u32]
     L.dcb200_ctx_create.argtypes = [C.c_int, C.POINTER(_p)]
     L.dcb200_ctx_destroy.argtypes = [_p]
     L.dcb200_ctx_stream.argtypes = [_p]

@@ -71,11 +71,40 @@ int dcb200_screening_step(const float* sorted_coords, size_t n_cols, size_t m_pr
  *   dcb200_sigma2:               mean squared nearest-neighbour distance  (compute_sigma2, :334-343)
  *   dcb200_screening:            one free-energy threshold, = reference screening() (density_clustering_common.cpp:37-134);
  *                                initial: NULL or the labels of the previous (lower) threshold; labels: uint32 [n_rows], 0 = unassigned.
- *                                The pair scan inside runs on the GPU(s) through dcb200_screening_step. */
+ *                                The pair scan inside runs on the GPU(s) through dcb200_screening_step.
+ *   dcb200_assign_low_density_frames / dcb200_sorted_cluster_names: the microstate step after the screening
+ *                                (`clustering density -i`): assign_low_density_frames (density_clustering.cpp:345-360) and
+ *                                sorted_cluster_names (:458-493); uint32 [n_rows] in and out, 0 = no state */
 int dcb200_sorted_free_energies(const float* fe, size_t n_rows, uint32_t* order);
+int dcb200_assign_low_density_frames(const uint32_t* initial, const uint32_t* hd_idx, const float* fe, size_t n_rows,
+                                     uint32_t* states);
+int dcb200_sorted_cluster_names(const uint32_t* states, size_t n_rows, uint32_t* renamed);
 int dcb200_sigma2(const float* nn_d2, size_t n_rows, double* sigma2);
 int dcb200_screening(const float* fe, const float* nn_d2, float threshold, const float* coords, size_t n_rows,
                      size_t n_cols, const uint32_t* initial, uint32_t* labels);
+
+/* ---- file formats of `clustering density` ---------------------------------------------------------------
+ * Byte-compatible with the reference's writers (src/tools.cpp:42-56, :64-70, :144-174, :267-277, tools.hxx:256-272) and
+ * tolerant like its readers (tools.hxx:39-111, :229-253, tools.cpp:103-133, :229-265).  header: the "# ..." block every
+ * file starts with (clustering.cpp:467-482); keys/vals: the "#@ key = value" parameters (zero values are not written).
+ * Readers: pass out = NULL (or a small capacity) to query the size first.  I/O errors print a message and exit, exactly
+ * like the reference's tools. */
+int dcb200_io_write_pops(const char* filename, const uint32_t* pops, size_t n, const char* header, const char* const* keys,
+                         const float* vals, size_t n_comments);
+int dcb200_io_write_fes(const char* filename, const float* fe, size_t n, const char* header, const char* const* keys,
+                        const float* vals, size_t n_comments);
+int dcb200_io_write_states(const char* filename, const uint32_t* states, size_t n, const char* header, const char* const* keys,
+                           const float* vals, size_t n_comments);
+int dcb200_io_write_neighborhood(const char* filename, const uint32_t* nn_idx, const float* nn_d2, const uint32_t* hd_idx,
+                                 const float* hd_d2, size_t n, const char* header, const char* const* keys, const float* vals,
+                                 size_t n_comments);
+int dcb200_io_read_coords(const char* filename, float* out, size_t capacity, size_t* n_rows, size_t* n_cols);
+int dcb200_io_read_column_float(const char* filename, float* out, size_t capacity, size_t* n);
+int dcb200_io_read_column_uint(const char* filename, uint32_t* out, size_t capacity, size_t* n);
+int dcb200_io_read_neighborhood(const char* filename, uint32_t* nn_idx, float* nn_d2, uint32_t* hd_idx, float* hd_d2,
+                                size_t capacity, size_t* n);
+/* value of "#@ key = ..." in the file (current: the value known so far, returned unchanged if the key is absent) */
+int dcb200_io_read_comment(const char* filename, const char* key, float current, float* value);
 
 /* ---- (2) device-resident session ---------------------------------------------------------- */
 /* A context holds the frames in HBM in its own order ("positions"): by default a spatial (Morton) order, so

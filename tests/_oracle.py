@@ -125,7 +125,44 @@ class Ref:
         L.dcref_screening.argtypes = [_f, _u64, _f, C.c_float, _f, _sz, _sz, C.c_void_p, _u64]
         L.dcref_assign_low_density_frames.argtypes = [_u64, _u64, _f, _f, _sz, _u64]
         L.dcref_sorted_cluster_names.argtypes = [_u64, _sz, _u64]
+        _kv = [C.c_char_p, C.POINTER(C.c_char_p), _f, C.c_int]
+        L.dcref_write_pops.argtypes = [C.c_char_p, _u64, _sz] + _kv
+        L.dcref_write_fes.argtypes = [C.c_char_p, _f, _sz] + _kv
+        L.dcref_write_clustered_trajectory.argtypes = [C.c_char_p, _u64, _sz] + _kv
+        L.dcref_write_neighborhood.argtypes = [C.c_char_p, _u64, _f, _u64, _f, _sz] + _kv
+        L.dcref_read_coords.argtypes = [C.c_char_p, _f, _sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         self.L = L
+
+    # ---- the reference's own file writers / coordinate reader (tools.cpp, tools.hxx)
+    @staticmethod
+    def _kv(comments):
+        keys = (C.c_char_p * len(comments))(*[k.encode() for k in comments])
+        vals = np.array(list(comments.values()), np.float32)
+        return keys, vals, len(comments)
+
+    def write_pops(self, fname, pops, header, comments):
+        pops = _c(pops, np.uint64)
+        self.L.dcref_write_pops(fname.encode(), pops, pops.size, header.encode(), *self._kv(comments))
+
+    def write_fes(self, fname, fe, header, comments):
+        fe = _c(fe, np.float32)
+        self.L.dcref_write_fes(fname.encode(), fe, fe.size, header.encode(), *self._kv(comments))
+
+    def write_states(self, fname, states, header, comments):
+        states = _c(states, np.uint64)
+        self.L.dcref_write_clustered_trajectory(fname.encode(), states, states.size, header.encode(), *self._kv(comments))
+
+    def write_neighborhood(self, fname, ni, nd, hi, hd, header, comments):
+        ni = _c(ni, np.uint64); hi = _c(hi, np.uint64)
+        self.L.dcref_write_neighborhood(fname.encode(), ni, _c(nd, np.float32), hi, _c(hd, np.float32), ni.size, header.encode(),
+                                        *self._kv(comments))
+
+    def read_coords(self, fname, cap=1 << 22):
+        out = np.empty(cap, np.float32)
+        r, k = C.c_uint64(0), C.c_uint64(0)
+        rc = self.L.dcref_read_coords(fname.encode(), out, cap, C.byref(r), C.byref(k))
+        assert rc == 0
+        return out[: r.value * k.value].reshape(r.value, k.value).copy()
 
     def set_threads(self, n):
         self.L.dcref_set_threads(int(n))
