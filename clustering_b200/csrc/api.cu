@@ -810,26 +810,38 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     if (!(v == v)) return fail("dcb200_ctx_populations: NaN radius");
   const size_t ld_cnt = (rows + 255) / 256 * 256;
   const int tj = tile_width(c->d);
-  // one or two distinct radii: branch-free count mode (pops_count_kernel)
-  const bool count_mode = uniq.size() <= 2 && c->d <= (size_t) MAX_TEMPLATE_D;
-  for (size_t b0 = 0; b0 < uniq.size(); b0 += MAX_BINS) {
-    const int nb = (int) std::min<size_t>(MAX_BINS, uniq.size() - b0);
+  // specialised dims and up to two passes' worth of radii: branch-free count mode (pops_count_kernel), up to 8 (D <= 6) or
+  // 4 distinct radii per pass, largest radii first so that every pass is pruned by its own r_max.  Long radius lists
+  // (every pass re-evaluates the distances) and other dims: the histogram kernel, up to 31 radii per pass.
+  const size_t count_pass = c->d <= 6 ? 8 : 4;
+  const bool count_mode = c->d <= (size_t) MAX_TEMPLATE_D && uniq.size() <= 2 * count_pass;
+  const size_t pass_max = count_mode ? count_pass : (size_t) MAX_BINS;
+  size_t hi = uniq.size();                        // radii [b0, hi) of uniq go into the next pass
+  while (hi > 0) {
+    size_t n_pass = std::min(pass_max, hi);
+    int nb = (int) n_pass;                        // kernel variant: the smallest instantiated count >= n_pass
+    if (count_mode) {
+      if (n_pass == 5) nb = 6;
+      if (n_pass == 7) nb = 8;
+    }
+    const size_t b0 = hi - n_pass;
     PopsArgs a;
     int grid = 0;
     CKI(fill_geom(c, row_begin, row_end, tj, count_mode ? occ_pops_count((int) c->d, nb) : occ_pops((int) c->d, nb),
                   nb > 4 ? 64u : 32u, &a.g, &grid, count_mode ? 0xffffffffu : (uint32_t) (57344 / tj)));
     a.n_bins = nb;
-    a.band[0] = a.band[1] = 0.f;
+    for (int q = 0; q < 8; ++q) a.band[q] = 0.f;
     if (count_mode) {
-      // radius-dependent part of the band: e_rel * r^2 (fast path) + roundings of r^2 - |x'|^2 and of the subtraction
+      // radius-dependent part of the band: e_rel * r^2 (fast path) + roundings of s = acc + |x'|^2 and of s - r^2
       const double u = ldexp(1.0, -24);
-      for (int q = 0; q < nb; ++q) {
+      for (size_t q = 0; q < n_pass; ++q) {
         const double r2 = (double) uniq[b0 + q];
         a.band[q] = up((1.02 * (double) a.g.e_rel + 4.0 * u) * r2 + 1e-37);
       }
     }
-    for (int q = 0; q < 32; ++q) a.rad2[q] = q < nb ? uniq[b0 + q] : INFINITY;
-    const double rmax2 = (double) uniq[b0 + nb - 1];
+    // unused slots: count mode -1 (nothing is ever inside, far outside every band), histogram mode +inf
+    for (int q = 0; q < 32; ++q) a.rad2[q] = q < (int) n_pass ? uniq[b0 + q] : (count_mode ? -1.f : INFINITY);
+    const double rmax2 = (double) uniq[hi - 1];
     a.thr_fast = up(rmax2 * (1.0 + 1.01 * (double) a.g.e_rel));
     // a tile whose bounding-box distance exceeds this cannot contain a pair with exact d2 < r_max^2
     a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.prune_slack);
@@ -854,7 +866,7 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     };
     for (size_t r = 0; r < n_radii; ++r) {
       const size_t bin = std::lower_bound(uniq.begin(), uniq.end(), rad2[r]) - uniq.begin();
-      if (bin < b0 || bin >= b0 + (size_t) nb) continue;
+      if (bin < b0 || bin >= hi) continue;
       uint32_t mult = 0;
       for (size_t q = 0; q < n_radii; ++q) mult += (radii[q] == radii[r]);
       f.out_row[f.n_out] = (int) r;
@@ -864,6 +876,7 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
       if (++f.n_out == MAX_BINS * 4) CKI(flush());
     }
     CKI(flush());
+    hi = b0;
   }
   return 0;
 }

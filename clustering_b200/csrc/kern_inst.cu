@@ -19,30 +19,40 @@ cudaError_t DCB_CAT(launch_pops_d, DCB_D)(const PopsArgs& a, int grid, cudaStrea
 }
 
 #if DCB_D >= 1
-// count mode: one or two distinct radii
+// count mode: 1, 2, 3, 4 (and for D <= 6 also 6 or 8) distinct radii per pass
+#if DCB_D <= 6
+#define DCB_COUNT_NB(X) X(1) X(2) X(3) X(4) X(6) X(8)
+#else
+#define DCB_COUNT_NB(X) X(1) X(2) X(3) X(4)
+#endif
 cudaError_t DCB_CAT(launch_pops_count_d, DCB_D)(const PopsArgs& a, int grid, cudaStream_t st) {
   const size_t smem = pops_count_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d));
-  cudaError_t e;
-  if (a.n_bins == 1) {
-    e = cudaFuncSetAttribute(pops_count_kernel<DCB_D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
-    pops_count_kernel<DCB_D, 1><<<grid, CTA_THREADS, smem, st>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(pops_count_kernel<DCB_D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
-    pops_count_kernel<DCB_D, 2><<<grid, CTA_THREADS, smem, st>>>(a);
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (a.n_bins) {
+#define DCB_CASE(NB)                                                                                                  \
+  case NB:                                                                                                            \
+    e = cudaFuncSetAttribute(pops_count_kernel<DCB_D, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);  \
+    if (e != cudaSuccess) return e;                                                                                   \
+    pops_count_kernel<DCB_D, NB><<<grid, CTA_THREADS, smem, st>>>(a);                                                 \
+    break;
+    DCB_COUNT_NB(DCB_CASE)
+#undef DCB_CASE
+    default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 int DCB_CAT(occupancy_pops_count_d, DCB_D)(int n_bins, int d) {
   int nb = 0;
   const size_t smem = pops_count_smem_bytes(SmemRing<DCB_D>::bytes(d));
-  if (n_bins == 1) {
-    cudaFuncSetAttribute(pops_count_kernel<DCB_D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pops_count_kernel<DCB_D, 1>, CTA_THREADS, smem);
-  } else {
-    cudaFuncSetAttribute(pops_count_kernel<DCB_D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pops_count_kernel<DCB_D, 2>, CTA_THREADS, smem);
+  switch (n_bins) {
+#define DCB_CASE(NB)                                                                                              \
+  case NB:                                                                                                        \
+    cudaFuncSetAttribute(pops_count_kernel<DCB_D, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);  \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pops_count_kernel<DCB_D, NB>, CTA_THREADS, smem);          \
+    break;
+    DCB_COUNT_NB(DCB_CASE)
+#undef DCB_CASE
+    default: break;
   }
   return nb;
 }

@@ -501,7 +501,7 @@ struct PopsArgs {
   int n_bins;               // distinct radii in this pass (<= MAX_BINS)
   float rad2[32];           // ascending squared radii, padded with +inf
   float thr_fast;           // rad2[n_bins-1] (1 + e_rel): relative part of the filter margin (absolute part: Rows::eabs)
-  float band[2];            // count mode: the part of the error band around rad2[b] that depends on the radius only
+  float band[8];            // count mode: the part of the error band around rad2[b] that depends on the radius only
   uint32_t* cnt;            // [n_bins][ld_cnt]: #{j != i : rad2[b-1] <= d2(i,j) < rad2[b]}, rows relative to row_begin
   size_t ld_cnt;
 };
@@ -609,14 +609,15 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
 }
 
 // ------------------------------------------------------------------------------------------------
-// populations, count mode (one or two distinct radii, D <= MAX_TEMPLATE_D): no filter and no slow path
-// for ordinary hits.  Per pair and radius: v = acc - (r^2 - |x'|^2) (one FADD), the count takes the sign
-// bit of v (one integer op), and a running min of |v| per row tells whether any pair of the step lies
-// inside the rounding-error band of the radius; only those (rare) pairs are re-decided with dist2_exact.
-// Cost per pair: D FFMA + ~2.75 instructions per radius, independent of the hit rate -- the tiles that
-// survive the bounding-box pruning have hit rates of 5-20 %, where a per-hit handler costs far more.
+// populations, count mode (up to 8 distinct radii per pass, D <= MAX_TEMPLATE_D): no filter and no slow path for
+// ordinary hits.  Per pair: s = acc + |x'|^2 (the fast squared distance, one FADD); per pair and radius:
+// v = s - r_b^2 (one FADD against a constant), the count takes the sign bit of v (one integer op), and a running min
+// of |v| per row tells whether any pair of the step lies inside the rounding-error band of the radius; only those
+// (rare) pairs are re-decided with dist2_exact.  Cost per pair: D FFMA + 1 + ~3 per radius, independent of the hit
+// rate -- the tiles that survive the bounding-box pruning have hit rates of 5-25 %, where a per-hit handler costs far
+// more.  More radii than a pass holds: api.cu runs several passes, largest radii first, each pruned by its own r_max.
 // cnt[b][row] receives #{j : d2(i,j) < rad2[b]} INCLUDING the frame itself when rad2[b] > 0
-// (pops_finalize removes it again).
+// (pops_finalize removes it again).  Unused slots of a pass carry rad2 = -1 (nothing is ever inside).
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t pops_count_smem_bytes(size_t ring_bytes) { return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES; }
 
@@ -629,7 +630,7 @@ __device__ __forceinline__ void add4u(uint32_t (&v)[RI], int r, uint32_t x) {
 
 template <int D, int NB>
 __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ PopsArgs a) {
-  static_assert(D >= 1 && NB >= 1 && NB <= 2, "count mode: specialised dims, one or two radii");
+  static_assert(D >= 1 && NB >= 1 && NB <= 8, "count mode: specialised dims, at most eight radii per pass");
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int TJ = TileW<D>::tj;
   const ScanGeom& g = a.g;
@@ -646,8 +647,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
   const int tid = threadIdx.x;
   Rows<D> R;
   WarpBox<D> wb;
-  float tm[NB][RI];           // decision boundary of radius b for row r in accumulator units: rad2[b] - |x'_r|^2
-  float w[NB][RI];            // half width of the rounding-error band around it (depends on the row and the tile)
+  float wrow[RI];             // row part of the band half width: fast-path error bound + roundings of s and v
   uint32_t cnt[NB][RI];
   Pipe<StagesOf<D>::n> cp;
   SlowStats st;
@@ -667,14 +667,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
       ++st.wtiles;
       R.retarget(g, tl + (D + 1) * TJ);
+      // |v - (d2_exact - r_b^2)| < wrow[r] + band[b]: fast-path error (eabs + e_rel r^2) + roundings of s and of v
 #pragma unroll
-      for (int b = 0; b < NB; ++b)
-#pragma unroll
-        for (int r = 0; r < RI; ++r) {
-          tm[b][r] = a.rad2[b] - R.xn[r];
-          // |v - (d2_exact - r^2)| < w: fast-path error (eabs + e_rel r^2) + roundings of tm and of v
-          w[b][r] = fmaf(1.01f, R.eabs[r], a.band[b]) + 2.4e-7f * R.xn[r];
-        }
+      for (int r = 0; r < RI; ++r) wrow[r] = fmaf(1.01f, R.eabs[r], 2.4e-7f * R.xn[r]);
 #pragma unroll 1
       for (int gcol = 0; gcol < TJ; gcol += CJ) {
         float acc[RI][CJ];
@@ -702,33 +697,36 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
         }
         bool band = false;
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
+        for (int r = 0; r < RI; ++r) {
+          const float s0 = acc[r][0] + R.xn[r], s1 = acc[r][1] + R.xn[r];
+          const float s2 = acc[r][2] + R.xn[r], s3 = acc[r][3] + R.xn[r];
 #pragma unroll
-          for (int r = 0; r < RI; ++r) {
-            const float v0 = acc[r][0] - tm[b][r], v1 = acc[r][1] - tm[b][r];
-            const float v2 = acc[r][2] - tm[b][r], v3 = acc[r][3] - tm[b][r];
+          for (int b = 0; b < NB; ++b) {
+            const float v0 = s0 - a.rad2[b], v1 = s1 - a.rad2[b], v2 = s2 - a.rad2[b], v3 = s3 - a.rad2[b];
             cnt[b][r] += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
             cnt[b][r] += (__float_as_uint(v2) >> 31) + (__float_as_uint(v3) >> 31);
             const float mn = fminf(fminf(fabsf(v0), fabsf(v1)), fminf(fabsf(v2), fabsf(v3)));
-            band |= mn < w[b][r];
+            band |= mn < wrow[r] + a.band[b];
           }
+        }
         if (band) {
           // rare: some pair of this 4x4 block is within the error band of a radius.  One compact loop
           // (block parked in shared memory) replaces the sign-bit decision of those pairs by the exact one.
 #pragma unroll
           for (int r = 0; r < RI; ++r)
 #pragma unroll
-            for (int c = 0; c < CJ; ++c) scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c];
+            for (int c = 0; c < CJ; ++c) scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c] + R.xn[r];
 #pragma unroll 1
           for (int p = 0; p < RI * CJ; ++p) {
             const int r = p / CJ;
-            const float av = scratch[p * N_CONSUMERS];
+            const float sv = scratch[p * N_CONSUMERS];
+            const float wr = sel4(wrow, r);
             float d2 = 0.f;
             bool have = false;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-              const float v = av - sel4(tm[b], r);
-              if (fabsf(v) < sel4(w[b], r) && R.row(r) < g.row_end) {
+              const float v = sv - a.rad2[b];
+              if (fabsf(v) < wr + a.band[b] && R.row(r) < g.row_end) {
                 ++st.slow;
                 if (!have) {
                   d2 = dist2_exact(g.xT, g.ld, D, R.row(r), m.col0 + gcol + (p % CJ));
