@@ -70,6 +70,13 @@ def ncu_traffic(kernel_name):
     return None
 
 
+def workload_label(name, cfg):
+    """the same `config.workload` string in both arms"""
+    radii = ", ".join(f"{r:g}" for r in cfg["radii"])
+    return (f"{name}: clustering density, {cfg['n']} frames x {cfg['d']} dims, radius {radii}: "
+            "populations + free energies + nearest neighbours (-b)")
+
+
 def pair_dims_per_step(n, d):
     return 2.0 * float(n) * float(n) * float(d)      # populations scan + neighbour scan, ordered N x N pairs each
 
@@ -178,8 +185,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: clustering density, {cfg['n']} frames x {d} dims, radius {cfg['radii'][0]}: populations + free energies + nearest neighbours",
-                   "sample_frames": ns},
+        "config": {"workload": workload_label(args.workload, cfg), "sample_frames": ns},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -343,7 +349,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: clustering density, {n} frames x {d} dims, radii {[float(r) for r in radii]}: layout build + populations + free energies + nearest neighbours (+ lower-free-energy neighbour)",
+            "config": {"workload": workload_label(args.workload, cfg),
+                       "step": "layout build + populations + free energies + nearest neighbours (+ lower-free-energy neighbour)",
                        "pair_dims_per_step": pd, "parallelism": f"rows sharded over {world} GPU(s), coords replicated, NCCL all-gather of populations and neighbour keys",
                        "l2": "flushed between timed steps (256 MiB write)", "seed": cfg["seed"],
                        "pairs_evaluated_frac": evaluated_frac},
