@@ -133,22 +133,23 @@ __global__ void morton_keys_kernel(const float* __restrict__ coords, size_t n, i
 
 // One block per column tile (tj = 128 or 64 frames, one thread per frame).  Row-major coords ->
 //   xT   [d][ld]     original values (padding: NaN, so that no exact '<' ever passes)
-//   cT   [d+1][ld]   tile-local column pack: y' = x - c_t with c_t = mean of the tile's frames (any point near the
-//                    tile works; the mean keeps |y'| smallest): rows 0..d-1 = -2 y', row d = |y'|^2
-//                    (padding: 0, ..., 0, +inf: the accumulator of a padded column is +inf for every row)
-//   tcen [tiles][dp] c_t[0..d-1], max |y'|^2 over the tile's real frames, then the tile's bounding box lo[d], hi[d]
-//                    in globally centred coordinates
+//   cT   [tiles][(d+1)*tj + dp]  tile-major records (one bulk copy each).  Pack rows: y' = x - c_t with c_t = mean of the
+//                    tile's frames (any point near the tile works; the mean keeps |y'| smallest): rows 0..d-1 = -2 y',
+//                    row d = |y'|^2 (padding: 0, ..., 0, +inf: the accumulator of a padded column is +inf for every row).
+//                    Header [dp]: c_t[0..d-1], max |y'|^2 over the tile's real frames, then the tile's bounding box
+//                    lo[d], hi[d] in globally centred coordinates
 //   bbox [ld/64][2d] bounding boxes of 64-frame groups in globally centred coordinates (tile pruning)
 // in the order given by perm (position -> frame; nullptr = frame order).  Fixed-order reductions => the same
 // bits on every GPU.
 __global__ void pack_tiles_kernel(const float* __restrict__ coords, size_t n, int d, size_t ld, int dp,
                                   const float* __restrict__ centre, const uint32_t* __restrict__ perm, float* __restrict__ xT,
-                                  float* __restrict__ cT, float* __restrict__ tcen, float* __restrict__ bbox,
-                                  unsigned int* __restrict__ maxnorm_bits) {
+                                  float* __restrict__ cT, float* __restrict__ bbox, unsigned int* __restrict__ maxnorm_bits) {
   __shared__ float sh_sum[4], sh_lo[4], sh_hi[4];
   const int tj = blockDim.x;                      // 128 or 64
   const int nw = tj / 32;
   const size_t tile = blockIdx.x;
+  float* __restrict__ rec = cT + tile * ((size_t) (d + 1) * tj + dp);       // this tile's record: pack rows, then header
+  float* __restrict__ tcen = rec + (size_t) (d + 1) * tj;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const size_t p = tile * tj + t;
   const bool real = p < n;
@@ -180,18 +181,18 @@ __global__ void pack_tiles_kernel(const float* __restrict__ coords, size_t n, in
     if (t == 0) {                                 // box of the whole tile, for the consumers' warp-level pruning
       float tlo = INFINITY, thi = -INFINITY;
       for (int q = 0; q < nw; ++q) { tlo = fminf(tlo, sh_lo[q]); thi = fmaxf(thi, sh_hi[q]); }
-      tcen[tile * dp + d + 1 + k] = tlo;
-      tcen[tile * dp + 2 * d + 1 + k] = thi;
+      tcen[d + 1 + k] = tlo;
+      tcen[2 * d + 1 + k] = thi;
     }
     __syncthreads();
     const float yl = x - c;
     xT[(size_t) k * ld + p] = real ? x : nan;
-    cT[(size_t) k * ld + p] = real ? -2.0f * yl : 0.f;
+    rec[(size_t) k * tj + t] = real ? -2.0f * yl : 0.f;
     nrm_local = fmaf(yl, yl, nrm_local);
     nrm_global = fmaf(xg, xg, nrm_global);
-    if (t == 0) tcen[tile * dp + k] = c;
+    if (t == 0) tcen[k] = c;
   }
-  cT[(size_t) d * ld + p] = real ? nrm_local : INFINITY;
+  rec[(size_t) d * tj + t] = real ? nrm_local : INFINITY;
   float mx = real ? nrm_local : 0.f;
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) sh_sum[warp] = mx;
@@ -199,8 +200,8 @@ __global__ void pack_tiles_kernel(const float* __restrict__ coords, size_t n, in
   if (t == 0) {
     float m = 0.f;
     for (int q = 0; q < nw; ++q) m = fmaxf(m, sh_sum[q]);
-    tcen[tile * dp + d] = m;
-    for (int k = 3 * d + 1; k < dp; ++k) tcen[tile * dp + k] = 0.f;
+    tcen[d] = m;
+    for (int k = 3 * d + 1; k < dp; ++k) tcen[k] = 0.f;
   }
   if (real) atomicMax(maxnorm_bits, __float_as_uint(nrm_global));      // >= 0: the bit pattern orders like the value
 }
@@ -456,9 +457,8 @@ struct dcb200_ctx {
   cudaStream_t stream = nullptr;
   size_t n = 0, d = 0, ld = 0;
   bool spatial = false;             // frames are held in spatial (Morton) order; perm maps position -> frame
-  DevBuf<float> xT, cT;             // [d][ld] original coords, [d+1][ld] column pack (context order)
+  DevBuf<float> xT, cT;             // [d][ld] original coords; tile-major column pack records (context order)
   DevBuf<float> bbox;               // [ld/64][2d]
-  DevBuf<float> tcen;               // [ld/tile][dp] tile centres + max local norm
   DevBuf<float> rbbox;              // [row blocks of the current launch][2d]
   DevBuf<float> blk_thr;            // [row blocks][N_CONSUMER_WARPS] neighbour search pruning bounds
   DevBuf<uint32_t> perm;            // [n] position -> frame (identity when !spatial)
@@ -510,7 +510,6 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, in
   g->xT = c->xT.p;
   g->cT = c->cT.p;
   g->bbox = c->bbox.p;
-  g->tcen = c->tcen.p;
   g->dp = (int) ((3 * c->d + 1 + 3) / 4 * 4);
   g->centre = c->centre.p;
   g->prune_thr = INFINITY;
@@ -664,7 +663,7 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->xT.release(); c->cT.release(); c->bbox.release(); c->tcen.release(); c->rbbox.release(); c->blk_thr.release();
+  c->xT.release(); c->cT.release(); c->bbox.release(); c->rbbox.release(); c->blk_thr.release();
   c->perm.release(); c->lo.release(); c->lof.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release();
   c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
@@ -722,11 +721,10 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
   c->nn_ready = false;
   c->spatial = !keep_order;
   CK(c->xT.reserve(d * ld));
-  CK(c->cT.reserve((d + 1) * ld));
+  CK(c->cT.reserve((d + 1) * ld + ld / (d <= (size_t) MAX_TEMPLATE_D ? TileW<1>::tj : TileW<0>::tj) * ((3 * d + 1 + 3) / 4 * 4)));
   CK(c->bbox.reserve(ld / 64 * 2 * d));
   const int tj = d <= (size_t) MAX_TEMPLATE_D ? TileW<1>::tj : TileW<0>::tj;
   const int dp = (int) ((3 * d + 1 + 3) / 4 * 4);
-  CK(c->tcen.reserve(ld / tj * dp));
   CK(c->centre.reserve(2 * d));
   CK(c->perm.reserve(n));
   CK(cudaMemsetAsync(c->scalars + 1, 0, sizeof(unsigned int), c->stream));
@@ -745,8 +743,8 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
     c->launches += 1;
   }
   pack_tiles_kernel<<<(unsigned int) (ld / tj), tj, 0, c->stream>>>(dev_coords, n, (int) d, ld, dp, c->centre.p,
-                                                                    c->spatial ? c->perm.p : nullptr, c->xT.p, c->cT.p, c->tcen.p,
-                                                                    c->bbox.p, c->scalars + 1);
+                                                                    c->spatial ? c->perm.p : nullptr, c->xT.p, c->cT.p, c->bbox.p,
+                                                                    c->scalars + 1);
   c->launches += 1;
   CK(cudaGetLastError());
   unsigned int bits = 0;

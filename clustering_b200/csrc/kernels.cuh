@@ -31,13 +31,14 @@ namespace dcb {
 
 struct ScanGeom {
   const float* xT;          // [D][ld]   original coordinates, dim-major, NaN padded
-  const float* cT;          // [D+1][ld] column pack, tile-local: with c_t the centre of the tile a column belongs to and
-                            //           y' = y - c_t: rows 0..D-1 = -2*y', row D = |y'|^2 (padding: 0, ..., 0, +inf)
+  const float* cT;          // [n_col_tiles][(D+1)*TJ + dp] tile-major column pack, one contiguous record per tile (= one bulk
+                            //           copy): with c_t the centre of the tile and y' = y - c_t: rows 0..D-1 = -2*y' [TJ],
+                            //           row D = |y'|^2 [TJ] (padding: 0, ..., 0, +inf), then the tile's header (tcen below)
   const float* xrow;        // optional extra per-column row [ld] streamed with every tile (neighbour search: free-energy
                             // ranks as floats), nullptr = none; the kernel's SmemRing must be built with xrows = 1
-  const float* tcen;        // [n_col_tiles][dp] per tile: centre c_t[0..D-1], max |y'|^2 over the tile, then the tile's bounding
+                            // header [dp]: centre c_t[0..D-1], max |y'|^2 over the tile, then the tile's bounding
                             // box lo[0..D-1], hi[0..D-1] in globally centred coordinates (x - centre)
-  int dp;                   // floats per tcen entry (multiple of 4, >= 3D+1)
+  int dp;                   // floats per header (multiple of 4, >= 3D+1)
   const float* centre;      // [D] global centre the bounding boxes refer to
   size_t ld;                // padded frame count (multiple of 256)
   int d;                    // n_cols (== D for the specialised kernels)
@@ -203,7 +204,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
           if (__shfl_sync(0xffffffffu, lb, src) > thr) continue;
         }
         if (lane == 0) {
-          mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+          mbar_wait_backoff(&ring.empty[pp.stage], pp.phase ^ 1);
           TileMeta m;
           m.row_block = (int32_t) rb;
           m.col0 = tt * TJ;
@@ -214,11 +215,11 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
         }
         __syncwarp();
         {
+          // one bulk copy for the tile's record (pack + header), one more for the optional extra row
           float* dst = ring.tiles + pp.stage * ring.tile_floats;
-          const float* src = g.cT + (size_t) tt * TJ;
-          for (int k = lane; k <= d; k += 32) tma_load_1d(dst + k * TJ, src + (size_t) k * g.ld, TJ * 4, &ring.full[pp.stage]);
-          if (lane == 31) tma_load_1d(dst + (d + 1) * TJ, g.tcen + (size_t) tt * g.dp, (uint32_t) g.dp * 4, &ring.full[pp.stage]);
-          if (lane == 30 && g.xrow) tma_load_1d(dst + (d + 1) * TJ + g.dp, g.xrow + (size_t) tt * TJ, TJ * 4, &ring.full[pp.stage]);
+          const uint32_t rec = (uint32_t) ((d + 1) * TJ + g.dp);
+          if (lane == 0) tma_load_1d(dst, g.cT + (size_t) tt * rec, rec * 4, &ring.full[pp.stage]);
+          if (lane == 1 && g.xrow) tma_load_1d(dst + rec, g.xrow + (size_t) tt * TJ, TJ * 4, &ring.full[pp.stage]);
         }
         first = false;
         ++streamed;
@@ -226,7 +227,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
       }
     }
     if (!first && lane == 0) {                    // end-of-item marker
-      mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+      mbar_wait_backoff(&ring.empty[pp.stage], pp.phase ^ 1);
       TileMeta m;
       m.row_block = (int32_t) rb;
       m.col0 = 0;
@@ -238,7 +239,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
     if (!first) pp.advance();
   }
   if (lane == 0) {
-    mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+    mbar_wait_backoff(&ring.empty[pp.stage], pp.phase ^ 1);
     ring.meta[pp.stage].row_block = -1;
     mbar_arrive(&ring.full[pp.stage]);
     if (g.stats && streamed) atomicAdd(g.stats + 2, streamed);
