@@ -26,7 +26,7 @@ cudaError_t DCB_CAT(launch_pops_d, DCB_D)(const PopsArgs& a, int grid, cudaStrea
 #define DCB_COUNT_NB(X) X(1) X(2) X(3) X(4)
 #endif
 cudaError_t DCB_CAT(launch_pops_count_d, DCB_D)(const PopsArgs& a, int grid, cudaStream_t st) {
-  const size_t smem = pops_count_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d));
+  const size_t smem = pops_count_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d), a.n_bins);
   cudaError_t e = cudaErrorInvalidValue;
   switch (a.n_bins) {
 #define DCB_CASE(NB)                                                                                                  \
@@ -43,7 +43,7 @@ cudaError_t DCB_CAT(launch_pops_count_d, DCB_D)(const PopsArgs& a, int grid, cud
 }
 int DCB_CAT(occupancy_pops_count_d, DCB_D)(int n_bins, int d) {
   int nb = 0;
-  const size_t smem = pops_count_smem_bytes(SmemRing<DCB_D>::bytes(d));
+  const size_t smem = pops_count_smem_bytes(SmemRing<DCB_D>::bytes(d), n_bins);
   switch (n_bins) {
 #define DCB_CASE(NB)                                                                                              \
   case NB:                                                                                                        \

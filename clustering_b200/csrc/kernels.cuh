@@ -93,13 +93,14 @@ struct SmemRing {
   uint64_t* full;          // STAGES
   uint64_t* empty;         // STAGES
   TileMeta* meta;          // STAGES
-  unsigned long long* wthr;   // N_CONSUMER_WARPS: (item << 32 | float bits) pruning threshold published per warp
+  unsigned long long* wthr;   // N_CONSUMER_WARPS: (item << 32 | float bits) pruning threshold published per row group
+  uint32_t* unext;         // STAGES: next (row group, tile) unit of the stage to hand out (dynamic kernels)
   float* rbb;              // 2*d: bounding box of the current row block (producer scratch)
   size_t tile_floats;
   __host__ __device__ static int dp_of(int d) { return (3 * d + 1 + 3) / 4 * 4; }
   __host__ __device__ static size_t bytes(int d, int xrows = 0) {
     return (size_t) STAGES * ((d + 1 + xrows) * TJ + dp_of(d)) * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta) + N_CONSUMER_WARPS * 8 +
-           (size_t) 2 * d * 4;
+           (size_t) STAGES * 4 + (size_t) 2 * d * 4 + 16;
   }
   __device__ SmemRing(unsigned char* base, int d, int xrows = 0) {
     tile_floats = (size_t) (d + 1 + xrows) * TJ + dp_of(d);
@@ -108,7 +109,8 @@ struct SmemRing {
     empty = full + STAGES;
     meta = reinterpret_cast<TileMeta*>(empty + STAGES);
     wthr = reinterpret_cast<unsigned long long*>(meta + STAGES);
-    rbb = reinterpret_cast<float*>(wthr + N_CONSUMER_WARPS);
+    unext = reinterpret_cast<uint32_t*>(wthr + N_CONSUMER_WARPS);
+    rbb = reinterpret_cast<float*>(unext + STAGES);
   }
   __device__ void init() {
     if (threadIdx.x == 0) {
@@ -211,6 +213,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
           m.flags = first ? 1u : 0u;
           m.aux = item;
           ring.meta[pp.stage] = m;
+          ring.unext[pp.stage] = 0;
           mbar_arrive_expect_tx(&ring.full[pp.stage], (uint32_t) (ring.tile_floats * 4));
         }
         __syncwarp();
@@ -267,6 +270,13 @@ struct Rows {
 #pragma unroll
     for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);     // rows past the end: clamped, results discarded
   }
+  // rows of row group gi (128 consecutive rows of the block), whichever warp works on them
+  __device__ __forceinline__ void load_group(const ScanGeom& g, uint32_t rb, uint32_t gi, int lane) {
+    stride = 32u;
+    row0 = g.row_begin + rb * ROWS_PER_CTA + gi * (32u * RI) + (uint32_t) lane;
+#pragma unroll
+    for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
+  }
   __device__ __forceinline__ void retarget(const ScanGeom& g, const float* __restrict__ cen) {
     float c[D];
 #pragma unroll
@@ -296,6 +306,12 @@ struct Rows<0> {
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid, bool coherent = true) {
     stride = coherent ? 32u : (uint32_t) N_CONSUMERS;
     row0 = g.row_begin + rb * ROWS_PER_CTA + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
+  }
+  __device__ __forceinline__ void load_group(const ScanGeom& g, uint32_t rb, uint32_t gi, int lane) {
+    stride = 32u;
+    row0 = g.row_begin + rb * ROWS_PER_CTA + gi * (32u * RI) + (uint32_t) lane;
 #pragma unroll
     for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
   }
@@ -367,6 +383,34 @@ struct WarpBox<0> {
   __device__ __forceinline__ void compute(const ScanGeom&, const Rows<0>&, int) {}
   __device__ __forceinline__ bool reach(const float*, int, float) const { return true; }
 };
+
+// Dynamic kernels (populations count mode, neighbour search): the eight row groups of a block are NOT tied to the
+// eight consumer warps.  For every streamed tile each warp works out which groups can reach it (their boxes live in
+// shared memory) and the warps then claim (group, tile) units from a per-stage counter until none is left; a warp
+// whose nearby groups have nothing to do with a tile helps with another group's unit instead of idling, and may run
+// up to a ring depth ahead.  GBOX_DIMS floats per bound keep the rows 64 B apart.
+constexpr int GBOX_DIMS = 16;
+__host__ __device__ inline size_t gbox_bytes() { return (size_t) N_CONSUMER_WARPS * 2 * GBOX_DIMS * 4; }
+
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(N_CONSUMERS) : "memory"); }
+
+// bit 4*gi of the result: row group gi comes within thr[gi] (d2 units) of the tile whose header is cen
+template <int D>
+__device__ __forceinline__ uint32_t groups_in_reach(const float* __restrict__ gbox, const float* __restrict__ cen, int lane, float thr_of_group) {
+  if (D == 0) return 0x11111111u;                 // run-time-D kernels keep no boxes: every group scans every streamed tile
+  const int gi = lane >> 2, q = lane & 3;
+  const float* lo = gbox + gi * 2 * GBOX_DIMS;
+  const float* hi = lo + GBOX_DIMS;
+  float s = 0.f;
+#pragma unroll
+  for (int k = q; k < D; k += 4) {
+    const float gap = fmaxf(fmaxf(lo[k] - cen[2 * D + 1 + k], cen[D + 1 + k] - hi[k]), 0.f);
+    s = fmaf(gap, gap, s);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  return __ballot_sync(0xffffffffu, !(s * 0.999f > thr_of_group)) & 0x11111111u;     // NaN keeps
+}
 
 // register arrays must not be indexed dynamically (that would spill them to local memory)
 __device__ __forceinline__ float sel4(const float (&v)[RI], int r) {
@@ -620,7 +664,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
 // cnt[b][row] receives #{j : d2(i,j) < rad2[b]} INCLUDING the frame itself when rad2[b] > 0
 // (pops_finalize removes it again).  Unused slots of a pass carry rad2 = -1 (nothing is ever inside).
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t pops_count_smem_bytes(size_t ring_bytes) { return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES; }
+__host__ __device__ inline size_t pops_count_smem_bytes(size_t ring_bytes, int n_bins) {
+  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + gbox_bytes() + (size_t) n_bins * ROWS_PER_CTA * 4;
+}
 
 __device__ __forceinline__ uint32_t sel4u(const uint32_t (&v)[RI], int r) {
   return r == 0 ? v[0] : r == 1 ? v[1] : r == 2 ? v[2] : v[3];
@@ -636,7 +682,10 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
   constexpr int TJ = TileW<D>::tj;
   const ScanGeom& g = a.g;
   SmemRing<D> ring(smem, D);
-  float* scratch = reinterpret_cast<float*>(smem + ((SmemRing<D>::bytes(D) + 15) & ~size_t(15))) + threadIdx.x;
+  unsigned char* extra = smem + ((SmemRing<D>::bytes(D) + 15) & ~size_t(15));
+  float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
+  float* gbox = reinterpret_cast<float*>(extra + SCRATCH_BYTES);
+  uint32_t* cnt_s = reinterpret_cast<uint32_t*>(extra + SCRATCH_BYTES + gbox_bytes());      // [NB][ROWS_PER_CTA], per item
   ring.init();
   __syncthreads();
 
@@ -645,9 +694,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
     produce<D>(g, ring, false, [](uint32_t, uint32_t&, uint32_t&) {}, [&](uint32_t, int) { return g.prune_thr; });
     return;
   }
-  const int tid = threadIdx.x;
   Rows<D> R;
-  WarpBox<D> wb;
   float wrow[RI];             // row part of the band half width: fast-path error bound + roundings of s and v
   uint32_t cnt[NB][RI];
   Pipe<StagesOf<D>::n> cp;
@@ -657,99 +704,132 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
     const TileMeta m = ring.meta[cp.stage];
     if (m.row_block < 0) break;
     if (m.flags & 1u) {
-      R.load(g, (uint32_t) m.row_block, tid);
+      // first tile of an item: this warp prepares row group `warp` (box, zeroed counters) for everybody
+      WarpBox<D> wb;
+      R.load_group(g, (uint32_t) m.row_block, (uint32_t) warp, lane);
       wb.compute(g, R, lane);
+      if (lane < D) {
+        gbox[warp * 2 * GBOX_DIMS + lane] = wb.wlo;
+        gbox[warp * 2 * GBOX_DIMS + GBOX_DIMS + lane] = wb.whi;
+      }
 #pragma unroll
       for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int r = 0; r < RI; ++r) cnt[b][r] = 0;
+        for (int r = 0; r < RI; ++r) cnt_s[b * ROWS_PER_CTA + warp * (32 * RI) + r * 32 + lane] = 0;
+      consumer_barrier();
     }
-    if (!(m.flags & 4u) && wb.reach(ring.tiles + cp.stage * ring.tile_floats + (D + 1) * TJ, lane, g.prune_thr)) {
+    if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
-      ++st.wtiles;
-      R.retarget(g, tl + (D + 1) * TJ);
-      // |v - (d2_exact - r_b^2)| < wrow[r] + band[b]: fast-path error (eabs + e_rel r^2) + roundings of s and of v
+      const uint32_t reach = groups_in_reach<D>(gbox, tl + (D + 1) * TJ, lane, g.prune_thr);
+      const uint32_t n_units = __popc(reach);
+      for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(&ring.unext[cp.stage], 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const uint32_t gi = __fns(reach, 0, (int) u + 1) >> 2;
+        ++st.wtiles;
+        R.load_group(g, (uint32_t) m.row_block, gi, lane);
+        R.retarget(g, tl + (D + 1) * TJ);
+        // |v - (d2_exact - r_b^2)| < wrow[r] + band[b]: fast-path error (eabs + e_rel r^2) + roundings of s and of v
 #pragma unroll
-      for (int r = 0; r < RI; ++r) wrow[r] = fmaf(1.01f, R.eabs[r], 2.4e-7f * R.xn[r]);
+        for (int r = 0; r < RI; ++r) wrow[r] = fmaf(1.01f, R.eabs[r], 2.4e-7f * R.xn[r]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int r = 0; r < RI; ++r) cnt[b][r] = 0;
 #pragma unroll 1
-      for (int gcol = 0; gcol < TJ; gcol += CJ) {
-        float acc[RI][CJ];
-        {
-          const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + gcol);
-          const float4 y4 = *reinterpret_cast<const float4*>(tl + gcol);
+        for (int gcol = 0; gcol < TJ; gcol += CJ) {
+          float acc[RI][CJ];
+          {
+            const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + gcol);
+            const float4 y4 = *reinterpret_cast<const float4*>(tl + gcol);
+#pragma unroll
+            for (int r = 0; r < RI; ++r) {
+              acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
+              acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
+              acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
+              acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
+            }
+          }
+#pragma unroll
+          for (int k = 1; k < D; ++k) {
+            const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + gcol);
+#pragma unroll
+            for (int r = 0; r < RI; ++r) {
+              acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
+              acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
+              acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
+              acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
+            }
+          }
+          bool band = false;
 #pragma unroll
           for (int r = 0; r < RI; ++r) {
-            acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
-            acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
-            acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
-            acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
-          }
-        }
-#pragma unroll
-        for (int k = 1; k < D; ++k) {
-          const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + gcol);
-#pragma unroll
-          for (int r = 0; r < RI; ++r) {
-            acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
-            acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
-            acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
-            acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
-          }
-        }
-        bool band = false;
-#pragma unroll
-        for (int r = 0; r < RI; ++r) {
-          const float s0 = acc[r][0] + R.xn[r], s1 = acc[r][1] + R.xn[r];
-          const float s2 = acc[r][2] + R.xn[r], s3 = acc[r][3] + R.xn[r];
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            const float v0 = s0 - a.rad2[b], v1 = s1 - a.rad2[b], v2 = s2 - a.rad2[b], v3 = s3 - a.rad2[b];
-            cnt[b][r] += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
-            cnt[b][r] += (__float_as_uint(v2) >> 31) + (__float_as_uint(v3) >> 31);
-            const float mn = fminf(fminf(fabsf(v0), fabsf(v1)), fminf(fabsf(v2), fabsf(v3)));
-            band |= mn < wrow[r] + a.band[b];
-          }
-        }
-        if (band) {
-          // rare: some pair of this 4x4 block is within the error band of a radius.  One compact loop
-          // (block parked in shared memory) replaces the sign-bit decision of those pairs by the exact one.
-#pragma unroll
-          for (int r = 0; r < RI; ++r)
-#pragma unroll
-            for (int c = 0; c < CJ; ++c) scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c] + R.xn[r];
-#pragma unroll 1
-          for (int p = 0; p < RI * CJ; ++p) {
-            const int r = p / CJ;
-            const float sv = scratch[p * N_CONSUMERS];
-            const float wr = sel4(wrow, r);
-            float d2 = 0.f;
-            bool have = false;
+            const float s0 = acc[r][0] + R.xn[r], s1 = acc[r][1] + R.xn[r];
+            const float s2 = acc[r][2] + R.xn[r], s3 = acc[r][3] + R.xn[r];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-              const float v = sv - a.rad2[b];
-              if (fabsf(v) < wr + a.band[b] && R.row(r) < g.row_end) {
-                ++st.slow;
-                if (!have) {
-                  d2 = dist2_exact(g.xT, g.ld, D, R.row(r), m.col0 + gcol + (p % CJ));
-                  have = true;
-                  ++st.exact;
+              const float v0 = s0 - a.rad2[b], v1 = s1 - a.rad2[b], v2 = s2 - a.rad2[b], v3 = s3 - a.rad2[b];
+              cnt[b][r] += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
+              cnt[b][r] += (__float_as_uint(v2) >> 31) + (__float_as_uint(v3) >> 31);
+              const float mn = fminf(fminf(fabsf(v0), fabsf(v1)), fminf(fabsf(v2), fabsf(v3)));
+              band |= mn < wrow[r] + a.band[b];
+            }
+          }
+          if (band) {
+            // rare: some pair of this 4x4 block is within the error band of a radius.  One compact loop
+            // (block parked in shared memory) replaces the sign-bit decision of those pairs by the exact one.
+#pragma unroll
+            for (int r = 0; r < RI; ++r)
+#pragma unroll
+              for (int c = 0; c < CJ; ++c) scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c] + R.xn[r];
+#pragma unroll 1
+            for (int p = 0; p < RI * CJ; ++p) {
+              const int r = p / CJ;
+              const float sv = scratch[p * N_CONSUMERS];
+              const float wr = sel4(wrow, r);
+              float d2 = 0.f;
+              bool have = false;
+#pragma unroll
+              for (int b = 0; b < NB; ++b) {
+                const float v = sv - a.rad2[b];
+                if (fabsf(v) < wr + a.band[b] && R.row(r) < g.row_end) {
+                  ++st.slow;
+                  if (!have) {
+                    d2 = dist2_exact(g.xT, g.ld, D, R.row(r), m.col0 + gcol + (p % CJ));
+                    have = true;
+                    ++st.exact;
+                  }
+                  const uint32_t inside = d2 < a.rad2[b] ? 1u : 0u;      // NaN (padding) -> outside
+                  add4u(cnt[b], r, inside - (__float_as_uint(v) >> 31));
                 }
-                const uint32_t inside = d2 < a.rad2[b] ? 1u : 0u;      // NaN (padding) -> outside
-                add4u(cnt[b], r, inside - (__float_as_uint(v) >> 31));
               }
             }
           }
         }
+        // the unit's counts join the group's (another warp may be adding to the same rows from another tile)
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int r = 0; r < RI; ++r)
+            if (cnt[b][r]) atomicAdd(&cnt_s[b * ROWS_PER_CTA + gi * (32 * RI) + r * 32 + lane], cnt[b][r]);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
     if (m.flags & 2u) {
+      // end of the item: every unit is done once all consumer warps are here; this warp writes group `warp` back
+      consumer_barrier();
 #pragma unroll
       for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int r = 0; r < RI; ++r)
-          if (R.row(r) < g.row_end && cnt[b][r]) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + (R.row(r) - g.row_begin), cnt[b][r]);
+        for (int r = 0; r < RI; ++r) {
+          const uint32_t slot = (uint32_t) warp * (32 * RI) + (uint32_t) r * 32 + (uint32_t) lane;
+          const uint32_t row = g.row_begin + (uint32_t) m.row_block * ROWS_PER_CTA + slot;
+          const uint32_t c = cnt_s[b * ROWS_PER_CTA + slot];
+          if (row < g.row_end && c) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + (row - g.row_begin), c);
+        }
     }
     cp.advance();
   }
