@@ -95,12 +95,13 @@ struct SmemRing {
   TileMeta* meta;          // STAGES
   unsigned long long* wthr;   // N_CONSUMER_WARPS: (item << 32 | float bits) pruning threshold published per row group
   uint32_t* unext;         // STAGES: next (row group, tile) unit of the stage to hand out (dynamic kernels)
+  uint32_t* umask;         // STAGES: the stage's unit mask as computed by the first warp that got there (0xffffffff = not yet)
   float* rbb;              // 2*d: bounding box of the current row block (producer scratch)
   size_t tile_floats;
   __host__ __device__ static int dp_of(int d) { return (3 * d + 1 + 3) / 4 * 4; }
   __host__ __device__ static size_t bytes(int d, int xrows = 0) {
     return (size_t) STAGES * ((d + 1 + xrows) * TJ + dp_of(d)) * 4 + 2 * STAGES * 8 + STAGES * sizeof(TileMeta) + N_CONSUMER_WARPS * 8 +
-           (size_t) STAGES * 4 + (size_t) 2 * d * 4 + 16;
+           (size_t) STAGES * 8 + (size_t) 2 * d * 4 + 16;
   }
   __device__ SmemRing(unsigned char* base, int d, int xrows = 0) {
     tile_floats = (size_t) (d + 1 + xrows) * TJ + dp_of(d);
@@ -110,7 +111,8 @@ struct SmemRing {
     meta = reinterpret_cast<TileMeta*>(empty + STAGES);
     wthr = reinterpret_cast<unsigned long long*>(meta + STAGES);
     unext = reinterpret_cast<uint32_t*>(wthr + N_CONSUMER_WARPS);
-    rbb = reinterpret_cast<float*>(unext + STAGES);
+    umask = unext + STAGES;
+    rbb = reinterpret_cast<float*>(umask + STAGES);
   }
   __device__ void init() {
     if (threadIdx.x == 0) {
@@ -214,6 +216,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
           m.aux = item;
           ring.meta[pp.stage] = m;
           ring.unext[pp.stage] = 0;
+          ring.umask[pp.stage] = 0xffffffffu;
           mbar_arrive_expect_tx(&ring.full[pp.stage], (uint32_t) (ring.tile_floats * 4));
         }
         __syncwarp();
@@ -380,6 +383,7 @@ struct WarpBox {
 };
 template <>
 struct WarpBox<0> {
+  float wlo = 0.f, whi = 0.f;
   __device__ __forceinline__ void compute(const ScanGeom&, const Rows<0>&, int) {}
   __device__ __forceinline__ bool reach(const float*, int, float) const { return true; }
 };
@@ -855,7 +859,8 @@ struct NnArgs {
 __host__ __device__ inline size_t screen_smem_bytes(size_t ring_bytes) { return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES; }
 
 __host__ __device__ inline size_t nn_smem_bytes(size_t ring_bytes) {
-  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + (size_t) 2 * ROWS_PER_CTA * 8 + (size_t) ROWS_PER_CTA * 4;
+  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + (size_t) 2 * ROWS_PER_CTA * 8 + (size_t) 2 * ROWS_PER_CTA * 4 + gbox_bytes() +
+         (size_t) 3 * N_CONSUMER_WARPS * 4;
 }
 
 __device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as_float((uint32_t) (k >> 32)); }
@@ -1003,9 +1008,17 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
   SmemRing<D> ring(smem, d, 1);
   unsigned char* extra = smem + ((SmemRing<D>::bytes(d, 1) + 15) & ~size_t(15));
   float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
-  // best[0][slot] = nearest-neighbour key, best[1][slot] = nearest neighbour with lower free energy
-  unsigned long long* best = reinterpret_cast<unsigned long long*>(extra + SCRATCH_BYTES) + threadIdx.x;
-  uint32_t* lo_s = reinterpret_cast<uint32_t*>(extra + SCRATCH_BYTES + (size_t) 2 * ROWS_PER_CTA * 8) + threadIdx.x;
+  // per row of the block (slot = group * 128 + r * 32 + lane): best[0][slot] = nearest-neighbour key, best[1][slot] =
+  // nearest neighbour with lower free energy, lo_s = free-energy rank, lor_s = the same rank as the filter's float
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(extra + SCRATCH_BYTES);
+  uint32_t* lo_s = reinterpret_cast<uint32_t*>(extra + SCRATCH_BYTES + (size_t) 2 * ROWS_PER_CTA * 8);
+  float* lor_s = reinterpret_cast<float*>(lo_s + ROWS_PER_CTA);
+  float* gbox = lor_s + ROWS_PER_CTA;
+  // per row group (float bits, d2 units, pruning margins included): gthr_nn = what its rows still accept as nearest neighbour,
+  // gthr_hd = the same for the lower-free-energy neighbour (rows that can have one), glor = its largest filter rank
+  unsigned int* gthr_nn = reinterpret_cast<unsigned int*>(gbox + N_CONSUMER_WARPS * 2 * GBOX_DIMS);
+  unsigned int* gthr_hd = gthr_nn + N_CONSUMER_WARPS;
+  float* glor = reinterpret_cast<float*>(gthr_hd + N_CONSUMER_WARPS);
   ring.init();
   __syncthreads();
 
@@ -1026,11 +1039,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     });
     return;
   }
-  const int tid = threadIdx.x;
   Rows<D> R;
-  WarpBox<D> wb;
   NnFilter F;
-  uint32_t col0 = 0;
+  uint32_t col0 = 0, slot0 = 0;          // slot0: first slot of the group being worked on + lane
   Pipe<StagesOf<D>::n> cp;
   SlowStats st;
   // every column whose exact d2 is <= `d2` satisfies acc < thr(d2) (api.cu: error_bounds)
@@ -1041,135 +1052,168 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     ++st.slow;
     if (j == i || j >= g.n || i >= g.row_end) return;
     const float tn = sel4(F.t_nn, r), th = sel4(F.t_hd, r);
-    const bool hd_cand = __ldg(a.lo + j) < lo_s[r * N_CONSUMERS];
+    const uint32_t slot = slot0 + (uint32_t) r * 32u;
+    const bool hd_cand = __ldg(a.lo + j) < lo_s[slot];
     if (!(accv < tn) && !(hd_cand && accv < th)) return;      // thresholds may have tightened since the block was filtered
     const float d2 = dist2_exact(g.xT, g.ld, d, i, j);
     ++st.exact;
     if (!(d2 < FLT_MAX)) return;
     const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | __ldg(a.perm + j);
-    unsigned long long* b0 = best + r * N_CONSUMERS;
-    unsigned long long* b1 = b0 + ROWS_PER_CTA;
+    // another warp may be working on the same rows with another tile: the keys are only ever lowered, atomically
     const float xnr = sel4(R.xn, r), ear = sel4(R.eabs, r);
     bool changed = false;
-    if (key < *b0) {
-      *b0 = key;
+    if (key < atomicMin(best + slot, key)) {
       const float v = thr(d2, ear, xnr);
       put4(F.t_nn, r, v);
-      if (lo_s[r * N_CONSUMERS] == 0) put4(F.t_hd, r, v);
+      if (lo_s[slot] == 0) put4(F.t_hd, r, v);
       changed = true;
     }
-    if (hd_cand && key < *b1) { *b1 = key; put4(F.t_hd, r, thr(d2, ear, xnr)); changed = true; }
+    if (hd_cand && key < atomicMin(best + ROWS_PER_CTA + slot, key)) { put4(F.t_hd, r, thr(d2, ear, xnr)); changed = true; }
     if (changed) F.set_dl(r);
-  };
-  // pruning threshold of this warp's rows in fast-value units (acc + xn), published for the producer
-  uint32_t last_pub = 0x7f800000u;        // what this warp published last (float bits, +inf = nothing yet)
-  auto publish = [&](uint32_t item) {
-    float v = 0.f;
-#pragma unroll
-    for (int r = 0; r < RI; ++r)
-      if (R.row(r) < g.row_end) v = fmaxf(v, (fmaxf(F.t_nn[r], F.t_hd[r]) + R.xn[r]) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
-    if (!(v < INFINITY)) v = INFINITY;
-    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));   // v >= 0: bits order like values
-    if (lane == 0) ring.wthr[warp] = ((unsigned long long) item << 32) | m;
-    last_pub = m;
   };
   for (;;) {
     mbar_wait(&ring.full[cp.stage], cp.phase);
     const TileMeta m = ring.meta[cp.stage];
     if (m.row_block < 0) break;
     if (m.flags & 1u) {
-      R.load(g, (uint32_t) m.row_block, tid);
+      // first tile of an item: this warp prepares row group `warp` for everybody: keys warm-started from what the seeds
+      // and earlier items found, ranks, box, and the group's bound
+      R.load_group(g, (uint32_t) m.row_block, (uint32_t) warp, lane);
+      float v = 0.f, vh = 0.f, lmax = 0.f;
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
         unsigned long long k0 = ~0ull, k1 = ~0ull;
         uint32_t lo_i = 0;
         float lf = 0.f;
-        if (R.row(r) < g.row_end) {                     // warm start from what earlier items already found
+        if (R.row(r) < g.row_end) {
           k0 = a.key_nn[R.row(r) - g.row_begin];
           k1 = a.key_hd[R.row(r) - g.row_begin];
           lo_i = __ldg(a.lo + R.row(r));
           lf = __ldg(a.lof + R.row(r));
+          v = fmaxf(v, key_d2(k0));
+          if (lo_i != 0) {
+            vh = fmaxf(vh, key_d2(k1));
+            lmax = fmaxf(lmax, lf + a.lo_bias);
+          }
         }
-        best[r * N_CONSUMERS] = k0;
-        best[ROWS_PER_CTA + r * N_CONSUMERS] = k1;
-        lo_s[r * N_CONSUMERS] = lo_i;
-        F.lor[r] = lf + a.lo_bias;
+        const uint32_t slot = (uint32_t) warp * (32u * RI) + (uint32_t) r * 32u + (uint32_t) lane;
+        best[slot] = k0;
+        best[ROWS_PER_CTA + slot] = k1;
+        lo_s[slot] = lo_i;
+        lor_s[slot] = lf + a.lo_bias;
       }
-      wb.compute(g, R, lane);
-      // what this warp's rows accept at the start of the item (d2 units, pruning margins included)
-      float v = 0.f;
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        if (R.row(r) < g.row_end) {
-          const float dn = key_d2(best[r * N_CONSUMERS]);
-          const float dh = lo_s[r * N_CONSUMERS] == 0 ? dn : key_d2(best[ROWS_PER_CTA + r * N_CONSUMERS]);
-          v = fmaxf(v, fmaxf(dn, dh));
+      if constexpr (D > 0) {
+        WarpBox<D> wb;
+        wb.compute(g, R, lane);
+        if (lane < D) {
+          gbox[warp * 2 * GBOX_DIMS + lane] = wb.wlo;
+          gbox[warp * 2 * GBOX_DIMS + GBOX_DIMS + lane] = wb.whi;
         }
       }
       v = (fmaf(g.e_rel, v, v) + g.prune_slack) * 1.00001f;
+      vh = (fmaf(g.e_rel, vh, vh) + g.prune_slack) * 1.00001f;
       if (!(v < INFINITY)) v = INFINITY;
-      last_pub = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));
-      if (lane == 0) ring.wthr[warp] = ((unsigned long long) m.aux << 32) | last_pub;
+      if (!(vh < INFINITY)) vh = INFINITY;
+      const uint32_t vb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));
+      const uint32_t vhb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(vh, 0.f)));
+      const uint32_t lb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(lmax, 0.f)));
+      if (lane == 0) {
+        gthr_nn[warp] = vb;
+        gthr_hd[warp] = vhb;
+        glor[warp] = __uint_as_float(lb);
+        ring.wthr[warp] = ((unsigned long long) m.aux << 32) | max(vb, vhb);
+      }
+      consumer_barrier();
     }
     col0 = m.col0;
-    bool scan = !(m.flags & 4u);
-    if (scan) {
-      // Does this warp need the tile?  Row r accepts columns within its nearest-neighbour bound, and within its (usually
-      // much larger, for density peaks inter-cluster sized) lower-free-energy bound only if the tile holds a frame with a
-      // lower free energy than r at all: the smallest rank of the tile decides that.
+    if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
-      const float* lrow = tl + (d + 1) * TJ + g.dp;
-      float lomin;
-      if (TJ == 128) {
-        const float4 q = *reinterpret_cast<const float4*>(lrow + 4 * lane);
-        lomin = fminf(fminf(q.x, q.y), fminf(q.z, q.w));
-      } else {
-        const float2 q = *reinterpret_cast<const float2*>(lrow + 2 * lane);
-        lomin = fminf(q.x, q.y);
+      const float* cen = tl + (d + 1) * TJ;
+      // Which groups need the tile?  A group accepts columns within its nearest-neighbour bound, and within its (for density
+      // peaks inter-cluster sized) lower-free-energy bound only if the tile holds a frame of lower rank than its largest
+      // one at all.  The first warp to get here decides for everybody, so that unit numbers mean the same to all.
+      uint32_t reach;
+      {
+        const float* lrow = cen + g.dp;
+        float lomin;
+        if (TJ == 128) {
+          const float4 q = *reinterpret_cast<const float4*>(lrow + 4 * lane);
+          lomin = fminf(fminf(q.x, q.y), fminf(q.z, q.w));
+        } else {
+          const float2 q = *reinterpret_cast<const float2*>(lrow + 2 * lane);
+          lomin = fminf(q.x, q.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lomin = fminf(lomin, __shfl_xor_sync(0xffffffffu, lomin, o));
+        const int gq = lane >> 2;
+        float bound = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(gthr_nn + gq));
+        if (lomin < glor[gq]) bound = fmaxf(bound, __uint_as_float(*reinterpret_cast<volatile unsigned int*>(gthr_hd + gq)));
+        const uint32_t mine = groups_in_reach<D>(gbox, cen, lane, bound);
+        uint32_t seen = 0xffffffffu;
+        if (lane == 0) seen = atomicCAS(&ring.umask[cp.stage], 0xffffffffu, mine);
+        seen = __shfl_sync(0xffffffffu, seen, 0);
+        reach = seen == 0xffffffffu ? mine : seen;
       }
+      const uint32_t n_units = __popc(reach);
+      for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(&ring.unext[cp.stage], 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const uint32_t gi = __fns(reach, 0, (int) u + 1) >> 2;
+        ++st.wtiles;
+        slot0 = gi * (32u * RI) + (uint32_t) lane;
+        R.load_group(g, (uint32_t) m.row_block, gi, lane);
+        R.retarget(g, cen);
+        // filter thresholds of this unit from the group's best keys so far (the error margin depends on the tile)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) lomin = fminf(lomin, __shfl_xor_sync(0xffffffffu, lomin, o));
-      float v = 0.f;
+        for (int r = 0; r < RI; ++r) {
+          const uint32_t slot = slot0 + (uint32_t) r * 32u;
+          F.lor[r] = lor_s[slot];
+          F.t_nn[r] = thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + slot)), R.eabs[r], R.xn[r]);
+          // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
+          F.t_hd[r] = lo_s[slot] == 0 ? F.t_nn[r]
+                                      : thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + ROWS_PER_CTA + slot)), R.eabs[r], R.xn[r]);
+          F.set_dl(r);
+        }
+        scan_tile_nn(g, tl, cen + g.dp, R, F, scratch, hit);
+        // what the group's rows still accept (d2 units, pruning margins included): for the warps' reach tests, for the
+        // producer's dynamic pruning of this item, and (at the end of the item) for the later items of the row block
+        float v = 0.f, vh = 0.f;
 #pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        if (R.row(r) < g.row_end) {
-          const float dn = key_d2(best[r * N_CONSUMERS]);
-          const bool hd_here = lo_s[r * N_CONSUMERS] != 0 && lomin < F.lor[r];
-          v = fmaxf(v, hd_here ? fmaxf(dn, key_d2(best[ROWS_PER_CTA + r * N_CONSUMERS])) : dn);
+        for (int r = 0; r < RI; ++r)
+          if (R.row(r) < g.row_end) {
+            v = fmaxf(v, (F.t_nn[r] + R.xn[r]) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
+            if (lo_s[slot0 + (uint32_t) r * 32u] != 0) vh = fmaxf(vh, (F.t_hd[r] + R.xn[r]) * 1.000001f + g.prune_slack);
+          }
+        if (!(v < INFINITY)) v = INFINITY;
+        if (!(vh < INFINITY)) vh = INFINITY;
+        const uint32_t vb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));   // v >= 0: bits order like values
+        const uint32_t vhb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(vh, 0.f)));
+        if (lane == 0) {
+          const uint32_t now = min(atomicMin(gthr_nn + gi, vb), vb);
+          const uint32_t nowh = min(atomicMin(gthr_hd + gi, vhb), vhb);
+          ring.wthr[gi] = ((unsigned long long) m.aux << 32) | max(now, nowh);
         }
       }
-      v = (fmaf(g.e_rel, v, v) + g.prune_slack) * 1.00001f;
-      if (!(v < INFINITY)) v = INFINITY;
-      const uint32_t vb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v, 0.f)));
-      scan = wb.reach(tl + (d + 1) * TJ, lane, __uint_as_float(vb));
-    }
-    if (scan) {
-      const float* tl = ring.tiles + cp.stage * ring.tile_floats;
-      ++st.wtiles;
-      R.retarget(g, tl + (d + 1) * TJ);
-      // filter thresholds of this tile from the best keys so far (the error margin depends on the tile)
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        F.t_nn[r] = thr(key_d2(best[r * N_CONSUMERS]), R.eabs[r], R.xn[r]);
-        // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
-        F.t_hd[r] = lo_s[r * N_CONSUMERS] == 0 ? F.t_nn[r] : thr(key_d2(best[ROWS_PER_CTA + r * N_CONSUMERS]), R.eabs[r], R.xn[r]);
-        F.set_dl(r);
-      }
-      scan_tile_nn(g, tl, tl + (d + 1) * TJ + g.dp, R, F, scratch, hit);
-      publish(m.aux);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
     if (m.flags & 2u) {
+      // end of the item: every unit is done once all consumer warps are here; this warp writes group `warp` back
+      consumer_barrier();
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
-        if (R.row(r) < g.row_end) {
-          atomicMin(a.key_nn + (R.row(r) - g.row_begin), best[r * N_CONSUMERS]);
-          atomicMin(a.key_hd + (R.row(r) - g.row_begin), best[ROWS_PER_CTA + r * N_CONSUMERS]);
+        const uint32_t slot = (uint32_t) warp * (32u * RI) + (uint32_t) r * 32u + (uint32_t) lane;
+        const uint32_t row = g.row_begin + (uint32_t) m.row_block * ROWS_PER_CTA + slot;
+        if (row < g.row_end) {
+          atomicMin(a.key_nn + (row - g.row_begin), best[slot]);
+          atomicMin(a.key_hd + (row - g.row_begin), best[ROWS_PER_CTA + slot]);
         }
       }
-      // what this warp's rows still accept bounds every later item of the row block (positive floats order like their bits)
-      if (lane == 0) atomicMin(reinterpret_cast<unsigned int*>(g.blk_thr) + (size_t) m.row_block * N_CONSUMER_WARPS + warp, last_pub);
+      // what this group's rows still accept bounds every later item of the row block (positive floats order like their bits)
+      if (lane == 0)
+        atomicMin(reinterpret_cast<unsigned int*>(g.blk_thr) + (size_t) m.row_block * N_CONSUMER_WARPS + warp, max(gthr_nn[warp], gthr_hd[warp]));
     }
     cp.advance();
   }
