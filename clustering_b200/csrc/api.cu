@@ -109,22 +109,44 @@ __global__ void centre_kernel(const float* __restrict__ coords, size_t n, int d,
   }
 }
 
-// Spatial ordering key: Morton code of the first m = min(d, 6) dims, each quantised to `bits` bits over
-// centre +- 4 spread.  Frames that are close in space end up close in the array, so that the column
-// tiles (and the row blocks) have small bounding boxes and whole tiles can be skipped.
-__global__ void morton_keys_kernel(const float* __restrict__ coords, size_t n, int d, const float* __restrict__ centre,
-                                   const float* __restrict__ spread, int m, int bits, uint32_t* __restrict__ keys,
-                                   uint32_t* __restrict__ iota) {
+// Spatial ordering key: Hilbert-curve index of the first m = min(d, 6) dims, each quantised to `bits` bits over
+// centre +- 4 spread (Skilling's transpose algorithm: Gray-code the cell coordinates level by level, then interleave
+// the bits).  Frames that are close in space end up close in the array, so that the column tiles (and the row
+// groups) have small bounding boxes and whole tiles can be skipped; unlike a Z-order curve the Hilbert curve never
+// jumps, so a run of 128 consecutive frames never straddles two far-apart cells.
+__global__ void spatial_keys_kernel(const float* __restrict__ coords, size_t n, int d, const float* __restrict__ centre,
+                                    const float* __restrict__ spread, int m, int bits, unsigned long long* __restrict__ keys,
+                                    uint32_t* __restrict__ iota) {
   const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t q[6];
+  uint32_t q[6] = {0, 0, 0, 0, 0, 0};
   const float cells = (float) (1u << bits);
   for (int k = 0; k < m; ++k) {
     const float u = (coords[i * d + k] - centre[k]) / (8.0f * spread[k]) + 0.5f;
     const float v = fminf(fmaxf(u * cells, 0.0f), cells - 1.0f);
     q[k] = (v == v) ? (uint32_t) v : 0u;
   }
-  uint32_t key = 0;
+  if (m > 1) {
+    const uint32_t top = 1u << (bits - 1);
+    for (uint32_t Q = top; Q > 1; Q >>= 1) {           // inverse undo of the excess work
+      const uint32_t P = Q - 1;
+      for (int k = 0; k < m; ++k) {
+        if (q[k] & Q) {
+          q[0] ^= P;
+        } else {
+          const uint32_t t = (q[0] ^ q[k]) & P;
+          q[0] ^= t;
+          q[k] ^= t;
+        }
+      }
+    }
+    for (int k = 1; k < m; ++k) q[k] ^= q[k - 1];      // Gray encode
+    uint32_t t = 0;
+    for (uint32_t Q = top; Q > 1; Q >>= 1)
+      if (q[m - 1] & Q) t ^= Q - 1;
+    for (int k = 0; k < m; ++k) q[k] ^= t;
+  }
+  unsigned long long key = 0;
   for (int b = bits - 1; b >= 0; --b)
     for (int k = 0; k < m; ++k) key = (key << 1) | ((q[k] >> b) & 1u);
   keys[i] = key;
@@ -456,7 +478,7 @@ struct dcb200_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   size_t n = 0, d = 0, ld = 0;
-  bool spatial = false;             // frames are held in spatial (Morton) order; perm maps position -> frame
+  bool spatial = false;             // frames are held in spatial (Hilbert curve) order; perm maps position -> frame
   DevBuf<float> xT, cT;             // [d][ld] original coords; tile-major column pack records (context order)
   DevBuf<float> bbox;               // [ld/64][2d]
   DevBuf<float> rbbox;              // [row blocks of the current launch][2d]
@@ -466,6 +488,7 @@ struct dcb200_ctx {
   DevBuf<float> lof;                // [ld] the same ranks as floats (>> lo_shift), +inf padded
   int lo_shift = 0;
   DevBuf<uint32_t> keys_a, keys_b, iota, tmp_u32, tmp2_u32;
+  DevBuf<unsigned long long> skeys_a, skeys_b;     // spatial (Hilbert) keys, up to 60 bits
   DevBuf<unsigned char> cub_tmp;
   DevBuf<float> stage;              // row-major staging for host uploads
   DevBuf<float> centre;             // [2d] centre, spread
@@ -664,7 +687,7 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->xT.release(); c->cT.release(); c->bbox.release(); c->rbbox.release(); c->blk_thr.release();
-  c->perm.release(); c->lo.release(); c->lof.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release();
+  c->perm.release(); c->lo.release(); c->lof.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release(); c->skeys_a.release(); c->skeys_b.release();
   c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
   c->io_u32.release(); c->io_f32.release();
@@ -703,6 +726,16 @@ extern "C" int dcb200_ctx_stats(dcb200_ctx* c, uint64_t stats[6], int reset) {
   return 0;
 }
 
+static int sort_pairs_u64(dcb200_ctx* c, const unsigned long long* keys_in, unsigned long long* keys_out, const uint32_t* vals_in,
+                          uint32_t* vals_out, size_t n, int end_bit) {
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int) n, 0, end_bit, c->stream));
+  CK(c->cub_tmp.reserve(tmp_bytes));
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int) n, 0, end_bit, c->stream));
+  c->launches += 8;
+  return 0;
+}
+
 static int sort_pairs_u32(dcb200_ctx* c, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
                           size_t n, int end_bit) {
   size_t tmp_bytes = 0;
@@ -732,12 +765,12 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
   c->launches += 1;
   if (c->spatial) {
     const int m = (int) std::min<size_t>(d, 6);
-    const int bits = std::min(10, 30 / m);
-    CK(c->keys_a.reserve(n)); CK(c->keys_b.reserve(n)); CK(c->iota.reserve(n));
-    morton_keys_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(dev_coords, n, (int) d, c->centre.p, c->centre.p + d, m, bits,
-                                                                   c->keys_a.p, c->iota.p);
+    const int bits = std::min(16, 60 / m);        // cells far smaller than a 128-frame tile even in the densest regions
+    CK(c->skeys_a.reserve(n)); CK(c->skeys_b.reserve(n)); CK(c->iota.reserve(n));
+    spatial_keys_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(dev_coords, n, (int) d, c->centre.p, c->centre.p + d, m, bits,
+                                                                   c->skeys_a.p, c->iota.p);
     c->launches += 1;
-    CKI(sort_pairs_u32(c, c->keys_a.p, c->keys_b.p, c->iota.p, c->perm.p, n, m * bits));
+    CKI(sort_pairs_u64(c, c->skeys_a.p, c->skeys_b.p, c->iota.p, c->perm.p, n, m * bits));
   } else {
     iota_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->perm.p, n);
     c->launches += 1;

@@ -107,7 +107,7 @@ int dcb200_io_read_neighborhood(const char* filename, uint32_t* nn_idx, float* n
 int dcb200_io_read_comment(const char* filename, const char* key, float current, float* value);
 
 /* ---- (2) device-resident session ---------------------------------------------------------- */
-/* A context holds the frames in HBM in its own order ("positions"): by default a spatial (Morton) order, so
+/* A context holds the frames in HBM in its own order ("positions"): by default a spatial (Hilbert curve) order, so
  * that column tiles have small bounding boxes and tiles out of reach of a row block are never scanned.
  * Scans take ranges of POSITIONS (any partition of [0, n_rows) may be spread over devices -- every device
  * builds the same deterministic order) and return results in position order; dcb200_ctx_to_frame_order /

@@ -1,5 +1,5 @@
 set -x
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for w in C2 C4 C1 C3; do timeout 300 python scripts/profile_kernels.py $w >> gpurun_out/r30_prof.jsonl 2>&1; done
-cat gpurun_out/r30_prof.jsonl
+for w in C2 C4 C1 C3; do timeout 300 python scripts/profile_kernels.py $w >> gpurun_out/r35_prof.jsonl 2>&1; done
+cat gpurun_out/r35_prof.jsonl
 timeout 300 python scripts/profile_kernels.py C5 100000 1 | tail -1
