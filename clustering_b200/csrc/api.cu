@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "gemm_kernels.cuh"
 #include "launch.h"
 
 using namespace dcb;
@@ -502,6 +503,17 @@ struct dcb200_ctx {
   bool nn_ready = false;
   uint64_t launches = 0;
   uint64_t pairs_scheduled = 0;     // pairs of the full row x column ranges of the scans since the last reset
+  // GEMM-form (tcgen05) path for 32 <= d <= 256, spatial order only (gemm_kernels.cuh)
+  bool gemm = false;
+  int g_kc = 0, g_k8 = 0;
+  size_t g_tiles = 0;               // ld / 128
+  float g_nymax = 0.f;              // max |x~|^2
+  DevBuf<float> gT, gnorm, xR;      // operand images, norms of the rounded values, row-major exact copy (context order)
+  DevBuf<float> thdr;               // tile geometry: tcen [d][T], tlo [d][T], thi [d][T], trad [T]
+  DevBuf<float> lbmat;              // lower bounds of the tile pairs for row tiles [lb_s0, lb_s1)
+  uint32_t lb_s0 = 0, lb_s1 = 0;
+  DevBuf<float> lomin, gthr;        // per-tile min rank; per row tile and quarter: thr_nn, thr_hd, lormax
+  float* gcheck = nullptr;          // [2] diagnostics of the CHECK kernel
 };
 
 static float up(double v) {          // smallest float >= v
@@ -691,6 +703,8 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
   c->io_u32.release(); c->io_f32.release();
+  c->gT.release(); c->gnorm.release(); c->xR.release(); c->thdr.release(); c->lbmat.release(); c->lomin.release(); c->gthr.release();
+  if (c->gcheck) cudaFree(c->gcheck);
   cudaFree(c->scalars);
   cudaFree(c->stats);
   cudaStreamDestroy(c->stream);
@@ -718,7 +732,7 @@ extern "C" int dcb200_ctx_stats(dcb200_ctx* c, uint64_t stats[6], int reset) {
   stats[2] = h[1];
   stats[3] = h[3];                                       // (warp, tile) scans: a warp owns 32*RI rows
   stats[4] = c->pairs_scheduled;
-  stats[5] = (uint64_t) tile_width(c->d) * 32 * RI;
+  stats[5] = c->gemm ? (uint64_t) GT * GT : (uint64_t) tile_width(c->d) * 32 * RI;
   if (reset) {
     CK(cudaMemsetAsync(c->stats, 0, 4 * sizeof(unsigned long long), c->stream));
     c->pairs_scheduled = 0;
@@ -743,6 +757,77 @@ static int sort_pairs_u32(dcb200_ctx* c, const uint32_t* keys_in, uint32_t* keys
   CK(c->cub_tmp.reserve(tmp_bytes));
   CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int) n, 0, end_bit, c->stream));
   c->launches += 4;
+  return 0;
+}
+
+// The GEMM-form path serves the high-dimensional inputs where the pair scan really is a dense contraction (BASELINE config 5).
+// DCB200_GEMM=0 keeps such inputs on the run-time-D FFMA kernels (A/B comparisons, tests).
+static bool gemm_eligible(size_t n, size_t d, bool spatial) {
+  const char* e = getenv("DCB200_GEMM");
+  if (e && e[0] == '0') return false;
+  if (!spatial || d < (size_t) G_MIN_D || d > (size_t) G_MAX_D) return false;
+  const size_t tiles = (n + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN / GT;
+  return tiles * tiles * sizeof(float) <= (size_t(4) << 30);        // the tile-pair lower bounds must fit comfortably
+}
+
+// lower bounds of the tile pairs for the row tiles of [row_begin, row_end), cached until the layout changes
+static int ensure_tile_lb(dcb200_ctx* c, size_t row_begin, size_t row_end) {
+  const uint32_t s0 = (uint32_t) (row_begin / GT), s1 = (uint32_t) ((row_end + GT - 1) / GT);
+  if (s0 >= c->lb_s0 && s1 <= c->lb_s1) return 0;
+  CK(c->lbmat.reserve((size_t) (s1 - s0) * c->g_tiles));
+  const size_t d = c->d;
+  float* tcen = c->thdr.p;
+  float* tlo = tcen + d * c->g_tiles;
+  float* thi = tlo + d * c->g_tiles;
+  float* trad = thi + d * c->g_tiles;
+  CK(launch_tile_lb(tcen, tlo, thi, trad, (int) d, c->g_tiles, s0, s1, c->lbmat.p, c->stream));
+  c->launches += 1;
+  c->lb_s0 = s0;
+  c->lb_s1 = s1;
+  return 0;
+}
+
+static int fill_ggeom(dcb200_ctx* c, size_t row_begin, size_t row_end, GemmGeom* g, int* grid) {
+  memset(g, 0, sizeof(*g));
+  if (row_begin % GT) return fail("dcb200: the GEMM-form path needs position ranges that start at a multiple of 128");
+  CKI(ensure_tile_lb(c, row_begin, row_end));
+  g->gT = c->gT.p;
+  g->gnorm = c->gnorm.p;
+  g->xR = c->xR.p;
+  g->lb = c->lbmat.p + (size_t) (row_begin / GT - c->lb_s0) * c->g_tiles;
+  g->d = (int) c->d;
+  g->kc = c->g_kc;
+  g->k8 = c->g_k8;
+  int dev_smem = 0;
+  CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  g->n_stages = 8;
+  while (g->n_stages > 2 && gemm_smem_bytes(g->kc, g->n_stages) > (size_t) dev_smem) --g->n_stages;
+  if (gemm_smem_bytes(g->kc, g->n_stages) > (size_t) dev_smem) return fail("dcb200: GEMM-form kernel does not fit in shared memory");
+  g->n = (uint32_t) c->n;
+  g->n_tiles = (uint32_t) c->g_tiles;
+  g->row_begin = (uint32_t) row_begin;
+  g->row_end = (uint32_t) row_end;
+  g->n_row_tiles = (uint32_t) ((row_end - row_begin + GT - 1) / GT);
+  // about 8 column items per row tile: the row tile's operand image is loaded once per item
+  g->tiles_per_item = std::max(1u, std::min(g->n_tiles, std::max(32u, (g->n_tiles + 7) / 8)));
+  g->n_col_items = (g->n_tiles + g->tiles_per_item - 1) / g->tiles_per_item;
+  if ((uint64_t) g->n_row_tiles * g->n_col_items >= 0x7fffffffull) return fail("too many work items");
+  *grid = (int) std::min<uint64_t>((uint64_t) c->sm_count, (uint64_t) g->n_row_tiles * g->n_col_items);
+  g->work_counter = c->scalars;
+  g->stats = c->stats;
+  // error model of the fast value (gemm_kernels.cuh): |dx| <= 2^-11 |x - centre| per operand (round to nearest TF32; the
+  // subtraction of the centre adds 2^-24), accumulation: norms are FMA chains over K terms, the tensor core adds 9 terms per
+  // K=8 step with at worst truncation to 2^-23 (factor 2 on top), a few FP32 roundings at the end; safety factor 1.5
+  float c_loc, prune_slack;
+  error_bounds(c->d, c->maxnorm2, &c_loc, &g->e_rel, &prune_slack);
+  const double u = ldexp(1.0, -24);
+  g->rho_c = up(ldexp(1.0, -11) * (1.0 + ldexp(1.0, -8)));
+  g->c_acc = up(1.5 * (((double) c->g_kc * GK + 32.0) * u + (double) c->g_k8 * 9.0 * ldexp(1.0, -22)));
+  g->nymax = c->g_nymax;
+  g->prune_slack = prune_slack;
+  g->prune_thr = INFINITY;
+  c->launches += 0;
+  c->pairs_scheduled += (uint64_t) (row_end - row_begin) * (uint64_t) c->n;
   return 0;
 }
 
@@ -780,11 +865,38 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
                                                                     c->scalars + 1);
   c->launches += 1;
   CK(cudaGetLastError());
-  unsigned int bits = 0;
-  CK(cudaMemcpyAsync(&bits, c->scalars + 1, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+  c->gemm = gemm_eligible(n, d, c->spatial);
+  c->lb_s0 = c->lb_s1 = 0;
+  if (c->gemm) {
+    // operand images for the tensor-core path, norms of the rounded values, row-major exact copy, tile geometry
+    c->g_kc = (int) ((d + GK - 1) / GK);
+    c->g_k8 = (int) ((d + 7) / 8);
+    c->g_tiles = ld / GT;
+    CK(c->gT.reserve(c->g_tiles * (size_t) c->g_kc * G_CHUNK_FLOATS));
+    CK(c->gnorm.reserve(ld));
+    CK(c->xR.reserve(ld * d));
+    CK(c->thdr.reserve((3 * d + 1) * c->g_tiles));
+    float* tcen = c->thdr.p;
+    float* tlo = tcen + d * c->g_tiles;
+    float* thi = tlo + d * c->g_tiles;
+    float* trad = thi + d * c->g_tiles;
+    CK(launch_gpack(dev_coords, n, (int) d, c->g_kc, c->g_tiles, c->centre.p, c->perm.p, c->gT.p, c->gnorm.p, c->xR.p, tcen, tlo, thi, trad,
+                    c->stream));
+    CK(cudaMemsetAsync(c->scalars + 3, 0, sizeof(unsigned int), c->stream));
+    max_u32_kernel<<<std::min(blocks_for(n, 256), 1024u), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->gnorm.p), n,
+                                                                            c->scalars + 3);
+    c->launches += 2;
+    CK(cudaGetLastError());
+  }
+  unsigned int bits[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(bits, c->scalars + 1, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  memcpy(&c->maxnorm2, &bits, 4);
+  memcpy(&c->maxnorm2, &bits[0], 4);
   if (!(c->maxnorm2 == c->maxnorm2) || c->maxnorm2 > FLT_MAX) return fail("dcb200: coordinates contain NaN or infinite values");
+  if (c->gemm) {
+    memcpy(&c->g_nymax, &bits[2], 4);
+    c->g_nymax = nextafterf(c->g_nymax, INFINITY);
+  }
   return 0;
 }
 
@@ -823,6 +935,68 @@ extern "C" int dcb200_ctx_to_frame_order(dcb200_ctx* c, const uint32_t* dev_src,
 }
 
 // ---- populations ----------------------------------------------------------------------------
+// GEMM-form passes (tensor cores): up to eight distinct radii per pass, largest radii first, each pass pruned by its own r_max
+static int gemm_populations(dcb200_ctx* c, const float* radii, size_t n_radii, const std::vector<float>& rad2, const std::vector<float>& uniq,
+                            size_t row_begin, size_t row_end, size_t ld_cnt, uint32_t* dev_pops) {
+  const size_t rows = row_end - row_begin;
+  const char* chk = getenv("DCB200_GEMM_CHECK");
+  const bool check = chk && chk[0] == '1' && uniq.size() == 1;
+  if (check && !c->gcheck) {
+    CK(cudaMalloc(&c->gcheck, 2 * sizeof(float)));
+    CK(cudaMemsetAsync(c->gcheck, 0, 2 * sizeof(float), c->stream));
+  }
+  size_t hi = uniq.size();
+  while (hi > 0) {
+    const size_t n_pass = std::min<size_t>(8, hi);
+    const int nb = n_pass <= 1 ? 1 : n_pass <= 2 ? 2 : n_pass <= 4 ? 4 : 8;
+    const size_t b0 = hi - n_pass;
+    GPopsArgs a;
+    int grid = 0;
+    CKI(fill_ggeom(c, row_begin, row_end, &a.g, &grid));
+    a.n_bins = nb;
+    for (int q = 0; q < 8; ++q) {
+      a.rad2[q] = q < (int) n_pass ? uniq[b0 + q] : -1.f;
+      a.rad[q] = q < (int) n_pass ? up(sqrt((double) uniq[b0 + q]) * (1.0 + 1e-7)) : 0.f;
+    }
+    // a tile pair whose lower bound exceeds this cannot contain a pair with exact d2 < r_max^2
+    const double rmax2 = (double) uniq[hi - 1];
+    a.g.prune_thr = up(rmax2 * (1.0 + 1.01 * (double) a.g.e_rel) * 1.0001 + 2.0 * (double) a.g.prune_slack);
+    a.g.check = check ? c->gcheck : nullptr;
+    CK(c->cnt.reserve((size_t) nb * ld_cnt));
+    a.cnt = c->cnt.p;
+    a.ld_cnt = ld_cnt;
+    CK(cudaMemsetAsync(c->cnt.p, 0, (size_t) nb * ld_cnt * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+    CK(launch_gpops(a, grid, check, c->stream));
+    c->launches += 1;
+    FinalizeArgs f;
+    f.n_out = 0;
+    f.cumulative = 1;
+    auto flush = [&]() -> int {
+      if (f.n_out == 0) return 0;
+      pops_finalize_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->cnt.p, ld_cnt, rows, dev_pops, f);
+      c->launches += 1;
+      f.n_out = 0;
+      CK(cudaGetLastError());
+      return 0;
+    };
+    for (size_t r = 0; r < n_radii; ++r) {
+      const size_t bin = std::lower_bound(uniq.begin(), uniq.end(), rad2[r]) - uniq.begin();
+      if (bin < b0 || bin >= hi) continue;
+      uint32_t mult = 0;
+      for (size_t q = 0; q < n_radii; ++q) mult += (radii[q] == radii[r]);
+      f.out_row[f.n_out] = (int) r;
+      f.bin[f.n_out] = (int) (bin - b0);
+      f.mult[f.n_out] = mult;
+      f.self[f.n_out] = rad2[r] > 0.f ? 1u : 0u;      // d2(i,i) = 0 < r^2
+      if (++f.n_out == MAX_BINS * 4) CKI(flush());
+    }
+    CKI(flush());
+    hi = b0;
+  }
+  return 0;
+}
+
 extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t n_radii, size_t row_begin, size_t row_end,
                                       uint32_t* dev_pops) {
   if (!c || (!radii && n_radii) || !dev_pops) return fail("null argument");
@@ -840,6 +1014,7 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
   for (float v : uniq)
     if (!(v == v)) return fail("dcb200_ctx_populations: NaN radius");
   const size_t ld_cnt = (rows + 255) / 256 * 256;
+  if (c->gemm && row_begin % GT == 0) return gemm_populations(c, radii, n_radii, rad2, uniq, row_begin, row_end, ld_cnt, dev_pops);
   const int tj = tile_width(c->d);
   // specialised dims and up to two passes' worth of radii: branch-free count mode (pops_count_kernel), up to 8 (D <= 6) or
   // 4 distinct radii per pass, largest radii first so that every pass is pruned by its own r_max.  Long radius lists
@@ -966,6 +1141,43 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
   nn_seed_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->xT.p, c->ld, (int) c->d, (uint32_t) c->n, c->perm.p, c->lo.p,
                                                                (uint32_t) pos_begin, (uint32_t) pos_end, 8, none,
                                                                (unsigned long long*) dev_keys_nn, (unsigned long long*) dev_keys_hd);
+  if (c->gemm && pos_begin % GT == 0) {
+    // GEMM-form scan (tensor cores): window pass over every row tile's own neighbourhood, then all tiles
+    GNnArgs ga;
+    int ggrid = 0;
+    CKI(fill_ggeom(c, pos_begin, pos_end, &ga.g, &ggrid));
+    ga.perm = c->perm.p;
+    ga.lo = c->lo.p;
+    ga.lof = c->lof.p;
+    ga.lo_bias = c->lo_shift ? 1.f : 0.f;
+    CK(c->lomin.reserve(c->g_tiles));
+    CK(launch_tile_min(c->lof.p, c->g_tiles, c->lomin.p, c->stream));
+    ga.lomin = c->lomin.p;
+    CK(c->gthr.reserve((size_t) ga.g.n_row_tiles * 12));
+    ga.thr_nn = c->gthr.p;
+    ga.thr_hd = ga.thr_nn + (size_t) ga.g.n_row_tiles * 4;
+    ga.lormax = ga.thr_hd + (size_t) ga.g.n_row_tiles * 4;
+    ga.key_nn = (unsigned long long*) dev_keys_nn;
+    ga.key_hd = (unsigned long long*) dev_keys_hd;
+    CK(launch_gnn_tile_thr(ga.key_nn, ga.key_hd, c->lo.p, c->lof.p, ga.lo_bias, (uint32_t) pos_begin, (uint32_t) pos_end, ga.g.n_row_tiles,
+                           ga.g.e_rel, ga.g.prune_slack, ga.thr_nn, ga.thr_hd, ga.lormax, c->stream));
+    const uint32_t full_tpi = ga.g.tiles_per_item, full_items = ga.g.n_col_items;
+    if (ga.g.n_tiles > 96) {
+      ga.window = 16;
+      ga.g.tiles_per_item = ga.g.n_tiles;
+      ga.g.n_col_items = 1;
+      CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+      CK(launch_gnn(ga, (int) std::min<uint64_t>((uint64_t) ggrid, ga.g.n_row_tiles), c->stream));
+      c->launches += 1;
+    }
+    ga.window = 0;
+    ga.g.tiles_per_item = full_tpi;
+    ga.g.n_col_items = full_items;
+    CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+    CK(launch_gnn(ga, ggrid, c->stream));
+    c->launches += 4;
+    return 0;
+  }
   NnArgs a;
   int grid = 0;
   CKI(fill_geom(c, pos_begin, pos_end, tile_width(c->d), occ_nn((int) c->d), 32u, &a.g, &grid));
@@ -1058,6 +1270,23 @@ extern "C" int dcb200_ctx_screening_merge(dcb200_ctx* c, size_t m_new, uint32_t*
   uf_merge_kernel<<<blocks_for(m_new, 256), 256, 0, c->stream>>>(dev_comp, dev_other, m_new);
   c->launches += 1;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// Diagnostics of the GEMM-form path: active = 1 if the current coordinates are served by the tensor-core kernels;
+// check_ratio = max observed |fast - exact| / (proven band) over all pairs of the populations calls made with
+// DCB200_GEMM_CHECK=1 (single radius) since the context was created; must stay below 1.
+extern "C" int dcb200_ctx_gemm_info(dcb200_ctx* c, int* active, float* check_ratio) {
+  if (!c) return fail("null context");
+  if (active) *active = c->gemm ? 1 : 0;
+  if (check_ratio) {
+    *check_ratio = 0.f;
+    if (c->gcheck) {
+      CK(cudaSetDevice(c->device));
+      CK(cudaMemcpyAsync(check_ratio, c->gcheck, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+  }
   return 0;
 }
 

@@ -1,0 +1,994 @@
+// GEMM-form pair scans for high-dimensional inputs (32 <= n_cols <= 256), written for sm_100a tensor cores:
+//
+//   gscan_pops_kernel<NB>   multi-radius neighbourhood population count   (density_clustering.cpp:126-195)
+//   gscan_nn_kernel         nearest neighbour + nearest neighbour with lower free energy (density_clustering.cpp:230-288)
+//
+// Where the path really is a dense contraction the squared distance is evaluated as
+//     F = |x~|^2 + |y~|^2 - 2 x~.y~ ,        x~ = tf32(x - centre)
+// with the dot products on the 5th-generation tensor cores: tcgen05.mma kind::tf32, 128 x 128 x 8 per instruction,
+// operands in shared memory (K-major, 128-byte swizzle), accumulators in tensor memory (two 128-column stages), read back
+// by the epilogue warps with tcgen05.ld (one thread = one row of the accumulator).  F is the exact squared distance of
+// the ROUNDED points up to FP32 accumulation error, so its distance to the true value is ~ 2 d (|dx| + |dy|) with
+// |dx| <= 2^-11 |x - centre|: proportional to d, small for close pairs.  As in the FFMA kernels the fast value never
+// decides alone: a pair whose F lies within the proven band of a decision boundary is re-evaluated with dist2_exact_rm,
+// the reference's own arithmetic, so that populations and neighbours stay bit-identical.
+//
+// Structure of a CTA (one per SM, persistent):
+//   warp 0      producer: claims work items (row tile x range of column tiles), drops the column tiles whose precomputed
+//               lower bound (tile_lb_kernel: boxes and spheres in all n_cols dims) is out of reach, streams the others with
+//               1-D bulk TMA: the row tile's operand image once per item, the column tiles' images in 16 KB K-chunks
+//               through a ring, plus a small per-tile side record (|y~|^2, free-energy ranks)
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma for every chunk and commits to the mbarriers that
+//               free the ring slot / publish the accumulator stage
+//   warps 2..9  two epilogue warpgroups, one per accumulator stage: tcgen05.ld 32 columns at a time, branch-free
+//               count / filter logic per pair, compact exact handler for the rare band pairs
+// The operand images are written by gpack_kernel exactly as they must sit in shared memory, so that no tensor map is
+// needed: a chunk is one contiguous 16 KB block = one cp.async.bulk.
+#pragma once
+#include "common.cuh"
+#include <float.h>
+
+namespace dcb {
+
+constexpr int GT = 128;                      // rows / columns per tile (= UMMA M = UMMA N)
+constexpr int GK = 32;                       // floats per K-chunk row = 128 bytes = the swizzle width
+constexpr int G_CHUNK_FLOATS = GT * GK;      // 4096 floats = 16 KB
+constexpr int G_CHUNK_BYTES = G_CHUNK_FLOATS * 4;
+constexpr int G_MIN_D = 32, G_MAX_D = 256;
+constexpr int G_SIDE_SLOTS = 4;              // per-tile side records in flight
+constexpr int G_SIDE_FLOATS = 4 + 2 * GT;    // meta (16 B), |y~|^2 [128], rank floats [128]
+constexpr int G_EPI_WARPS = 8;
+constexpr int G_EPI_THREADS = G_EPI_WARPS * 32;
+constexpr int G_THREADS = 64 + G_EPI_THREADS;       // producer warp + MMA warp + two epilogue warpgroups
+constexpr int G_HALF = 16;                   // columns per band / hit test
+
+// ------------------------------------------------------------------------------------------------
+// launch arguments (shared with the host code in api.cu)
+// ------------------------------------------------------------------------------------------------
+struct GemmGeom {
+  const float* gT;            // operand images [tiles][kc][4096]
+  const float* gnorm;         // [ld]
+  const float* xR;            // [ld][d]
+  const float* lb;            // [row tiles of this launch][n_tiles]
+  int d, kc, k8;              // dims, K-chunks per tile, total K=8 MMA steps (ceil(d/8))
+  int n_stages;               // ring depth (chunks)
+  uint32_t n;                 // real frame count
+  uint32_t n_tiles;           // column tiles (= ld / 128)
+  uint32_t row_begin, row_end;   // positions of this shard, row_begin % 128 == 0
+  uint32_t n_row_tiles;
+  uint32_t tiles_per_item, n_col_items;
+  unsigned int* work_counter;
+  unsigned long long* stats;  // [0] pairs handed to the handler, [1] exact evaluations, [2] tiles streamed, [3] tile scans
+  float rho_c;                // rho = rho_c (sqrt(|x~|^2) + sqrt(max |y~|^2)) bounds |dx| + |dy|
+  float nymax;                // max |y~|^2 over all frames (rounded up)
+  float c_acc;                // eps = c_acc (|x~|^2 + nymax): accumulation / FP32 rounding part of the band
+  float e_rel;                // relative error of the reference's own arithmetic against the real-number distance
+  float prune_slack;          // absolute slack of the tile lower bounds
+  float prune_thr;            // static pruning threshold (d2 units); +inf: none
+  float* check;               // optional [2]: max observed |F - d2e| / band (float bits, atomicMax), CHECK builds only
+};
+
+struct GPopsArgs {
+  GemmGeom g;
+  int n_bins;
+  float rad2[8];             // squared radii of this pass; unused slots -1 (nothing is ever inside)
+  float rad[8];              // sqrt(rad2), rounded up; unused 0
+  uint32_t* cnt;             // [n_bins][ld_cnt]  #{j : d2(i,j) < rad2[b]} including the frame itself when rad2[b] > 0
+  size_t ld_cnt;
+};
+
+struct GNnArgs {
+  GemmGeom g;
+  const uint32_t* perm;         // [n] position -> frame
+  const uint32_t* lo;           // [n] number of frames with a strictly lower free energy, by position
+  const float* lof;             // [ld] (float)(lo >> shift), +inf padded: streamed with every tile
+  const float* lomin;           // [n_tiles] min of lof over the tile
+  float lo_bias;
+  uint32_t window;              // > 0: only column tiles within `window` tiles of the row tile (first pass)
+  unsigned long long* key_nn;   // [row_end - row_begin] (d2 bits << 32 | frame), atomicMin'ed
+  unsigned long long* key_hd;
+  float* thr_nn;                // [n_row_tiles][4] per 32-row quarter of a row tile: bound (d2 units, margins included) of what
+                                // its rows still accept as nearest neighbour; lowered by atomicMin as items finish
+  float* thr_hd;                // the same for the lower-free-energy neighbour; 0 where no row can have one
+  float* lormax;                // [n_row_tiles][4] largest filter rank (+ bias) among the rows that can have such a neighbour
+};
+
+// everything below is device code, compiled in gemm_inst.cu only
+#ifdef DCB_GEMM_KERNELS
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 / TMEM wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, 128 x 128 x 8, TF32 inputs, FP32 accumulation
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+}
+
+// Shared-memory matrix descriptor of a [128 rows][32 floats] K-major operand chunk with 128-byte swizzle:
+// start address >> 4 in bits [0,14), leading byte offset (unused for swizzled K-major) 1 in [16,30), stride byte offset
+// (8 rows x 128 B = 1024 B) >> 4 in [32,46), descriptor version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+// A K step of 8 floats (32 bytes) inside the swizzle atom advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t g_smem_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t) ((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t) 1 << 16;
+  d |= (uint64_t) (1024 >> 4) << 32;
+  d |= (uint64_t) 1 << 46;
+  d |= (uint64_t) 2 << 61;
+  return d;
+}
+// instruction descriptor: D format F32 (1 << 4), A and B format TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t G_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (GT >> 3) << 17) | ((uint32_t) (GT >> 4) << 24);
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// squared distance of positions i and j in the reference's rounding order (see dist2_exact, common.cuh) on the
+// row-major copy xR [ld][D] of the original coordinates in context order
+static __device__ __noinline__ float dist2_exact_rm(const float* __restrict__ xR, int D, uint32_t i, uint32_t j) {
+  const float* __restrict__ a = xR + (size_t) i * D;
+  const float* __restrict__ b = xR + (size_t) j * D;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= D; k += 4) {
+    const float c0 = __fsub_rn(__ldg(a + k), __ldg(b + k));
+    const float c1 = __fsub_rn(__ldg(a + k + 1), __ldg(b + k + 1));
+    const float c2 = __fsub_rn(__ldg(a + k + 2), __ldg(b + k + 2));
+    const float c3 = __fsub_rn(__ldg(a + k + 3), __ldg(b + k + 3));
+    a0 = __fadd_rn(a0, __fmul_rn(c0, c0));
+    a1 = __fadd_rn(a1, __fmul_rn(c1, c1));
+    a2 = __fadd_rn(a2, __fmul_rn(c2, c2));
+    a3 = __fadd_rn(a3, __fmul_rn(c3, c3));
+  }
+  float l0 = __fadd_rn(a0, a2);
+  float l1 = __fadd_rn(a1, a3);
+  float s;
+  if (D - k >= 2) {
+    const float c0 = __fsub_rn(__ldg(a + k), __ldg(b + k));
+    const float c1 = __fsub_rn(__ldg(a + k + 1), __ldg(b + k + 1));
+    l0 = __fadd_rn(l0, __fmul_rn(c0, c0));
+    l1 = __fadd_rn(l1, __fmul_rn(c1, c1));
+    s = __fadd_rn(l1, l0);
+    k += 2;
+  } else {
+    s = __fadd_rn(l0, l1);
+  }
+  if (k < D) {
+    const float c = __fsub_rn(__ldg(a + k), __ldg(b + k));
+    s = __fadd_rn(s, __fmul_rn(c, c));
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout: operand images, norms, row-major exact copy, tile geometry
+// ------------------------------------------------------------------------------------------------
+// One block (128 threads) per tile of 128 consecutive positions.
+//   gT    [tiles][kc][128][32]  tf32(x - centre), K-major rows of 128 bytes, 16-byte pieces XOR-swizzled with (row & 7):
+//                               the canonical SWIZZLE_128B layout; K padded with zeros; padded positions: zeros
+//   gnorm [ld]                  |x~|^2 of the rounded values (FP32 FMA chain), +inf for padded positions
+//   xR    [ld][d]               original coordinates in context order (padding: NaN)
+//   tcen / tlo / thi [d][tiles] mean and bounding box of the tile in centred coordinates (x - centre), trad [tiles] the radius
+//                               of the tile's frames around tcen (rounded up); empty tiles: box (+inf,-inf), radius 0
+__global__ void gpack_kernel(const float* __restrict__ coords, size_t n, int d, int kc, size_t n_tiles, const float* __restrict__ centre,
+                             const uint32_t* __restrict__ perm, float* __restrict__ gT, float* __restrict__ gnorm, float* __restrict__ xR,
+                             float* __restrict__ tcen, float* __restrict__ tlo, float* __restrict__ thi, float* __restrict__ trad) {
+  extern __shared__ float sm[];                      // [128][pitch] centred coordinates, then [d] tile centre
+  const int pitch = d + 1 + (d & 1);                 // odd: conflict-free both along rows and along dims
+  float* cen = sm + (size_t) GT * pitch;
+  __shared__ float red[4];
+  const size_t tile = blockIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const size_t p0 = tile * GT;
+  const int real_rows = p0 < n ? (int) (n - p0 < (size_t) GT ? n - p0 : (size_t) GT) : 0;
+  const float nan = __int_as_float(0x7fc00000);
+  // rows: one warp per row, coalesced along the dims
+  for (int r = warp; r < GT; r += 4) {
+    const size_t p = p0 + r;
+    const bool real = r < real_rows;
+    const size_t src = real ? (perm ? (size_t) perm[p] : p) : 0;
+    for (int k = lane; k < d; k += 32) {
+      const float x = real ? coords[src * d + k] : nan;
+      xR[p * d + k] = x;
+      sm[(size_t) r * pitch + k] = real ? x - centre[k] : 0.f;
+    }
+  }
+  __syncthreads();
+  // per dim: mean and box
+  for (int k = t; k < d; k += GT) {
+    float s = 0.f, lo = INFINITY, hi = -INFINITY;
+    for (int r = 0; r < real_rows; ++r) {
+      const float v = sm[(size_t) r * pitch + k];
+      s += v;
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+    float c = real_rows ? s / (float) real_rows : 0.f;
+    if (!(fabsf(c) < FLT_MAX)) c = 0.f;
+    cen[k] = c;
+    tcen[(size_t) k * n_tiles + tile] = c;
+    tlo[(size_t) k * n_tiles + tile] = lo;
+    thi[(size_t) k * n_tiles + tile] = hi;
+  }
+  __syncthreads();
+  // per row: norm of the rounded values, distance to the tile centre
+  {
+    float nrm = 0.f, dc = 0.f;
+    for (int k = 0; k < d; ++k) {
+      const float v = sm[(size_t) t * pitch + k];
+      const float vr = to_tf32(v);
+      nrm = fmaf(vr, vr, nrm);
+      const float e = v - cen[k];
+      dc = fmaf(e, e, dc);
+    }
+    const bool real = t < real_rows;
+    gnorm[p0 + t] = real ? nrm : INFINITY;
+    float rad = real ? sqrtf(dc) * 1.00001f + 1e-30f : 0.f;
+    for (int o = 16; o > 0; o >>= 1) rad = fmaxf(rad, __shfl_xor_sync(0xffffffffu, rad, o));
+    if (lane == 0) red[warp] = rad;
+  }
+  __syncthreads();
+  if (t == 0) trad[tile] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  // operand image: 8 consecutive threads write the 8 sixteen-byte pieces of one 128-byte row
+  float* __restrict__ img = gT + tile * (size_t) kc * G_CHUNK_FLOATS;
+  for (int q = 0; q < kc; ++q) {
+    for (int pass = 0; pass < GT / 16; ++pass) {
+      const int r = pass * 16 + (t >> 3);
+      const int pc = t & 7;                       // physical piece
+      const int lc = pc ^ (r & 7);                // logical piece: columns lc*4 .. lc*4+3 of the chunk
+      float4 v;
+      const int k0 = q * GK + lc * 4;
+      v.x = k0 + 0 < d ? to_tf32(sm[(size_t) r * pitch + k0 + 0]) : 0.f;
+      v.y = k0 + 1 < d ? to_tf32(sm[(size_t) r * pitch + k0 + 1]) : 0.f;
+      v.z = k0 + 2 < d ? to_tf32(sm[(size_t) r * pitch + k0 + 2]) : 0.f;
+      v.w = k0 + 3 < d ? to_tf32(sm[(size_t) r * pitch + k0 + 3]) : 0.f;
+      *reinterpret_cast<float4*>(img + (size_t) q * G_CHUNK_FLOATS + r * GK + pc * 4) = v;
+    }
+  }
+}
+
+// lb[(s - s0)][t] = 0.999 x a lower bound of the squared distance between any frame of tile s and any frame of tile t:
+// max(box-to-box gap, (centre distance - radius_s - radius_t)^2); rounding slack is added by the caller's thresholds.
+// Block: 128 column tiles x LB_ROWS row tiles.
+constexpr int LB_ROWS = 8;
+__global__ void tile_lb_kernel(const float* __restrict__ tcen, const float* __restrict__ tlo, const float* __restrict__ thi,
+                               const float* __restrict__ trad, int d, size_t n_tiles, uint32_t s0, uint32_t s1, float* __restrict__ lb) {
+  extern __shared__ float sh[];                      // [LB_ROWS][3][d]
+  const uint32_t sb = s0 + blockIdx.y * LB_ROWS;
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  for (int q = threadIdx.x; q < LB_ROWS * d; q += blockDim.x) {
+    const int r = q / d, k = q % d;
+    const uint32_t s = min(sb + (uint32_t) r, s1 - 1);
+    sh[(r * 3 + 0) * d + k] = tcen[(size_t) k * n_tiles + s];
+    sh[(r * 3 + 1) * d + k] = tlo[(size_t) k * n_tiles + s];
+    sh[(r * 3 + 2) * d + k] = thi[(size_t) k * n_tiles + s];
+  }
+  __syncthreads();
+  if (t >= n_tiles) return;
+  float gap[LB_ROWS], cd[LB_ROWS];
+#pragma unroll
+  for (int r = 0; r < LB_ROWS; ++r) gap[r] = cd[r] = 0.f;
+  for (int k = 0; k < d; ++k) {
+    const float c = tcen[(size_t) k * n_tiles + t], lo = tlo[(size_t) k * n_tiles + t], hi = thi[(size_t) k * n_tiles + t];
+#pragma unroll
+    for (int r = 0; r < LB_ROWS; ++r) {
+      const float g = fmaxf(fmaxf(sh[(r * 3 + 1) * d + k] - hi, lo - sh[(r * 3 + 2) * d + k]), 0.f);
+      gap[r] = fmaf(g, g, gap[r]);
+      const float e = sh[(r * 3 + 0) * d + k] - c;
+      cd[r] = fmaf(e, e, cd[r]);
+    }
+  }
+  const float rt = trad[t];
+#pragma unroll
+  for (int r = 0; r < LB_ROWS; ++r) {
+    const uint32_t s = sb + (uint32_t) r;
+    if (s >= s1) break;
+    const float sph = fmaxf(sqrtf(cd[r]) * 0.9999f - trad[s] - rt, 0.f);
+    float v = fmaxf(gap[r], sph * sph) * 0.999f;
+    if (!(v == v)) v = 0.f;                        // empty tiles (inf - inf): never pruned, they hold nothing anyway
+    lb[(size_t) (s - s0) * n_tiles + t] = v;
+  }
+}
+
+// per-tile minimum of the float free-energy ranks (neighbour search: "the tile holds no frame of lower free energy")
+__global__ void tile_min_kernel(const float* __restrict__ lof, size_t n_tiles, float* __restrict__ lomin) {
+  const size_t tile = (size_t) blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const float4 q = *reinterpret_cast<const float4*>(lof + tile * GT + 4 * lane);
+  float m = fminf(fminf(q.x, q.y), fminf(q.z, q.w));
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) lomin[tile] = m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan geometry and shared memory
+// ------------------------------------------------------------------------------------------------
+
+struct GSmem {
+  float* a;                   // kc chunks
+  float* ring;                // n_stages chunks
+  float* side;                // G_SIDE_SLOTS records
+  float* scratch;             // G_EPI_THREADS x G_HALF
+  uint64_t *full, *empty;     // ring
+  uint64_t *side_full, *side_empty;
+  uint64_t *tmem_full, *tmem_empty;      // 2 each
+  uint64_t *a_full, *a_empty;
+  uint32_t* tmem_addr;
+  unsigned long long* wthr;   // [8 epilogue warps][2]: (item << 32 | float bits) bounds published for the producer (nn, hd)
+  __host__ __device__ static size_t bytes(int kc, int n_stages) {
+    return 1024 + (size_t) (kc + n_stages) * G_CHUNK_BYTES + (size_t) G_SIDE_SLOTS * G_SIDE_FLOATS * 4 +
+           (size_t) G_EPI_THREADS * G_HALF * 4 + (size_t) (2 * 8 + 2 * G_SIDE_SLOTS + 4 + 2) * 8 + 16 + 2 * G_EPI_WARPS * 8;
+  }
+  __device__ GSmem(unsigned char* raw, int kc, int n_stages) {
+    const uint32_t a0 = smem_u32(raw);
+    unsigned char* base = raw + ((1024u - (a0 & 1023u)) & 1023u);       // SWIZZLE_128B atoms need 1024-byte alignment
+    a = reinterpret_cast<float*>(base);
+    ring = a + (size_t) kc * G_CHUNK_FLOATS;
+    side = ring + (size_t) n_stages * G_CHUNK_FLOATS;
+    scratch = side + G_SIDE_SLOTS * G_SIDE_FLOATS;
+    full = reinterpret_cast<uint64_t*>(scratch + G_EPI_THREADS * G_HALF);
+    empty = full + 8;
+    side_full = empty + 8;
+    side_empty = side_full + G_SIDE_SLOTS;
+    tmem_full = side_empty + G_SIDE_SLOTS;
+    tmem_empty = tmem_full + 2;
+    a_full = tmem_empty + 2;
+    a_empty = a_full + 1;
+    wthr = reinterpret_cast<unsigned long long*>(a_empty + 1);
+    tmem_addr = reinterpret_cast<uint32_t*>(wthr + 2 * G_EPI_WARPS);
+  }
+};
+
+// side record meta
+struct GMeta {
+  uint32_t row_tile;       // row tile of the item, relative to row_begin / 128
+  uint32_t col0;           // first column (position) of the tile
+  uint32_t flags;          // 0: tile, 1: end of item, 2: end of stream
+  uint32_t item;
+};
+constexpr uint32_t G_END = 1u, G_EXIT = 2u;
+
+// work item -> (row tile, range of column tiles): column-step-major like item_coords (kernels.cuh), own neighbourhood first
+__device__ __forceinline__ void g_item_coords(const GemmGeom& g, uint32_t item, uint32_t* rb, uint32_t* ci) {
+  const uint32_t step = item / g.n_row_tiles;
+  *rb = item % g.n_row_tiles;
+  const uint32_t diag = min((g.row_begin / GT + *rb) / g.tiles_per_item, g.n_col_items - 1);
+  const uint32_t k = (step + 1) >> 1;
+  const uint32_t n = g.n_col_items;
+  *ci = (step & 1) ? (diag + k) % n : (diag + n - (k % n)) % n;
+}
+
+// Producer warp.  keep(rb, t, lbv, item, lane): warp-uniform decision taken right before a tile is streamed (dynamic bounds);
+// thr0(rb): the bound an item starts with; range(rb, lim0, lim1): restricts the column tiles (window pass).
+template <class Thr0, class Keep, class Range>
+__device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const float* __restrict__ side_extra, Thr0&& thr0, Keep&& keep,
+                                          Range&& range) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t total = g.n_row_tiles * g.n_col_items;
+  uint32_t stage = 0, phase = 0;          // chunk ring
+  uint32_t sseq = 0;                      // side records issued
+  uint32_t a_uses = 0;                    // items that loaded a row tile
+  unsigned long long streamed = 0;
+  const uint32_t side_bytes = (side_extra ? 2u : 1u) * GT * 4u;
+  auto side_slot = [&](uint32_t flags, uint32_t rb, uint32_t col0, uint32_t item, uint32_t tile, bool data) {
+    // lane 0 only
+    const uint32_t s = sseq % G_SIDE_SLOTS;
+    mbar_wait(&S.side_empty[s], ((sseq / G_SIDE_SLOTS) & 1u) ^ 1u);
+    float* rec = S.side + s * G_SIDE_FLOATS;
+    GMeta m;
+    m.row_tile = rb; m.col0 = col0; m.flags = flags; m.item = item;
+    *reinterpret_cast<GMeta*>(rec) = m;
+    if (data) {
+      mbar_arrive_expect_tx(&S.side_full[s], side_bytes);
+      tma_load_1d(rec + 4, g.gnorm + (size_t) tile * GT, GT * 4, &S.side_full[s]);
+      if (side_extra) tma_load_1d(rec + 4 + GT, side_extra + (size_t) tile * GT, GT * 4, &S.side_full[s]);
+    } else {
+      mbar_arrive(&S.side_full[s]);
+    }
+    ++sseq;
+  };
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(g.work_counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    uint32_t rb, ci;
+    g_item_coords(g, item, &rb, &ci);
+    uint32_t t0 = ci * g.tiles_per_item;
+    uint32_t t1 = min(t0 + g.tiles_per_item, g.n_tiles);
+    uint32_t lim0 = 0, lim1 = g.n_tiles;
+    range(rb, lim0, lim1);
+    t0 = max(t0, lim0);
+    t1 = min(t1, lim1);
+    if (t0 >= t1) continue;
+    const float th0 = thr0(rb);
+    const float* __restrict__ lbrow = g.lb + (size_t) rb * g.n_tiles;
+    bool first = true;
+    for (uint32_t base = t0; base < t1; base += 32) {
+      const uint32_t t = base + lane;
+      const float lbv = t < t1 ? __ldg(lbrow + t) : INFINITY;
+      uint32_t mask = __ballot_sync(0xffffffffu, t < t1 && !(lbv > th0));
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t tt = base + (uint32_t) src;
+        if (!keep(rb, tt, __shfl_sync(0xffffffffu, lbv, src), item, lane)) continue;
+        if (lane == 0) {
+          if (first) {
+            // the row tile's operand image: resident for the whole item
+            mbar_wait(&S.a_empty[0], (a_uses & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&S.a_full[0], (uint32_t) g.kc * G_CHUNK_BYTES);
+            const float* src_a = g.gT + (size_t) (g.row_begin / GT + rb) * g.kc * G_CHUNK_FLOATS;
+            for (int q = 0; q < g.kc; ++q)
+              tma_load_1d(S.a + (size_t) q * G_CHUNK_FLOATS, src_a + (size_t) q * G_CHUNK_FLOATS, G_CHUNK_BYTES, &S.a_full[0]);
+          }
+          side_slot(0u, rb, tt * GT, item, tt, true);
+          const float* src_b = g.gT + (size_t) tt * g.kc * G_CHUNK_FLOATS;
+          for (int q = 0; q < g.kc; ++q) {
+            mbar_wait(&S.empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&S.full[stage], G_CHUNK_BYTES);
+            tma_load_1d(S.ring + (size_t) stage * G_CHUNK_FLOATS, src_b + (size_t) q * G_CHUNK_FLOATS, G_CHUNK_BYTES, &S.full[stage]);
+            if (++stage == (uint32_t) g.n_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        if (first) ++a_uses;
+        first = false;
+        ++streamed;
+        __syncwarp();
+      }
+    }
+    if (!first && lane == 0) {
+      // end of the item: one marker for each epilogue warpgroup (consecutive sequence numbers have both parities)
+      side_slot(G_END, rb, 0, item, 0, false);
+      side_slot(G_END, rb, 1, item, 0, false);
+    }
+  }
+  if (lane == 0) {
+    side_slot(G_EXIT, 0, 0, 0xffffffffu, 0, false);
+    side_slot(G_EXIT, 0, 1, 0xffffffffu, 0, false);
+    if (g.stats && streamed) atomicAdd(g.stats + 2, streamed);
+  }
+}
+
+// MMA warp: follows the side records; per tile kc chunks x (up to 4) K=8 steps into accumulator stage (sequence & 1)
+__device__ __forceinline__ void g_mma(const GemmGeom& g, GSmem& S, uint32_t tmem_base) {
+  const int lane = threadIdx.x & 31;
+  uint32_t stage = 0, phase = 0, seq = 0, a_uses = 0;
+  uint32_t acc_uses[2] = {0u, 0u};
+  bool need_a = true;
+  for (;;) {
+    const uint32_t s = seq % G_SIDE_SLOTS;
+    mbar_wait(&S.side_full[s], (seq / G_SIDE_SLOTS) & 1u);
+    const GMeta m = *reinterpret_cast<const GMeta*>(S.side + s * G_SIDE_FLOATS);
+    if (m.flags & G_EXIT) break;
+    if (m.flags & G_END) {
+      if (m.col0 == 0) {
+        if (lane == 0) tc_commit(&S.a_empty[0]);     // the row tile may be replaced once every MMA of the item has read it
+        need_a = true;
+      }
+    } else {
+      if (need_a) {
+        mbar_wait(&S.a_full[0], a_uses & 1u);
+        ++a_uses;
+        need_a = false;
+      }
+      const uint32_t acc = seq & 1u;
+      mbar_wait(&S.tmem_empty[acc], (acc_uses[acc] & 1u) ^ 1u);
+      acc_uses[acc] += 1;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t) GT;
+      for (int q = 0; q < g.kc; ++q) {
+        mbar_wait(&S.full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t ad = g_smem_desc(smem_u32(S.a + (size_t) q * G_CHUNK_FLOATS));
+          const uint64_t bd = g_smem_desc(smem_u32(S.ring + (size_t) stage * G_CHUNK_FLOATS));
+          const int steps = min(4, g.k8 - 4 * q);
+          for (int k = 0; k < steps; ++k)
+            tc_mma_tf32(d_tmem, ad + (uint64_t) (2 * k), bd + (uint64_t) (2 * k), G_IDESC, (q | k) ? 1u : 0u);
+          tc_commit(&S.empty[stage]);
+          if (q == g.kc - 1) tc_commit(&S.tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t) g.n_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.side_empty[s]);
+    ++seq;
+  }
+}
+
+__device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    for (int s = 0; s < G_SIDE_SLOTS; ++s) {
+      mbar_init(&S.side_full[s], 1);
+      mbar_init(&S.side_empty[s], 5);          // MMA warp + the four warps of the warpgroup that owns the record
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&S.tmem_full[s], 1);
+      mbar_init(&S.tmem_empty[s], 4);
+    }
+    mbar_init(&S.a_full[0], 1);
+    mbar_init(&S.a_empty[0], 1);
+    for (int q = 0; q < 2 * G_EPI_WARPS; ++q) S.wthr[q] = ~0ull;
+    fence_mbar_init();
+  }
+}
+
+// band half width around a decision value at distance r (d2 = r^2):  2 r rho + rho^2 + eps + e_rel r^2, rounded up
+__device__ __forceinline__ float g_band(float r, float r2, float rho, float eps, float e_rel) {
+  return fmaf(e_rel, r2, fmaf(2.0f * r, rho, fmaf(rho, rho, eps))) * 1.0001f;
+}
+
+// ================================================================================================
+// populations (count mode, up to 8 radii per pass)
+// ================================================================================================
+
+template <int NB, bool CHECK>
+__global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_constant__ GPopsArgs a) {
+  extern __shared__ unsigned char g_smem_raw[];
+  const GemmGeom& g = a.g;
+  GSmem S(g_smem_raw, g.kc, g.n_stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  g_init(g, S);
+  __syncthreads();
+  if (warp == 1) tmem_alloc(S.tmem_addr, 2 * GT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(S.tmem_addr);
+
+  if (warp == 0) {
+    g_produce(g, S, nullptr, [&](uint32_t) { return g.prune_thr; }, [](uint32_t, uint32_t, float, uint32_t, int) { return true; },
+              [](uint32_t, uint32_t&, uint32_t&) {});
+  } else if (warp == 1) {
+    g_mma(g, S, tmem_base);
+  } else {
+    const uint32_t wg = (uint32_t) (warp - 2) >> 2;                 // accumulator stage this warpgroup serves
+    const uint32_t quarter = (uint32_t) warp & 3u;                  // TMEM lanes 32 quarter .. 32 quarter + 31
+    const uint32_t row_in_tile = quarter * 32u + (uint32_t) lane;
+    const int et = (warp - 2) * 32 + lane;
+    float* scratch = S.scratch + et;
+    uint32_t seq = wg, uses = 0, cur_item = 0xfffffffeu, row = 0;
+    bool valid = false;
+    float q[NB], E[NB], xn = INFINITY;
+    uint32_t cnt[NB];
+    uint32_t n_slow = 0, n_exact = 0, n_tiles = 0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { cnt[b] = 0; q[b] = INFINITY; E[b] = 0.f; }
+    for (;;) {
+      const uint32_t s = seq % G_SIDE_SLOTS;
+      mbar_wait(&S.side_full[s], (seq / G_SIDE_SLOTS) & 1u);
+      const float* rec = S.side + s * G_SIDE_FLOATS;
+      const GMeta m = *reinterpret_cast<const GMeta*>(rec);
+      if (m.flags & G_EXIT) break;
+      if (m.flags & G_END) {
+        if (cur_item == m.item && valid) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            if (cnt[b]) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + (row - g.row_begin), cnt[b]);
+        }
+        cur_item = 0xfffffffeu;
+      } else {
+        if (cur_item != m.item) {
+          cur_item = m.item;
+          row = g.row_begin + m.row_tile * GT + row_in_tile;
+          valid = row < g.row_end;
+          xn = valid ? __ldg(g.gnorm + row) : INFINITY;
+          const float rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
+          const float eps = g.c_acc * (xn + g.nymax);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            cnt[b] = 0;
+            q[b] = xn - a.rad2[b];
+            // the sign of F - r^2 decides outside the band; monotonicity of d^2 -+ band(d) needs r > rho
+            E[b] = (a.rad[b] > 1.01f * rho) ? g_band(a.rad[b], a.rad2[b], rho, eps, g.e_rel) + 4.8e-7f * fabsf(q[b]) : INFINITY;
+            if (a.rad2[b] < 0.f) E[b] = -1.f;                         // unused slot
+          }
+        }
+        mbar_wait(&S.tmem_full[wg], uses & 1u);
+        ++uses;
+        tc_fence_after();
+        ++n_tiles;
+        const float* ny = rec + 4;
+#pragma unroll 1
+        for (int c0 = 0; c0 < GT; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((quarter * 32u) << 16) + wg * (uint32_t) GT + (uint32_t) c0, v);
+#pragma unroll
+          for (int h = 0; h < 32; h += G_HALF) {
+            float mn[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) mn[b] = INFINITY;
+#pragma unroll
+            for (int c4 = 0; c4 < G_HALF; c4 += 4) {
+              const float4 n4 = *reinterpret_cast<const float4*>(ny + c0 + h + c4);
+              const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float w = fmaf(v[h + c4 + c], -2.0f, nn[c]);
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                  const float vv = w + q[b];
+                  cnt[b] += __float_as_uint(vv) >> 31;
+                  mn[b] = fminf(mn[b], fabsf(vv));
+                }
+              }
+            }
+            bool band = false;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) band |= mn[b] <= E[b];
+            if (CHECK || band) {
+              // rare: a pair of these 16 columns lies within the band of a radius; replace its sign decision by the exact one
+#pragma unroll
+              for (int c = 0; c < G_HALF; ++c) scratch[c * G_EPI_THREADS] = v[h + c];
+#pragma unroll 1
+              for (int c = 0; c < G_HALF; ++c) {
+                const float w = fmaf(scratch[c * G_EPI_THREADS], -2.0f, ny[c0 + h + c]);
+                const uint32_t col = m.col0 + (uint32_t) (c0 + h + c);
+                float d2 = 0.f;
+                bool have = false;
+                if (CHECK && valid && col < g.n && g.check) {
+                  d2 = dist2_exact_rm(g.xR, g.d, row, col);
+                  have = true;
+                  const float rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
+                  const float bnd = g_band(sqrtf(d2), d2, rho, g.c_acc * (xn + g.nymax), g.e_rel);
+                  const float ratio = fabsf((w + xn) - d2) / bnd;
+                  atomicMax(reinterpret_cast<unsigned int*>(g.check), __float_as_uint(ratio));
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                  const float vv = w + q[b];
+                  if (fabsf(vv) <= E[b] && valid) {
+                    ++n_slow;
+                    if (!have) {
+                      d2 = dist2_exact_rm(g.xR, g.d, row, col);
+                      have = true;
+                      ++n_exact;
+                    }
+                    const uint32_t inside = d2 < a.rad2[b] ? 1u : 0u;      // NaN (padding) -> outside
+                    cnt[b] += inside - (__float_as_uint(vv) >> 31);
+                  }
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.side_empty[s]);
+      seq += 2;
+    }
+    // statistics
+    for (int o = 16; o > 0; o >>= 1) {
+      n_slow += __shfl_xor_sync(0xffffffffu, n_slow, o);
+      n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+    }
+    if (lane == 0 && g.stats) {
+      if (n_slow) atomicAdd(g.stats, (unsigned long long) n_slow);
+      if (n_exact) atomicAdd(g.stats + 1, (unsigned long long) n_exact);
+      if (n_tiles && quarter == 0) atomicAdd(g.stats + 3, (unsigned long long) n_tiles);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * GT);
+}
+
+// ================================================================================================
+// nearest neighbours
+// ================================================================================================
+
+__device__ __forceinline__ float g_key_d2(unsigned long long k) { return __uint_as_float((uint32_t) (k >> 32)); }
+
+__global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_constant__ GNnArgs a) {
+  extern __shared__ unsigned char g_smem_raw[];
+  const GemmGeom& g = a.g;
+  GSmem S(g_smem_raw, g.kc, g.n_stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  g_init(g, S);
+  __syncthreads();
+  if (warp == 1) tmem_alloc(S.tmem_addr, 2 * GT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(S.tmem_addr);
+
+  if (warp == 0) {
+    // A tile is needed if it can hold a nearest neighbour of some row (lb <= thr_nn), or a lower-free-energy neighbour
+    // (lb <= thr_hd) and it holds a frame of lower rank than the rows' largest one at all.
+    float bound_nn = 0.f, bound_hd = 0.f, lmax = 0.f;
+    g_produce(g, S, a.lof,
+              [&](uint32_t rb) {
+                // max over the four quarters of the row tile
+                const int ql = lane & 3;
+                float bn = *reinterpret_cast<volatile float*>(a.thr_nn + (size_t) rb * 4 + ql);
+                float bh = *reinterpret_cast<volatile float*>(a.thr_hd + (size_t) rb * 4 + ql);
+                float lm = __ldg(a.lormax + (size_t) rb * 4 + ql);
+                if (!(bn < INFINITY)) bn = INFINITY;
+                if (!(bh < INFINITY)) bh = INFINITY;
+                bound_nn = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(bn, 0.f))));
+                bound_hd = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(bh, 0.f))));
+                lmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(lm, 0.f))));
+                return fmaxf(bound_nn, bound_hd);
+              },
+              [&](uint32_t, uint32_t tt, float lbv, uint32_t item, int ln) {
+                // What the epilogue warps found since the item started.  Lane l < 16 reads slot l: warp l >> 1 (warps 0-3:
+                // warpgroup 0, 4-7: warpgroup 1), l & 1: nn / hd.  A warpgroup's bound is the max over its four warps (a warp
+                // that has not published for this item yet: +inf); both warpgroups hold valid bounds for the same rows, so
+                // the tighter one counts.
+                uint32_t bits = 0x7f800000u;
+                if (ln < 16) {
+                  const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(S.wthr + ln);
+                  if ((uint32_t) (v >> 32) == item) bits = (uint32_t) v;
+                }
+                // lanes with equal (l & 1) and equal (l >> 3): xor 2, 4 combine the four warps of a warpgroup
+                bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, 2));
+                bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, 4));
+                const float bn = fminf(bound_nn, fminf(__uint_as_float(__shfl_sync(0xffffffffu, bits, 0)),
+                                                       __uint_as_float(__shfl_sync(0xffffffffu, bits, 8))));
+                const float bh = fminf(bound_hd, fminf(__uint_as_float(__shfl_sync(0xffffffffu, bits, 1)),
+                                                       __uint_as_float(__shfl_sync(0xffffffffu, bits, 9))));
+                if (!(lbv > bn)) return true;
+                return !(lbv > bh) && __ldg(a.lomin + tt) < lmax;
+              },
+              [&](uint32_t rb, uint32_t& lim0, uint32_t& lim1) {
+                if (a.window) {
+                  const uint32_t t = g.row_begin / GT + rb;
+                  lim0 = t > a.window ? t - a.window : 0u;
+                  lim1 = min(lim1, t + a.window + 1);
+                }
+              });
+  } else if (warp == 1) {
+    g_mma(g, S, tmem_base);
+  } else {
+    const uint32_t wg = (uint32_t) (warp - 2) >> 2;
+    const uint32_t quarter = (uint32_t) warp & 3u;
+    const uint32_t row_in_tile = quarter * 32u + (uint32_t) lane;
+    const int et = (warp - 2) * 32 + lane;
+    float* scratch = S.scratch + et;
+    uint32_t seq = wg, uses = 0, cur_item = 0xfffffffeu, row = 0, lo_i = 0;
+    bool valid = false;
+    float xn = INFINITY, rho = 0.f, eps = 0.f, lor = 0.f;
+    float t_nn = -INFINITY, t_hd = -INFINITY, dl = 0.f;
+    unsigned long long best_nn = ~0ull, best_hd = ~0ull;
+    uint32_t n_slow = 0, n_exact = 0, n_tiles = 0;
+    // every column whose exact d2 is <= b satisfies  fma(acc, -2, |y~|^2) < thr(b)
+    auto thr = [&](float b) {
+      if (!(b < FLT_MAX)) return INFINITY;
+      const float b1 = fmaf(1.01f * g.e_rel, b, b);
+      const float T = b1 + g_band(sqrtf(b1) * 1.000001f, b1, rho, eps, g.e_rel);
+      return next_up(next_up(fmaf(T, 1.000001f, -xn) + 2.4e-7f * (T + xn)));
+    };
+    auto set_dl = [&]() {
+      float v = 0.f;
+      if (t_nn < INFINITY) v = t_hd < INFINITY ? fminf(next_up((t_hd - t_nn) * 1.000001f), 1e37f) : 1e37f;
+      dl = fmaxf(v, 0.f);
+    };
+    // bound (d2 units, pruning margins included) of what this row still accepts
+    auto row_bound = [&](unsigned long long key) {
+      const float b = g_key_d2(key);
+      float v = (fmaf(g.e_rel, b, b) + g.prune_slack) * 1.00001f;
+      if (!(v < INFINITY)) v = INFINITY;
+      return v;
+    };
+    auto publish = [&]() {
+      float vn = valid ? row_bound(best_nn) : 0.f;
+      float vh = (valid && lo_i != 0) ? row_bound(best_hd) : 0.f;
+      const uint32_t bn = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(vn, 0.f)));
+      const uint32_t bh = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(vh, 0.f)));
+      return make_uint2(bn, bh);
+    };
+    for (;;) {
+      const uint32_t s = seq % G_SIDE_SLOTS;
+      mbar_wait(&S.side_full[s], (seq / G_SIDE_SLOTS) & 1u);
+      const float* rec = S.side + s * G_SIDE_FLOATS;
+      const GMeta m = *reinterpret_cast<const GMeta*>(rec);
+      if (m.flags & G_EXIT) break;
+      if (m.flags & G_END) {
+        if (cur_item == m.item) {
+          if (valid) {
+            atomicMin(a.key_nn + (row - g.row_begin), best_nn);
+            atomicMin(a.key_hd + (row - g.row_begin), best_hd);
+          }
+          // what this warp's rows still accept bounds every later item of the row tile (the other warpgroup's warp of the
+          // same quarter holds the same rows: both bounds are valid, atomicMin keeps the tighter)
+          const uint2 b = publish();
+          if (lane == 0) {
+            atomicMin(reinterpret_cast<unsigned int*>(a.thr_nn) + (size_t) m.row_tile * 4 + quarter, b.x);
+            atomicMin(reinterpret_cast<unsigned int*>(a.thr_hd) + (size_t) m.row_tile * 4 + quarter, b.y);
+          }
+        }
+        cur_item = 0xfffffffeu;
+      } else {
+        const bool first_of_item = cur_item != m.item;
+        if (first_of_item) {
+          cur_item = m.item;
+          row = g.row_begin + m.row_tile * GT + row_in_tile;
+          valid = row < g.row_end;
+          xn = valid ? __ldg(g.gnorm + row) : INFINITY;
+          rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
+          eps = g.c_acc * (xn + g.nymax);
+          best_nn = valid ? a.key_nn[row - g.row_begin] : 0ull;
+          best_hd = valid ? a.key_hd[row - g.row_begin] : 0ull;
+          lo_i = valid ? __ldg(a.lo + row) : 0u;
+          lor = valid ? __ldg(a.lof + row) + a.lo_bias : 0.f;
+          t_nn = valid ? thr(g_key_d2(best_nn)) : -INFINITY;
+          // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
+          t_hd = (valid && lo_i != 0) ? thr(g_key_d2(best_hd)) : t_nn;
+          set_dl();
+        }
+        mbar_wait(&S.tmem_full[wg], uses & 1u);
+        ++uses;
+        tc_fence_after();
+        ++n_tiles;
+        const float* ny = rec + 4;
+        const float* lc = rec + 4 + GT;
+        bool improved = false;
+#pragma unroll 1
+        for (int c0 = 0; c0 < GT; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((quarter * 32u) << 16) + wg * (uint32_t) GT + (uint32_t) c0, v);
+#pragma unroll
+          for (int h = 0; h < 32; h += G_HALF) {
+            bool any = false;
+#pragma unroll
+            for (int c4 = 0; c4 < G_HALF; c4 += 4) {
+              const float4 n4 = *reinterpret_cast<const float4*>(ny + c0 + h + c4);
+              const float4 l4 = *reinterpret_cast<const float4*>(lc + c0 + h + c4);
+              const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float w = fmaf(v[h + c4 + c], -2.0f, nn[c]);
+                any |= w < fmaf(__saturatef(lor - ll[c]), dl, t_nn);
+              }
+            }
+            if (any) {
+#pragma unroll
+              for (int c = 0; c < G_HALF; ++c) scratch[c * G_EPI_THREADS] = v[h + c];
+#pragma unroll 1
+              for (int c = 0; c < G_HALF; ++c) {
+                const float w = fmaf(scratch[c * G_EPI_THREADS], -2.0f, ny[c0 + h + c]);
+                if (!(w < fmaf(__saturatef(lor - lc[c0 + h + c]), dl, t_nn))) continue;
+                const uint32_t j = m.col0 + (uint32_t) (c0 + h + c);
+                ++n_slow;
+                if (j == row || j >= g.n || !valid) continue;
+                const bool hd_cand = __ldg(a.lo + j) < lo_i;
+                if (!(w < t_nn) && !(hd_cand && w < t_hd)) continue;
+                const float d2 = dist2_exact_rm(g.xR, g.d, row, j);
+                ++n_exact;
+                if (!(d2 < FLT_MAX)) continue;
+                const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | __ldg(a.perm + j);
+                bool changed = false;
+                if (key < best_nn) {
+                  best_nn = key;
+                  t_nn = thr(d2);
+                  if (lo_i == 0) t_hd = t_nn;
+                  changed = true;
+                }
+                if (hd_cand && key < best_hd) {
+                  best_hd = key;
+                  t_hd = thr(d2);
+                  changed = true;
+                }
+                if (changed) { set_dl(); improved = true; }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+        // bounds for the producer's dynamic pruning of this item: one slot pair per epilogue warp
+        if (first_of_item || __any_sync(0xffffffffu, improved)) {
+          const uint2 b = publish();
+          if (lane == 0) {
+            S.wthr[2 * (warp - 2)] = ((unsigned long long) m.item << 32) | b.x;
+            S.wthr[2 * (warp - 2) + 1] = ((unsigned long long) m.item << 32) | b.y;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.side_empty[s]);
+      seq += 2;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      n_slow += __shfl_xor_sync(0xffffffffu, n_slow, o);
+      n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+    }
+    if (lane == 0 && g.stats) {
+      if (n_slow) atomicAdd(g.stats, (unsigned long long) n_slow);
+      if (n_exact) atomicAdd(g.stats + 1, (unsigned long long) n_exact);
+      if (n_tiles && quarter == 0) atomicAdd(g.stats + 3, (unsigned long long) n_tiles);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * GT);
+}
+
+// per 32-row quarter of every row tile: bounds after seeding (max over the rows' seeded d2, margins included) and the
+// largest filter rank among the rows that can have a lower-free-energy neighbour
+__global__ void gnn_tile_thr_kernel(const unsigned long long* __restrict__ key_nn, const unsigned long long* __restrict__ key_hd,
+                                    const uint32_t* __restrict__ lo, const float* __restrict__ lof, float lo_bias, uint32_t row_begin,
+                                    uint32_t row_end, float e_rel, float slack, float* __restrict__ thr_nn, float* __restrict__ thr_hd,
+                                    float* __restrict__ lormax) {
+  const uint32_t rb = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t i = row_begin + rb * GT + threadIdx.x;
+  float vn = 0.f, vh = 0.f, lm = 0.f;
+  if (i < row_end) {
+    const float dn = __uint_as_float((uint32_t) (key_nn[i - row_begin] >> 32));
+    vn = (fmaf(e_rel, dn, dn) + slack) * 1.00001f;
+    if (!(vn < INFINITY)) vn = INFINITY;
+    if (lo[i] != 0) {
+      const float dh = __uint_as_float((uint32_t) (key_hd[i - row_begin] >> 32));
+      vh = (fmaf(e_rel, dh, dh) + slack) * 1.00001f;
+      if (!(vh < INFINITY)) vh = INFINITY;
+      lm = lof[i] + lo_bias;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    vn = fmaxf(vn, __shfl_xor_sync(0xffffffffu, vn, o));
+    vh = fmaxf(vh, __shfl_xor_sync(0xffffffffu, vh, o));
+    lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+  }
+  if (lane == 0) {
+    thr_nn[(size_t) rb * 4 + warp] = vn;
+    thr_hd[(size_t) rb * 4 + warp] = vh;
+    lormax[(size_t) rb * 4 + warp] = lm;
+  }
+}
+
+#endif  // DCB_GEMM_KERNELS
+
+}  // namespace dcb

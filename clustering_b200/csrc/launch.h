@@ -1,6 +1,8 @@
 // Host-callable launchers of the per-dimension kernel instantiations (kern_inst.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
 
 namespace dcb {
 struct PopsArgs;
@@ -20,4 +22,19 @@ struct ScreenArgs;
   int occupancy_screen_d##D(int d);
 DCB_FOR_EACH_D(DCB_DECL)
 #undef DCB_DECL
+
+// GEMM-form (tcgen05) path, gemm_inst.cu
+struct GPopsArgs;
+struct GNnArgs;
+size_t gemm_smem_bytes(int kc, int n_stages);
+cudaError_t launch_gpack(const float* coords, size_t n, int d, int kc, size_t n_tiles, const float* centre, const uint32_t* perm, float* gT,
+                         float* gnorm, float* xR, float* tcen, float* tlo, float* thi, float* trad, cudaStream_t st);
+cudaError_t launch_tile_lb(const float* tcen, const float* tlo, const float* thi, const float* trad, int d, size_t n_tiles, uint32_t s0,
+                           uint32_t s1, float* lb, cudaStream_t st);
+cudaError_t launch_tile_min(const float* lof, size_t n_tiles, float* lomin, cudaStream_t st);
+cudaError_t launch_gpops(const GPopsArgs& a, int grid, bool check, cudaStream_t st);
+cudaError_t launch_gnn(const GNnArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_gnn_tile_thr(const unsigned long long* key_nn, const unsigned long long* key_hd, const uint32_t* lo, const float* lof,
+                                float lo_bias, uint32_t row_begin, uint32_t row_end, uint32_t n_row_tiles, float e_rel, float slack,
+                                float* thr_nn, float* thr_hd, float* lormax, cudaStream_t st);
 }  // namespace dcb

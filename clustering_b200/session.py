@@ -54,6 +54,12 @@ class Session:
         lib.check(self.L.dcb200_ctx_ffma_peak(self.h, float(ms_target), C.byref(t)))
         return t.value
 
+    def gemm_info(self):
+        """(active, check_ratio) of the GEMM-form tensor-core path (32 <= n_cols <= 256), see dcb200_ctx_gemm_info."""
+        a, r = C.c_int(0), C.c_float(0.0)
+        lib.check(self.L.dcb200_ctx_gemm_info(self.h, C.byref(a), C.byref(r)))
+        return bool(a.value), float(r.value)
+
     # ---- coordinates
     def set_coords(self, coords, keep_order=False):
         """coords: numpy [n][d] (host upload) or a CUDA torch tensor [n][d] (adopted from device memory).
