@@ -514,6 +514,7 @@ struct dcb200_ctx {
   uint32_t lb_s0 = 0, lb_s1 = 0;
   DevBuf<float> lomin, gthr;        // per-tile min rank; per row tile and quarter: thr_nn, thr_hd, lormax
   float* gcheck = nullptr;          // [2] diagnostics of the CHECK kernel
+  unsigned long long* gprof = nullptr;   // [16] cycle counters of the GEMM-form kernels (DCB200_GEMM_PROF=1)
 };
 
 static float up(double v) {          // smallest float >= v
@@ -705,6 +706,7 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   c->io_u32.release(); c->io_f32.release();
   c->gT.release(); c->gnorm.release(); c->xR.release(); c->thdr.release(); c->lbmat.release(); c->lomin.release(); c->gthr.release();
   if (c->gcheck) cudaFree(c->gcheck);
+  if (c->gprof) cudaFree(c->gprof);
   cudaFree(c->scalars);
   cudaFree(c->stats);
   cudaStreamDestroy(c->stream);
@@ -800,9 +802,12 @@ static int fill_ggeom(dcb200_ctx* c, size_t row_begin, size_t row_end, GemmGeom*
   g->k8 = c->g_k8;
   int dev_smem = 0;
   CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  g->n_stages = 8;
-  while (g->n_stages > 2 && gemm_smem_bytes(g->kc, g->n_stages) > (size_t) dev_smem) --g->n_stages;
-  if (gemm_smem_bytes(g->kc, g->n_stages) > (size_t) dev_smem) return fail("dcb200: GEMM-form kernel does not fit in shared memory");
+  int avail = 8;
+  while (avail > 2 && gemm_smem_bytes(g->kc, avail) > (size_t) dev_smem) --avail;
+  if (gemm_smem_bytes(g->kc, avail) > (size_t) dev_smem) return fail("dcb200: GEMM-form kernel does not fit in shared memory");
+  // ring slots are freed in commit groups of cb chunks (at least two groups in the ring)
+  g->cb = avail >= 8 ? 4 : avail >= 4 ? 2 : 1;
+  g->n_stages = avail / g->cb * g->cb;
   g->n = (uint32_t) c->n;
   g->n_tiles = (uint32_t) c->g_tiles;
   g->row_begin = (uint32_t) row_begin;
@@ -826,7 +831,15 @@ static int fill_ggeom(dcb200_ctx* c, size_t row_begin, size_t row_end, GemmGeom*
   g->nymax = c->g_nymax;
   g->prune_slack = prune_slack;
   g->prune_thr = INFINITY;
-  c->launches += 0;
+  g->spin = 0;
+  {
+    const char* e = getenv("DCB200_GEMM_PROF");
+    if (e && e[0] == '1') {
+      if (!c->gprof) CK(cudaMalloc(&c->gprof, 16 * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(c->gprof, 0, 16 * sizeof(unsigned long long), c->stream));
+      g->prof = c->gprof;
+    }
+  }
   c->pairs_scheduled += (uint64_t) (row_end - row_begin) * (uint64_t) c->n;
   return 0;
 }
@@ -934,6 +947,19 @@ extern "C" int dcb200_ctx_to_frame_order(dcb200_ctx* c, const uint32_t* dev_src,
   return 0;
 }
 
+static int dump_gprof(dcb200_ctx* c, const char* what, int grid) {
+  if (!c->gprof || !getenv("DCB200_GEMM_PROF")) return 0;
+  unsigned long long h[16];
+  CK(cudaMemcpyAsync(h, c->gprof, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  static const char* names[12] = {"prod side_empty wait", "prod ring empty wait", "prod a_empty wait", "prod total", "mma side_full wait",
+                                  "mma a_full wait", "mma tmem_empty wait", "mma ring full wait", "mma total", "epi side_full wait",
+                                  "epi tmem_full wait", "epi total"};
+  fprintf(stderr, "[dcb200] %s: cycles per CTA (grid %d)\n", what, grid);
+  for (int q = 0; q < 12; ++q) fprintf(stderr, "[dcb200]   %-22s %12.0f\n", names[q], (double) h[q] / grid / (q >= 9 ? 2 : 1));
+  return 0;
+}
+
 // ---- populations ----------------------------------------------------------------------------
 // GEMM-form passes (tensor cores): up to eight distinct radii per pass, largest radii first, each pass pruned by its own r_max
 static int gemm_populations(dcb200_ctx* c, const float* radii, size_t n_radii, const std::vector<float>& rad2, const std::vector<float>& uniq,
@@ -969,6 +995,7 @@ static int gemm_populations(dcb200_ctx* c, const float* radii, size_t n_radii, c
     CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
     CK(launch_gpops(a, grid, check, c->stream));
     c->launches += 1;
+    CKI(dump_gprof(c, "gscan_pops", grid));
     FinalizeArgs f;
     f.n_out = 0;
     f.cumulative = 1;

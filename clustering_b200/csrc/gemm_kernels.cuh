@@ -35,7 +35,8 @@ constexpr int GK = 32;                       // floats per K-chunk row = 128 byt
 constexpr int G_CHUNK_FLOATS = GT * GK;      // 4096 floats = 16 KB
 constexpr int G_CHUNK_BYTES = G_CHUNK_FLOATS * 4;
 constexpr int G_MIN_D = 32, G_MAX_D = 256;
-constexpr int G_SIDE_SLOTS = 4;              // per-tile side records in flight
+constexpr int G_SIDE_SLOTS = 8;              // per-tile side records in flight
+constexpr int G_ACC = 4;                     // accumulator stages in tensor memory (4 x 128 columns = all of it)
 constexpr int G_SIDE_FLOATS = 4 + 2 * GT;    // meta (16 B), |y~|^2 [128], rank floats [128]
 constexpr int G_EPI_WARPS = 8;
 constexpr int G_EPI_THREADS = G_EPI_WARPS * 32;
@@ -51,7 +52,8 @@ struct GemmGeom {
   const float* xR;            // [ld][d]
   const float* lb;            // [row tiles of this launch][n_tiles]
   int d, kc, k8;              // dims, K-chunks per tile, total K=8 MMA steps (ceil(d/8))
-  int n_stages;               // ring depth (chunks)
+  int n_stages;               // ring depth (chunks), a multiple of cb
+  int cb;                     // chunks per commit group: the MMA warp frees ring slots cb at a time (tcgen05.commit is not free)
   uint32_t n;                 // real frame count
   uint32_t n_tiles;           // column tiles (= ld / 128)
   uint32_t row_begin, row_end;   // positions of this shard, row_begin % 128 == 0
@@ -65,6 +67,8 @@ struct GemmGeom {
   float e_rel;                // relative error of the reference's own arithmetic against the real-number distance
   float prune_slack;          // absolute slack of the tile lower bounds
   float prune_thr;            // static pruning threshold (d2 units); +inf: none
+  unsigned long long* prof;   // optional [16] cycle counters per role (diagnostics, DCB200_GEMM_PROF=1), see g_prof_names in api.cu
+  int spin;                   // experiment: 1 = waits on tensor-core-committed barriers spin without a suspend hint
   float* check;               // optional [2]: max observed |F - d2e| / band (float bits, atomicMax), CHECK builds only
 };
 
@@ -123,23 +127,45 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// 32 consecutive accumulator columns of this thread's TMEM lane: asynchronous load, then a wait that every later use of
+// the registers depends on (the "+r" operands), so that the next load can be in flight while a chunk is processed
+#define G_R32(X, r) X(r[0]), X(r[1]), X(r[2]), X(r[3]), X(r[4]), X(r[5]), X(r[6]), X(r[7]), X(r[8]), X(r[9]), X(r[10]), X(r[11]), X(r[12]), \
+    X(r[13]), X(r[14]), X(r[15]), X(r[16]), X(r[17]), X(r[18]), X(r[19]), X(r[20]), X(r[21]), X(r[22]), X(r[23]), X(r[24]), X(r[25]),     \
+    X(r[26]), X(r[27]), X(r[28]), X(r[29]), X(r[30]), X(r[31])
+#define G_OUT(x) "=r"(x)
+#define G_INOUT(x) "+r"(x)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : G_R32(G_OUT, r)
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : G_R32(G_INOUT, r)::"memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32_issue(taddr, r);
+  tmem_ld32_wait(r);
 #pragma unroll
   for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform (role dispatch, uniform-datapath operands of tcgen05.mma)
+__device__ __forceinline__ int uniform_warp() { return __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0); }
 
 // Shared-memory matrix descriptor of a [128 rows][32 floats] K-major operand chunk with 128-byte swizzle:
 // start address >> 4 in bits [0,14), leading byte offset (unused for swizzled K-major) 1 in [16,30), stride byte offset
@@ -349,15 +375,15 @@ struct GSmem {
   float* ring;                // n_stages chunks
   float* side;                // G_SIDE_SLOTS records
   float* scratch;             // G_EPI_THREADS x G_HALF
-  uint64_t *full, *empty;     // ring
+  uint64_t *full, *empty;     // ring: full per slot, empty per commit group of cb slots
   uint64_t *side_full, *side_empty;
-  uint64_t *tmem_full, *tmem_empty;      // 2 each
+  uint64_t *tmem_full, *tmem_empty;      // G_ACC each
   uint64_t *a_full, *a_empty;
   uint32_t* tmem_addr;
   unsigned long long* wthr;   // [8 epilogue warps][2]: (item << 32 | float bits) bounds published for the producer (nn, hd)
   __host__ __device__ static size_t bytes(int kc, int n_stages) {
     return 1024 + (size_t) (kc + n_stages) * G_CHUNK_BYTES + (size_t) G_SIDE_SLOTS * G_SIDE_FLOATS * 4 +
-           (size_t) G_EPI_THREADS * G_HALF * 4 + (size_t) (2 * 8 + 2 * G_SIDE_SLOTS + 4 + 2) * 8 + 16 + 2 * G_EPI_WARPS * 8;
+           (size_t) G_EPI_THREADS * G_HALF * 4 + (size_t) (2 * 8 + 2 * G_SIDE_SLOTS + 2 * G_ACC + 2) * 8 + 16 + 2 * G_EPI_WARPS * 8;
   }
   __device__ GSmem(unsigned char* raw, int kc, int n_stages) {
     const uint32_t a0 = smem_u32(raw);
@@ -371,13 +397,25 @@ struct GSmem {
     side_full = empty + 8;
     side_empty = side_full + G_SIDE_SLOTS;
     tmem_full = side_empty + G_SIDE_SLOTS;
-    tmem_empty = tmem_full + 2;
-    a_full = tmem_empty + 2;
+    tmem_empty = tmem_full + G_ACC;
+    a_full = tmem_empty + G_ACC;
     a_empty = a_full + 1;
     wthr = reinterpret_cast<unsigned long long*>(a_empty + 1);
     tmem_addr = reinterpret_cast<uint32_t*>(wthr + 2 * G_EPI_WARPS);
   }
 };
+
+// diagnostics: time a wait when profiling is on
+#define G_TIMED(slot, stmt)                                   \
+  do {                                                        \
+    if (g.prof) {                                             \
+      const long long t0__ = clock64();                       \
+      stmt;                                                   \
+      pacc[slot] += (unsigned long long) (clock64() - t0__);  \
+    } else {                                                  \
+      stmt;                                                   \
+    }                                                         \
+  } while (0)
 
 // side record meta
 struct GMeta {
@@ -409,11 +447,13 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
   uint32_t sseq = 0;                      // side records issued
   uint32_t a_uses = 0;                    // items that loaded a row tile
   unsigned long long streamed = 0;
+  unsigned long long pacc[4] = {0, 0, 0, 0};
+  const long long t_begin = clock64();
   const uint32_t side_bytes = (side_extra ? 2u : 1u) * GT * 4u;
   auto side_slot = [&](uint32_t flags, uint32_t rb, uint32_t col0, uint32_t item, uint32_t tile, bool data) {
     // lane 0 only
     const uint32_t s = sseq % G_SIDE_SLOTS;
-    mbar_wait(&S.side_empty[s], ((sseq / G_SIDE_SLOTS) & 1u) ^ 1u);
+    G_TIMED(0, mbar_wait(&S.side_empty[s], ((sseq / G_SIDE_SLOTS) & 1u) ^ 1u));
     float* rec = S.side + s * G_SIDE_FLOATS;
     GMeta m;
     m.row_tile = rb; m.col0 = col0; m.flags = flags; m.item = item;
@@ -456,7 +496,7 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
         if (lane == 0) {
           if (first) {
             // the row tile's operand image: resident for the whole item
-            mbar_wait(&S.a_empty[0], (a_uses & 1u) ^ 1u);
+            G_TIMED(2, mbar_wait(&S.a_empty[0], (a_uses & 1u) ^ 1u));
             mbar_arrive_expect_tx(&S.a_full[0], (uint32_t) g.kc * G_CHUNK_BYTES);
             const float* src_a = g.gT + (size_t) (g.row_begin / GT + rb) * g.kc * G_CHUNK_FLOATS;
             for (int q = 0; q < g.kc; ++q)
@@ -465,7 +505,7 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
           side_slot(0u, rb, tt * GT, item, tt, true);
           const float* src_b = g.gT + (size_t) tt * g.kc * G_CHUNK_FLOATS;
           for (int q = 0; q < g.kc; ++q) {
-            mbar_wait(&S.empty[stage], phase ^ 1u);
+            if (stage % (uint32_t) g.cb == 0) G_TIMED(1, mbar_wait(&S.empty[stage / (uint32_t) g.cb], phase ^ 1u));
             mbar_arrive_expect_tx(&S.full[stage], G_CHUNK_BYTES);
             tma_load_1d(S.ring + (size_t) stage * G_CHUNK_FLOATS, src_b + (size_t) q * G_CHUNK_FLOATS, G_CHUNK_BYTES, &S.full[stage]);
             if (++stage == (uint32_t) g.n_stages) { stage = 0; phase ^= 1u; }
@@ -487,55 +527,72 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
     side_slot(G_EXIT, 0, 0, 0xffffffffu, 0, false);
     side_slot(G_EXIT, 0, 1, 0xffffffffu, 0, false);
     if (g.stats && streamed) atomicAdd(g.stats + 2, streamed);
+    if (g.prof) {
+      pacc[3] = (unsigned long long) (clock64() - t_begin);
+      for (int q = 0; q < 4; ++q) atomicAdd(g.prof + q, pacc[q]);
+    }
   }
 }
 
-// MMA warp: follows the side records; per tile kc chunks x (up to 4) K=8 steps into accumulator stage (sequence & 1)
+// MMA warp: follows the side records; per tile kc chunks x (up to 4) K=8 steps into accumulator stage (sequence & 3).
+// The whole warp runs the loop with warp-uniform values (descriptors live in uniform registers) and one elected lane
+// issues; ring slots are handed back cb at a time and the accumulator is published once per tile, because every
+// tcgen05.commit stalls the issue for a few hundred cycles that only queued MMA work can hide.
 __device__ __forceinline__ void g_mma(const GemmGeom& g, GSmem& S, uint32_t tmem_base) {
-  const int lane = threadIdx.x & 31;
   uint32_t stage = 0, phase = 0, seq = 0, a_uses = 0;
-  uint32_t acc_uses[2] = {0u, 0u};
+  uint32_t acc_uses = 0;                    // bit field: parity of the uses of each accumulator stage
   bool need_a = true;
+  unsigned long long pacc[5] = {0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
+  const uint64_t a_desc0 = g_smem_desc(smem_u32(S.a));
+  const uint64_t b_desc0 = g_smem_desc(smem_u32(S.ring));
+  const uint32_t cb = (uint32_t) g.cb;
+  const bool leader = elect_one();
   for (;;) {
     const uint32_t s = seq % G_SIDE_SLOTS;
-    mbar_wait(&S.side_full[s], (seq / G_SIDE_SLOTS) & 1u);
+    G_TIMED(0, mbar_wait(&S.side_full[s], (seq / G_SIDE_SLOTS) & 1u));
     const GMeta m = *reinterpret_cast<const GMeta*>(S.side + s * G_SIDE_FLOATS);
     if (m.flags & G_EXIT) break;
     if (m.flags & G_END) {
       if (m.col0 == 0) {
-        if (lane == 0) tc_commit(&S.a_empty[0]);     // the row tile may be replaced once every MMA of the item has read it
+        if (leader) tc_commit(&S.a_empty[0]);        // the row tile may be replaced once every MMA of the item has read it
         need_a = true;
       }
     } else {
       if (need_a) {
-        mbar_wait(&S.a_full[0], a_uses & 1u);
+        G_TIMED(1, mbar_wait(&S.a_full[0], a_uses & 1u));
         ++a_uses;
         need_a = false;
       }
-      const uint32_t acc = seq & 1u;
-      mbar_wait(&S.tmem_empty[acc], (acc_uses[acc] & 1u) ^ 1u);
-      acc_uses[acc] += 1;
+      const uint32_t acc = seq & (G_ACC - 1);
+      G_TIMED(2, mbar_wait(&S.tmem_empty[acc], ((acc_uses >> acc) & 1u) ^ 1u));
+      acc_uses ^= 1u << acc;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * (uint32_t) GT;
       for (int q = 0; q < g.kc; ++q) {
-        mbar_wait(&S.full[stage], phase);
+        G_TIMED(3, mbar_wait(&S.full[stage], phase));
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t ad = g_smem_desc(smem_u32(S.a + (size_t) q * G_CHUNK_FLOATS));
-          const uint64_t bd = g_smem_desc(smem_u32(S.ring + (size_t) stage * G_CHUNK_FLOATS));
-          const int steps = min(4, g.k8 - 4 * q);
-          for (int k = 0; k < steps; ++k)
-            tc_mma_tf32(d_tmem, ad + (uint64_t) (2 * k), bd + (uint64_t) (2 * k), G_IDESC, (q | k) ? 1u : 0u);
-          tc_commit(&S.empty[stage]);
+        // chunk q of the row tile against ring slot `stage`: +1024 per 16 KB chunk and +2 per K step in the address field
+        const uint64_t ad = a_desc0 + (uint64_t) q * (G_CHUNK_BYTES >> 4);
+        const uint64_t bd = b_desc0 + (uint64_t) stage * (G_CHUNK_BYTES >> 4);
+        const int steps = min(4, g.k8 - 4 * q);
+        if (leader) {
+          tc_mma_tf32(d_tmem, ad, bd, G_IDESC, q ? 1u : 0u);
+          if (steps > 1) tc_mma_tf32(d_tmem, ad + 2, bd + 2, G_IDESC, 1u);
+          if (steps > 2) tc_mma_tf32(d_tmem, ad + 4, bd + 4, G_IDESC, 1u);
+          if (steps > 3) tc_mma_tf32(d_tmem, ad + 6, bd + 6, G_IDESC, 1u);
+          if ((stage + 1) % cb == 0) tc_commit(&S.empty[stage / cb]);
           if (q == g.kc - 1) tc_commit(&S.tmem_full[acc]);
         }
-        __syncwarp();
         if (++stage == (uint32_t) g.n_stages) { stage = 0; phase ^= 1u; }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&S.side_empty[s]);
+    if (leader) mbar_arrive(&S.side_empty[s]);
     ++seq;
+  }
+  if (g.prof && leader) {
+    pacc[4] = (unsigned long long) (clock64() - t_begin);
+    for (int q = 0; q < 5; ++q) atomicAdd(g.prof + 4 + q, pacc[q]);
   }
 }
 
@@ -549,7 +606,7 @@ __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
       mbar_init(&S.side_full[s], 1);
       mbar_init(&S.side_empty[s], 5);          // MMA warp + the four warps of the warpgroup that owns the record
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < G_ACC; ++s) {
       mbar_init(&S.tmem_full[s], 1);
       mbar_init(&S.tmem_empty[s], 4);
     }
@@ -557,6 +614,30 @@ __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
     mbar_init(&S.a_empty[0], 1);
     for (int q = 0; q < 2 * G_EPI_WARPS; ++q) S.wthr[q] = ~0ull;
     fence_mbar_init();
+  }
+}
+
+// Epilogue of one accumulator tile: four 32-column loads, each in flight while the previous chunk is processed; the
+// accumulator stage is handed back to the MMA warp as soon as the last load has landed in registers.
+template <class Proc>
+__device__ __forceinline__ void g_epilogue_tile(GSmem& S, uint32_t tmem_base, uint32_t quarter, uint32_t acc, int lane, Proc&& proc) {
+  uint32_t ra[32], rb[32];
+  const uint32_t t0 = tmem_base + ((quarter * 32u) << 16) + acc * (uint32_t) GT;
+  tmem_ld32_issue(t0, ra);
+#pragma unroll 1
+  for (int it = 0; it < 2; ++it) {
+    tmem_ld32_wait(ra);
+    tmem_ld32_issue(t0 + (uint32_t) (it * 64 + 32), rb);
+    proc(ra, it * 64);
+    tmem_ld32_wait(rb);
+    if (it == 0) {
+      tmem_ld32_issue(t0 + 64u, ra);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
+    }
+    proc(rb, it * 64 + 32);
   }
 }
 
@@ -574,10 +655,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
   extern __shared__ unsigned char g_smem_raw[];
   const GemmGeom& g = a.g;
   GSmem S(g_smem_raw, g.kc, g.n_stages);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp(), lane = threadIdx.x & 31;
   g_init(g, S);
   __syncthreads();
-  if (warp == 1) tmem_alloc(S.tmem_addr, 2 * GT);
+  if (warp == 1) tmem_alloc(S.tmem_addr, G_ACC * GT);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -589,7 +670,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
   } else if (warp == 1) {
     g_mma(g, S, tmem_base);
   } else {
-    const uint32_t wg = (uint32_t) (warp - 2) >> 2;                 // accumulator stage this warpgroup serves
+    const uint32_t wg = (uint32_t) (warp - 2) >> 2;                 // this warpgroup serves the side records of parity wg
     const uint32_t quarter = (uint32_t) warp & 3u;                  // TMEM lanes 32 quarter .. 32 quarter + 31
     const uint32_t row_in_tile = quarter * 32u + (uint32_t) lane;
     const int et = (warp - 2) * 32 + lane;
@@ -599,11 +680,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
     float q[NB], E[NB], xn = INFINITY;
     uint32_t cnt[NB];
     uint32_t n_slow = 0, n_exact = 0, n_tiles = 0;
+    unsigned long long pacc[3] = {0, 0, 0};
+    const long long t_begin = clock64();
 #pragma unroll
     for (int b = 0; b < NB; ++b) { cnt[b] = 0; q[b] = INFINITY; E[b] = 0.f; }
     for (;;) {
       const uint32_t s = seq % G_SIDE_SLOTS;
-      mbar_wait(&S.side_full[s], (seq / G_SIDE_SLOTS) & 1u);
+      G_TIMED(0, mbar_wait(&S.side_full[s], (seq / G_SIDE_SLOTS) & 1u));
       const float* rec = S.side + s * G_SIDE_FLOATS;
       const GMeta m = *reinterpret_cast<const GMeta*>(rec);
       if (m.flags & G_EXIT) break;
@@ -631,15 +714,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             if (a.rad2[b] < 0.f) E[b] = -1.f;                         // unused slot
           }
         }
-        mbar_wait(&S.tmem_full[wg], uses & 1u);
-        ++uses;
+        const uint32_t acc = seq & (G_ACC - 1);
+        G_TIMED(1, mbar_wait(&S.tmem_full[acc], (uses >> acc) & 1u));
+        uses ^= 1u << acc;
         tc_fence_after();
         ++n_tiles;
         const float* ny = rec + 4;
-#pragma unroll 1
-        for (int c0 = 0; c0 < GT; c0 += 32) {
-          float v[32];
-          tmem_ld32(tmem_base + ((quarter * 32u) << 16) + wg * (uint32_t) GT + (uint32_t) c0, v);
+        auto proc = [&](const uint32_t (&v)[32], int c0) {
 #pragma unroll
           for (int h = 0; h < 32; h += G_HALF) {
             float mn[NB];
@@ -651,7 +732,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
               const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const float w = fmaf(v[h + c4 + c], -2.0f, nn[c]);
+                const float w = fmaf(__uint_as_float(v[h + c4 + c]), -2.0f, nn[c]);
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                   const float vv = w + q[b];
@@ -666,7 +747,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             if (CHECK || band) {
               // rare: a pair of these 16 columns lies within the band of a radius; replace its sign decision by the exact one
 #pragma unroll
-              for (int c = 0; c < G_HALF; ++c) scratch[c * G_EPI_THREADS] = v[h + c];
+              for (int c = 0; c < G_HALF; ++c) scratch[c * G_EPI_THREADS] = __uint_as_float(v[h + c]);
 #pragma unroll 1
               for (int c = 0; c < G_HALF; ++c) {
                 const float w = fmaf(scratch[c * G_EPI_THREADS], -2.0f, ny[c0 + h + c]);
@@ -698,14 +779,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
               }
             }
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+        };
+        g_epilogue_tile(S, tmem_base, quarter, acc, lane, proc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.side_empty[s]);
       seq += 2;
+    }
+    if (g.prof && lane == 0 && quarter == 0) {
+      pacc[2] = (unsigned long long) (clock64() - t_begin);
+      for (int q = 0; q < 3; ++q) atomicAdd(g.prof + 9 + q, pacc[q]);
     }
     // statistics
     for (int o = 16; o > 0; o >>= 1) {
@@ -720,7 +803,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * GT);
+  if (warp == 1) tmem_dealloc(tmem_base, G_ACC * GT);
 }
 
 // ================================================================================================
@@ -733,10 +816,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
   extern __shared__ unsigned char g_smem_raw[];
   const GemmGeom& g = a.g;
   GSmem S(g_smem_raw, g.kc, g.n_stages);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp(), lane = threadIdx.x & 31;
   g_init(g, S);
   __syncthreads();
-  if (warp == 1) tmem_alloc(S.tmem_addr, 2 * GT);
+  if (warp == 1) tmem_alloc(S.tmem_addr, G_ACC * GT);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -866,17 +949,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
           t_hd = (valid && lo_i != 0) ? thr(g_key_d2(best_hd)) : t_nn;
           set_dl();
         }
-        mbar_wait(&S.tmem_full[wg], uses & 1u);
-        ++uses;
+        const uint32_t acc = seq & (G_ACC - 1);
+        mbar_wait(&S.tmem_full[acc], (uses >> acc) & 1u);
+        uses ^= 1u << acc;
         tc_fence_after();
         ++n_tiles;
         const float* ny = rec + 4;
         const float* lc = rec + 4 + GT;
         bool improved = false;
-#pragma unroll 1
-        for (int c0 = 0; c0 < GT; c0 += 32) {
-          float v[32];
-          tmem_ld32(tmem_base + ((quarter * 32u) << 16) + wg * (uint32_t) GT + (uint32_t) c0, v);
+        auto proc = [&](const uint32_t (&v)[32], int c0) {
 #pragma unroll
           for (int h = 0; h < 32; h += G_HALF) {
             bool any = false;
@@ -888,13 +969,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
               const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const float w = fmaf(v[h + c4 + c], -2.0f, nn[c]);
+                const float w = fmaf(__uint_as_float(v[h + c4 + c]), -2.0f, nn[c]);
                 any |= w < fmaf(__saturatef(lor - ll[c]), dl, t_nn);
               }
             }
             if (any) {
 #pragma unroll
-              for (int c = 0; c < G_HALF; ++c) scratch[c * G_EPI_THREADS] = v[h + c];
+              for (int c = 0; c < G_HALF; ++c) scratch[c * G_EPI_THREADS] = __uint_as_float(v[h + c]);
 #pragma unroll 1
               for (int c = 0; c < G_HALF; ++c) {
                 const float w = fmaf(scratch[c * G_EPI_THREADS], -2.0f, ny[c0 + h + c]);
@@ -924,10 +1005,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
               }
             }
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.tmem_empty[wg]);
+        };
+        g_epilogue_tile(S, tmem_base, quarter, acc, lane, proc);
         // bounds for the producer's dynamic pruning of this item: one slot pair per epilogue warp
         if (first_of_item || __any_sync(0xffffffffu, improved)) {
           const uint2 b = publish();
@@ -953,7 +1032,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * GT);
+  if (warp == 1) tmem_dealloc(tmem_base, G_ACC * GT);
 }
 
 // per 32-row quarter of every row tile: bounds after seeding (max over the rows' seeded d2, margins included) and the
