@@ -802,18 +802,24 @@ static int fill_ggeom(dcb200_ctx* c, size_t row_begin, size_t row_end, GemmGeom*
   g->k8 = c->g_k8;
   int dev_smem = 0;
   CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  // two row tiles per work item when both operand images fit next to a ring of at least four chunks (n_cols <= 128) and the
+  // range starts at a multiple of 256: every streamed column chunk then feeds 256 rows
+  const char* ra_env = getenv("DCB200_GEMM_RA");
+  g->ra = (row_begin % (2 * GT) == 0 && gemm_smem_bytes(2 * g->kc, 4) <= (size_t) dev_smem && !(ra_env && ra_env[0] == '1')) ? 2 : 1;
   int avail = 8;
-  while (avail > 2 && gemm_smem_bytes(g->kc, avail) > (size_t) dev_smem) --avail;
-  if (gemm_smem_bytes(g->kc, avail) > (size_t) dev_smem) return fail("dcb200: GEMM-form kernel does not fit in shared memory");
+  while (avail > 2 && gemm_smem_bytes(g->ra * g->kc, avail) > (size_t) dev_smem) --avail;
+  if (gemm_smem_bytes(g->ra * g->kc, avail) > (size_t) dev_smem) return fail("dcb200: GEMM-form kernel does not fit in shared memory");
   // ring slots are freed in commit groups of cb chunks (at least two groups in the ring)
   g->cb = avail >= 8 ? 4 : avail >= 4 ? 2 : 1;
+  g->cb_log2 = g->cb == 4 ? 2 : g->cb == 2 ? 1 : 0;
   g->n_stages = avail / g->cb * g->cb;
   g->n = (uint32_t) c->n;
   g->n_tiles = (uint32_t) c->g_tiles;
   g->row_begin = (uint32_t) row_begin;
   g->row_end = (uint32_t) row_end;
-  g->n_row_tiles = (uint32_t) ((row_end - row_begin + GT - 1) / GT);
-  // about 8 column items per row tile: the row tile's operand image is loaded once per item
+  g->n_row_tiles128 = (uint32_t) ((row_end - row_begin + GT - 1) / GT);
+  g->n_row_tiles = (g->n_row_tiles128 + g->ra - 1) / g->ra;
+  // about 8 column items per row block: the row tiles' operand images are loaded once per item
   g->tiles_per_item = std::max(1u, std::min(g->n_tiles, std::max(32u, (g->n_tiles + 7) / 8)));
   g->n_col_items = (g->n_tiles + g->tiles_per_item - 1) / g->tiles_per_item;
   if ((uint64_t) g->n_row_tiles * g->n_col_items >= 0x7fffffffull) return fail("too many work items");
@@ -831,7 +837,6 @@ static int fill_ggeom(dcb200_ctx* c, size_t row_begin, size_t row_end, GemmGeom*
   g->nymax = c->g_nymax;
   g->prune_slack = prune_slack;
   g->prune_thr = INFINITY;
-  g->spin = 0;
   {
     const char* e = getenv("DCB200_GEMM_PROF");
     if (e && e[0] == '1') {
@@ -1180,13 +1185,14 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
     CK(c->lomin.reserve(c->g_tiles));
     CK(launch_tile_min(c->lof.p, c->g_tiles, c->lomin.p, c->stream));
     ga.lomin = c->lomin.p;
-    CK(c->gthr.reserve((size_t) ga.g.n_row_tiles * 12));
+    const uint32_t thr_tiles = ga.g.n_row_tiles * (uint32_t) ga.g.ra;      // 128-row tiles incl. the empty second tile of a last block
+    CK(c->gthr.reserve((size_t) thr_tiles * 12));
     ga.thr_nn = c->gthr.p;
-    ga.thr_hd = ga.thr_nn + (size_t) ga.g.n_row_tiles * 4;
-    ga.lormax = ga.thr_hd + (size_t) ga.g.n_row_tiles * 4;
+    ga.thr_hd = ga.thr_nn + (size_t) thr_tiles * 4;
+    ga.lormax = ga.thr_hd + (size_t) thr_tiles * 4;
     ga.key_nn = (unsigned long long*) dev_keys_nn;
     ga.key_hd = (unsigned long long*) dev_keys_hd;
-    CK(launch_gnn_tile_thr(ga.key_nn, ga.key_hd, c->lo.p, c->lof.p, ga.lo_bias, (uint32_t) pos_begin, (uint32_t) pos_end, ga.g.n_row_tiles,
+    CK(launch_gnn_tile_thr(ga.key_nn, ga.key_hd, c->lo.p, c->lof.p, ga.lo_bias, (uint32_t) pos_begin, (uint32_t) pos_end, thr_tiles,
                            ga.g.e_rel, ga.g.prune_slack, ga.thr_nn, ga.thr_hd, ga.lormax, c->stream));
     const uint32_t full_tpi = ga.g.tiles_per_item, full_items = ga.g.n_col_items;
     if (ga.g.n_tiles > 96) {

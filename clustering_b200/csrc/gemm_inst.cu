@@ -32,7 +32,7 @@ cudaError_t launch_tile_min(const float* lof, size_t n_tiles, float* lomin, cuda
 
 template <int NB, bool CHECK>
 static cudaError_t launch_gpops_nb(const GPopsArgs& a, int grid, cudaStream_t st) {
-  const size_t smem = GSmem::bytes(a.g.kc, a.g.n_stages);
+  const size_t smem = GSmem::bytes(a.g.ra * a.g.kc, a.g.n_stages);
   cudaError_t e = cudaFuncSetAttribute(gscan_pops_kernel<NB, CHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
   gscan_pops_kernel<NB, CHECK><<<grid, G_THREADS, smem, st>>>(a);
@@ -51,7 +51,7 @@ cudaError_t launch_gpops(const GPopsArgs& a, int grid, bool check, cudaStream_t 
 }
 
 cudaError_t launch_gnn(const GNnArgs& a, int grid, cudaStream_t st) {
-  const size_t smem = GSmem::bytes(a.g.kc, a.g.n_stages);
+  const size_t smem = GSmem::bytes(a.g.ra * a.g.kc, a.g.n_stages);
   cudaError_t e = cudaFuncSetAttribute(gscan_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
   gscan_nn_kernel<<<grid, G_THREADS, smem, st>>>(a);

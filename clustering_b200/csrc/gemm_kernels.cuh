@@ -53,11 +53,15 @@ struct GemmGeom {
   const float* lb;            // [row tiles of this launch][n_tiles]
   int d, kc, k8;              // dims, K-chunks per tile, total K=8 MMA steps (ceil(d/8))
   int n_stages;               // ring depth (chunks), a multiple of cb
-  int cb;                     // chunks per commit group: the MMA warp frees ring slots cb at a time (tcgen05.commit is not free)
+  int cb;                     // chunks per commit group (a power of two): the MMA warp frees ring slots cb at a time (tcgen05.commit is not free)
+  int cb_log2;
   uint32_t n;                 // real frame count
   uint32_t n_tiles;           // column tiles (= ld / 128)
   uint32_t row_begin, row_end;   // positions of this shard, row_begin % 128 == 0
-  uint32_t n_row_tiles;
+  uint32_t n_row_tiles;       // row BLOCKS of this launch: ra row tiles (128 ra rows) each
+  uint32_t n_row_tiles128;    // 128-row tiles of this launch that hold at least one row (rows of g.lb)
+  int ra;                     // row tiles per work item: 2 when two operand images fit (every streamed column chunk then feeds
+                              // 256 rows: the L2 -> SM stream, ~50 B/clk per SM, is what limits the scan otherwise), else 1
   uint32_t tiles_per_item, n_col_items;
   unsigned int* work_counter;
   unsigned long long* stats;  // [0] pairs handed to the handler, [1] exact evaluations, [2] tiles streamed, [3] tile scans
@@ -68,7 +72,6 @@ struct GemmGeom {
   float prune_slack;          // absolute slack of the tile lower bounds
   float prune_thr;            // static pruning threshold (d2 units); +inf: none
   unsigned long long* prof;   // optional [16] cycle counters per role (diagnostics, DCB200_GEMM_PROF=1), see g_prof_names in api.cu
-  int spin;                   // experiment: 1 = waits on tensor-core-committed barriers spin without a suspend hint
   float* check;               // optional [2]: max observed |F - d2e| / band (float bits, atomicMax), CHECK builds only
 };
 
@@ -371,7 +374,7 @@ __global__ void tile_min_kernel(const float* __restrict__ lof, size_t n_tiles, f
 // ------------------------------------------------------------------------------------------------
 
 struct GSmem {
-  float* a;                   // kc chunks
+  float* a;                   // ra x kc chunks
   float* ring;                // n_stages chunks
   float* side;                // G_SIDE_SLOTS records
   float* scratch;             // G_EPI_THREADS x G_HALF
@@ -381,11 +384,11 @@ struct GSmem {
   uint64_t *a_full, *a_empty;
   uint32_t* tmem_addr;
   unsigned long long* wthr;   // [8 epilogue warps][2]: (item << 32 | float bits) bounds published for the producer (nn, hd)
-  __host__ __device__ static size_t bytes(int kc, int n_stages) {
-    return 1024 + (size_t) (kc + n_stages) * G_CHUNK_BYTES + (size_t) G_SIDE_SLOTS * G_SIDE_FLOATS * 4 +
+  __host__ __device__ static size_t bytes(int akc, int n_stages) {        // akc = ra * kc
+    return 1024 + (size_t) (akc + n_stages) * G_CHUNK_BYTES + (size_t) G_SIDE_SLOTS * G_SIDE_FLOATS * 4 +
            (size_t) G_EPI_THREADS * G_HALF * 4 + (size_t) (2 * 8 + 2 * G_SIDE_SLOTS + 2 * G_ACC + 2) * 8 + 16 + 2 * G_EPI_WARPS * 8;
   }
-  __device__ GSmem(unsigned char* raw, int kc, int n_stages) {
+  __device__ GSmem(unsigned char* raw, int kc, int n_stages) {            // kc here = ra * kc
     const uint32_t a0 = smem_u32(raw);
     unsigned char* base = raw + ((1024u - (a0 & 1023u)) & 1023u);       // SWIZZLE_128B atoms need 1024-byte alignment
     a = reinterpret_cast<float*>(base);
@@ -405,7 +408,9 @@ struct GSmem {
   }
 };
 
-// diagnostics: time a wait when profiling is on
+// diagnostics: time a wait when the library is built with -DDCB_GEMM_PROF (the counters cost issue slots in the
+// single-warp producer / MMA loops, so they are compiled out by default)
+#ifdef DCB_GEMM_PROF
 #define G_TIMED(slot, stmt)                                   \
   do {                                                        \
     if (g.prof) {                                             \
@@ -416,10 +421,17 @@ struct GSmem {
       stmt;                                                   \
     }                                                         \
   } while (0)
+#else
+#define G_TIMED(slot, stmt) \
+  do {                      \
+    (void) pacc;            \
+    stmt;                   \
+  } while (0)
+#endif
 
 // side record meta
 struct GMeta {
-  uint32_t row_tile;       // row tile of the item, relative to row_begin / 128
+  uint32_t row_tile;       // row block of the item (ra row tiles), relative to row_begin
   uint32_t col0;           // first column (position) of the tile
   uint32_t flags;          // 0: tile, 1: end of item, 2: end of stream
   uint32_t item;
@@ -430,7 +442,7 @@ constexpr uint32_t G_END = 1u, G_EXIT = 2u;
 __device__ __forceinline__ void g_item_coords(const GemmGeom& g, uint32_t item, uint32_t* rb, uint32_t* ci) {
   const uint32_t step = item / g.n_row_tiles;
   *rb = item % g.n_row_tiles;
-  const uint32_t diag = min((g.row_begin / GT + *rb) / g.tiles_per_item, g.n_col_items - 1);
+  const uint32_t diag = min((g.row_begin / GT + *rb * (uint32_t) g.ra) / g.tiles_per_item, g.n_col_items - 1);
   const uint32_t k = (step + 1) >> 1;
   const uint32_t n = g.n_col_items;
   *ci = (step & 1) ? (diag + k) % n : (diag + n - (k % n)) % n;
@@ -482,11 +494,14 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
     t1 = min(t1, lim1);
     if (t0 >= t1) continue;
     const float th0 = thr0(rb);
-    const float* __restrict__ lbrow = g.lb + (size_t) rb * g.n_tiles;
+    const uint32_t rt0 = rb * (uint32_t) g.ra;                       // first 128-row tile of the block
+    const float* __restrict__ lbrow = g.lb + (size_t) rt0 * g.n_tiles;
+    const bool two = g.ra == 2 && rt0 + 1 < g.n_row_tiles128;        // the block's second row tile holds rows
     bool first = true;
     for (uint32_t base = t0; base < t1; base += 32) {
       const uint32_t t = base + lane;
-      const float lbv = t < t1 ? __ldg(lbrow + t) : INFINITY;
+      float lbv = t < t1 ? __ldg(lbrow + t) : INFINITY;
+      if (two && t < t1) lbv = fminf(lbv, __ldg(lbrow + g.n_tiles + t));
       uint32_t mask = __ballot_sync(0xffffffffu, t < t1 && !(lbv > th0));
       while (mask) {
         const int src = __ffs(mask) - 1;
@@ -495,17 +510,17 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
         if (!keep(rb, tt, __shfl_sync(0xffffffffu, lbv, src), item, lane)) continue;
         if (lane == 0) {
           if (first) {
-            // the row tile's operand image: resident for the whole item
+            // the row tiles' operand images (consecutive tiles = one contiguous block): resident for the whole item
             G_TIMED(2, mbar_wait(&S.a_empty[0], (a_uses & 1u) ^ 1u));
-            mbar_arrive_expect_tx(&S.a_full[0], (uint32_t) g.kc * G_CHUNK_BYTES);
-            const float* src_a = g.gT + (size_t) (g.row_begin / GT + rb) * g.kc * G_CHUNK_FLOATS;
-            for (int q = 0; q < g.kc; ++q)
+            mbar_arrive_expect_tx(&S.a_full[0], (uint32_t) (g.ra * g.kc) * G_CHUNK_BYTES);
+            const float* src_a = g.gT + (size_t) (g.row_begin / GT + rt0) * g.kc * G_CHUNK_FLOATS;
+            for (int q = 0; q < g.ra * g.kc; ++q)
               tma_load_1d(S.a + (size_t) q * G_CHUNK_FLOATS, src_a + (size_t) q * G_CHUNK_FLOATS, G_CHUNK_BYTES, &S.a_full[0]);
           }
           side_slot(0u, rb, tt * GT, item, tt, true);
           const float* src_b = g.gT + (size_t) tt * g.kc * G_CHUNK_FLOATS;
           for (int q = 0; q < g.kc; ++q) {
-            if (stage % (uint32_t) g.cb == 0) G_TIMED(1, mbar_wait(&S.empty[stage / (uint32_t) g.cb], phase ^ 1u));
+            if ((stage & (uint32_t) (g.cb - 1)) == 0) G_TIMED(1, mbar_wait(&S.empty[stage >> g.cb_log2], phase ^ 1u));
             mbar_arrive_expect_tx(&S.full[stage], G_CHUNK_BYTES);
             tma_load_1d(S.ring + (size_t) stage * G_CHUNK_FLOATS, src_b + (size_t) q * G_CHUNK_FLOATS, G_CHUNK_BYTES, &S.full[stage]);
             if (++stage == (uint32_t) g.n_stages) { stage = 0; phase ^= 1u; }
@@ -518,82 +533,109 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
       }
     }
     if (!first && lane == 0) {
-      // end of the item: one marker for each epilogue warpgroup (consecutive sequence numbers have both parities)
-      side_slot(G_END, rb, 0, item, 0, false);
-      side_slot(G_END, rb, 1, item, 0, false);
+      side_slot(G_END, rb, 0, item, 0, false);     // end of the item
     }
   }
   if (lane == 0) {
     side_slot(G_EXIT, 0, 0, 0xffffffffu, 0, false);
-    side_slot(G_EXIT, 0, 1, 0xffffffffu, 0, false);
     if (g.stats && streamed) atomicAdd(g.stats + 2, streamed);
+#ifdef DCB_GEMM_PROF
     if (g.prof) {
       pacc[3] = (unsigned long long) (clock64() - t_begin);
       for (int q = 0; q < 4; ++q) atomicAdd(g.prof + q, pacc[q]);
     }
+#else
+    (void) t_begin;
+#endif
   }
 }
 
-// MMA warp: follows the side records; per tile kc chunks x (up to 4) K=8 steps into accumulator stage (sequence & 3).
-// The whole warp runs the loop with warp-uniform values (descriptors live in uniform registers) and one elected lane
-// issues; ring slots are handed back cb at a time and the accumulator is published once per tile, because every
-// tcgen05.commit stalls the issue for a few hundred cycles that only queued MMA work can hide.
+// MMA warp: follows the side records; per column tile kc chunks x RA row tiles x (up to 4) K=8 steps into accumulator
+// stage p = tile count % (G_ACC / RA), TMEM columns (p RA + r) 128.  The whole warp runs the loop with warp-uniform
+// values (descriptors live in uniform registers) and one elected lane issues.  The per-chunk code is kept minimal: one
+// warp executes it serially, so every extra instruction between two tcgen05.mma is exposed latency (the first version
+// spent ~300 SASS instructions per chunk and reached 1/3 of the MMA rate).  Ring slots are handed back cb at a time and
+// the accumulators are published once per column tile (tcgen05.commit is not free either).
+template <int RA>
 __device__ __forceinline__ void g_mma(const GemmGeom& g, GSmem& S, uint32_t tmem_base) {
-  uint32_t stage = 0, phase = 0, seq = 0, a_uses = 0;
+  uint32_t stage = 0, phase = 0, seq = 0, a_uses = 0, tiles = 0;
   uint32_t acc_uses = 0;                    // bit field: parity of the uses of each accumulator stage
   bool need_a = true;
   unsigned long long pacc[5] = {0, 0, 0, 0, 0};
   const long long t_begin = clock64();
   const uint64_t a_desc0 = g_smem_desc(smem_u32(S.a));
   const uint64_t b_desc0 = g_smem_desc(smem_u32(S.ring));
-  const uint32_t cb = (uint32_t) g.cb;
+  const uint32_t cb_mask = (uint32_t) g.cb - 1u, cb_log2 = (uint32_t) g.cb_log2;
+  constexpr uint32_t p_mask = (uint32_t) (G_ACC / RA) - 1u;      // 4 or 2 accumulator stages
+  const int kc = g.kc;
+  const int kc_full = g.k8 >> 2;                                 // chunks with all four K steps
+  const int tail_steps = g.k8 & 3;                               // K steps of the last chunk if it is partial
+  const uint64_t a_row_stride = (uint64_t) kc * (G_CHUNK_BYTES >> 4);   // second row tile's image in the address field
+  const uint32_t n_stages = (uint32_t) g.n_stages;
   const bool leader = elect_one();
   for (;;) {
     const uint32_t s = seq % G_SIDE_SLOTS;
     G_TIMED(0, mbar_wait(&S.side_full[s], (seq / G_SIDE_SLOTS) & 1u));
-    const GMeta m = *reinterpret_cast<const GMeta*>(S.side + s * G_SIDE_FLOATS);
-    if (m.flags & G_EXIT) break;
-    if (m.flags & G_END) {
-      if (m.col0 == 0) {
-        if (leader) tc_commit(&S.a_empty[0]);        // the row tile may be replaced once every MMA of the item has read it
-        need_a = true;
-      }
+    const uint32_t flags = reinterpret_cast<const GMeta*>(S.side + s * G_SIDE_FLOATS)->flags;
+    if (flags & G_EXIT) break;
+    if (flags & G_END) {
+      if (leader) tc_commit(&S.a_empty[0]);          // the row tiles may be replaced once every MMA of the item has read them
+      need_a = true;
     } else {
       if (need_a) {
         G_TIMED(1, mbar_wait(&S.a_full[0], a_uses & 1u));
         ++a_uses;
         need_a = false;
       }
-      const uint32_t acc = seq & (G_ACC - 1);
-      G_TIMED(2, mbar_wait(&S.tmem_empty[acc], ((acc_uses >> acc) & 1u) ^ 1u));
-      acc_uses ^= 1u << acc;
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * (uint32_t) GT;
-      for (int q = 0; q < g.kc; ++q) {
+      const uint32_t p = tiles & p_mask;
+      ++tiles;
+      G_TIMED(2, mbar_wait(&S.tmem_empty[p], ((acc_uses >> p) & 1u) ^ 1u));
+      acc_uses ^= 1u << p;
+      const uint32_t d_tmem = tmem_base + p * (uint32_t) (RA * GT);
+      uint64_t ad = a_desc0;
+      for (int q = 0; q < kc; ++q, ad += (G_CHUNK_BYTES >> 4)) {
         G_TIMED(3, mbar_wait(&S.full[stage], phase));
         tc_fence_after();
-        // chunk q of the row tile against ring slot `stage`: +1024 per 16 KB chunk and +2 per K step in the address field
-        const uint64_t ad = a_desc0 + (uint64_t) q * (G_CHUNK_BYTES >> 4);
+        // chunk q of the row tiles against ring slot `stage`: +1024 per 16 KB chunk and +2 per K step in the address field
         const uint64_t bd = b_desc0 + (uint64_t) stage * (G_CHUNK_BYTES >> 4);
-        const int steps = min(4, g.k8 - 4 * q);
         if (leader) {
-          tc_mma_tf32(d_tmem, ad, bd, G_IDESC, q ? 1u : 0u);
-          if (steps > 1) tc_mma_tf32(d_tmem, ad + 2, bd + 2, G_IDESC, 1u);
-          if (steps > 2) tc_mma_tf32(d_tmem, ad + 4, bd + 4, G_IDESC, 1u);
-          if (steps > 3) tc_mma_tf32(d_tmem, ad + 6, bd + 6, G_IDESC, 1u);
-          if ((stage + 1) % cb == 0) tc_commit(&S.empty[stage / cb]);
-          if (q == g.kc - 1) tc_commit(&S.tmem_full[acc]);
+          if (q < kc_full) {
+#pragma unroll
+            for (int r = 0; r < RA; ++r) {
+              const uint64_t adr = ad + (uint64_t) r * a_row_stride;
+              const uint32_t dt = d_tmem + (uint32_t) (r * GT);
+              tc_mma_tf32(dt, adr, bd, G_IDESC, q ? 1u : 0u);
+              tc_mma_tf32(dt, adr + 2, bd + 2, G_IDESC, 1u);
+              tc_mma_tf32(dt, adr + 4, bd + 4, G_IDESC, 1u);
+              tc_mma_tf32(dt, adr + 6, bd + 6, G_IDESC, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < RA; ++r) {
+              const uint64_t adr = ad + (uint64_t) r * a_row_stride;
+              const uint32_t dt = d_tmem + (uint32_t) (r * GT);
+              tc_mma_tf32(dt, adr, bd, G_IDESC, q ? 1u : 0u);
+              if (tail_steps > 1) tc_mma_tf32(dt, adr + 2, bd + 2, G_IDESC, 1u);
+              if (tail_steps > 2) tc_mma_tf32(dt, adr + 4, bd + 4, G_IDESC, 1u);
+            }
+          }
+          if (((stage + 1) & cb_mask) == 0) tc_commit(&S.empty[stage >> cb_log2]);
         }
-        if (++stage == (uint32_t) g.n_stages) { stage = 0; phase ^= 1u; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
+      if (leader) tc_commit(&S.tmem_full[p]);
     }
     if (leader) mbar_arrive(&S.side_empty[s]);
     ++seq;
   }
+#ifdef DCB_GEMM_PROF
   if (g.prof && leader) {
     pacc[4] = (unsigned long long) (clock64() - t_begin);
     for (int q = 0; q < 5; ++q) atomicAdd(g.prof + 4 + q, pacc[q]);
   }
+#else
+  (void) t_begin;
+#endif
 }
 
 __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
@@ -604,11 +646,11 @@ __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
     }
     for (int s = 0; s < G_SIDE_SLOTS; ++s) {
       mbar_init(&S.side_full[s], 1);
-      mbar_init(&S.side_empty[s], 5);          // MMA warp + the four warps of the warpgroup that owns the record
+      mbar_init(&S.side_empty[s], 1 + G_EPI_WARPS);      // MMA warp + the eight epilogue warps
     }
     for (int s = 0; s < G_ACC; ++s) {
       mbar_init(&S.tmem_full[s], 1);
-      mbar_init(&S.tmem_empty[s], 4);
+      mbar_init(&S.tmem_empty[s], G_EPI_WARPS);
     }
     mbar_init(&S.a_full[0], 1);
     mbar_init(&S.a_empty[0], 1);
@@ -617,27 +659,29 @@ __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
   }
 }
 
-// Epilogue of one accumulator tile: four 32-column loads, each in flight while the previous chunk is processed; the
-// accumulator stage is handed back to the MMA warp as soon as the last load has landed in registers.
+// Epilogue of one warpgroup's share of an accumulator stage: n_loads (2 or 4) 32-column loads starting at column c_lo of
+// accumulator `acc_col`, each in flight while the previous chunk is processed; the stage is handed back to the MMA warp
+// as soon as the last load has landed in registers.  proc(regs, first column within the tile).
 template <class Proc>
-__device__ __forceinline__ void g_epilogue_tile(GSmem& S, uint32_t tmem_base, uint32_t quarter, uint32_t acc, int lane, Proc&& proc) {
+__device__ __forceinline__ void g_epilogue_tile(GSmem& S, uint32_t tmem_base, uint32_t quarter, uint32_t acc_col, uint32_t p, int c_lo,
+                                                int n_loads, int lane, Proc&& proc) {
   uint32_t ra[32], rb[32];
-  const uint32_t t0 = tmem_base + ((quarter * 32u) << 16) + acc * (uint32_t) GT;
+  const uint32_t t0 = tmem_base + ((quarter * 32u) << 16) + acc_col + (uint32_t) c_lo;
   tmem_ld32_issue(t0, ra);
 #pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
+  for (int it = 0; 2 * it < n_loads; ++it) {
     tmem_ld32_wait(ra);
     tmem_ld32_issue(t0 + (uint32_t) (it * 64 + 32), rb);
-    proc(ra, it * 64);
+    proc(ra, c_lo + it * 64);
     tmem_ld32_wait(rb);
-    if (it == 0) {
-      tmem_ld32_issue(t0 + 64u, ra);
+    if (2 * it + 2 < n_loads) {
+      tmem_ld32_issue(t0 + (uint32_t) (it * 64 + 64), ra);
     } else {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
+      if (lane == 0) mbar_arrive(&S.tmem_empty[p]);
     }
-    proc(rb, it * 64 + 32);
+    proc(rb, c_lo + it * 64 + 32);
   }
 }
 
@@ -654,7 +698,7 @@ template <int NB, bool CHECK>
 __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_constant__ GPopsArgs a) {
   extern __shared__ unsigned char g_smem_raw[];
   const GemmGeom& g = a.g;
-  GSmem S(g_smem_raw, g.kc, g.n_stages);
+  GSmem S(g_smem_raw, g.ra * g.kc, g.n_stages);
   const int warp = uniform_warp(), lane = threadIdx.x & 31;
   g_init(g, S);
   __syncthreads();
@@ -668,14 +712,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
     g_produce(g, S, nullptr, [&](uint32_t) { return g.prune_thr; }, [](uint32_t, uint32_t, float, uint32_t, int) { return true; },
               [](uint32_t, uint32_t&, uint32_t&) {});
   } else if (warp == 1) {
-    g_mma(g, S, tmem_base);
+    if (g.ra == 2) g_mma<2>(g, S, tmem_base); else g_mma<1>(g, S, tmem_base);
   } else {
-    const uint32_t wg = (uint32_t) (warp - 2) >> 2;                 // this warpgroup serves the side records of parity wg
+    // ra == 2: warpgroup wg owns row tile wg of the block (all 128 columns of its accumulator); ra == 1: both warpgroups hold the
+    // same 128 rows and split the columns of the one accumulator (wg 0: 0..63, wg 1: 64..127)
+    const uint32_t wg = (uint32_t) (warp - 2) >> 2;
     const uint32_t quarter = (uint32_t) warp & 3u;                  // TMEM lanes 32 quarter .. 32 quarter + 31
     const uint32_t row_in_tile = quarter * 32u + (uint32_t) lane;
     const int et = (warp - 2) * 32 + lane;
     float* scratch = S.scratch + et;
-    uint32_t seq = wg, uses = 0, cur_item = 0xfffffffeu, row = 0;
+    uint32_t seq = 0, tiles = 0, uses = 0, cur_item = 0xfffffffeu, row = 0;
     bool valid = false;
     float q[NB], E[NB], xn = INFINITY;
     uint32_t cnt[NB];
@@ -700,7 +746,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
       } else {
         if (cur_item != m.item) {
           cur_item = m.item;
-          row = g.row_begin + m.row_tile * GT + row_in_tile;
+          row = g.row_begin + (m.row_tile * (uint32_t) g.ra + (g.ra == 2 ? wg : 0u)) * GT + row_in_tile;
           valid = row < g.row_end;
           xn = valid ? __ldg(g.gnorm + row) : INFINITY;
           const float rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
@@ -714,11 +760,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             if (a.rad2[b] < 0.f) E[b] = -1.f;                         // unused slot
           }
         }
-        const uint32_t acc = seq & (G_ACC - 1);
-        G_TIMED(1, mbar_wait(&S.tmem_full[acc], (uses >> acc) & 1u));
-        uses ^= 1u << acc;
+        const uint32_t p = tiles & ((uint32_t) (G_ACC / g.ra) - 1u);
+        ++tiles;
+        G_TIMED(1, mbar_wait(&S.tmem_full[p], (uses >> p) & 1u));
+        uses ^= 1u << p;
         tc_fence_after();
-        ++n_tiles;
+        if (g.ra == 2 || wg == 0) ++n_tiles;
         const float* ny = rec + 4;
         auto proc = [&](const uint32_t (&v)[32], int c0) {
 #pragma unroll
@@ -780,16 +827,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             }
           }
         };
-        g_epilogue_tile(S, tmem_base, quarter, acc, lane, proc);
+        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, (p * 2u + wg) * (uint32_t) GT, p, 0, 4, lane, proc);
+        else g_epilogue_tile(S, tmem_base, quarter, p * (uint32_t) GT, p, (int) wg * 64, 2, lane, proc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.side_empty[s]);
-      seq += 2;
+      ++seq;
     }
+#ifdef DCB_GEMM_PROF
     if (g.prof && lane == 0 && quarter == 0) {
       pacc[2] = (unsigned long long) (clock64() - t_begin);
       for (int q = 0; q < 3; ++q) atomicAdd(g.prof + 9 + q, pacc[q]);
     }
+#else
+    (void) t_begin;
+#endif
     // statistics
     for (int o = 16; o > 0; o >>= 1) {
       n_slow += __shfl_xor_sync(0xffffffffu, n_slow, o);
@@ -815,7 +867,7 @@ __device__ __forceinline__ float g_key_d2(unsigned long long k) { return __uint_
 __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_constant__ GNnArgs a) {
   extern __shared__ unsigned char g_smem_raw[];
   const GemmGeom& g = a.g;
-  GSmem S(g_smem_raw, g.kc, g.n_stages);
+  GSmem S(g_smem_raw, g.ra * g.kc, g.n_stages);
   const int warp = uniform_warp(), lane = threadIdx.x & 31;
   g_init(g, S);
   __syncthreads();
@@ -831,11 +883,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
     float bound_nn = 0.f, bound_hd = 0.f, lmax = 0.f;
     g_produce(g, S, a.lof,
               [&](uint32_t rb) {
-                // max over the four quarters of the row tile
-                const int ql = lane & 3;
-                float bn = *reinterpret_cast<volatile float*>(a.thr_nn + (size_t) rb * 4 + ql);
-                float bh = *reinterpret_cast<volatile float*>(a.thr_hd + (size_t) rb * 4 + ql);
-                float lm = __ldg(a.lormax + (size_t) rb * 4 + ql);
+                // max over the 4 ra quarters of the row block
+                const int ql = lane % (4 * g.ra);
+                float bn = *reinterpret_cast<volatile float*>(a.thr_nn + (size_t) rb * 4 * g.ra + ql);
+                float bh = *reinterpret_cast<volatile float*>(a.thr_hd + (size_t) rb * 4 * g.ra + ql);
+                float lm = __ldg(a.lormax + (size_t) rb * 4 * g.ra + ql);
                 if (!(bn < INFINITY)) bn = INFINITY;
                 if (!(bh < INFINITY)) bh = INFINITY;
                 bound_nn = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(bn, 0.f))));
@@ -856,29 +908,30 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
                 // lanes with equal (l & 1) and equal (l >> 3): xor 2, 4 combine the four warps of a warpgroup
                 bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, 2));
                 bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, 4));
-                const float bn = fminf(bound_nn, fminf(__uint_as_float(__shfl_sync(0xffffffffu, bits, 0)),
-                                                       __uint_as_float(__shfl_sync(0xffffffffu, bits, 8))));
-                const float bh = fminf(bound_hd, fminf(__uint_as_float(__shfl_sync(0xffffffffu, bits, 1)),
-                                                       __uint_as_float(__shfl_sync(0xffffffffu, bits, 9))));
+                const float n0 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 0)), n1 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 8));
+                const float h0 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 1)), h1 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 9));
+                // ra == 2: the warpgroups hold different rows (the block needs the max); ra == 1: the same rows (the tighter counts)
+                const float bn = fminf(bound_nn, g.ra == 2 ? fmaxf(n0, n1) : fminf(n0, n1));
+                const float bh = fminf(bound_hd, g.ra == 2 ? fmaxf(h0, h1) : fminf(h0, h1));
                 if (!(lbv > bn)) return true;
                 return !(lbv > bh) && __ldg(a.lomin + tt) < lmax;
               },
               [&](uint32_t rb, uint32_t& lim0, uint32_t& lim1) {
                 if (a.window) {
-                  const uint32_t t = g.row_begin / GT + rb;
+                  const uint32_t t = g.row_begin / GT + rb * (uint32_t) g.ra;
                   lim0 = t > a.window ? t - a.window : 0u;
-                  lim1 = min(lim1, t + a.window + 1);
+                  lim1 = min(lim1, t + (uint32_t) g.ra + a.window);
                 }
               });
   } else if (warp == 1) {
-    g_mma(g, S, tmem_base);
+    if (g.ra == 2) g_mma<2>(g, S, tmem_base); else g_mma<1>(g, S, tmem_base);
   } else {
     const uint32_t wg = (uint32_t) (warp - 2) >> 2;
     const uint32_t quarter = (uint32_t) warp & 3u;
     const uint32_t row_in_tile = quarter * 32u + (uint32_t) lane;
     const int et = (warp - 2) * 32 + lane;
     float* scratch = S.scratch + et;
-    uint32_t seq = wg, uses = 0, cur_item = 0xfffffffeu, row = 0, lo_i = 0;
+    uint32_t seq = 0, tiles = 0, uses = 0, cur_item = 0xfffffffeu, row = 0, lo_i = 0;
     bool valid = false;
     float xn = INFINITY, rho = 0.f, eps = 0.f, lor = 0.f;
     float t_nn = -INFINITY, t_hd = -INFINITY, dl = 0.f;
@@ -926,8 +979,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
           // same quarter holds the same rows: both bounds are valid, atomicMin keeps the tighter)
           const uint2 b = publish();
           if (lane == 0) {
-            atomicMin(reinterpret_cast<unsigned int*>(a.thr_nn) + (size_t) m.row_tile * 4 + quarter, b.x);
-            atomicMin(reinterpret_cast<unsigned int*>(a.thr_hd) + (size_t) m.row_tile * 4 + quarter, b.y);
+            const size_t rt = (size_t) m.row_tile * g.ra + (g.ra == 2 ? wg : 0u);
+            atomicMin(reinterpret_cast<unsigned int*>(a.thr_nn) + rt * 4 + quarter, b.x);
+            atomicMin(reinterpret_cast<unsigned int*>(a.thr_hd) + rt * 4 + quarter, b.y);
           }
         }
         cur_item = 0xfffffffeu;
@@ -935,7 +989,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
         const bool first_of_item = cur_item != m.item;
         if (first_of_item) {
           cur_item = m.item;
-          row = g.row_begin + m.row_tile * GT + row_in_tile;
+          row = g.row_begin + (m.row_tile * (uint32_t) g.ra + (g.ra == 2 ? wg : 0u)) * GT + row_in_tile;
           valid = row < g.row_end;
           xn = valid ? __ldg(g.gnorm + row) : INFINITY;
           rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
@@ -949,11 +1003,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
           t_hd = (valid && lo_i != 0) ? thr(g_key_d2(best_hd)) : t_nn;
           set_dl();
         }
-        const uint32_t acc = seq & (G_ACC - 1);
-        mbar_wait(&S.tmem_full[acc], (uses >> acc) & 1u);
-        uses ^= 1u << acc;
+        const uint32_t p = tiles & ((uint32_t) (G_ACC / g.ra) - 1u);
+        ++tiles;
+        mbar_wait(&S.tmem_full[p], (uses >> p) & 1u);
+        uses ^= 1u << p;
         tc_fence_after();
-        ++n_tiles;
+        if (g.ra == 2 || wg == 0) ++n_tiles;
         const float* ny = rec + 4;
         const float* lc = rec + 4 + GT;
         bool improved = false;
@@ -1006,7 +1061,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
             }
           }
         };
-        g_epilogue_tile(S, tmem_base, quarter, acc, lane, proc);
+        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, (p * 2u + wg) * (uint32_t) GT, p, 0, 4, lane, proc);
+        else g_epilogue_tile(S, tmem_base, quarter, p * (uint32_t) GT, p, (int) wg * 64, 2, lane, proc);
         // bounds for the producer's dynamic pruning of this item: one slot pair per epilogue warp
         if (first_of_item || __any_sync(0xffffffffu, improved)) {
           const uint2 b = publish();
@@ -1018,7 +1074,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.side_empty[s]);
-      seq += 2;
+      ++seq;
     }
     for (int o = 16; o > 0; o >>= 1) {
       n_slow += __shfl_xor_sync(0xffffffffu, n_slow, o);

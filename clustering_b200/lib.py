@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libdcb200.so")
+# DCB200_LIB: alternative build of the same library (e.g. the -DDCB_GEMM_PROF diagnostics build)
+SO_PATH = os.environ.get("DCB200_LIB") or os.path.join(HERE, "libdcb200.so")
 
 # every symbol include/dcb200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
