@@ -809,8 +809,11 @@ static int fill_ggeom(dcb200_ctx* c, size_t row_begin, size_t row_end, GemmGeom*
   int avail = 8;
   while (avail > 2 && gemm_smem_bytes(g->ra * g->kc, avail) > (size_t) dev_smem) --avail;
   if (gemm_smem_bytes(g->ra * g->kc, avail) > (size_t) dev_smem) return fail("dcb200: GEMM-form kernel does not fit in shared memory");
-  // ring slots are freed in commit groups of cb chunks (at least two groups in the ring)
-  g->cb = avail >= 8 ? 4 : avail >= 4 ? 2 : 1;
+  // ring slots are freed in commit groups of cb chunks = 8 MMAs (512 tensor-pipe cycles, enough to hide the commit); finer
+  // groups keep more refills in flight: with 4 slots and groups of 2 the refill latency of half a tile was exposed
+  g->cb = g->ra == 2 ? 1 : (avail >= 4 ? 2 : 1);
+  { const char* e = getenv("DCB200_GEMM_CB"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) g->cb = e[0] - '0'; }
+  if (g->cb > avail / 2) g->cb = avail >= 4 ? 2 : 1;
   g->cb_log2 = g->cb == 4 ? 2 : g->cb == 2 ? 1 : 0;
   g->n_stages = avail / g->cb * g->cb;
   g->n = (uint32_t) c->n;
@@ -819,8 +822,8 @@ static int fill_ggeom(dcb200_ctx* c, size_t row_begin, size_t row_end, GemmGeom*
   g->row_end = (uint32_t) row_end;
   g->n_row_tiles128 = (uint32_t) ((row_end - row_begin + GT - 1) / GT);
   g->n_row_tiles = (g->n_row_tiles128 + g->ra - 1) / g->ra;
-  // about 8 column items per row block: the row tiles' operand images are loaded once per item
-  g->tiles_per_item = std::max(1u, std::min(g->n_tiles, std::max(32u, (g->n_tiles + 7) / 8)));
+  // about 16 column items per row block (load balance); the row tiles' operand images are loaded once per item
+  g->tiles_per_item = std::max(1u, std::min(g->n_tiles, std::max(32u, (g->n_tiles + 15) / 16)));
   g->n_col_items = (g->n_tiles + g->tiles_per_item - 1) / g->tiles_per_item;
   if ((uint64_t) g->n_row_tiles * g->n_col_items >= 0x7fffffffull) return fail("too many work items");
   *grid = (int) std::min<uint64_t>((uint64_t) c->sm_count, (uint64_t) g->n_row_tiles * g->n_col_items);

@@ -38,10 +38,11 @@ constexpr int G_MIN_D = 32, G_MAX_D = 256;
 constexpr int G_SIDE_SLOTS = 8;              // per-tile side records in flight
 constexpr int G_ACC = 4;                     // accumulator stages in tensor memory (4 x 128 columns = all of it)
 constexpr int G_SIDE_FLOATS = 4 + 2 * GT;    // meta (16 B), |y~|^2 [128], rank floats [128]
-constexpr int G_EPI_WARPS = 8;
+constexpr int G_EPI_WARPS = 16;
 constexpr int G_EPI_THREADS = G_EPI_WARPS * 32;
-constexpr int G_THREADS = 64 + G_EPI_THREADS;       // producer warp + MMA warp + two epilogue warpgroups
-constexpr int G_HALF = 16;                   // columns per band / hit test
+constexpr int G_THREADS = 64 + G_EPI_THREADS;       // producer warp + MMA warp + four epilogue warpgroups
+constexpr int G_LD = 16;                     // accumulator columns per TMEM load
+constexpr int G_HALF = 8;                    // columns per band / hit test
 
 // ------------------------------------------------------------------------------------------------
 // launch arguments (shared with the host code in api.cu)
@@ -130,31 +131,22 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 consecutive accumulator columns of this thread's TMEM lane: asynchronous load, then a wait that every later use of
+// 16 consecutive accumulator columns of this thread's TMEM lane: asynchronous load, then a wait that every later use of
 // the registers depends on (the "+r" operands), so that the next load can be in flight while a chunk is processed
-#define G_R32(X, r) X(r[0]), X(r[1]), X(r[2]), X(r[3]), X(r[4]), X(r[5]), X(r[6]), X(r[7]), X(r[8]), X(r[9]), X(r[10]), X(r[11]), X(r[12]), \
-    X(r[13]), X(r[14]), X(r[15]), X(r[16]), X(r[17]), X(r[18]), X(r[19]), X(r[20]), X(r[21]), X(r[22]), X(r[23]), X(r[24]), X(r[25]),     \
-    X(r[26]), X(r[27]), X(r[28]), X(r[29]), X(r[30]), X(r[31])
+#define G_R16(X, r) X(r[0]), X(r[1]), X(r[2]), X(r[3]), X(r[4]), X(r[5]), X(r[6]), X(r[7]), X(r[8]), X(r[9]), X(r[10]), X(r[11]), X(r[12]), \
+    X(r[13]), X(r[14]), X(r[15])
 #define G_OUT(x) "=r"(x)
 #define G_INOUT(x) "+r"(x)
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[G_LD]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : G_R32(G_OUT, r)
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : G_R16(G_OUT, r)
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : G_R32(G_INOUT, r)::"memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  tmem_ld32_issue(taddr, r);
-  tmem_ld32_wait(r);
-#pragma unroll
-  for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[G_LD]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : G_R16(G_INOUT, r)::"memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -377,13 +369,13 @@ struct GSmem {
   float* a;                   // ra x kc chunks
   float* ring;                // n_stages chunks
   float* side;                // G_SIDE_SLOTS records
-  float* scratch;             // G_EPI_THREADS x G_HALF
+  float* scratch;             // G_HALF x G_EPI_THREADS
   uint64_t *full, *empty;     // ring: full per slot, empty per commit group of cb slots
   uint64_t *side_full, *side_empty;
   uint64_t *tmem_full, *tmem_empty;      // G_ACC each
   uint64_t *a_full, *a_empty;
   uint32_t* tmem_addr;
-  unsigned long long* wthr;   // [8 epilogue warps][2]: (item << 32 | float bits) bounds published for the producer (nn, hd)
+  unsigned long long* wthr;   // [16 epilogue warps][2]: (item << 32 | float bits) bounds published for the producer (nn, hd)
   __host__ __device__ static size_t bytes(int akc, int n_stages) {        // akc = ra * kc
     return 1024 + (size_t) (akc + n_stages) * G_CHUNK_BYTES + (size_t) G_SIDE_SLOTS * G_SIDE_FLOATS * 4 +
            (size_t) G_EPI_THREADS * G_HALF * 4 + (size_t) (2 * 8 + 2 * G_SIDE_SLOTS + 2 * G_ACC + 2) * 8 + 16 + 2 * G_EPI_WARPS * 8;
@@ -646,7 +638,7 @@ __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
     }
     for (int s = 0; s < G_SIDE_SLOTS; ++s) {
       mbar_init(&S.side_full[s], 1);
-      mbar_init(&S.side_empty[s], 1 + G_EPI_WARPS);      // MMA warp + the eight epilogue warps
+      mbar_init(&S.side_empty[s], 1 + G_EPI_WARPS);      // MMA warp + the sixteen epilogue warps
     }
     for (int s = 0; s < G_ACC; ++s) {
       mbar_init(&S.tmem_full[s], 1);
@@ -659,29 +651,29 @@ __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
   }
 }
 
-// Epilogue of one warpgroup's share of an accumulator stage: n_loads (2 or 4) 32-column loads starting at column c_lo of
+// Epilogue of one warpgroup's share of an accumulator stage: n_loads (2 or 4) 16-column loads starting at column c_lo of
 // accumulator `acc_col`, each in flight while the previous chunk is processed; the stage is handed back to the MMA warp
 // as soon as the last load has landed in registers.  proc(regs, first column within the tile).
 template <class Proc>
 __device__ __forceinline__ void g_epilogue_tile(GSmem& S, uint32_t tmem_base, uint32_t quarter, uint32_t acc_col, uint32_t p, int c_lo,
                                                 int n_loads, int lane, Proc&& proc) {
-  uint32_t ra[32], rb[32];
+  uint32_t ra[G_LD], rb[G_LD];
   const uint32_t t0 = tmem_base + ((quarter * 32u) << 16) + acc_col + (uint32_t) c_lo;
-  tmem_ld32_issue(t0, ra);
+  tmem_ld16_issue(t0, ra);
 #pragma unroll 1
   for (int it = 0; 2 * it < n_loads; ++it) {
-    tmem_ld32_wait(ra);
-    tmem_ld32_issue(t0 + (uint32_t) (it * 64 + 32), rb);
-    proc(ra, c_lo + it * 64);
-    tmem_ld32_wait(rb);
+    tmem_ld16_wait(ra);
+    tmem_ld16_issue(t0 + (uint32_t) (it * 2 * G_LD + G_LD), rb);
+    proc(ra, c_lo + it * 2 * G_LD);
+    tmem_ld16_wait(rb);
     if (2 * it + 2 < n_loads) {
-      tmem_ld32_issue(t0 + (uint32_t) (it * 64 + 64), ra);
+      tmem_ld16_issue(t0 + (uint32_t) (it * 2 * G_LD + 2 * G_LD), ra);
     } else {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.tmem_empty[p]);
     }
-    proc(rb, c_lo + it * 64 + 32);
+    proc(rb, c_lo + it * 2 * G_LD + G_LD);
   }
 }
 
@@ -714,9 +706,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
   } else if (warp == 1) {
     if (g.ra == 2) g_mma<2>(g, S, tmem_base); else g_mma<1>(g, S, tmem_base);
   } else {
-    // ra == 2: warpgroup wg owns row tile wg of the block (all 128 columns of its accumulator); ra == 1: both warpgroups hold the
-    // same 128 rows and split the columns of the one accumulator (wg 0: 0..63, wg 1: 64..127)
+    // Four epilogue warpgroups, thread = one accumulator row.  ra == 2: warpgroup wg serves row tile (wg & 1) of the block,
+    // columns 64 (wg >> 1) .. + 63 of its accumulator; ra == 1: all four hold the same 128 rows, 32 columns each.
     const uint32_t wg = (uint32_t) (warp - 2) >> 2;
+    const uint32_t my_tile = g.ra == 2 ? (wg & 1u) : 0u;            // row tile of the block this thread's row belongs to
     const uint32_t quarter = (uint32_t) warp & 3u;                  // TMEM lanes 32 quarter .. 32 quarter + 31
     const uint32_t row_in_tile = quarter * 32u + (uint32_t) lane;
     const int et = (warp - 2) * 32 + lane;
@@ -746,7 +739,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
       } else {
         if (cur_item != m.item) {
           cur_item = m.item;
-          row = g.row_begin + (m.row_tile * (uint32_t) g.ra + (g.ra == 2 ? wg : 0u)) * GT + row_in_tile;
+          row = g.row_begin + (m.row_tile * (uint32_t) g.ra + my_tile) * GT + row_in_tile;
           valid = row < g.row_end;
           xn = valid ? __ldg(g.gnorm + row) : INFINITY;
           const float rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
@@ -765,11 +758,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
         G_TIMED(1, mbar_wait(&S.tmem_full[p], (uses >> p) & 1u));
         uses ^= 1u << p;
         tc_fence_after();
-        if (g.ra == 2 || wg == 0) ++n_tiles;
+        if (wg < (uint32_t) g.ra) ++n_tiles;                 // 128 x 128 units: one count per row tile of the record
         const float* ny = rec + 4;
-        auto proc = [&](const uint32_t (&v)[32], int c0) {
+        auto proc = [&](const uint32_t (&v)[G_LD], int c0) {
 #pragma unroll
-          for (int h = 0; h < 32; h += G_HALF) {
+          for (int h = 0; h < G_LD; h += G_HALF) {
             float mn[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) mn[b] = INFINITY;
@@ -827,8 +820,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             }
           }
         };
-        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, (p * 2u + wg) * (uint32_t) GT, p, 0, 4, lane, proc);
-        else g_epilogue_tile(S, tmem_base, quarter, p * (uint32_t) GT, p, (int) wg * 64, 2, lane, proc);
+        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, (p * 2u + my_tile) * (uint32_t) GT, p, (int) (wg >> 1) * 64, 4, lane, proc);
+        else g_epilogue_tile(S, tmem_base, quarter, p * (uint32_t) GT, p, (int) wg * 32, 2, lane, proc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.side_empty[s]);
@@ -896,23 +889,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
                 return fmaxf(bound_nn, bound_hd);
               },
               [&](uint32_t, uint32_t tt, float lbv, uint32_t item, int ln) {
-                // What the epilogue warps found since the item started.  Lane l < 16 reads slot l: warp l >> 1 (warps 0-3:
-                // warpgroup 0, 4-7: warpgroup 1), l & 1: nn / hd.  A warpgroup's bound is the max over its four warps (a warp
-                // that has not published for this item yet: +inf); both warpgroups hold valid bounds for the same rows, so
-                // the tighter one counts.
+                // What the epilogue warps found since the item started.  Lane l reads slot l: epilogue warp l >> 1 (warpgroup
+                // l >> 3), l & 1: nn / hd.  A warpgroup's bound is the max over its four warps (a warp that has not published
+                // for this item yet: +inf).  Warpgroups that hold the same rows both give valid bounds (the tighter counts);
+                // the block needs the max over its row tiles.
                 uint32_t bits = 0x7f800000u;
-                if (ln < 16) {
+                {
                   const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(S.wthr + ln);
                   if ((uint32_t) (v >> 32) == item) bits = (uint32_t) v;
                 }
-                // lanes with equal (l & 1) and equal (l >> 3): xor 2, 4 combine the four warps of a warpgroup
                 bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, 2));
                 bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, 4));
-                const float n0 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 0)), n1 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 8));
-                const float h0 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 1)), h1 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 9));
-                // ra == 2: the warpgroups hold different rows (the block needs the max); ra == 1: the same rows (the tighter counts)
-                const float bn = fminf(bound_nn, g.ra == 2 ? fmaxf(n0, n1) : fminf(n0, n1));
-                const float bh = fminf(bound_hd, g.ra == 2 ? fmaxf(h0, h1) : fminf(h0, h1));
+                const int kind = ln & 1;
+                const float w0 = __uint_as_float(__shfl_sync(0xffffffffu, bits, kind)), w1 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 8 + kind));
+                const float w2 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 16 + kind)), w3 = __uint_as_float(__shfl_sync(0xffffffffu, bits, 24 + kind));
+                // ra == 2: warpgroups 0, 2 hold row tile 0 and 1, 3 row tile 1; ra == 1: all four hold the same rows
+                const float mine = g.ra == 2 ? fmaxf(fminf(w0, w2), fminf(w1, w3)) : fminf(fminf(w0, w1), fminf(w2, w3));
+                const float bn = fminf(bound_nn, __shfl_sync(0xffffffffu, mine, 0));
+                const float bh = fminf(bound_hd, __shfl_sync(0xffffffffu, mine, 1));
                 if (!(lbv > bn)) return true;
                 return !(lbv > bh) && __ldg(a.lomin + tt) < lmax;
               },
@@ -926,7 +920,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
   } else if (warp == 1) {
     if (g.ra == 2) g_mma<2>(g, S, tmem_base); else g_mma<1>(g, S, tmem_base);
   } else {
-    const uint32_t wg = (uint32_t) (warp - 2) >> 2;
+    const uint32_t wg = (uint32_t) (warp - 2) >> 2;                 // see gscan_pops_kernel
+    const uint32_t my_tile = g.ra == 2 ? (wg & 1u) : 0u;
     const uint32_t quarter = (uint32_t) warp & 3u;
     const uint32_t row_in_tile = quarter * 32u + (uint32_t) lane;
     const int et = (warp - 2) * 32 + lane;
@@ -979,7 +974,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
           // same quarter holds the same rows: both bounds are valid, atomicMin keeps the tighter)
           const uint2 b = publish();
           if (lane == 0) {
-            const size_t rt = (size_t) m.row_tile * g.ra + (g.ra == 2 ? wg : 0u);
+            const size_t rt = (size_t) m.row_tile * g.ra + my_tile;
             atomicMin(reinterpret_cast<unsigned int*>(a.thr_nn) + rt * 4 + quarter, b.x);
             atomicMin(reinterpret_cast<unsigned int*>(a.thr_hd) + rt * 4 + quarter, b.y);
           }
@@ -989,7 +984,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
         const bool first_of_item = cur_item != m.item;
         if (first_of_item) {
           cur_item = m.item;
-          row = g.row_begin + (m.row_tile * (uint32_t) g.ra + (g.ra == 2 ? wg : 0u)) * GT + row_in_tile;
+          row = g.row_begin + (m.row_tile * (uint32_t) g.ra + my_tile) * GT + row_in_tile;
           valid = row < g.row_end;
           xn = valid ? __ldg(g.gnorm + row) : INFINITY;
           rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
@@ -1008,13 +1003,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
         mbar_wait(&S.tmem_full[p], (uses >> p) & 1u);
         uses ^= 1u << p;
         tc_fence_after();
-        if (g.ra == 2 || wg == 0) ++n_tiles;
+        if (wg < (uint32_t) g.ra) ++n_tiles;                 // 128 x 128 units: one count per row tile of the record
         const float* ny = rec + 4;
         const float* lc = rec + 4 + GT;
         bool improved = false;
-        auto proc = [&](const uint32_t (&v)[32], int c0) {
+        auto proc = [&](const uint32_t (&v)[G_LD], int c0) {
 #pragma unroll
-          for (int h = 0; h < 32; h += G_HALF) {
+          for (int h = 0; h < G_LD; h += G_HALF) {
             bool any = false;
 #pragma unroll
             for (int c4 = 0; c4 < G_HALF; c4 += 4) {
@@ -1061,8 +1056,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
             }
           }
         };
-        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, (p * 2u + wg) * (uint32_t) GT, p, 0, 4, lane, proc);
-        else g_epilogue_tile(S, tmem_base, quarter, p * (uint32_t) GT, p, (int) wg * 64, 2, lane, proc);
+        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, (p * 2u + my_tile) * (uint32_t) GT, p, (int) (wg >> 1) * 64, 4, lane, proc);
+        else g_epilogue_tile(S, tmem_base, quarter, p * (uint32_t) GT, p, (int) wg * 32, 2, lane, proc);
         // bounds for the producer's dynamic pruning of this item: one slot pair per epilogue warp
         if (first_of_item || __any_sync(0xffffffffu, improved)) {
           const uint2 b = publish();
