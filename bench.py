@@ -271,7 +271,8 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(x_dev)
     barrier()
-    peak_tflops = sess.ffma_peak(300.0)
+    tensor_path = sess.gemm_info()[0]                   # 32 <= n_cols <= 256: the scans run on the tensor cores (tcgen05, TF32)
+    peak_tflops = sess.tf32_peak(300.0) if tensor_path else sess.ffma_peak(300.0)
     s0 = sess.stats(reset=True)
     barrier()
     ms = timed(x_dev, args.steps)
@@ -347,8 +348,8 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "tf32 filter + f32 exact recheck" if tensor_path else "f32", "data": "synthetic",
             "config": {"workload": workload_label(args.workload, cfg),
                        "step": "layout build + populations + free energies + nearest neighbours (+ lower-free-energy neighbour)",
                        "pair_dims_per_step": pd, "parallelism": f"rows sharded over {world} GPU(s), coords replicated, NCCL all-gather of populations and neighbour keys",
@@ -363,19 +364,24 @@ def run_ours(args):
             pairs = float(n) * float(n)
             achieved = FLOP_EXECUTED_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12
             line["roofline"] = {
-                "bound": "fp32", "kernel": kname,
+                "bound": "tensor" if tensor_path else "fp32", "kernel": kname,
                 "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                 "kernel_ms": kms,
                 "pairs_evaluated_per_launch": k_pairs, "pairs_evaluated_frac": k_pairs / pairs,
                 "evaluated_gpair_dim_per_s": k_pairs * d / (kms * 1e-3) / 1e9,
                 "effective_gpair_dim_per_s": pairs * d / (kms * 1e-3) / 1e9,
                 "algorithmic_3flop_tflops_on_evaluated_pairs": FLOP_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12,
-                "peak_source": "FFMA-only microbenchmark in this run (dcb200_ctx_ffma_peak); MEASURED_PEAKS.json has no FP32 entry",
-                "traffic": ncu_traffic(kname),
+                "peak_source": ("tcgen05.mma kind::tf32 128x128x8 back to back on resident operands, measured in this run "
+                                "(dcb200_ctx_tf32_peak); MEASURED_PEAKS.json holds bf16 only (TF32 runs at half the bf16 rate)") if tensor_path else
+                               "FFMA-only microbenchmark in this run (dcb200_ctx_ffma_peak); MEASURED_PEAKS.json has no FP32 entry",
+                "traffic": ncu_traffic(("gscan_" + ("nn" if kname.startswith("nn") else "pops")) if tensor_path else kname),
                 "other_scans": {k: {"kernel_ms": v[0], "pairs_evaluated_frac": v[1] / pairs,
                                     "achieved_tflops": FLOP_EXECUTED_PER_PAIR_DIM * v[1] * d / (v[0] * 1e-3) / 1e12}
                                 for k, v in scans.items() if k != kname},
-                "note": "compute-bound path (SURVEY.md 8d): the roofline is the FP32 FFMA pipe, not HBM. achieved = 2 flop (one FFMA) per "
+                "note": ("GEMM-form path (n_cols >= 32): the roofline is the tensor pipe (TF32). achieved = 2 flop per pair.dim x the pairs of "
+                         "the 128 x 128 tile pairs the kernel really multiplied; pruned tile pairs are not counted; the headline value "
+                         "counts the full N x N matrix") if tensor_path else
+                        "compute-bound path (SURVEY.md 8d): the roofline is the FP32 FFMA pipe, not HBM. achieved = 2 flop (one FFMA) per "
                         "pair.dim x the pairs the kernel really evaluated = (warp, tile) scans x 128 rows x 128 columns; tiles out of reach "
                         "of a row block / of a warp's rows are pruned and not counted; the headline value counts the full N x N matrix. "
                         "traffic = dram bytes per launch from the committed ncu capture (profiles/), null if none",

@@ -1326,6 +1326,41 @@ extern "C" int dcb200_ctx_gemm_info(dcb200_ctx* c, int* active, float* check_rat
   return 0;
 }
 
+// Diagnostics: throughput of tcgen05.mma kind::tf32 (128 x 128 x 8, operands resident in shared memory, random data) on all
+// SMs, in TFLOP/s (2 flop per multiply-add), timed with CUDA events: the denominator of the tensor roofline of the GEMM-form scans.
+extern "C" int dcb200_ctx_tf32_peak(dcb200_ctx* c, double ms_target, double* tflops) {
+  if (!c || !tflops) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  long long* out = nullptr;
+  CK(cudaMalloc(&out, (size_t) c->sm_count * sizeof(long long)));
+  const int iters = 1 << 16;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(launch_tf32_peak(c->sm_count, iters, out, c->stream));        // warm-up
+  CK(cudaStreamSynchronize(c->stream));
+  double best = 0.0, spent = 0.0;
+  int launches = 1;
+  while (spent < ms_target) {
+    CK(cudaEventRecord(e0, c->stream));
+    CK(launch_tf32_peak(c->sm_count, iters, out, c->stream));
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    spent += ms;
+    launches += 1;
+    const double fl = 2.0 * GT * GT * 8.0 * (double) iters * (double) c->sm_count;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  c->launches += launches;
+  *tflops = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return 0;
+}
+
 // Diagnostics: sustained FFMA throughput of the device (TFLOP/s, 2 flop per FFMA), measured with CUDA
 // events over `ms_target` milliseconds of back-to-back launches.  Used by bench.py as the FP32 roofline peak.
 extern "C" int dcb200_ctx_ffma_peak(dcb200_ctx* c, double ms_target, double* tflops) {

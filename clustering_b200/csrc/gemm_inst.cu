@@ -65,4 +65,12 @@ cudaError_t launch_gnn_tile_thr(const unsigned long long* key_nn, const unsigned
   return cudaGetLastError();
 }
 
+cudaError_t launch_tf32_peak(int grid, int iters, long long* out, cudaStream_t st) {
+  const size_t smem = 1024 + (size_t) G_CHUNK_BYTES * 8;
+  cudaError_t e = cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  tf32_peak_kernel<<<grid, 64, smem, st>>>(iters, out);
+  return cudaGetLastError();
+}
+
 }  // namespace dcb

@@ -1119,6 +1119,47 @@ __global__ void gnn_tile_thr_kernel(const unsigned long long* __restrict__ key_n
   }
 }
 
+// tcgen05.mma kind::tf32 128 x 128 x 8 issued back to back on resident operands: the denominator of the tensor roofline
+// (out[blockIdx.x] = cycles for `iters` MMAs)
+__global__ void __launch_bounds__(64, 1) tf32_peak_kernel(int iters, long long* out) {
+  extern __shared__ unsigned char g_smem_raw[];
+  __shared__ uint64_t fin;
+  __shared__ uint32_t taddr;
+  unsigned char* base = g_smem_raw + ((1024u - (smem_u32(g_smem_raw) & 1023u)) & 1023u);
+  float* a = reinterpret_cast<float*>(base);
+  for (int i = threadIdx.x; i < G_CHUNK_FLOATS * 8; i += blockDim.x) {
+    uint32_t h = (uint32_t) i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    a[i] = to_tf32(((float) (h & 0xffffffu) / 16777216.0f - 0.5f) * 2.0f);         // random operands (power draw like real data)
+  }
+  if (threadIdx.x == 0) { mbar_init(&fin, 1); fence_mbar_init(); }
+  __syncthreads();
+  const int warp = uniform_warp();
+  if (warp == 1) tmem_alloc(&taddr, 2 * GT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *reinterpret_cast<volatile uint32_t*>(&taddr);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) {
+    const bool leader = elect_one();
+    const uint64_t a0 = g_smem_desc(smem_u32(a)), b0 = g_smem_desc(smem_u32(a + 4 * G_CHUNK_FLOATS));
+    const long long t0 = clock64();
+    if (leader) {
+      for (uint32_t i = 0; i < (uint32_t) iters; ++i) {
+        const uint64_t off = (uint64_t) ((i >> 2) & 3) * (G_CHUNK_BYTES >> 4) + 2 * (i & 3);
+        tc_mma_tf32(tb + ((i >> 4) & 1) * (uint32_t) GT, a0 + off, b0 + off, G_IDESC, (i & 15) ? 1u : 0u);
+      }
+      tc_commit(&fin);
+      mbar_wait(&fin, 0);
+      out[blockIdx.x] = clock64() - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tb, 2 * GT);
+}
+
 #endif  // DCB_GEMM_KERNELS
 
 }  // namespace dcb

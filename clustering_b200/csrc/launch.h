@@ -32,6 +32,7 @@ cudaError_t launch_gpack(const float* coords, size_t n, int d, int kc, size_t n_
 cudaError_t launch_tile_lb(const float* tcen, const float* tlo, const float* thi, const float* trad, int d, size_t n_tiles, uint32_t s0,
                            uint32_t s1, float* lb, cudaStream_t st);
 cudaError_t launch_tile_min(const float* lof, size_t n_tiles, float* lomin, cudaStream_t st);
+cudaError_t launch_tf32_peak(int grid, int iters, long long* out, cudaStream_t st);
 cudaError_t launch_gpops(const GPopsArgs& a, int grid, bool check, cudaStream_t st);
 cudaError_t launch_gnn(const GNnArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_gnn_tile_thr(const unsigned long long* key_nn, const unsigned long long* key_hd, const uint32_t* lo, const float* lof,

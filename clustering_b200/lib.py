@@ -22,7 +22,7 @@ SYMBOLS = [
     "dcb200_ctx_to_frame_order", "dcb200_ctx_populations",
     "dcb200_ctx_free_energies", "dcb200_ctx_nn_prepare", "dcb200_ctx_nn_scan", "dcb200_ctx_nn_finish",
     "dcb200_ctx_screening_scan", "dcb200_ctx_screening_flatten", "dcb200_ctx_screening_merge", "dcb200_ctx_stats", "dcb200_ctx_ffma_peak",
-    "dcb200_ctx_gemm_info",
+    "dcb200_ctx_gemm_info", "dcb200_ctx_tf32_peak",
 ]
 
 _f = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
@@ -78,6 +78,7 @@ def load():
     L.dcb200_ctx_order.argtypes = [_p, _p]
     L.dcb200_ctx_to_frame_order.argtypes = [_p, _p, _sz, _p]
     L.dcb200_ctx_ffma_peak.argtypes = [_p, C.c_double, C.POINTER(C.c_double)]
+    L.dcb200_ctx_tf32_peak.argtypes = [_p, C.c_double, C.POINTER(C.c_double)]
     L.dcb200_ctx_gemm_info.argtypes = [_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
     _lib = L
     return L

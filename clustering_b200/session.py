@@ -54,6 +54,11 @@ class Session:
         lib.check(self.L.dcb200_ctx_ffma_peak(self.h, float(ms_target), C.byref(t)))
         return t.value
 
+    def tf32_peak(self, ms_target=200.0):
+        t = C.c_double(0.0)
+        lib.check(self.L.dcb200_ctx_tf32_peak(self.h, float(ms_target), C.byref(t)))
+        return t.value
+
     def gemm_info(self):
         """(active, check_ratio) of the GEMM-form tensor-core path (32 <= n_cols <= 256), see dcb200_ctx_gemm_info."""
         a, r = C.c_int(0), C.c_float(0.0)

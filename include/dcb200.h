@@ -171,6 +171,10 @@ int dcb200_ctx_stats(dcb200_ctx* ctx, uint64_t stats[6], int reset);
  * populations calls made with DCB200_GEMM_CHECK=1 in the environment (0 if none); either pointer may be NULL */
 int dcb200_ctx_gemm_info(dcb200_ctx* ctx, int* active, float* check_ratio);
 
+/* diagnostics: tcgen05.mma kind::tf32 throughput of the device in TFLOP/s (operands resident in shared memory), the tensor
+ * roofline denominator of the GEMM-form scans */
+int dcb200_ctx_tf32_peak(dcb200_ctx* ctx, double ms_target, double* tflops);
+
 /* diagnostics: FFMA-only throughput of the device in TFLOP/s (2 flop per FFMA), the FP32 roofline denominator */
 int dcb200_ctx_ffma_peak(dcb200_ctx* ctx, double ms_target, double* tflops);
 
