@@ -192,6 +192,38 @@ def run_reference(args):
     }))
 
 
+def reference_cuda_arm(x, radii, d, density):
+    """The reference's own CUDA path (unmodified .cu files built for sm_100a, oracle/_ref/libdcrefcuda.so) on a bounded sample of
+    the workload, next to this library on the same sample: the "kernel to beat" of BASELINE.json's north_star.  Reported, never
+    used as a parity oracle (its semantics differ from the CPU path: d2 <= r2, duplicates excluded)."""
+    try:
+        from _oracle import RefCuda, REFCUDA_SO
+        if not os.path.exists(REFCUDA_SO):
+            return {"unavailable": "oracle/_ref/libdcrefcuda.so not built (make -C oracle refcuda needs /root/reference)"}
+        if d > 12:
+            return {"unavailable": f"the reference's population kernel needs 2*512*n_cols*4 B <= 48 KB of shared memory: n_cols <= 12, workload has {d}"}
+        rc = RefCuda()
+        ns = min(len(x), 250_000)
+        xs = np.ascontiguousarray(x[:ns])
+        r1 = np.ascontiguousarray(radii[:1])
+        rc.populations(xs[:20000], r1)                       # warm-up (context, module load)
+        t0 = time.perf_counter(); pr = rc.populations(xs, r1); t_p = time.perf_counter() - t0
+        fe = density.calculate_free_energies(pr[0].astype(np.uint32))
+        t0 = time.perf_counter(); rc.nearest_neighbors(xs, fe); t_n = time.perf_counter() - t0
+        density.calculate_populations(xs[:20000], r1)
+        t0 = time.perf_counter(); po = density.calculate_populations(xs, r1); t_po = time.perf_counter() - t0
+        t0 = time.perf_counter(); density.nearest_neighbors(xs, fe); t_no = time.perf_counter() - t0
+        return {"sample": f"first {ns} frames of the workload, radius {float(r1[0]):g}; host-pointer calls (H2D/D2H inside), wall clock",
+                "populations_ms": t_p * 1e3, "nearest_neighbors_ms": t_n * 1e3,
+                "value": pair_dims_per_step(ns, d) / (t_p + t_n) / 1e9, "unit": UNIT,
+                "ours_same_sample": {"populations_ms": t_po * 1e3, "nearest_neighbors_ms": t_no * 1e3,
+                                     "value": pair_dims_per_step(ns, d) / (t_po + t_no) / 1e9},
+                "population_counts_differing": int(np.count_nonzero(pr[0] != po[0])),
+                "note": "differences in counts come from the reference CUDA path's own rounding (sequential FMA) and '<=' test"}
+    except Exception as ex:
+        return {"unavailable": f"failed: {ex}"}
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -396,6 +428,8 @@ def run_ours(args):
                     "sample": f"first {ns} frames of the workload, one pops+FE+NN step in {sec:.1f} s (brute-force NN is quadratic; pops is box-pruned, counted as full N x N)"}
             except Exception as ex:                       # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+        if not args.no_cpu_baseline and world == 1:
+            line["reference_cuda"] = reference_cuda_arm(x, radii, d, density)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -12,6 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "libdcoracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libdcref.so")
+REFCUDA_SO = os.path.join(ROOT, "oracle", "_ref", "libdcrefcuda.so")
 
 _f = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _u32 = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
@@ -223,3 +224,33 @@ class Ref:
         out = np.empty(clustering.size, np.uint64)
         self.L.dcref_sorted_cluster_names(clustering, clustering.size, out)
         return out
+
+
+class RefCuda:
+    """The reference's own CUDA path (oracle/_ref/libdcrefcuda.so, built by `make -C oracle refcuda` from the unmodified
+    reference .cu files for sm_100a).  Benchmark comparator only: its semantics differ from the CPU path."""
+
+    def __init__(self):
+        self.L = C.CDLL(REFCUDA_SO)
+        f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+        u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+        self.L.dcrefcuda_populations.argtypes = [f32, C.c_uint64, C.c_uint64, f32, C.c_uint64, u64]
+        self.L.dcrefcuda_nearest_neighbors.argtypes = [f32, C.c_uint64, C.c_uint64, f32, u64, f32, u64, f32]
+
+    def num_gpus(self):
+        return self.L.dcrefcuda_num_gpus()
+
+    def populations(self, coords, radii):
+        coords = _c(coords, np.float32); n, d = coords.shape
+        radii = _c(radii, np.float32)
+        out = np.empty((radii.size, n), np.uint64)
+        self.L.dcrefcuda_populations(coords, n, d, radii, radii.size, out)
+        return out
+
+    def nearest_neighbors(self, coords, fe):
+        coords = _c(coords, np.float32); n, d = coords.shape
+        fe = _c(fe, np.float32)
+        ni = np.empty(n, np.uint64); nd = np.empty(n, np.float32)
+        hi = np.empty(n, np.uint64); hd = np.empty(n, np.float32)
+        self.L.dcrefcuda_nearest_neighbors(coords, n, d, fe, ni, nd, hi, hd)
+        return ni, nd, hi, hd
