@@ -313,9 +313,12 @@ int density_main(const Args& args, const std::string& header_comment) {
       if (!args.count("radius")) {
         // no radius given: the clustering radius is the lumping radius sqrt(4 sigma^2) of a first pass with radius 1
         log << "    computing lumping radius" << std::endl;
-        const std::vector<uint32_t> pops = populations_single(coords, radius_lump);
-        free_energies = free_energies_of(pops);
-        const Neighbours nb = nearest_neighbours(coords, free_energies);
+        // The reference runs populations(r = 1) + free energies + neighbours here (density_clustering.cpp:646-673, with a TODO
+        // that only sigma is needed).  sigma^2 is the mean squared NEAREST-neighbour distance, which does not depend on the
+        // free energies: one neighbour scan with a constant free energy (no frame has a lower one, so the lower-free-energy
+        // search is empty) gives the same bits and saves the most expensive population pass of the run.
+        const std::vector<float> flat(coords.n_rows, 0.f);
+        const Neighbours nb = nearest_neighbours(coords, flat);
         const double sigma2 = sigma2_of(nb.nn_d2);
         radius_lump = sqrt(4 * sigma2);
         log << "        d_lump=" << radius_lump << std::endl;

@@ -1010,17 +1010,29 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
         auto proc = [&](const uint32_t (&v)[G_LD], int c0) {
 #pragma unroll
           for (int h = 0; h < G_LD; h += G_HALF) {
-            bool any = false;
+            // two-level filter: most tile pairs are far (only the lower-free-energy search reaches them) and hold nothing below
+            // even the looser threshold t_hd >= t_nn: one FFMA + one min per pair settles those; the per-pair free-energy-aware
+            // threshold is evaluated only where the group's minimum gets under t_hd
+            float w[G_HALF];
+            float wmin = INFINITY;
 #pragma unroll
             for (int c4 = 0; c4 < G_HALF; c4 += 4) {
               const float4 n4 = *reinterpret_cast<const float4*>(ny + c0 + h + c4);
-              const float4 l4 = *reinterpret_cast<const float4*>(lc + c0 + h + c4);
               const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const float w = fmaf(__uint_as_float(v[h + c4 + c]), -2.0f, nn[c]);
-                any |= w < fmaf(__saturatef(lor - ll[c]), dl, t_nn);
+                w[c4 + c] = fmaf(__uint_as_float(v[h + c4 + c]), -2.0f, nn[c]);
+                wmin = fminf(wmin, w[c4 + c]);
+              }
+            }
+            bool any = false;
+            if (wmin < t_hd) {
+#pragma unroll
+              for (int c4 = 0; c4 < G_HALF; c4 += 4) {
+                const float4 l4 = *reinterpret_cast<const float4*>(lc + c0 + h + c4);
+                const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) any |= w[c4 + c] < fmaf(__saturatef(lor - ll[c]), dl, t_nn);
               }
             }
             if (any) {
