@@ -742,6 +742,16 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
         for (int b = 0; b < NB; ++b)
 #pragma unroll
           for (int r = 0; r < RI; ++r) cnt[b][r] = 0;
+        // one or two radii: v = acc + (|x'|^2 - r^2) with the row constant formed once per unit, one FADD per pair and radius
+        // (the two roundings -- of the constant, <= u max(|x'|^2, r^2), and of v -- are inside the band like those of s and v)
+        constexpr bool FOLD = NB <= 2;
+        float qrow[FOLD ? NB : 1][RI];
+        if (FOLD) {
+#pragma unroll
+          for (int b = 0; b < (FOLD ? NB : 1); ++b)
+#pragma unroll
+            for (int r = 0; r < RI; ++r) qrow[b][r] = R.xn[r] - a.rad2[b];
+        }
 #pragma unroll 1
         for (int gcol = 0; gcol < TJ; gcol += CJ) {
           float acc[RI][CJ];
@@ -770,11 +780,12 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
           bool band = false;
 #pragma unroll
           for (int r = 0; r < RI; ++r) {
-            const float s0 = acc[r][0] + R.xn[r], s1 = acc[r][1] + R.xn[r];
-            const float s2 = acc[r][2] + R.xn[r], s3 = acc[r][3] + R.xn[r];
+            const float s0 = FOLD ? acc[r][0] : acc[r][0] + R.xn[r], s1 = FOLD ? acc[r][1] : acc[r][1] + R.xn[r];
+            const float s2 = FOLD ? acc[r][2] : acc[r][2] + R.xn[r], s3 = FOLD ? acc[r][3] : acc[r][3] + R.xn[r];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-              const float v0 = s0 - a.rad2[b], v1 = s1 - a.rad2[b], v2 = s2 - a.rad2[b], v3 = s3 - a.rad2[b];
+              const float sub = FOLD ? qrow[FOLD ? b : 0][r] : -a.rad2[b];
+              const float v0 = s0 + sub, v1 = s1 + sub, v2 = s2 + sub, v3 = s3 + sub;
               cnt[b][r] += (__float_as_uint(v0) >> 31) + (__float_as_uint(v1) >> 31);
               cnt[b][r] += (__float_as_uint(v2) >> 31) + (__float_as_uint(v3) >> 31);
               const float mn = fminf(fminf(fabsf(v0), fabsf(v1)), fminf(fabsf(v2), fabsf(v3)));
@@ -787,7 +798,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
 #pragma unroll
             for (int r = 0; r < RI; ++r)
 #pragma unroll
-              for (int c = 0; c < CJ; ++c) scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c] + R.xn[r];
+              for (int c = 0; c < CJ; ++c) scratch[(r * CJ + c) * N_CONSUMERS] = FOLD ? acc[r][c] : acc[r][c] + R.xn[r];
 #pragma unroll 1
             for (int p = 0; p < RI * CJ; ++p) {
               const int r = p / CJ;
@@ -797,7 +808,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
               bool have = false;
 #pragma unroll
               for (int b = 0; b < NB; ++b) {
-                const float v = sv - a.rad2[b];
+                const float v = FOLD ? sv + sel4(qrow[FOLD ? b : 0], r) : sv - a.rad2[b];      // the very value the sign-bit count used
                 if (fabsf(v) < wr + a.band[b] && R.row(r) < g.row_end) {
                   ++st.slow;
                   if (!have) {
