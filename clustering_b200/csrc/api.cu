@@ -809,11 +809,13 @@ static int fill_ggeom(dcb200_ctx* c, size_t row_begin, size_t row_end, GemmGeom*
   int avail = 8;
   while (avail > 2 && gemm_smem_bytes(g->ra * g->kc, avail) > (size_t) dev_smem) --avail;
   if (gemm_smem_bytes(g->ra * g->kc, avail) > (size_t) dev_smem) return fail("dcb200: GEMM-form kernel does not fit in shared memory");
-  // ring slots are freed in commit groups of cb chunks = 8 MMAs (512 tensor-pipe cycles, enough to hide the commit); finer
-  // groups keep more refills in flight: with 4 slots and groups of 2 the refill latency of half a tile was exposed
-  g->cb = g->ra == 2 ? 1 : (avail >= 4 ? 2 : 1);
-  { const char* e = getenv("DCB200_GEMM_CB"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) g->cb = e[0] - '0'; }
-  if (g->cb > avail / 2) g->cb = avail >= 4 ? 2 : 1;
+  // ring slots are filled and freed in groups of cb chunks (one mbarrier wait, one fence and one tcgen05.commit per group in the
+  // single MMA-issuing warp, whose serial instruction stream is what limits the scan); cb divides kc so that a group never
+  // straddles two tiles, and the ring holds at least two groups
+  g->cb = 1;
+  for (int cand = 4; cand >= 2; cand >>= 1)
+    if (g->kc % cand == 0 && avail / cand >= 2) { g->cb = cand; break; }
+  { const char* e = getenv("DCB200_GEMM_CB"); const int v = e ? atoi(e) : 0; if ((v == 1 || v == 2 || v == 4) && g->kc % v == 0 && avail / v >= 2) g->cb = v; }
   g->cb_log2 = g->cb == 4 ? 2 : g->cb == 2 ? 1 : 0;
   g->n_stages = avail / g->cb * g->cb;
   g->n = (uint32_t) c->n;

@@ -40,7 +40,8 @@ constexpr int G_ACC = 4;                     // accumulator stages in tensor mem
 constexpr int G_SIDE_FLOATS = 4 + 2 * GT;    // meta (16 B), |y~|^2 [128], rank floats [128]
 constexpr int G_EPI_WARPS = 16;
 constexpr int G_EPI_THREADS = G_EPI_WARPS * 32;
-constexpr int G_THREADS = 64 + G_EPI_THREADS;       // producer warp + MMA warp + four epilogue warpgroups
+constexpr int G_THREADS = 64 + G_EPI_THREADS + 32;  // producer warp, MMA warp, four epilogue warpgroups, second MMA warp (ra == 2)
+constexpr int G_MMA2_WARP = 2 + G_EPI_WARPS;        // warp index of the second MMA issuer
 constexpr int G_LD = 16;                     // accumulator columns per TMEM load
 constexpr int G_HALF = 8;                    // columns per band / hit test
 
@@ -370,7 +371,7 @@ struct GSmem {
   float* ring;                // n_stages chunks
   float* side;                // G_SIDE_SLOTS records
   float* scratch;             // G_HALF x G_EPI_THREADS
-  uint64_t *full, *empty;     // ring: full per slot, empty per commit group of cb slots
+  uint64_t *full, *empty;     // ring: one full / empty barrier per group of cb slots
   uint64_t *side_full, *side_empty;
   uint64_t *tmem_full, *tmem_empty;      // G_ACC each
   uint64_t *a_full, *a_empty;
@@ -512,9 +513,13 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
           side_slot(0u, rb, tt * GT, item, tt, true);
           const float* src_b = g.gT + (size_t) tt * g.kc * G_CHUNK_FLOATS;
           for (int q = 0; q < g.kc; ++q) {
-            if ((stage & (uint32_t) (g.cb - 1)) == 0) G_TIMED(1, mbar_wait(&S.empty[stage >> g.cb_log2], phase ^ 1u));
-            mbar_arrive_expect_tx(&S.full[stage], G_CHUNK_BYTES);
-            tma_load_1d(S.ring + (size_t) stage * G_CHUNK_FLOATS, src_b + (size_t) q * G_CHUNK_FLOATS, G_CHUNK_BYTES, &S.full[stage]);
+            // ring slots are filled and freed in groups of cb chunks (cb divides kc: a group never straddles two tiles)
+            const uint32_t grp = stage >> g.cb_log2;
+            if ((stage & (uint32_t) (g.cb - 1)) == 0) {
+              G_TIMED(1, mbar_wait(&S.empty[grp], phase ^ 1u));
+              mbar_arrive_expect_tx(&S.full[grp], (uint32_t) g.cb * G_CHUNK_BYTES);
+            }
+            tma_load_1d(S.ring + (size_t) stage * G_CHUNK_FLOATS, src_b + (size_t) q * G_CHUNK_FLOATS, G_CHUNK_BYTES, &S.full[grp]);
             if (++stage == (uint32_t) g.n_stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -549,20 +554,20 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
 // spent ~300 SASS instructions per chunk and reached 1/3 of the MMA rate).  Ring slots are handed back cb at a time and
 // the accumulators are published once per column tile (tcgen05.commit is not free either).
 template <int RA>
-__device__ __forceinline__ void g_mma(const GemmGeom& g, GSmem& S, uint32_t tmem_base) {
+__device__ __forceinline__ void g_mma(const GemmGeom& g, GSmem& S, uint32_t tmem_base, uint32_t r_mine) {
   uint32_t stage = 0, phase = 0, seq = 0, a_uses = 0, tiles = 0;
-  uint32_t acc_uses = 0;                    // bit field: parity of the uses of each accumulator stage
+  uint32_t acc_uses = 0;                    // bit field: parity of the uses of each accumulator
   bool need_a = true;
   unsigned long long pacc[5] = {0, 0, 0, 0, 0};
   const long long t_begin = clock64();
-  const uint64_t a_desc0 = g_smem_desc(smem_u32(S.a));
-  const uint64_t b_desc0 = g_smem_desc(smem_u32(S.ring));
   const uint32_t cb_mask = (uint32_t) g.cb - 1u, cb_log2 = (uint32_t) g.cb_log2;
   constexpr uint32_t p_mask = (uint32_t) (G_ACC / RA) - 1u;      // 4 or 2 accumulator stages
   const int kc = g.kc;
   const int kc_full = g.k8 >> 2;                                 // chunks with all four K steps
   const int tail_steps = g.k8 & 3;                               // K steps of the last chunk if it is partial
-  const uint64_t a_row_stride = (uint64_t) kc * (G_CHUNK_BYTES >> 4);   // second row tile's image in the address field
+  // this warp's row tile: its operand image follows the first one in shared memory
+  const uint64_t a_desc0 = g_smem_desc(smem_u32(S.a)) + (uint64_t) r_mine * (uint64_t) kc * (G_CHUNK_BYTES >> 4);
+  const uint64_t b_desc0 = g_smem_desc(smem_u32(S.ring));
   const uint32_t n_stages = (uint32_t) g.n_stages;
   const bool leader = elect_one();
   for (;;) {
@@ -579,49 +584,40 @@ __device__ __forceinline__ void g_mma(const GemmGeom& g, GSmem& S, uint32_t tmem
         ++a_uses;
         need_a = false;
       }
-      const uint32_t p = tiles & p_mask;
+      const uint32_t acc = (tiles & p_mask) * RA + r_mine;       // accumulator = TMEM columns acc * 128 ..
       ++tiles;
-      G_TIMED(2, mbar_wait(&S.tmem_empty[p], ((acc_uses >> p) & 1u) ^ 1u));
-      acc_uses ^= 1u << p;
-      const uint32_t d_tmem = tmem_base + p * (uint32_t) (RA * GT);
+      G_TIMED(2, mbar_wait(&S.tmem_empty[acc], ((acc_uses >> acc) & 1u) ^ 1u));
+      acc_uses ^= 1u << acc;
+      const uint32_t dt = tmem_base + acc * (uint32_t) GT;
       uint64_t ad = a_desc0;
       for (int q = 0; q < kc; ++q, ad += (G_CHUNK_BYTES >> 4)) {
-        G_TIMED(3, mbar_wait(&S.full[stage], phase));
-        tc_fence_after();
-        // chunk q of the row tiles against ring slot `stage`: +1024 per 16 KB chunk and +2 per K step in the address field
+        if ((stage & cb_mask) == 0) {
+          G_TIMED(3, mbar_wait(&S.full[stage >> cb_log2], phase));
+          tc_fence_after();
+        }
+        // chunk q of the row tile against ring slot `stage`: +1024 per 16 KB chunk and +2 per K step in the address field
         const uint64_t bd = b_desc0 + (uint64_t) stage * (G_CHUNK_BYTES >> 4);
         if (leader) {
+          tc_mma_tf32(dt, ad, bd, G_IDESC, q ? 1u : 0u);
           if (q < kc_full) {
-#pragma unroll
-            for (int r = 0; r < RA; ++r) {
-              const uint64_t adr = ad + (uint64_t) r * a_row_stride;
-              const uint32_t dt = d_tmem + (uint32_t) (r * GT);
-              tc_mma_tf32(dt, adr, bd, G_IDESC, q ? 1u : 0u);
-              tc_mma_tf32(dt, adr + 2, bd + 2, G_IDESC, 1u);
-              tc_mma_tf32(dt, adr + 4, bd + 4, G_IDESC, 1u);
-              tc_mma_tf32(dt, adr + 6, bd + 6, G_IDESC, 1u);
-            }
+            tc_mma_tf32(dt, ad + 2, bd + 2, G_IDESC, 1u);
+            tc_mma_tf32(dt, ad + 4, bd + 4, G_IDESC, 1u);
+            tc_mma_tf32(dt, ad + 6, bd + 6, G_IDESC, 1u);
           } else {
-#pragma unroll
-            for (int r = 0; r < RA; ++r) {
-              const uint64_t adr = ad + (uint64_t) r * a_row_stride;
-              const uint32_t dt = d_tmem + (uint32_t) (r * GT);
-              tc_mma_tf32(dt, adr, bd, G_IDESC, q ? 1u : 0u);
-              if (tail_steps > 1) tc_mma_tf32(dt, adr + 2, bd + 2, G_IDESC, 1u);
-              if (tail_steps > 2) tc_mma_tf32(dt, adr + 4, bd + 4, G_IDESC, 1u);
-            }
+            if (tail_steps > 1) tc_mma_tf32(dt, ad + 2, bd + 2, G_IDESC, 1u);
+            if (tail_steps > 2) tc_mma_tf32(dt, ad + 4, bd + 4, G_IDESC, 1u);
           }
           if (((stage + 1) & cb_mask) == 0) tc_commit(&S.empty[stage >> cb_log2]);
         }
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
-      if (leader) tc_commit(&S.tmem_full[p]);
+      if (leader) tc_commit(&S.tmem_full[acc]);
     }
     if (leader) mbar_arrive(&S.side_empty[s]);
     ++seq;
   }
 #ifdef DCB_GEMM_PROF
-  if (g.prof && leader) {
+  if (g.prof && leader && r_mine == 0) {
     pacc[4] = (unsigned long long) (clock64() - t_begin);
     for (int q = 0; q < 5; ++q) atomicAdd(g.prof + 4 + q, pacc[q]);
   }
@@ -632,20 +628,21 @@ __device__ __forceinline__ void g_mma(const GemmGeom& g, GSmem& S, uint32_t tmem
 
 __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
   if (threadIdx.x == 0) {
+    const uint32_t n_mma = (uint32_t) g.ra;          // MMA-issuing warps: one per row tile of the block
     for (int s = 0; s < 8; ++s) {
       mbar_init(&S.full[s], 1);
-      mbar_init(&S.empty[s], 1);
+      mbar_init(&S.empty[s], n_mma);
     }
     for (int s = 0; s < G_SIDE_SLOTS; ++s) {
       mbar_init(&S.side_full[s], 1);
-      mbar_init(&S.side_empty[s], 1 + G_EPI_WARPS);      // MMA warp + the sixteen epilogue warps
+      mbar_init(&S.side_empty[s], n_mma + G_EPI_WARPS);      // MMA warps + the sixteen epilogue warps
     }
     for (int s = 0; s < G_ACC; ++s) {
       mbar_init(&S.tmem_full[s], 1);
-      mbar_init(&S.tmem_empty[s], G_EPI_WARPS);
+      mbar_init(&S.tmem_empty[s], G_EPI_WARPS / g.ra);       // the epilogue warps that read this accumulator
     }
     mbar_init(&S.a_full[0], 1);
-    mbar_init(&S.a_empty[0], 1);
+    mbar_init(&S.a_empty[0], n_mma);
     for (int q = 0; q < 2 * G_EPI_WARPS; ++q) S.wthr[q] = ~0ull;
     fence_mbar_init();
   }
@@ -655,7 +652,7 @@ __device__ __forceinline__ void g_init(const GemmGeom& g, GSmem& S) {
 // accumulator `acc_col`, each in flight while the previous chunk is processed; the stage is handed back to the MMA warp
 // as soon as the last load has landed in registers.  proc(regs, first column within the tile).
 template <class Proc>
-__device__ __forceinline__ void g_epilogue_tile(GSmem& S, uint32_t tmem_base, uint32_t quarter, uint32_t acc_col, uint32_t p, int c_lo,
+__device__ __forceinline__ void g_epilogue_tile(GSmem& S, uint32_t tmem_base, uint32_t quarter, uint32_t acc_col, uint32_t acc, int c_lo,
                                                 int n_loads, int lane, Proc&& proc) {
   uint32_t ra[G_LD], rb[G_LD];
   const uint32_t t0 = tmem_base + ((quarter * 32u) << 16) + acc_col + (uint32_t) c_lo;
@@ -671,7 +668,7 @@ __device__ __forceinline__ void g_epilogue_tile(GSmem& S, uint32_t tmem_base, ui
     } else {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.tmem_empty[p]);
+      if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
     }
     proc(rb, c_lo + it * 2 * G_LD + G_LD);
   }
@@ -704,7 +701,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
     g_produce(g, S, nullptr, [&](uint32_t) { return g.prune_thr; }, [](uint32_t, uint32_t, float, uint32_t, int) { return true; },
               [](uint32_t, uint32_t&, uint32_t&) {});
   } else if (warp == 1) {
-    if (g.ra == 2) g_mma<2>(g, S, tmem_base); else g_mma<1>(g, S, tmem_base);
+    if (g.ra == 2) g_mma<2>(g, S, tmem_base, 0u); else g_mma<1>(g, S, tmem_base, 0u);
+  } else if (warp == G_MMA2_WARP) {
+    if (g.ra == 2) g_mma<2>(g, S, tmem_base, 1u);       // the block's second row tile has its own issuing warp
   } else {
     // Four epilogue warpgroups, thread = one accumulator row.  ra == 2: warpgroup wg serves row tile (wg & 1) of the block,
     // columns 64 (wg >> 1) .. + 63 of its accumulator; ra == 1: all four hold the same 128 rows, 32 columns each.
@@ -753,10 +752,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             if (a.rad2[b] < 0.f) E[b] = -1.f;                         // unused slot
           }
         }
-        const uint32_t p = tiles & ((uint32_t) (G_ACC / g.ra) - 1u);
+        const uint32_t acc = (tiles & ((uint32_t) (G_ACC / g.ra) - 1u)) * (uint32_t) g.ra + my_tile;
         ++tiles;
-        G_TIMED(1, mbar_wait(&S.tmem_full[p], (uses >> p) & 1u));
-        uses ^= 1u << p;
+        G_TIMED(1, mbar_wait(&S.tmem_full[acc], (uses >> acc) & 1u));
+        uses ^= 1u << acc;
         tc_fence_after();
         if (wg < (uint32_t) g.ra) ++n_tiles;                 // 128 x 128 units: one count per row tile of the record
         const float* ny = rec + 4;
@@ -820,8 +819,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             }
           }
         };
-        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, (p * 2u + my_tile) * (uint32_t) GT, p, (int) (wg >> 1) * 64, 4, lane, proc);
-        else g_epilogue_tile(S, tmem_base, quarter, p * (uint32_t) GT, p, (int) wg * 32, 2, lane, proc);
+        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) (wg >> 1) * 64, 4, lane, proc);
+        else g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) wg * 32, 2, lane, proc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.side_empty[s]);
@@ -918,7 +917,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
                 }
               });
   } else if (warp == 1) {
-    if (g.ra == 2) g_mma<2>(g, S, tmem_base); else g_mma<1>(g, S, tmem_base);
+    if (g.ra == 2) g_mma<2>(g, S, tmem_base, 0u); else g_mma<1>(g, S, tmem_base, 0u);
+  } else if (warp == G_MMA2_WARP) {
+    if (g.ra == 2) g_mma<2>(g, S, tmem_base, 1u);       // the block's second row tile has its own issuing warp
   } else {
     const uint32_t wg = (uint32_t) (warp - 2) >> 2;                 // see gscan_pops_kernel
     const uint32_t my_tile = g.ra == 2 ? (wg & 1u) : 0u;
@@ -998,10 +999,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
           t_hd = (valid && lo_i != 0) ? thr(g_key_d2(best_hd)) : t_nn;
           set_dl();
         }
-        const uint32_t p = tiles & ((uint32_t) (G_ACC / g.ra) - 1u);
+        const uint32_t acc = (tiles & ((uint32_t) (G_ACC / g.ra) - 1u)) * (uint32_t) g.ra + my_tile;
         ++tiles;
-        mbar_wait(&S.tmem_full[p], (uses >> p) & 1u);
-        uses ^= 1u << p;
+        mbar_wait(&S.tmem_full[acc], (uses >> acc) & 1u);
+        uses ^= 1u << acc;
         tc_fence_after();
         if (wg < (uint32_t) g.ra) ++n_tiles;                 // 128 x 128 units: one count per row tile of the record
         const float* ny = rec + 4;
@@ -1068,8 +1069,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
             }
           }
         };
-        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, (p * 2u + my_tile) * (uint32_t) GT, p, (int) (wg >> 1) * 64, 4, lane, proc);
-        else g_epilogue_tile(S, tmem_base, quarter, p * (uint32_t) GT, p, (int) wg * 32, 2, lane, proc);
+        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) (wg >> 1) * 64, 4, lane, proc);
+        else g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) wg * 32, 2, lane, proc);
         // bounds for the producer's dynamic pruning of this item: one slot pair per epilogue warp
         if (first_of_item || __any_sync(0xffffffffu, improved)) {
           const uint2 b = publish();
