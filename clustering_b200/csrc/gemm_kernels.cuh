@@ -674,6 +674,32 @@ __device__ __forceinline__ void g_epilogue_tile(GSmem& S, uint32_t tmem_base, ui
   }
 }
 
+// Variant that hands the accumulator back first: all four loads of the warpgroup's 64 columns are issued at once, the
+// stage is released as soon as they have landed (~ one TMEM latency after the MMAs finished, instead of after three of
+// the four chunks have been processed), and the math runs from registers while the next MMAs already refill the stage.
+// Costs 64 live registers: used where the per-pair state is small (one or two radii, neighbour search).
+template <class Proc>
+__device__ __forceinline__ void g_epilogue_tile_early(GSmem& S, uint32_t tmem_base, uint32_t quarter, uint32_t acc_col, uint32_t acc, int c_lo,
+                                                      int lane, Proc&& proc) {
+  uint32_t r0[G_LD], r1[G_LD], r2[G_LD], r3[G_LD];
+  const uint32_t t0 = tmem_base + ((quarter * 32u) << 16) + acc_col + (uint32_t) c_lo;
+  tmem_ld16_issue(t0, r0);
+  tmem_ld16_issue(t0 + G_LD, r1);
+  tmem_ld16_issue(t0 + 2 * G_LD, r2);
+  tmem_ld16_issue(t0 + 3 * G_LD, r3);
+  tmem_ld16_wait(r0);                       // tcgen05.wait::ld covers every outstanding load; the other buffers are tied below
+  tmem_ld16_wait(r1);
+  tmem_ld16_wait(r2);
+  tmem_ld16_wait(r3);
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
+  proc(r0, c_lo);
+  proc(r1, c_lo + G_LD);
+  proc(r2, c_lo + 2 * G_LD);
+  proc(r3, c_lo + 3 * G_LD);
+}
+
 // band half width around a decision value at distance r (d2 = r^2):  2 r rho + rho^2 + eps + e_rel r^2, rounded up
 __device__ __forceinline__ float g_band(float r, float r2, float rho, float eps, float e_rel) {
   return fmaf(e_rel, r2, fmaf(2.0f * r, rho, fmaf(rho, rho, eps))) * 1.0001f;
@@ -819,8 +845,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             }
           }
         };
-        if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) (wg >> 1) * 64, 4, lane, proc);
-        else g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) wg * 32, 2, lane, proc);
+        if (g.ra == 2) {
+          if (NB <= 2) g_epilogue_tile_early(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) (wg >> 1) * 64, lane, proc);
+          else g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) (wg >> 1) * 64, 4, lane, proc);
+        } else {
+          g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) wg * 32, 2, lane, proc);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.side_empty[s]);
@@ -1069,6 +1099,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
             }
           }
         };
+        // (the early-release variant spills here: the neighbour state needs the registers)
         if (g.ra == 2) g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) (wg >> 1) * 64, 4, lane, proc);
         else g_epilogue_tile(S, tmem_base, quarter, acc * (uint32_t) GT, acc, (int) wg * 32, 2, lane, proc);
         // bounds for the producer's dynamic pruning of this item: one slot pair per epilogue warp

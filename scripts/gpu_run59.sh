@@ -1,0 +1,3 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_gemm.py -x -q 2>&1 | tail -n 3
+timeout 600 python scripts/profile_kernels.py C5 500000 2 2>&1 | tail -n 1 | cut -c1-400
