@@ -78,3 +78,49 @@ class DensityPass:
         keys = all_gather_positions(self.keys_loc, self.n, self.world, self.rank)
         nn = s.nn_finish(keys)
         return pops, fe, nn
+
+
+# ------------------------------------------------------------------------------------------------
+# screening (free-energy-sorted frames; SURVEY.md 8e: the one stage with an exchange per threshold)
+# ------------------------------------------------------------------------------------------------
+def screen_cuts(m_prev, m_new, world_size):
+    """Row ranges [cut[g], cut[g+1]) of the new sorted positions [m_prev, m_new): every rank gets about the same number of
+    PAIRS (row p has p candidate columns below it), like the in-process path of dcb200_screening_step."""
+    a, b = float(m_prev) ** 2, float(m_new) ** 2
+    cuts = [max(m_prev, min(m_new, int((a + (b - a) * g / world_size) ** 0.5))) for g in range(world_size)] + [m_new]
+    for g in range(1, world_size + 1):
+        cuts[g] = max(cuts[g], cuts[g - 1])
+    return cuts
+
+
+class ScreeningPass:
+    """One free-energy threshold at a time, sharded over the ranks of the default process group.
+
+    Every rank holds the free-energy-sorted coordinates (keep_order context) and the replicated union-find forest
+    `comp` (int32 [m], comp[p] <= p, roots = smallest sorted position of a cluster).  A step scans this rank's share of
+    the new rows against all lower positions, then ONE all-gather moves the per-rank forests and every rank unions them
+    on the device (dcb200_ctx_screening_merge) -- instead of the reference's per-sweep H2D / D2H / host merge
+    (density_clustering_cuda.cu:505-571)."""
+
+    def __init__(self, session, sorted_coords):
+        self.s = session
+        self.world, self.rank = world()
+        session.set_coords(sorted_coords, keep_order=True)
+
+    def step(self, m_prev, m_new, max_dist2, comp):
+        """comp: int32 device tensor with at least m_new entries; entries >= m_prev are (re)initialised here."""
+        s = self.s
+        comp[m_prev:m_new] = torch.arange(m_prev, m_new, dtype=comp.dtype, device=comp.device)
+        cuts = screen_cuts(m_prev, m_new, self.world)
+        s.screening_scan(m_prev, m_new, max_dist2, comp, cuts[self.rank], cuts[self.rank + 1])
+        s.screening_flatten(m_new, comp)
+        if self.world > 1:
+            mine = comp[:m_new].contiguous()
+            others = torch.empty((self.world, m_new), dtype=comp.dtype, device=comp.device)
+            with torch.cuda.stream(s.torch_stream()):
+                dist.all_gather_into_tensor(others, mine)
+                for g in range(self.world):
+                    if g != self.rank:
+                        s.screening_merge(m_new, comp, others[g])
+                s.screening_flatten(m_new, comp)
+        return comp

@@ -214,3 +214,53 @@ def test_medium_size_properties(oracle):
         else:
             assert hi[i] == n + 1
     assert np.all(hd >= nd)
+
+
+def test_sharded_screening_forests_merge_to_the_oracle_labels(oracle):
+    """The session-level screening the one-process-per-GPU driver uses (clustering_b200/dist.py: ScreeningPass): three
+    'ranks' scan their share of the new rows into their own forests, the forests are unioned on the device, and the
+    result must give the oracle's labels at every threshold."""
+    import torch
+    from clustering_b200.dist import screen_cuts
+    from clustering_b200.session import Session
+    x = gaussian_mixture(5000, 3, k=6, seed=404)
+    fe = oracle.free_energies(oracle.populations(x, [0.3])[0])
+    _, nd, _, _ = oracle.nearest_neighbors(x, fe)
+    order = density.sorted_free_energies(fe)
+    xs = np.ascontiguousarray(x[order])
+    fes = fe[order]
+    cut = np.float32(4.0 * density.compute_sigma2(nd))
+    G = 3
+    sess = [Session(0) for _ in range(G)]
+    for s in sess:
+        s.set_coords(xs, keep_order=True)
+    dev = sess[0].dev
+    comp = torch.arange(len(x), dtype=torch.int32, device=dev)
+    prev_o, m_prev = None, 0
+    t = np.float32(0.2)
+    while t < fe.max() + 0.3:
+        m_new = int(np.searchsorted(fes, t, side="right"))
+        cuts = screen_cuts(m_prev, m_new, G)
+        forests = []
+        for g in range(G):
+            c = comp.clone()
+            c[m_prev:m_new] = torch.arange(m_prev, m_new, dtype=torch.int32, device=dev)
+            sess[g].screening_scan(m_prev, m_new, float(cut), c, cuts[g], cuts[g + 1])
+            sess[g].screening_flatten(m_new, c)
+            sess[g].sync()
+            forests.append(c)
+        comp = forests[0]
+        for g in range(1, G):
+            sess[0].screening_merge(m_new, comp, forests[g])
+        sess[0].screening_flatten(m_new, comp)
+        sess[0].sync()
+        rep = comp[:m_new].cpu().numpy()
+        roots, lab = np.unique(rep, return_inverse=True)        # ascending representative = the reference's numbering
+        labels = np.zeros(len(x), np.uint32)
+        labels[order[:m_new]] = lab + 1
+        prev_o = oracle.screening(fe, nd, t, x, prev_o)
+        assert np.array_equal(labels, prev_o.astype(np.uint32)), float(t)
+        m_prev = m_new
+        t = np.float32(t + np.float32(0.4))
+    for s in sess:
+        s.close()

@@ -116,3 +116,14 @@ def test_gather_of_position_shards_gloo(tmp_path, world_size):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_screening_row_cuts_balance_pairs():
+    from clustering_b200.dist import screen_cuts
+    for m_prev, m_new, w in ((0, 1000, 4), (900, 1000, 3), (0, 5, 8), (10, 10, 2), (123456, 5000000, 8)):
+        cuts = screen_cuts(m_prev, m_new, w)
+        assert cuts[0] == m_prev and cuts[-1] == m_new and len(cuts) == w + 1
+        assert all(cuts[g] <= cuts[g + 1] for g in range(w))
+        if m_new - m_prev > 100 * w:
+            pairs = [sum(range(cuts[g], cuts[g + 1])) if m_new < 10000 else (cuts[g + 1] ** 2 - cuts[g] ** 2) / 2 for g in range(w)]
+            assert max(pairs) < 1.2 * (sum(pairs) / w) + m_new
