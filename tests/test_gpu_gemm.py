@@ -125,3 +125,30 @@ def test_gemm_matches_ffma_path_and_shards():
     kparts = torch.cat([s.nn_scan(0, 20480), s.nn_scan(20480, 40000)], dim=1)
     assert torch.equal(kfull, kparts)
     s.close()
+
+
+def test_gemm_edge_cases(oracle):
+    """Partial single tile, exactly one tile, a single frame, all frames identical, a radius far below the TF32 resolution
+    of the data (every pair goes through the exact path), a radius that contains everything, NaN input."""
+    from clustering_b200 import lib
+    for n in (1, 2, 97, 128, 129, 256, 257):
+        x = contact_like(n, 48, k=2, seed=n)
+        radii = np.array([0.45, 1e-4, 50.0], np.float32)
+        po, pg = oracle.populations(x, radii), density.calculate_populations(x, radii)
+        assert np.array_equal(po, pg), n
+        fe = oracle.free_energies(po[0])
+        assert same_nn(oracle.nearest_neighbors(x, fe), density.nearest_neighbors(x, fe)), n
+    x = np.tile(contact_like(1, 64, seed=3), (700, 1))                     # 700 identical frames: every distance is 0
+    po, pg = oracle.populations(x, [0.1, 0.0]), density.calculate_populations(x, [0.1, 0.0])
+    assert np.array_equal(po, pg) and pg[0].min() == 700 and pg[1].max() == 1
+    fe = np.zeros(700, np.float32)
+    fe[::7] = 1.0
+    assert same_nn(oracle.nearest_neighbors(x, fe), density.nearest_neighbors(x, fe))
+    x = gaussian_mixture(900, 40, k=3, seed=12) * np.float32(1e3) + np.float32(3e4)   # large scale: wide bands, many rechecks
+    dd = ((x[:200, None, :] - x[None, :200, :]) ** 2).sum(-1)
+    r = float(np.sqrt(np.percentile(dd[dd > 0], 10)))
+    assert np.array_equal(oracle.populations(x, [r, 0.5 * r]), density.calculate_populations(x, [r, 0.5 * r]))
+    bad = contact_like(300, 64, seed=1)
+    bad[17, 5] = np.nan
+    with pytest.raises(lib.Dcb200Error):
+        density.calculate_populations(bad, [0.5])
