@@ -1,0 +1,2 @@
+ncu --set full --clock-control none --import-source on -k regex:'gscan_pops' -c 1 -o gpurun_out/prof_gpops4 -f python scripts/profile_kernels.py C5 500000 1 > gpurun_out/prof_gpops4.log 2>&1
+tail -n 2 gpurun_out/prof_gpops4.log
