@@ -264,3 +264,66 @@ def test_sharded_screening_forests_merge_to_the_oracle_labels(oracle):
         t = np.float32(t + np.float32(0.4))
     for s in sess:
         s.close()
+
+
+@pytest.mark.parametrize("name", ["C2", "C5"])
+def test_full_size_properties(oracle, name):
+    """BASELINE.json's full sizes (C2: 1M x 5 on the FFMA kernels, C5: 500k x 128 on the tensor cores): size-independent
+    properties -- every pair is counted from both ends, sampled rows against the oracle's scalar distance over ALL frames,
+    nearest neighbours of sampled rows, and the lower-free-energy neighbour really has a lower free energy."""
+    from clustering_b200.synth import CONFIGS, config_data
+    cfg = CONFIGS[name]
+    x = config_data(name)
+    n, d = x.shape
+    radii = np.asarray(cfg["radii"][:1], np.float32)
+    pops = density.calculate_populations(x, radii)[0]
+    assert int(pops.astype(np.int64).sum() - n) % 2 == 0
+    fe = density.calculate_free_energies(pops)
+    ni, nd, hi, hd = density.nearest_neighbors(x, fe)
+    rng = np.random.default_rng(7)
+    r2 = np.float32(radii[0] * radii[0])
+    for i in rng.choice(n, 12, replace=False):
+        diff = x - x[i]
+        approx = np.einsum("ij,ij->i", diff, diff)
+        cand = np.nonzero(approx < r2 * np.float32(1.001) + np.float32(1e-6))[0]
+        exact = np.array([oracle.dist2(x[i], x[j]) for j in cand], np.float32)
+        assert pops[i] == 1 + int(np.count_nonzero((exact < r2) & (cand != i))), (name, i)
+        approx[i] = np.inf
+        c2 = np.nonzero(approx <= approx.min() * np.float32(1.001) + np.float32(1e-7))[0]
+        e2 = np.array([oracle.dist2(x[i], x[j]) for j in c2], np.float32)
+        assert ni[i] == c2[np.flatnonzero(e2 == e2.min())[0]] and bits(nd[i]) == bits(e2.min()), (name, i)
+        lower = np.nonzero(fe < fe[i])[0]
+        if lower.size:
+            a2 = approx[lower]
+            c3 = lower[np.nonzero(a2 <= a2.min() * np.float32(1.001) + np.float32(1e-7))[0]]
+            e3 = np.array([oracle.dist2(x[i], x[j]) for j in c3], np.float32)
+            assert hi[i] == c3[np.flatnonzero(e3 == e3.min())[0]] and bits(hd[i]) == bits(e3.min()), (name, i)
+        else:
+            assert hi[i] == n + 1
+    has = hi <= n
+    assert np.all(fe[hi[has]] < fe[has]) and np.all(hd >= nd)
+
+
+def test_full_size_screening_properties():
+    """C4 (5M x 3): the incremental screening over rising thresholds gives the same labels as one from-scratch call at the
+    last threshold; labels are 1..K without gaps below the threshold and 0 above it; clusters only ever merge or grow."""
+    from clustering_b200.synth import CONFIGS, config_data
+    cfg = CONFIGS["C4"]
+    x = config_data("C4")
+    pops = density.calculate_populations(x, np.asarray(cfg["radii"][:1], np.float32))[0]
+    fe = density.calculate_free_energies(pops)
+    _, nd, _, _ = density.nearest_neighbors(x, fe)
+    prev = None
+    for t in (np.float32(0.4), np.float32(1.2), np.float32(2.0)):
+        lab = density.screening(fe, nd, t, x, prev)
+        below = fe <= t
+        assert np.all(lab[~below] == 0) and np.all(lab[below] > 0)
+        k = int(lab.max())
+        assert np.array_equal(np.unique(lab[below]), np.arange(1, k + 1, dtype=lab.dtype))
+        if prev is not None:
+            old = prev > 0                              # frames clustered before stay together
+            pairs = np.unique(np.stack([prev[old], lab[old]], 1), axis=0)
+            assert len(np.unique(pairs[:, 0])) == len(pairs)      # an old cluster maps to exactly one new cluster
+        prev = lab
+    scratch = density.screening(fe, nd, np.float32(2.0), x, None)
+    assert np.array_equal(scratch, prev)
