@@ -303,7 +303,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(x_dev)
     barrier()
-    tensor_path = sess.gemm_info()[0]                   # 32 <= n_cols <= 256: the scans run on the tensor cores (tcgen05, TF32)
+    tensor_path = sess.gemm_info()[0]                   # 17 <= n_cols <= 256: the scans run on the tensor cores (tcgen05, TF32)
     peak_tflops = sess.tf32_peak(300.0) if tensor_path else sess.ffma_peak(300.0)
     s0 = sess.stats(reset=True)
     barrier()
@@ -410,7 +410,7 @@ def run_ours(args):
                 "other_scans": {k: {"kernel_ms": v[0], "pairs_evaluated_frac": v[1] / pairs,
                                     "achieved_tflops": FLOP_EXECUTED_PER_PAIR_DIM * v[1] * d / (v[0] * 1e-3) / 1e12}
                                 for k, v in scans.items() if k != kname},
-                "note": ("GEMM-form path (n_cols >= 32): the roofline is the tensor pipe (TF32). achieved = 2 flop per pair.dim x the pairs of "
+                "note": ("GEMM-form path (n_cols >= 17): the roofline is the tensor pipe (TF32). achieved = 2 flop per pair.dim x the pairs of "
                          "the 128 x 128 tile pairs the kernel really multiplied; pruned tile pairs are not counted; the headline value "
                          "counts the full N x N matrix") if tensor_path else
                         "compute-bound path (SURVEY.md 8d): the roofline is the FP32 FFMA pipe, not HBM. achieved = 2 flop (one FFMA) per "

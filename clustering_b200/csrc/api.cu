@@ -503,7 +503,7 @@ struct dcb200_ctx {
   bool nn_ready = false;
   uint64_t launches = 0;
   uint64_t pairs_scheduled = 0;     // pairs of the full row x column ranges of the scans since the last reset
-  // GEMM-form (tcgen05) path for 32 <= d <= 256, spatial order only (gemm_kernels.cuh)
+  // GEMM-form (tcgen05) path for 17 <= d <= 256, spatial order only (gemm_kernels.cuh)
   bool gemm = false;
   int g_kc = 0, g_k8 = 0;
   size_t g_tiles = 0;               // ld / 128

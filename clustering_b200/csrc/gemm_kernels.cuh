@@ -1,4 +1,4 @@
-// GEMM-form pair scans for high-dimensional inputs (32 <= n_cols <= 256), written for sm_100a tensor cores:
+// GEMM-form pair scans for high-dimensional inputs (17 <= n_cols <= 256), written for sm_100a tensor cores:
 //
 //   gscan_pops_kernel<NB>   multi-radius neighbourhood population count   (density_clustering.cpp:126-195)
 //   gscan_nn_kernel         nearest neighbour + nearest neighbour with lower free energy (density_clustering.cpp:230-288)
@@ -34,7 +34,7 @@ constexpr int GT = 128;                      // rows / columns per tile (= UMMA 
 constexpr int GK = 32;                       // floats per K-chunk row = 128 bytes = the swizzle width
 constexpr int G_CHUNK_FLOATS = GT * GK;      // 4096 floats = 16 KB
 constexpr int G_CHUNK_BYTES = G_CHUNK_FLOATS * 4;
-constexpr int G_MIN_D = 32, G_MAX_D = 256;
+constexpr int G_MIN_D = 17, G_MAX_D = 256;      // below: the register kernels (n_cols <= 16) are faster
 constexpr int G_SIDE_SLOTS = 8;              // per-tile side records in flight
 constexpr int G_ACC = 4;                     // accumulator stages in tensor memory (4 x 128 columns = all of it)
 constexpr int G_SIDE_FLOATS = 4 + 2 * GT;    // meta (16 B), |y~|^2 [128], rank floats [128]

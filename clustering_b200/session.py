@@ -60,7 +60,7 @@ class Session:
         return t.value
 
     def gemm_info(self):
-        """(active, check_ratio) of the GEMM-form tensor-core path (32 <= n_cols <= 256), see dcb200_ctx_gemm_info."""
+        """(active, check_ratio) of the GEMM-form tensor-core path (17 <= n_cols <= 256), see dcb200_ctx_gemm_info."""
         a, r = C.c_int(0), C.c_float(0.0)
         lib.check(self.L.dcb200_ctx_gemm_info(self.h, C.byref(a), C.byref(r)))
         return bool(a.value), float(r.value)

@@ -166,7 +166,7 @@ int dcb200_ctx_screening_merge(dcb200_ctx* ctx, size_t m_new, uint32_t* dev_comp
  * [3] (warp, tile) scans (a consumer warp owns 128 rows), [4] pairs of the full row x column ranges requested, [5] pairs per (warp, tile) scan */
 int dcb200_ctx_stats(dcb200_ctx* ctx, uint64_t stats[6], int reset);
 
-/* diagnostics of the GEMM-form (tcgen05 tensor core) path used for 32 <= n_cols <= 256: *active = 1 if the context's current
+/* diagnostics of the GEMM-form (tcgen05 tensor core) path used for 17 <= n_cols <= 256: *active = 1 if the context's current
  * coordinates are served by it; *check_ratio = max observed |fast value - exact d2| / proven error band over the pairs of the
  * populations calls made with DCB200_GEMM_CHECK=1 in the environment (0 if none); either pointer may be NULL */
 int dcb200_ctx_gemm_info(dcb200_ctx* ctx, int* active, float* check_ratio);

@@ -1,4 +1,4 @@
-"""GPU parity tests of the GEMM-form (tcgen05 tensor core) path that serves 32 <= n_cols <= 256
+"""GPU parity tests of the GEMM-form (tcgen05 tensor core) path that serves 17 <= n_cols <= 256
 (clustering_b200/csrc/gemm_kernels.cuh).  Everything goes through the C ABI and is compared bit for bit with the
 CPU oracle; the tensor-core value only filters, so populations, neighbour indices and squared distances must be
 identical to the reference's arithmetic."""
@@ -25,10 +25,10 @@ def same_nn(a, b):
 
 
 def test_gemm_path_is_active_and_bounded():
-    """32 <= d <= 256 in spatial order runs on the tensor cores, other inputs do not; with DCB200_GEMM_CHECK=1 every pair
+    """17 <= d <= 256 in spatial order runs on the tensor cores, other inputs do not; with DCB200_GEMM_CHECK=1 every pair
     is also evaluated exactly and the observed |fast - exact| must stay inside the proven band (ratio < 1)."""
     s = Session(0)
-    for d, want in ((16, False), (31, False), (32, True), (128, True), (256, True), (257, False)):
+    for d, want in ((16, False), (17, True), (32, True), (128, True), (256, True), (257, False)):
         s.set_coords(gaussian_mixture(700, d, seed=d))
         assert s.gemm_info()[0] == want, d
     s.set_coords(gaussian_mixture(700, 64, seed=1), keep_order=True)
@@ -52,7 +52,7 @@ def test_gemm_path_is_active_and_bounded():
     s.close()
 
 
-@pytest.mark.parametrize("d", [32, 33, 40, 64, 100, 128, 129, 200, 256])
+@pytest.mark.parametrize("d", [17, 20, 24, 31, 32, 33, 40, 64, 100, 128, 129, 200, 256])
 def test_gemm_vs_oracle_dims(oracle, d):
     n = 1300                                            # not a multiple of the tile: padded rows and columns
     x = contact_like(n, d, k=4, seed=700 + d) if d % 2 == 0 else gaussian_mixture(n, d, k=4, seed=700 + d)
