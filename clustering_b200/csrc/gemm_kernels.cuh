@@ -441,11 +441,11 @@ __device__ __forceinline__ void g_item_coords(const GemmGeom& g, uint32_t item, 
   *ci = (step & 1) ? (diag + k) % n : (diag + n - (k % n)) % n;
 }
 
-// Producer warp.  keep(rb, t, lbv, item, lane): warp-uniform decision taken right before a tile is streamed (dynamic bounds);
+// Producer warp.  keep(rb, t, lbv, tile_extra[t], item, lane): warp-uniform decision taken right before a tile is streamed (dynamic bounds);
 // thr0(rb): the bound an item starts with; range(rb, lim0, lim1): restricts the column tiles (window pass).
 template <class Thr0, class Keep, class Range>
-__device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const float* __restrict__ side_extra, Thr0&& thr0, Keep&& keep,
-                                          Range&& range) {
+__device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const float* __restrict__ side_extra,
+                                          const float* __restrict__ tile_extra, Thr0&& thr0, Keep&& keep, Range&& range) {
   const int lane = threadIdx.x & 31;
   const uint32_t total = g.n_row_tiles * g.n_col_items;
   uint32_t stage = 0, phase = 0;          // chunk ring
@@ -495,12 +495,15 @@ __device__ __forceinline__ void g_produce(const GemmGeom& g, GSmem& S, const flo
       const uint32_t t = base + lane;
       float lbv = t < t1 ? __ldg(lbrow + t) : INFINITY;
       if (two && t < t1) lbv = fminf(lbv, __ldg(lbrow + g.n_tiles + t));
+      // per-tile value the keep rule wants (neighbour search: the tile's smallest free-energy rank), fetched 32 tiles at a
+      // time here instead of one dependent global load per streamed tile on the producer's critical path
+      const float exv = (tile_extra && t < t1) ? __ldg(tile_extra + t) : 0.f;
       uint32_t mask = __ballot_sync(0xffffffffu, t < t1 && !(lbv > th0));
       while (mask) {
         const int src = __ffs(mask) - 1;
         mask &= mask - 1;
         const uint32_t tt = base + (uint32_t) src;
-        if (!keep(rb, tt, __shfl_sync(0xffffffffu, lbv, src), item, lane)) continue;
+        if (!keep(rb, tt, __shfl_sync(0xffffffffu, lbv, src), __shfl_sync(0xffffffffu, exv, src), item, lane)) continue;
         if (lane == 0) {
           if (first) {
             // the row tiles' operand images (consecutive tiles = one contiguous block): resident for the whole item
@@ -724,7 +727,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(S.tmem_addr);
 
   if (warp == 0) {
-    g_produce(g, S, nullptr, [&](uint32_t) { return g.prune_thr; }, [](uint32_t, uint32_t, float, uint32_t, int) { return true; },
+    g_produce(g, S, nullptr, nullptr, [&](uint32_t) { return g.prune_thr; }, [](uint32_t, uint32_t, float, float, uint32_t, int) { return true; },
               [](uint32_t, uint32_t&, uint32_t&) {});
   } else if (warp == 1) {
     if (g.ra == 2) g_mma<2>(g, S, tmem_base, 0u); else g_mma<1>(g, S, tmem_base, 0u);
@@ -903,7 +906,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
     // A tile is needed if it can hold a nearest neighbour of some row (lb <= thr_nn), or a lower-free-energy neighbour
     // (lb <= thr_hd) and it holds a frame of lower rank than the rows' largest one at all.
     float bound_nn = 0.f, bound_hd = 0.f, lmax = 0.f;
-    g_produce(g, S, a.lof,
+    g_produce(g, S, a.lof, a.lomin,
               [&](uint32_t rb) {
                 // max over the 4 ra quarters of the row block
                 const int ql = lane % (4 * g.ra);
@@ -917,7 +920,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
                 lmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(lm, 0.f))));
                 return fmaxf(bound_nn, bound_hd);
               },
-              [&](uint32_t, uint32_t tt, float lbv, uint32_t item, int ln) {
+              [&](uint32_t, uint32_t, float lbv, float lomin_t, uint32_t item, int ln) {
                 // What the epilogue warps found since the item started.  Lane l reads slot l: epilogue warp l >> 1 (warpgroup
                 // l >> 3), l & 1: nn / hd.  A warpgroup's bound is the max over its four warps (a warp that has not published
                 // for this item yet: +inf).  Warpgroups that hold the same rows both give valid bounds (the tighter counts);
@@ -937,7 +940,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
                 const float bn = fminf(bound_nn, __shfl_sync(0xffffffffu, mine, 0));
                 const float bh = fminf(bound_hd, __shfl_sync(0xffffffffu, mine, 1));
                 if (!(lbv > bn)) return true;
-                return !(lbv > bh) && __ldg(a.lomin + tt) < lmax;
+                return !(lbv > bh) && lomin_t < lmax;
               },
               [&](uint32_t rb, uint32_t& lim0, uint32_t& lim1) {
                 if (a.window) {
