@@ -10,7 +10,7 @@
 // by the epilogue warps with tcgen05.ld (one thread = one row of the accumulator).  F is the exact squared distance of
 // the ROUNDED points up to FP32 accumulation error, so its distance to the true value is ~ 2 d (|dx| + |dy|) with
 // |dx| <= 2^-11 |x - centre|: proportional to d, small for close pairs.  As in the FFMA kernels the fast value never
-// decides alone: a pair whose F lies within the proven band of a decision boundary is re-evaluated with dist2_exact_rm,
+// decides alone: a pair whose F lies within the proven band of a decision boundary is re-evaluated with dist2_exact_coop,
 // the reference's own arithmetic, so that populations and neighbours stay bit-identical.
 //
 // Structure of a CTA (one per SM, persistent):
@@ -184,23 +184,42 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// squared distance of positions i and j in the reference's rounding order (see dist2_exact, common.cuh) on the
-// row-major copy xR [ld][D] of the original coordinates in context order
-static __device__ __noinline__ float dist2_exact_rm(const float* __restrict__ xR, int D, uint32_t i, uint32_t j) {
+// Squared distance of positions i and j in the reference's rounding order (see dist2_exact, common.cuh) on the row-major copy
+// xR [ld][D] of the original coordinates in context order, computed by a whole warp for ONE pair (i, j): lane l takes columns 4l .. 4l+3 (coalesced 16-byte loads of
+// the two rows instead of 2 D scattered 4-byte loads by one thread), and the four lane accumulators of the reference's
+// loop are then summed in column order through shuffles, every lane running the identical chain: the reference's rounding
+// order, the same bits in all lanes.  Candidates are rare (usually one lane of a warp at a time), so one pair per call costs
+// ~1/3 of the instructions and 1/8 of the memory sectors of a per-thread loop (which lost even with many lanes active).
+static __device__ __noinline__ float dist2_exact_coop(const float* __restrict__ xR, int D, uint32_t i, uint32_t j, int lane) {
   const float* __restrict__ a = xR + (size_t) i * D;
   const float* __restrict__ b = xR + (size_t) j * D;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int k = 0;
-  for (; k + 4 <= D; k += 4) {
-    const float c0 = __fsub_rn(__ldg(a + k), __ldg(b + k));
-    const float c1 = __fsub_rn(__ldg(a + k + 1), __ldg(b + k + 1));
-    const float c2 = __fsub_rn(__ldg(a + k + 2), __ldg(b + k + 2));
-    const float c3 = __fsub_rn(__ldg(a + k + 3), __ldg(b + k + 3));
-    a0 = __fadd_rn(a0, __fmul_rn(c0, c0));
-    a1 = __fadd_rn(a1, __fmul_rn(c1, c1));
-    a2 = __fadd_rn(a2, __fmul_rn(c2, c2));
-    a3 = __fadd_rn(a3, __fmul_rn(c3, c3));
+  const int n4 = D >> 2;
+  const bool vec = (D & 3) == 0;                      // rows are 16-byte aligned
+  for (int base = 0; base < n4; base += 32) {
+    const int gq = base + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (gq < n4) {
+      float4 xa, xb;
+      if (vec) {
+        xa = __ldg(reinterpret_cast<const float4*>(a) + gq);
+        xb = __ldg(reinterpret_cast<const float4*>(b) + gq);
+      } else {
+        xa = make_float4(__ldg(a + 4 * gq), __ldg(a + 4 * gq + 1), __ldg(a + 4 * gq + 2), __ldg(a + 4 * gq + 3));
+        xb = make_float4(__ldg(b + 4 * gq), __ldg(b + 4 * gq + 1), __ldg(b + 4 * gq + 2), __ldg(b + 4 * gq + 3));
+      }
+      const float c0 = __fsub_rn(xa.x, xb.x), c1 = __fsub_rn(xa.y, xb.y), c2 = __fsub_rn(xa.z, xb.z), c3 = __fsub_rn(xa.w, xb.w);
+      s0 = __fmul_rn(c0, c0); s1 = __fmul_rn(c1, c1); s2 = __fmul_rn(c2, c2); s3 = __fmul_rn(c3, c3);
+    }
+    const int cnt = min(32, n4 - base);
+    for (int l = 0; l < cnt; ++l) {
+      a0 = __fadd_rn(a0, __shfl_sync(0xffffffffu, s0, l));
+      a1 = __fadd_rn(a1, __shfl_sync(0xffffffffu, s1, l));
+      a2 = __fadd_rn(a2, __shfl_sync(0xffffffffu, s2, l));
+      a3 = __fadd_rn(a3, __shfl_sync(0xffffffffu, s3, l));
+    }
   }
+  int k = 4 * n4;
   float l0 = __fadd_rn(a0, a2);
   float l1 = __fadd_rn(a1, a3);
   float s;
@@ -812,36 +831,43 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_pops_kernel(const __grid_c
             bool band = false;
 #pragma unroll
             for (int b = 0; b < NB; ++b) band |= mn[b] <= E[b];
-            if (CHECK || band) {
-              // rare: a pair of these 16 columns lies within the band of a radius; replace its sign decision by the exact one
+            if (CHECK || __any_sync(0xffffffffu, band)) {
+              // rare: some lane has a pair of these 8 columns within the band of a radius; its sign decision is replaced by the
+              // exact one.  Warp-uniform region: the exact distance of a wanted pair is computed by the whole warp.
 #pragma unroll
               for (int c = 0; c < G_HALF; ++c) scratch[c * G_EPI_THREADS] = __uint_as_float(v[h + c]);
 #pragma unroll 1
               for (int c = 0; c < G_HALF; ++c) {
                 const float w = fmaf(scratch[c * G_EPI_THREADS], -2.0f, ny[c0 + h + c]);
-                const uint32_t col = m.col0 + (uint32_t) (c0 + h + c);
-                float d2 = 0.f;
-                bool have = false;
-                if (CHECK && valid && col < g.n && g.check) {
-                  d2 = dist2_exact_rm(g.xR, g.d, row, col);
-                  have = true;
-                  const float rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
-                  const float bnd = g_band(sqrtf(d2), d2, rho, g.c_acc * (xn + g.nymax), g.e_rel);
-                  const float ratio = fabsf((w + xn) - d2) / bnd;
-                  atomicMax(reinterpret_cast<unsigned int*>(g.check), __float_as_uint(ratio));
-                }
+                const uint32_t col = m.col0 + (uint32_t) (c0 + h + c);          // the same column for every lane
+                const bool chk = CHECK && valid && col < g.n && g.check;
+                bool want = chk;
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                  const float vv = w + q[b];
-                  if (fabsf(vv) <= E[b] && valid) {
-                    ++n_slow;
-                    if (!have) {
-                      d2 = dist2_exact_rm(g.xR, g.d, row, col);
-                      have = true;
-                      ++n_exact;
+                for (int b = 0; b < NB; ++b) want |= fabsf(w + q[b]) <= E[b] && valid;
+                uint32_t mk = __ballot_sync(0xffffffffu, want);
+                float d2 = 0.f;
+                while (mk) {
+                  const int src = __ffs(mk) - 1;
+                  mk &= mk - 1;
+                  const float t = dist2_exact_coop(g.xR, g.d, __shfl_sync(0xffffffffu, row, src), col, lane);
+                  if (lane == src) d2 = t;
+                }
+                if (want) {
+                  ++n_exact;
+                  if (chk) {
+                    const float rho = g.rho_c * (sqrtf(xn) + sqrtf(g.nymax));
+                    const float bnd = g_band(sqrtf(d2), d2, rho, g.c_acc * (xn + g.nymax), g.e_rel);
+                    const float ratio = fabsf((w + xn) - d2) / bnd;
+                    atomicMax(reinterpret_cast<unsigned int*>(g.check), __float_as_uint(ratio));
+                  }
+#pragma unroll
+                  for (int b = 0; b < NB; ++b) {
+                    const float vv = w + q[b];
+                    if (fabsf(vv) <= E[b] && valid) {
+                      ++n_slow;
+                      const uint32_t inside = d2 < a.rad2[b] ? 1u : 0u;      // NaN (padding) -> outside
+                      cnt[b] += inside - (__float_as_uint(vv) >> 31);
                     }
-                    const uint32_t inside = d2 < a.rad2[b] ? 1u : 0u;      // NaN (padding) -> outside
-                    cnt[b] += inside - (__float_as_uint(vv) >> 31);
                   }
                 }
               }
@@ -1069,19 +1095,27 @@ __global__ void __launch_bounds__(G_THREADS, 1) gscan_nn_kernel(const __grid_con
                 for (int c = 0; c < 4; ++c) any |= w[c4 + c] < fmaf(__saturatef(lor - ll[c]), dl, t_nn);
               }
             }
-            if (any) {
+            if (__any_sync(0xffffffffu, any)) {
+              // warp-uniform region: the exact distance of a candidate is computed by the whole warp (dist2_exact_coop)
 #pragma unroll
               for (int c = 0; c < G_HALF; ++c) scratch[c * G_EPI_THREADS] = __uint_as_float(v[h + c]);
 #pragma unroll 1
               for (int c = 0; c < G_HALF; ++c) {
-                const float w = fmaf(scratch[c * G_EPI_THREADS], -2.0f, ny[c0 + h + c]);
-                if (!(w < fmaf(__saturatef(lor - lc[c0 + h + c]), dl, t_nn))) continue;
-                const uint32_t j = m.col0 + (uint32_t) (c0 + h + c);
-                ++n_slow;
-                if (j == row || j >= g.n || !valid) continue;
-                const bool hd_cand = __ldg(a.lo + j) < lo_i;
-                if (!(w < t_nn) && !(hd_cand && w < t_hd)) continue;
-                const float d2 = dist2_exact_rm(g.xR, g.d, row, j);
+                const float wc = fmaf(scratch[c * G_EPI_THREADS], -2.0f, ny[c0 + h + c]);
+                const uint32_t j = m.col0 + (uint32_t) (c0 + h + c);            // the same column for every lane
+                const bool pass = wc < fmaf(__saturatef(lor - lc[c0 + h + c]), dl, t_nn);
+                if (pass) ++n_slow;
+                const bool hd_cand = j < g.n && __ldg(a.lo + min(j, g.n - 1u)) < lo_i;
+                const bool want = pass && j != row && j < g.n && valid && (wc < t_nn || (hd_cand && wc < t_hd));
+                uint32_t mk = __ballot_sync(0xffffffffu, want);
+                float d2 = 0.f;
+                while (mk) {
+                  const int src = __ffs(mk) - 1;
+                  mk &= mk - 1;
+                  const float t = dist2_exact_coop(g.xR, g.d, __shfl_sync(0xffffffffu, row, src), j, lane);
+                  if (lane == src) d2 = t;
+                }
+                if (!want) continue;
                 ++n_exact;
                 if (!(d2 < FLT_MAX)) continue;
                 const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | __ldg(a.perm + j);
