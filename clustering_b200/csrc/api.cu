@@ -1212,8 +1212,10 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
     ga.g.tiles_per_item = full_tpi;
     ga.g.n_col_items = full_items;
     CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+    if (ga.g.prof) CK(cudaMemsetAsync(c->gprof, 0, 16 * sizeof(unsigned long long), c->stream));      // counters of the full pass only
     CK(launch_gnn(ga, ggrid, c->stream));
     c->launches += 4;
+    CKI(dump_gprof(c, "gscan_nn (full pass)", ggrid));
     return 0;
   }
   NnArgs a;
