@@ -212,11 +212,24 @@ static __device__ __noinline__ float dist2_exact_coop(const float* __restrict__ 
       s0 = __fmul_rn(c0, c0); s1 = __fmul_rn(c1, c1); s2 = __fmul_rn(c2, c2); s3 = __fmul_rn(c3, c3);
     }
     const int cnt = min(32, n4 - base);
-    for (int l = 0; l < cnt; ++l) {
-      a0 = __fadd_rn(a0, __shfl_sync(0xffffffffu, s0, l));
-      a1 = __fadd_rn(a1, __shfl_sync(0xffffffffu, s1, l));
-      a2 = __fadd_rn(a2, __shfl_sync(0xffffffffu, s2, l));
-      a3 = __fadd_rn(a3, __shfl_sync(0xffffffffu, s3, l));
+    if (cnt == 32) {
+      // straight-line: the 128 shuffles do not depend on the four add chains and pipeline ahead of them (a rolled loop
+      // exposed one shuffle latency per column group: ~1100 cycles per pair, which stalls the whole accumulator hand-off)
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        a0 = __fadd_rn(a0, __shfl_sync(0xffffffffu, s0, l));
+        a1 = __fadd_rn(a1, __shfl_sync(0xffffffffu, s1, l));
+        a2 = __fadd_rn(a2, __shfl_sync(0xffffffffu, s2, l));
+        a3 = __fadd_rn(a3, __shfl_sync(0xffffffffu, s3, l));
+      }
+    } else {
+#pragma unroll 4
+      for (int l = 0; l < cnt; ++l) {
+        a0 = __fadd_rn(a0, __shfl_sync(0xffffffffu, s0, l));
+        a1 = __fadd_rn(a1, __shfl_sync(0xffffffffu, s1, l));
+        a2 = __fadd_rn(a2, __shfl_sync(0xffffffffu, s2, l));
+        a3 = __fadd_rn(a3, __shfl_sync(0xffffffffu, s3, l));
+      }
     }
   }
   int k = 4 * n4;
