@@ -117,12 +117,13 @@ def test_gemm_matches_ffma_path_and_shards():
     s.set_coords(x)
     assert s.gemm_info()[0]
     full = s.populations(radii)
-    parts = [s.populations(radii, 0, 12800), s.populations(radii, 12800, 25000), s.populations(radii, 25000, 40000)]
+    # 0: two row tiles per item; 12928 = 101 x 128: one row tile per item (odd tile boundary); 25000: not a tile boundary -> FFMA kernels
+    parts = [s.populations(radii, 0, 12928), s.populations(radii, 12928, 25000), s.populations(radii, 25000, 40000)]
     assert torch.equal(full, torch.cat(parts, dim=1))
     fe_dev = torch.from_numpy(fe).to(full.device)
     s.nn_prepare(fe_dev)
     kfull = s.nn_scan()
-    kparts = torch.cat([s.nn_scan(0, 20480), s.nn_scan(20480, 40000)], dim=1)
+    kparts = torch.cat([s.nn_scan(0, 20480), s.nn_scan(20480, 30848), s.nn_scan(30848, 40000)], dim=1)      # 30848 = 241 x 128
     assert torch.equal(kfull, kparts)
     s.close()
 
