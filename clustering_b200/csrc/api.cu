@@ -1141,6 +1141,12 @@ extern "C" int dcb200_ctx_free_energies(dcb200_ctx* c, const uint32_t* dev_pops,
 }
 
 // ---- nearest neighbours -----------------------------------------------------------------------
+// tuning knobs (diagnostics): seeds per side, window of the first pass in tiles
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
 // dev_fe: free energies in FRAME order.  Builds lo[p] = #{frames with fe < fe[frame at position p]}.
 extern "C" int dcb200_ctx_nn_prepare(dcb200_ctx* c, const float* dev_fe) {
   if (!c || !dev_fe) return fail("null argument");
@@ -1176,7 +1182,7 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
   memcpy(&fbits, &fmax, 4);
   const unsigned long long none = ((unsigned long long) fbits << 32) | (unsigned long long) (uint32_t) (c->n + 1);
   nn_seed_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->xT.p, c->ld, (int) c->d, (uint32_t) c->n, c->perm.p, c->lo.p,
-                                                               (uint32_t) pos_begin, (uint32_t) pos_end, 8, none,
+                                                               (uint32_t) pos_begin, (uint32_t) pos_end, env_int("DCB200_NN_SEED_W", 8), none,
                                                                (unsigned long long*) dev_keys_nn, (unsigned long long*) dev_keys_hd);
   if (c->gemm && pos_begin % GT == 0) {
     // GEMM-form scan (tensor cores): window pass over every row tile's own neighbourhood, then all tiles
@@ -1201,7 +1207,7 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
                            ga.g.e_rel, ga.g.prune_slack, ga.thr_nn, ga.thr_hd, ga.lormax, c->stream));
     const uint32_t full_tpi = ga.g.tiles_per_item, full_items = ga.g.n_col_items;
     if (ga.g.n_tiles > 96) {
-      ga.window = 16;
+      ga.window = (uint32_t) env_int("DCB200_NN_WINDOW", 16);
       ga.g.tiles_per_item = ga.g.n_tiles;
       ga.g.n_col_items = 1;
       CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
@@ -1239,7 +1245,7 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
   const uint32_t full_tpi = a.g.tiles_per_item, full_items = a.g.n_col_items;
   const int full_grid = grid;
   if (c->spatial && a.g.n_col_tiles > 96) {
-    a.window = 16;
+    a.window = (uint32_t) env_int("DCB200_NN_WINDOW", 16);
     a.g.tiles_per_item = a.g.n_col_tiles;
     a.g.n_col_items = 1;
     grid = (int) std::min<uint64_t>((uint64_t) full_grid, a.g.n_row_blocks);
