@@ -36,7 +36,8 @@ def test_gemm_path_is_active_and_bounded():
     os.environ["DCB200_GEMM_CHECK"] = "1"
     try:
         worst = 0.0
-        for d, data in ((32, gaussian_mixture(3000, 32, k=4, seed=5)), (128, contact_like(3000, 128, k=4, seed=6)),
+        for d, data in ((17, gaussian_mixture(3000, 17, k=4, seed=3) * np.float32(7.0)), (24, contact_like(3000, 24, k=4, seed=4) - np.float32(9.0)),
+                        (32, gaussian_mixture(3000, 32, k=4, seed=5)), (128, contact_like(3000, 128, k=4, seed=6)),
                         (200, gaussian_mixture(2000, 200, k=3, seed=7) + np.float32(40.0)),
                         (256, contact_like(2000, 256, k=3, seed=8) * np.float32(30.0))):
             s.set_coords(data)
