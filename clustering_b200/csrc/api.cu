@@ -267,7 +267,8 @@ __global__ void iota_kernel(uint32_t* p, size_t n) {
 
 // pops[r][i] = 1 + mult[r] * sum_{b <= bin[r]} cnt[b][i]    (self counted by the initial 1, density_clustering.cpp:133;
 // a radius listed m times is one map entry incremented m times per hit, :131-134,:180)
-// cumulative (count mode): cnt[b] already holds #{d2 < rad2[b]}, including the frame itself iff self[q]
+// cumulative (count mode): cnt[b] already holds #{d2 < rad2[b]}; self[q] = 1 where the kernel counted the frame itself
+// (count and bin mode count it through d2(i,i) = 0 < r^2; the histogram kernel skips j == i)
 struct FinalizeArgs {
   int n_out;
   int cumulative;
@@ -276,8 +277,8 @@ struct FinalizeArgs {
   int bin[MAX_BINS * 4];
   uint32_t mult[MAX_BINS * 4];
 };
-__global__ void pops_finalize_kernel(const uint32_t* __restrict__ cnt, size_t ld_cnt, size_t rows, uint32_t* __restrict__ pops,
-                                     const FinalizeArgs f) {
+__global__ void pops_finalize_kernel(const uint32_t* __restrict__ cnt, size_t ld_cnt, size_t rows, size_t ld_out,
+                                     uint32_t* __restrict__ pops, const FinalizeArgs f) {
   const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   for (int q = 0; q < f.n_out; ++q) {
@@ -286,8 +287,9 @@ __global__ void pops_finalize_kernel(const uint32_t* __restrict__ cnt, size_t ld
       c = cnt[(size_t) f.bin[q] * ld_cnt + i] - f.self[q];
     } else {
       for (int b = 0; b <= f.bin[q]; ++b) c += cnt[(size_t) b * ld_cnt + i];     // d2 < rad2[bin] = all bins up to it
+      c -= f.self[q];
     }
-    pops[(size_t) f.out_row[q] * rows + i] = 1u + f.mult[q] * c;
+    pops[(size_t) f.out_row[q] * ld_out + i] = 1u + f.mult[q] * c;
   }
 }
 
@@ -336,10 +338,17 @@ __global__ void lower_bound_kernel(const uint32_t* __restrict__ keys, size_t n, 
 // context's spatial order (exact arithmetic, real candidates): the pair scan then starts from tight thresholds,
 // prunes far tiles from its first item on and re-evaluates only the few columns that really improve on the seed.
 __global__ void nn_seed_kernel(const float* __restrict__ xT, size_t ld, int d, uint32_t n, const uint32_t* __restrict__ perm,
-                               const uint32_t* __restrict__ lo, uint32_t row_begin, uint32_t row_end, int W,
-                               unsigned long long none, unsigned long long* __restrict__ key_nn, unsigned long long* __restrict__ key_hd) {
-  const uint32_t p = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= row_end) return;
+                               const uint32_t* __restrict__ lo, uint32_t row_begin, uint32_t row_end, uint32_t rb_stride, uint32_t n_out,
+                               int W, unsigned long long none, unsigned long long* __restrict__ key_nn,
+                               unsigned long long* __restrict__ key_hd) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;            // index in the launch's output arrays (kernels.cuh: out_index)
+  if (q >= n_out) return;
+  const uint32_t p = row_begin + (q / ROWS_PER_CTA) * rb_stride * ROWS_PER_CTA + q % ROWS_PER_CTA;
+  if (p >= row_end) {
+    key_nn[q] = none;
+    key_hd[q] = none;
+    return;
+  }
   unsigned long long knn = none, khd = none;
   const uint32_t lo_p = lo[p];
   for (int o = 1; o <= W; ++o) {
@@ -354,17 +363,17 @@ __global__ void nn_seed_kernel(const float* __restrict__ xT, size_t ld, int d, u
       if (lo[j] < lo_p) khd = min(khd, key);
     }
   }
-  key_nn[p - row_begin] = knn;
-  key_hd[p - row_begin] = khd;
+  key_nn[q] = knn;
+  key_hd[q] = khd;
 }
 
 // bounding boxes of the row blocks of one launch = union of the 64-frame group boxes they touch (one warp per block)
-__global__ void row_bbox_kernel(const float* __restrict__ bbox, int d, uint32_t row_begin, uint32_t row_end, uint32_t n_row_blocks,
-                                float* __restrict__ rbbox) {
+__global__ void row_bbox_kernel(const float* __restrict__ bbox, int d, uint32_t row_begin, uint32_t row_end, uint32_t rb_stride,
+                                uint32_t n_row_blocks, float* __restrict__ rbbox) {
   const uint32_t rb = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (rb >= n_row_blocks) return;
-  const uint32_t r0 = row_begin + rb * ROWS_PER_CTA;
+  const uint32_t r0 = row_begin + rb * rb_stride * ROWS_PER_CTA;
   const uint32_t r1 = min(r0 + (uint32_t) ROWS_PER_CTA, row_end);
   const uint32_t g0 = r0 / 64, g1 = (r1 - 1) / 64;
   for (int k = lane; k < d; k += 32) {
@@ -381,16 +390,18 @@ __global__ void row_bbox_kernel(const float* __restrict__ bbox, int d, uint32_t 
 // blk_thr[rb][w] = bound (d2 units, with the pruning margins) of what the rows of block rb owned by consumer warp w
 // still accept after seeding: max over its rows of the seeded d2 (nearest / nearest with lower free energy)
 __global__ void nn_block_thr_kernel(const unsigned long long* __restrict__ key_nn, const unsigned long long* __restrict__ key_hd,
-                                    const uint32_t* __restrict__ lo, uint32_t row_begin, uint32_t row_end, uint32_t n_row_blocks,
-                                    float e_rel, float slack, float* __restrict__ blk_thr) {
+                                    const uint32_t* __restrict__ lo, uint32_t row_begin, uint32_t row_end, uint32_t rb_stride,
+                                    uint32_t n_row_blocks, float e_rel, float slack, float* __restrict__ blk_thr) {
   const uint32_t rb = blockIdx.x;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;      // blockDim = N_CONSUMERS: thread = consumer slot
   float v = 0.f;
   for (int r = 0; r < RI; ++r) {
-    const uint32_t i = row_begin + rb * ROWS_PER_CTA + (uint32_t) w * (32u * RI) + (uint32_t) r * 32u + (uint32_t) lane;   // Rows::row
+    const uint32_t slot = (uint32_t) w * (32u * RI) + (uint32_t) r * 32u + (uint32_t) lane;
+    const uint32_t i = row_begin + rb * rb_stride * ROWS_PER_CTA + slot;   // Rows::row
     if (i >= row_end) continue;
-    const float dn = __uint_as_float((uint32_t) (key_nn[i - row_begin] >> 32));
-    const float dh = lo[i] == 0 ? dn : __uint_as_float((uint32_t) (key_hd[i - row_begin] >> 32));
+    const uint32_t q = rb * ROWS_PER_CTA + slot;                           // out_index
+    const float dn = __uint_as_float((uint32_t) (key_nn[q] >> 32));
+    const float dh = lo[i] == 0 ? dn : __uint_as_float((uint32_t) (key_hd[q] >> 32));
     v = fmaxf(v, fmaxf(dn, dh));
   }
   v = (fmaf(e_rel, v, v) + slack) * 1.00001f;
@@ -494,6 +505,7 @@ struct dcb200_ctx {
   DevBuf<float> stage;              // row-major staging for host uploads
   DevBuf<float> centre;             // [2d] centre, spread
   DevBuf<uint32_t> cnt;
+  DevBuf<float> lut;                // cell table of the bin-mode population kernel (one pass at a time)
   DevBuf<unsigned long long> knn, khd;
   DevBuf<uint32_t> io_u32;          // host-pointer entry points: device-side staging of inputs / outputs
   DevBuf<float> io_f32;
@@ -516,6 +528,13 @@ struct dcb200_ctx {
   float* gcheck = nullptr;          // [2] diagnostics of the CHECK kernel
   unsigned long long* gprof = nullptr;   // [16] cycle counters of the GEMM-form kernels (DCB200_GEMM_PROF=1)
 };
+
+// tuning knobs read from the environment (diagnostics)
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
 
 static float up(double v) {          // smallest float >= v
   float f = (float) v;
@@ -540,8 +559,22 @@ static void error_bounds(size_t d, float maxnorm2, float* c_loc, float* e_rel, f
   *prune_slack = up(1.5 * (5.0 * (double) d + 8.0) * u * (double) maxnorm2 + 1e-37);
 }
 
-static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, int occupancy, uint32_t tiles_per_item, ScanGeom* g,
-                     int* grid, uint32_t max_tiles_per_item = 0xffffffffu) {
+// rows of the launch: blocks of ROWS_PER_CTA rows starting at row_begin + rb * rb_stride * ROWS_PER_CTA, below row_end
+// (rb_stride = 1: the contiguous range; rb_stride = G with row_begin = g * ROWS_PER_CTA, row_end = n: block-cyclic shard g of G)
+static size_t launch_row_blocks(size_t row_begin, size_t row_end, size_t rb_stride) {
+  if (row_begin >= row_end) return 0;
+  const size_t step = rb_stride * ROWS_PER_CTA;
+  return (row_end - row_begin + step - 1) / step;
+}
+static size_t launch_rows(size_t row_begin, size_t row_end, size_t rb_stride) {      // valid rows = size of the compact outputs
+  const size_t nb = launch_row_blocks(row_begin, row_end, rb_stride);
+  if (nb == 0) return 0;
+  const size_t last0 = row_begin + (nb - 1) * rb_stride * ROWS_PER_CTA;
+  return (nb - 1) * ROWS_PER_CTA + std::min<size_t>(ROWS_PER_CTA, row_end - last0);
+}
+
+static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, size_t rb_stride, int tj, int occupancy, uint32_t tiles_per_item,
+                     ScanGeom* g, int* grid, uint32_t max_tiles_per_item = 0xffffffffu) {
   memset(g, 0, sizeof(*g));
   g->xT = c->xT.p;
   g->cT = c->cT.p;
@@ -554,7 +587,8 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, in
   g->n = (uint32_t) c->n;
   g->row_begin = (uint32_t) row_begin;
   g->row_end = (uint32_t) row_end;
-  g->n_row_blocks = (uint32_t) ((row_end - row_begin + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+  g->rb_stride = (uint32_t) rb_stride;
+  g->n_row_blocks = (uint32_t) launch_row_blocks(row_begin, row_end, rb_stride);
   g->n_col_tiles = (uint32_t) (c->ld / tj);
   if (occupancy < 1) return fail("kernel does not fit on an SM (shared memory / registers)");
   *grid = c->sm_count * occupancy;
@@ -570,10 +604,10 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, int tj, in
   error_bounds(c->d, c->maxnorm2, &g->c_loc, &g->e_rel, &g->prune_slack);
   CK(c->rbbox.reserve((size_t) g->n_row_blocks * 2 * c->d));
   g->rbbox = c->rbbox.p;
-  row_bbox_kernel<<<blocks_for(g->n_row_blocks, 8), 256, 0, c->stream>>>(c->bbox.p, (int) c->d, g->row_begin, g->row_end, g->n_row_blocks,
-                                                                         c->rbbox.p);
+  row_bbox_kernel<<<blocks_for(g->n_row_blocks, 8), 256, 0, c->stream>>>(c->bbox.p, (int) c->d, g->row_begin, g->row_end, g->rb_stride,
+                                                                         g->n_row_blocks, c->rbbox.p);
   c->launches += 1;
-  c->pairs_scheduled += (uint64_t) (row_end - row_begin) * (uint64_t) c->n;
+  c->pairs_scheduled += (uint64_t) launch_rows(row_begin, row_end, rb_stride) * (uint64_t) c->n;
   return 0;
 }
 
@@ -621,6 +655,22 @@ static cudaError_t launch_pops_count(int d, const PopsArgs& a, int grid, cudaStr
 static int occ_pops_count(int d, int nb) {
   switch (d <= MAX_TEMPLATE_D ? d : 0) {
 #define FN(D) occupancy_pops_count_d##D(nb, d)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return 0;
+}
+static cudaError_t launch_pops_bin(int d, const PopsArgs& a, int grid, cudaStream_t st) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) launch_pops_bin_d##D(a, grid, st)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return cudaErrorInvalidValue;
+}
+static int occ_pops_bin(int d, int nb, int lut_k) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) occupancy_pops_bin_d##D(nb, lut_k, d)
     DCB_FOR_EACH_D(DCB_DISPATCH)
 #undef FN
   }
@@ -702,7 +752,7 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   c->xT.release(); c->cT.release(); c->bbox.release(); c->rbbox.release(); c->blk_thr.release();
   c->perm.release(); c->lo.release(); c->lof.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release(); c->skeys_a.release(); c->skeys_b.release();
   c->tmp_u32.release(); c->tmp2_u32.release();
-  c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->knn.release(); c->khd.release();
+  c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->lut.release(); c->knn.release(); c->khd.release();
   c->io_u32.release(); c->io_f32.release();
   c->gT.release(); c->gnorm.release(); c->xR.release(); c->thdr.release(); c->lbmat.release(); c->lomin.release(); c->gthr.release();
   if (c->gcheck) cudaFree(c->gcheck);
@@ -970,11 +1020,55 @@ static int dump_gprof(dcb200_ctx* c, const char* what, int grid) {
   return 0;
 }
 
+
+// Cell table of pops_bin_kernel (kernels.cuh) for the ascending, distinct squared radii b2[0..nb): K cells over
+// s in [0, span], cell(s) = floor(sat(s / span) (K - 1)) up to a quarter-cell rounding.  A pair in cell i has
+// s in [i - 0.15, i + 1.15] w (w = span / (K - 1)) and is decided by the table only if its error band is narrower than
+// margin = w / 4, so the only radii it can be near lie in [i - 0.4, i + 1.4] w: the table exists iff no such range
+// holds two radii.  Entry: that radius with its index k in the low 5 mantissa bits (bin = k + (s >= entry)), else a
+// sentinel (+big | 0 if no radius lies below the cell, -big | (k - 1) if k do).  Returns K, 0 if there is no table
+// (radii too close together for 4096 cells, or r_max = 0): the histogram kernel serves such lists.
+static int build_bin_table(const float* b2, int nb, std::vector<float>* table, float* scale, float* margin) {
+  if (nb < 1 || nb > MAX_BINS || !(b2[nb - 1] > 1e-30f) || !(b2[nb - 1] < 1e30f)) return 0;
+  const double span = (double) b2[nb - 1] * 1.02;
+  for (int K = 256; K <= 4096; K *= 2) {
+    const double w = span / (double) (K - 1);
+    table->assign((size_t) K, 0.f);
+    bool ok = true;
+    int below = 0;                                   // radii below the current cell's range
+    for (int i = 0; i < K && ok; ++i) {
+      const double lo = ((double) i - 0.4) * w, hi = ((double) i + 1.4) * w;
+      while (below < nb && (double) b2[below] < lo) ++below;
+      int inside = 0;
+      while (below + inside < nb && (double) b2[below + inside] <= hi) ++inside;
+      uint32_t bits;
+      if (inside > 1) {
+        ok = false;
+        break;
+      } else if (inside == 1) {
+        memcpy(&bits, &b2[below], 4);
+        bits = (bits & ~31u) | (uint32_t) below;
+      } else if (below == 0) {
+        bits = 0x7f7fffe0u;                          // +big: s >= entry never holds, bin 0
+      } else {
+        bits = 0xff7fffe0u | (uint32_t) (below - 1);  // -big: s >= entry always holds, bin (below - 1) + 1
+      }
+      memcpy(&(*table)[i], &bits, 4);
+    }
+    if (ok) {
+      *scale = (float) (1.0 / span);
+      *margin = (float) (0.25 * w);
+      return K;
+    }
+  }
+  return 0;
+}
+
 // ---- populations ----------------------------------------------------------------------------
 // GEMM-form passes (tensor cores): up to eight distinct radii per pass, largest radii first, each pass pruned by its own r_max
 static int gemm_populations(dcb200_ctx* c, const float* radii, size_t n_radii, const std::vector<float>& rad2, const std::vector<float>& uniq,
                             size_t row_begin, size_t row_end, size_t ld_cnt, uint32_t* dev_pops) {
-  const size_t rows = row_end - row_begin;
+  const size_t rows = row_end - row_begin, ld_out = rows;
   const char* chk = getenv("DCB200_GEMM_CHECK");
   const bool check = chk && chk[0] == '1' && uniq.size() == 1;
   if (check && !c->gcheck) {
@@ -1011,7 +1105,7 @@ static int gemm_populations(dcb200_ctx* c, const float* radii, size_t n_radii, c
     f.cumulative = 1;
     auto flush = [&]() -> int {
       if (f.n_out == 0) return 0;
-      pops_finalize_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->cnt.p, ld_cnt, rows, dev_pops, f);
+      pops_finalize_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->cnt.p, ld_cnt, rows, ld_out, dev_pops, f);
       c->launches += 1;
       f.n_out = 0;
       CK(cudaGetLastError());
@@ -1034,14 +1128,15 @@ static int gemm_populations(dcb200_ctx* c, const float* radii, size_t n_radii, c
   return 0;
 }
 
-extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t n_radii, size_t row_begin, size_t row_end,
-                                      uint32_t* dev_pops) {
+// rows: blocks from row_begin with stride rb_stride (fill_geom); dev_pops: [n_radii][ld_out], the launch's rows in out_index order
+static int populations_impl(dcb200_ctx* c, const float* radii, size_t n_radii, size_t row_begin, size_t row_end, size_t rb_stride,
+                            size_t ld_out, uint32_t* dev_pops) {
   if (!c || (!radii && n_radii) || !dev_pops) return fail("null argument");
   if (c->n == 0) return fail("dcb200_ctx_populations: no coordinates set");
   if (row_begin > row_end || row_end > c->n) return fail("dcb200_ctx_populations: bad position range");
   if (n_radii == 0 || row_begin == row_end) return 0;
   CK(cudaSetDevice(c->device));
-  const size_t rows = row_end - row_begin;
+  const size_t rows = launch_rows(row_begin, row_end, rb_stride);
   // squared radii exactly as the reference forms them (float multiply, density_clustering.cpp:139)
   std::vector<float> rad2(n_radii);
   for (size_t r = 0; r < n_radii; ++r) rad2[r] = radii[r] * radii[r];
@@ -1050,18 +1145,41 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
   for (float v : uniq)
     if (!(v == v)) return fail("dcb200_ctx_populations: NaN radius");
-  const size_t ld_cnt = (rows + 255) / 256 * 256;
-  if (c->gemm && row_begin % GT == 0) return gemm_populations(c, radii, n_radii, rad2, uniq, row_begin, row_end, ld_cnt, dev_pops);
+  const size_t ld_cnt = launch_row_blocks(row_begin, row_end, rb_stride) * ROWS_PER_CTA;
+  if (c->gemm && row_begin % GT == 0 && rb_stride == 1) {
+    if (ld_out != rows) return fail("dcb200: the GEMM-form path writes compact outputs");
+    return gemm_populations(c, radii, n_radii, rad2, uniq, row_begin, row_end, ld_cnt, dev_pops);
+  }
   const int tj = tile_width(c->d);
-  // specialised dims and up to two passes' worth of radii: branch-free count mode (pops_count_kernel), up to 8 (D <= 6) or
-  // 4 distinct radii per pass, largest radii first so that every pass is pruned by its own r_max.  Long radius lists
-  // (every pass re-evaluates the distances) and other dims: the histogram kernel, up to 31 radii per pass.
+  // Three kernels for the specialised dims (kernels.cuh); any other shape runs the histogram kernel:
+  //   count  up to 8 (D <= 6) or 4 distinct radii per pass, branch-free sign-bit counting, ~3 instructions per pair and radius;
+  //   bin    up to 31 radii per pass through a cell table, ~14 instructions per pair of a step that holds candidates,
+  //          whatever the number of radii (needs row groups that coincide with tiles and radii a table can separate);
+  //   hist   up to 31 radii per pass, per-hit handler with a binary search (the general fallback).
+  // Passes take the largest radii first so that each is pruned by its own r_max.  DCB200_POPS_MODE=count|bin|hist forces one.
+  enum Mode { COUNT, BIN, HIST };
   const size_t count_pass = c->d <= 6 ? 8 : 4;
-  const bool count_mode = c->d <= (size_t) MAX_TEMPLATE_D && uniq.size() <= 2 * count_pass;
-  const size_t pass_max = count_mode ? count_pass : (size_t) MAX_BINS;
+  const bool specialised = c->d <= (size_t) MAX_TEMPLATE_D;
+  Mode mode = HIST;
+  if (specialised && uniq.size() <= 2 * count_pass) mode = COUNT;
+  if (specialised && uniq.size() >= (size_t) env_int("DCB200_BIN_MIN_RADII", 4) && row_begin % (32 * RI) == 0) mode = BIN;
+  if (const char* e = getenv("DCB200_POPS_MODE")) {
+    if (!strcmp(e, "count") && specialised && uniq.size() <= 2 * count_pass) mode = COUNT;
+    if (!strcmp(e, "bin") && specialised && row_begin % (32 * RI) == 0) mode = BIN;
+    if (!strcmp(e, "hist")) mode = HIST;
+  }
   size_t hi = uniq.size();                        // radii [b0, hi) of uniq go into the next pass
   while (hi > 0) {
-    size_t n_pass = std::min(pass_max, hi);
+    Mode pm = mode;
+    size_t n_pass = std::min(pm == COUNT ? count_pass : (size_t) MAX_BINS, hi);
+    std::vector<float> table;
+    float lut_scale = 0.f, lut_margin = 0.f;
+    int lut_k = 0;
+    if (pm == BIN) {
+      lut_k = build_bin_table(uniq.data() + (hi - n_pass), (int) n_pass, &table, &lut_scale, &lut_margin);
+      if (lut_k == 0 || occ_pops_bin((int) c->d, (int) n_pass, lut_k) < 1) pm = HIST;
+    }
+    const bool count_mode = pm == COUNT;
     int nb = (int) n_pass;                        // kernel variant: the smallest instantiated count >= n_pass
     if (count_mode) {
       if (n_pass == 5) nb = 6;
@@ -1070,9 +1188,14 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     const size_t b0 = hi - n_pass;
     PopsArgs a;
     int grid = 0;
-    CKI(fill_geom(c, row_begin, row_end, tj, count_mode ? occ_pops_count((int) c->d, nb) : occ_pops((int) c->d, nb),
-                  nb > 4 ? 64u : 32u, &a.g, &grid, count_mode ? 0xffffffffu : (uint32_t) (57344 / tj)));
+    const int occ = pm == COUNT ? occ_pops_count((int) c->d, nb) : pm == BIN ? occ_pops_bin((int) c->d, nb, lut_k) : occ_pops((int) c->d, nb);
+    CKI(fill_geom(c, row_begin, row_end, rb_stride, tj, occ, nb > 4 ? 64u : 32u, &a.g, &grid,
+                  count_mode ? 0xffffffffu : (uint32_t) (57344 / tj)));
     a.n_bins = nb;
+    a.lut = nullptr;
+    a.lut_k = 0;
+    a.lut_scale = a.lut_margin = a.band_max = 0.f;
+    a.dense_lanes = 0;
     for (int q = 0; q < 8; ++q) a.band[q] = 0.f;
     if (count_mode) {
       // radius-dependent part of the band: e_rel * r^2 (fast path) + roundings of s = acc + |x'|^2 and of s - r^2
@@ -1082,18 +1205,32 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
         a.band[q] = up((1.02 * (double) a.g.e_rel + 4.0 * u) * r2 + 1e-37);
       }
     }
-    // unused slots: count mode -1 (nothing is ever inside, far outside every band), histogram mode +inf
+    // unused slots: count mode -1 (nothing is ever inside, far outside every band), histogram / bin mode +inf
     for (int q = 0; q < 32; ++q) a.rad2[q] = q < (int) n_pass ? uniq[b0 + q] : (count_mode ? -1.f : INFINITY);
     const double rmax2 = (double) uniq[hi - 1];
     a.thr_fast = up(rmax2 * (1.0 + 1.01 * (double) a.g.e_rel));
     // a tile whose bounding-box distance exceeds this cannot contain a pair with exact d2 < r_max^2
     a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.prune_slack);
+    if (pm == BIN) {
+      CK(c->lut.reserve(4096));
+      CK(cudaMemcpyAsync(c->lut.p, table.data(), (size_t) lut_k * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      a.lut = c->lut.p;
+      a.lut_k = lut_k;
+      a.lut_scale = lut_scale;
+      a.lut_margin = lut_margin;
+      // radius part of the band for r_max (e_rel r^2 + roundings of s and of s - e, as in count mode) + the 31 ulp by which
+      // the table's entries may differ from the radii they stand for
+      a.band_max = up((1.02 * (double) a.g.e_rel + 4.0 * ldexp(1.0, -24) + 32.0 * ldexp(1.0, -23)) * rmax2 + 1e-37);
+      a.dense_lanes = env_int("DCB200_BIN_DENSE_LANES", 8);
+    }
+    const bool counts_self = pm != HIST;           // count and bin mode count the frame itself through d2 = 0 < r^2
     CK(c->cnt.reserve((size_t) nb * ld_cnt));
     a.cnt = c->cnt.p;
     a.ld_cnt = ld_cnt;
     CK(cudaMemsetAsync(c->cnt.p, 0, (size_t) nb * ld_cnt * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
-    CK(count_mode ? launch_pops_count((int) c->d, a, grid, c->stream) : launch_pops((int) c->d, a, grid, c->stream));
+    CK(pm == COUNT ? launch_pops_count((int) c->d, a, grid, c->stream)
+                   : pm == BIN ? launch_pops_bin((int) c->d, a, grid, c->stream) : launch_pops((int) c->d, a, grid, c->stream));
     c->launches += 1;
     // input radii served by this pass, in groups the finalize kernel's argument block can hold
     FinalizeArgs f;
@@ -1101,7 +1238,7 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
     f.cumulative = count_mode ? 1 : 0;
     auto flush = [&]() -> int {
       if (f.n_out == 0) return 0;
-      pops_finalize_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->cnt.p, ld_cnt, rows, dev_pops, f);
+      pops_finalize_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->cnt.p, ld_cnt, rows, ld_out, dev_pops, f);
       c->launches += 1;
       f.n_out = 0;
       CK(cudaGetLastError());
@@ -1115,12 +1252,101 @@ extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t 
       f.out_row[f.n_out] = (int) r;
       f.bin[f.n_out] = (int) (bin - b0);
       f.mult[f.n_out] = mult;
-      f.self[f.n_out] = rad2[r] > 0.f ? 1u : 0u;      // d2(i,i) = 0 < r^2
+      f.self[f.n_out] = (counts_self && rad2[r] > 0.f) ? 1u : 0u;      // d2(i,i) = 0 < r^2
       if (++f.n_out == MAX_BINS * 4) CKI(flush());
     }
     CKI(flush());
     hi = b0;
   }
+  return 0;
+}
+
+extern "C" int dcb200_ctx_populations(dcb200_ctx* c, const float* radii, size_t n_radii, size_t row_begin, size_t row_end,
+                                      uint32_t* dev_pops) {
+  if (row_begin > row_end) return fail("dcb200_ctx_populations: bad position range");
+  return populations_impl(c, radii, n_radii, row_begin, row_end, 1, row_end - row_begin, dev_pops);
+}
+
+// ---- shards -------------------------------------------------------------------------------------
+// The positions are dealt to n_shards shards in blocks of ROWS_PER_CTA: block b belongs to shard b % n_shards and a shard
+// keeps its blocks in order.  Block-cyclic instead of contiguous: the spatial order puts dense and sparse regions into long
+// runs, so contiguous shards of equal length cost very different amounts (SCALE_r01: efficiency 0.43 at 8 GPUs).
+// Contexts on the GEMM-form path (17 <= n_cols <= 256) keep contiguous shards of `capacity` positions (their work items are
+// 256-row pairs of tiles); dcb200_ctx_shards_to_frame_order / dcb200_ctx_nn_finish_shards undo whichever dealing was used.
+extern "C" size_t dcb200_shard_capacity(size_t n_rows, int n_shards) {
+  if (n_shards < 1) return 0;
+  const size_t blocks = (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  return (blocks + n_shards - 1) / n_shards * ROWS_PER_CTA;
+}
+static bool shard_ok(const dcb200_ctx* c, int shard, int n_shards) { return c && n_shards >= 1 && shard >= 0 && shard < n_shards; }
+// first row, end row and block stride of a shard's launch
+static void shard_range(const dcb200_ctx* c, int shard, int n_shards, size_t* b, size_t* e, size_t* stride) {
+  if (c->gemm) {
+    const size_t cap = dcb200_shard_capacity(c->n, n_shards);
+    *b = std::min(c->n, cap * shard);
+    *e = std::min(c->n, cap * (shard + 1));
+    *stride = 1;
+  } else {
+    *b = std::min(c->n, (size_t) shard * ROWS_PER_CTA);
+    *e = *b < c->n ? c->n : *b;
+    *stride = (size_t) n_shards;
+  }
+}
+extern "C" int dcb200_ctx_shard_rows(dcb200_ctx* c, int shard, int n_shards, size_t* rows) {
+  if (!shard_ok(c, shard, n_shards) || !rows) return fail("dcb200_ctx_shard_rows: bad arguments");
+  size_t b, e, stride;
+  shard_range(c, shard, n_shards, &b, &e, &stride);
+  *rows = launch_rows(b, e, stride);
+  return 0;
+}
+extern "C" int dcb200_ctx_populations_shard(dcb200_ctx* c, const float* radii, size_t n_radii, int shard, int n_shards,
+                                            uint32_t* dev_pops) {
+  if (!shard_ok(c, shard, n_shards)) return fail("dcb200_ctx_populations_shard: bad shard");
+  if (c->n == 0) return fail("dcb200_ctx_populations_shard: no coordinates set");
+  size_t b, e, stride;
+  shard_range(c, shard, n_shards, &b, &e, &stride);
+  const size_t cap = dcb200_shard_capacity(c->n, n_shards);
+  if (stride == 1 && c->gemm) {
+    // the GEMM-form kernels write compact rows: run into scratch, then copy row by row into the padded layout
+    const size_t rows = e - b;
+    if (rows == 0 || n_radii == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    CK(c->io_u32.reserve(n_radii * rows));
+    CKI(populations_impl(c, radii, n_radii, b, e, 1, rows, c->io_u32.p));
+    CK(cudaMemcpy2DAsync(dev_pops, cap * sizeof(uint32_t), c->io_u32.p, rows * sizeof(uint32_t), rows * sizeof(uint32_t), n_radii,
+                         cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+  }
+  return populations_impl(c, radii, n_radii, b, e, stride, cap, dev_pops);
+}
+
+// dst[a][frame] = src[shard][a][local] for the gathered shard outputs src [n_shards][n_arrays][capacity]
+__global__ void shards_to_frame_order_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ perm,
+                                             size_t n, size_t n_arrays, size_t cap, uint32_t n_shards, int cyclic) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  size_t shard, local;
+  if (cyclic) {
+    const size_t blk = p / ROWS_PER_CTA;
+    shard = blk % n_shards;
+    local = blk / n_shards * ROWS_PER_CTA + p % ROWS_PER_CTA;
+  } else {
+    shard = p / cap;
+    local = p % cap;
+  }
+  const size_t o = perm[p];
+  for (size_t a = 0; a < n_arrays; ++a) dst[a * n + o] = src[(shard * n_arrays + a) * cap + local];
+}
+extern "C" int dcb200_ctx_shards_to_frame_order(dcb200_ctx* c, const uint32_t* dev_src, size_t n_arrays, int n_shards, uint32_t* dev_dst) {
+  if (!c || !dev_src || !dev_dst || n_shards < 1) return fail("dcb200_ctx_shards_to_frame_order: bad arguments");
+  if (c->n == 0) return fail("dcb200_ctx_shards_to_frame_order: no coordinates set");
+  if (n_arrays == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  shards_to_frame_order_kernel<<<blocks_for(c->n, 256), 256, 0, c->stream>>>(dev_src, dev_dst, c->perm.p, c->n, n_arrays,
+                                                                             dcb200_shard_capacity(c->n, n_shards), (uint32_t) n_shards,
+                                                                             c->gemm ? 0 : 1);
+  c->launches += 1;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -1141,12 +1367,6 @@ extern "C" int dcb200_ctx_free_energies(dcb200_ctx* c, const uint32_t* dev_pops,
 }
 
 // ---- nearest neighbours -----------------------------------------------------------------------
-// tuning knobs (diagnostics): seeds per side, window of the first pass in tiles
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  const int v = e ? atoi(e) : 0;
-  return v > 0 ? v : dflt;
-}
 // dev_fe: free energies in FRAME order.  Builds lo[p] = #{frames with fe < fe[frame at position p]}.
 extern "C" int dcb200_ctx_nn_prepare(dcb200_ctx* c, const float* dev_fe) {
   if (!c || !dev_fe) return fail("null argument");
@@ -1169,22 +1389,24 @@ extern "C" int dcb200_ctx_nn_prepare(dcb200_ctx* c, const float* dev_fe) {
   return 0;
 }
 
-extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_end, uint64_t* dev_keys_nn, uint64_t* dev_keys_hd) {
+// rows: blocks from pos_begin with stride rb_stride (fill_geom); keys in out_index order
+static int nn_scan_impl(dcb200_ctx* c, size_t pos_begin, size_t pos_end, size_t rb_stride, uint64_t* dev_keys_nn, uint64_t* dev_keys_hd) {
   if (!c || !dev_keys_nn || !dev_keys_hd) return fail("null argument");
   if (!c->nn_ready) return fail("dcb200_ctx_nn_scan: call dcb200_ctx_nn_prepare first");
   if (pos_begin > pos_end || pos_end > c->n) return fail("dcb200_ctx_nn_scan: bad position range");
   if (pos_begin == pos_end) return 0;
   CK(cudaSetDevice(c->device));
-  const size_t rows = pos_end - pos_begin;
+  const size_t rows = launch_rows(pos_begin, pos_end, rb_stride);
   // "no neighbour" = (n_rows + 1, FLT_MAX)  (density_clustering.cpp:257-260)
   const float fmax = FLT_MAX;
   uint32_t fbits;
   memcpy(&fbits, &fmax, 4);
   const unsigned long long none = ((unsigned long long) fbits << 32) | (unsigned long long) (uint32_t) (c->n + 1);
   nn_seed_kernel<<<blocks_for(rows, 256), 256, 0, c->stream>>>(c->xT.p, c->ld, (int) c->d, (uint32_t) c->n, c->perm.p, c->lo.p,
-                                                               (uint32_t) pos_begin, (uint32_t) pos_end, env_int("DCB200_NN_SEED_W", 8), none,
-                                                               (unsigned long long*) dev_keys_nn, (unsigned long long*) dev_keys_hd);
-  if (c->gemm && pos_begin % GT == 0) {
+                                                               (uint32_t) pos_begin, (uint32_t) pos_end, (uint32_t) rb_stride, (uint32_t) rows,
+                                                               env_int("DCB200_NN_SEED_W", 8), none, (unsigned long long*) dev_keys_nn,
+                                                               (unsigned long long*) dev_keys_hd);
+  if (c->gemm && pos_begin % GT == 0 && rb_stride == 1) {
     // GEMM-form scan (tensor cores): window pass over every row tile's own neighbourhood, then all tiles
     GNnArgs ga;
     int ggrid = 0;
@@ -1226,7 +1448,7 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
   }
   NnArgs a;
   int grid = 0;
-  CKI(fill_geom(c, pos_begin, pos_end, tile_width(c->d), occ_nn((int) c->d), 32u, &a.g, &grid));
+  CKI(fill_geom(c, pos_begin, pos_end, rb_stride, tile_width(c->d), occ_nn((int) c->d), 32u, &a.g, &grid));
   a.perm = c->perm.p;
   a.lo = c->lo.p;
   a.lof = c->lof.p;
@@ -1236,8 +1458,8 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
   a.g.blk_thr = c->blk_thr.p;
   nn_block_thr_kernel<<<a.g.n_row_blocks, N_CONSUMERS, 0, c->stream>>>((const unsigned long long*) dev_keys_nn,
                                                                        (const unsigned long long*) dev_keys_hd, c->lo.p, (uint32_t) pos_begin,
-                                                                       (uint32_t) pos_end, a.g.n_row_blocks, a.g.e_rel, a.g.prune_slack,
-                                                                       c->blk_thr.p);
+                                                                       (uint32_t) pos_end, a.g.rb_stride, a.g.n_row_blocks, a.g.e_rel,
+                                                                       a.g.prune_slack, c->blk_thr.p);
   a.key_nn = (unsigned long long*) dev_keys_nn;
   a.key_hd = (unsigned long long*) dev_keys_hd;
   // pass 1: every row block against its own neighbourhood in the spatial order (one item per block): the nearest
@@ -1259,6 +1481,56 @@ extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_en
   CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
   CK(launch_nn((int) c->d, a, grid = full_grid, c->stream));
   c->launches += 3;
+  return 0;
+}
+
+extern "C" int dcb200_ctx_nn_scan(dcb200_ctx* c, size_t pos_begin, size_t pos_end, uint64_t* dev_keys_nn, uint64_t* dev_keys_hd) {
+  return nn_scan_impl(c, pos_begin, pos_end, 1, dev_keys_nn, dev_keys_hd);
+}
+
+// keys of one shard (dcb200_ctx_populations_shard's dealing), [capacity] each; entries past the shard's rows are not written
+extern "C" int dcb200_ctx_nn_scan_shard(dcb200_ctx* c, int shard, int n_shards, uint64_t* dev_keys_nn, uint64_t* dev_keys_hd) {
+  if (!shard_ok(c, shard, n_shards)) return fail("dcb200_ctx_nn_scan_shard: bad shard");
+  if (c->n == 0) return fail("dcb200_ctx_nn_scan_shard: no coordinates set");
+  size_t b, e, stride;
+  shard_range(c, shard, n_shards, &b, &e, &stride);
+  return nn_scan_impl(c, b, e, stride, dev_keys_nn, dev_keys_hd);
+}
+
+__global__ void nn_finish_shards_kernel(const unsigned long long* __restrict__ knn, const unsigned long long* __restrict__ khd,
+                                        const uint32_t* __restrict__ perm, size_t n, size_t cap, uint32_t n_shards, int cyclic,
+                                        uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2, uint32_t* __restrict__ hd_idx,
+                                        float* __restrict__ hd_d2) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  size_t shard, local;
+  if (cyclic) {
+    const size_t blk = p / ROWS_PER_CTA;
+    shard = blk % n_shards;
+    local = blk / n_shards * ROWS_PER_CTA + p % ROWS_PER_CTA;
+  } else {
+    shard = p / cap;
+    local = p % cap;
+  }
+  const size_t o = perm[p];
+  const unsigned long long a = knn[shard * cap + local], b = khd[shard * cap + local];
+  nn_idx[o] = (uint32_t) a;
+  nn_d2[o] = __uint_as_float((uint32_t) (a >> 32));
+  hd_idx[o] = (uint32_t) b;
+  hd_d2[o] = __uint_as_float((uint32_t) (b >> 32));
+}
+// gathered shard keys [n_shards][capacity] -> outputs in frame order
+extern "C" int dcb200_ctx_nn_finish_shards(dcb200_ctx* c, const uint64_t* dev_keys_nn, const uint64_t* dev_keys_hd, int n_shards,
+                                           uint32_t* dev_nn_idx, float* dev_nn_d2, uint32_t* dev_hd_idx, float* dev_hd_d2) {
+  if (!c || !dev_keys_nn || !dev_keys_hd || !dev_nn_idx || !dev_nn_d2 || !dev_hd_idx || !dev_hd_d2 || n_shards < 1)
+    return fail("dcb200_ctx_nn_finish_shards: bad arguments");
+  if (c->n == 0) return fail("dcb200_ctx_nn_finish_shards: no coordinates set");
+  CK(cudaSetDevice(c->device));
+  nn_finish_shards_kernel<<<blocks_for(c->n, 256), 256, 0, c->stream>>>(
+      (const unsigned long long*) dev_keys_nn, (const unsigned long long*) dev_keys_hd, c->perm.p, c->n,
+      dcb200_shard_capacity(c->n, n_shards), (uint32_t) n_shards, c->gemm ? 0 : 1, dev_nn_idx, dev_nn_d2, dev_hd_idx, dev_hd_d2);
+  c->launches += 1;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -1288,7 +1560,7 @@ extern "C" int dcb200_ctx_screening_scan(dcb200_ctx* c, size_t m_prev, size_t m_
   CK(cudaSetDevice(c->device));
   ScreenArgs a;
   int grid = 0;
-  CKI(fill_geom(c, row_begin, row_end, tile_width(c->d), occ_screen((int) c->d), 32u, &a.g, &grid));
+  CKI(fill_geom(c, row_begin, row_end, 1, tile_width(c->d), occ_screen((int) c->d), 32u, &a.g, &grid));
   a.cut = max_dist2;
   a.thr_fast = up((double) max_dist2 * (1.0 + 1.01 * (double) a.g.e_rel));
   a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.prune_slack);

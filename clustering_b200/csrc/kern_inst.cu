@@ -56,9 +56,29 @@ int DCB_CAT(occupancy_pops_count_d, DCB_D)(int n_bins, int d) {
   }
   return nb;
 }
+// bin mode: long radius lists through the cell table
+cudaError_t DCB_CAT(launch_pops_bin_d, DCB_D)(const PopsArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = pops_bin_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d), a.n_bins, a.lut_k);
+  cudaError_t e = cudaFuncSetAttribute(pops_bin_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  pops_bin_kernel<DCB_D><<<grid, CTA_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+int DCB_CAT(occupancy_pops_bin_d, DCB_D)(int n_bins, int lut_k, int d) {
+  int nb = 0;
+  const size_t smem = pops_bin_smem_bytes(SmemRing<DCB_D>::bytes(d), n_bins, lut_k);
+  if (cudaFuncSetAttribute(pops_bin_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pops_bin_kernel<DCB_D>, CTA_THREADS, smem);
+  return nb;
+}
 #else
 cudaError_t DCB_CAT(launch_pops_count_d, DCB_D)(const PopsArgs&, int, cudaStream_t) { return cudaErrorInvalidValue; }
 int DCB_CAT(occupancy_pops_count_d, DCB_D)(int, int) { return 0; }
+cudaError_t DCB_CAT(launch_pops_bin_d, DCB_D)(const PopsArgs&, int, cudaStream_t) { return cudaErrorInvalidValue; }
+int DCB_CAT(occupancy_pops_bin_d, DCB_D)(int, int, int) { return 0; }
 #endif
 
 cudaError_t DCB_CAT(launch_nn_d, DCB_D)(const NnArgs& a, int grid, cudaStream_t st) {

@@ -44,7 +44,10 @@ struct ScanGeom {
   int d;                    // n_cols (== D for the specialised kernels)
   uint32_t n;               // real frame count
   uint32_t row_begin, row_end;      // rows of this shard
-  uint32_t n_row_blocks;            // ceil((row_end-row_begin)/ROWS_PER_CTA)
+  uint32_t rb_stride;               // row block rb of the launch starts at row_begin + rb * rb_stride * ROWS_PER_CTA: 1 = the contiguous
+                                    // range [row_begin,row_end); G = block-cyclic shard of G (rank g: row_begin = g * ROWS_PER_CTA,
+                                    // row_end = n), which spreads dense and sparse regions of the spatial order over all ranks
+  uint32_t n_row_blocks;            // row blocks of the launch (blocks that start below row_end)
   uint32_t n_col_tiles;             // column tiles of this launch
   uint32_t tiles_per_item;          // column tiles per work item
   uint32_t n_col_items;             // ceil(n_col_tiles / tiles_per_item)
@@ -59,6 +62,12 @@ struct ScanGeom {
                                     // rows of a block owned by one consumer warp still accept; lowered by atomicMin as items finish
   float prune_thr;                  // static pruning threshold (fast-value units); +inf disables pruning
 };
+
+// first row of row block rb of the launch, and the index of a row of that block in the launch's (compact) output arrays
+__device__ __forceinline__ uint32_t block_row0(const ScanGeom& g, uint32_t rb) { return g.row_begin + rb * g.rb_stride * (uint32_t) ROWS_PER_CTA; }
+__device__ __forceinline__ uint32_t out_index(const ScanGeom& g, uint32_t rb, uint32_t row) {
+  return rb * (uint32_t) ROWS_PER_CTA + (row - block_row0(g, rb));
+}
 
 // per-thread slow-path counters, added to g.stats once per kernel
 struct SlowStats {
@@ -133,7 +142,7 @@ struct SmemRing {
 __device__ __forceinline__ void item_coords(const ScanGeom& g, uint32_t item, uint32_t TJ, uint32_t* rb, uint32_t* ci) {
   const uint32_t step = item / g.n_row_blocks;
   *rb = item % g.n_row_blocks;
-  const uint32_t diag = min((g.row_begin + *rb * ROWS_PER_CTA) / (g.tiles_per_item * TJ), g.n_col_items - 1);
+  const uint32_t diag = min(block_row0(g, *rb) / (g.tiles_per_item * TJ), g.n_col_items - 1);
   // offsets 0, +1, -1, +2, -2, ... folded into [0, n_col_items)
   const uint32_t k = (step + 1) >> 1;
   const uint32_t n = g.n_col_items;
@@ -264,19 +273,23 @@ struct Rows {
   float xn[RI];             // |x'|^2
   float eabs[RI];
   uint32_t row0;
+  uint32_t out0;            // index of row0 in the launch's output arrays (out_index)
   uint32_t p[RI];           // clamped positions
   uint32_t stride;          // 32: the warp owns 128 consecutive rows; N_CONSUMERS: rows interleaved over the whole block
   __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * stride; }
+  __device__ __forceinline__ uint32_t out(int r) const { return out0 + (uint32_t) r * stride; }
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid, bool coherent = true) {
     stride = coherent ? 32u : (uint32_t) N_CONSUMERS;
-    row0 = g.row_begin + rb * ROWS_PER_CTA + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
+    row0 = block_row0(g, rb) + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
+    out0 = rb * (uint32_t) ROWS_PER_CTA + (row0 - block_row0(g, rb));
 #pragma unroll
     for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);     // rows past the end: clamped, results discarded
   }
   // rows of row group gi (128 consecutive rows of the block), whichever warp works on them
   __device__ __forceinline__ void load_group(const ScanGeom& g, uint32_t rb, uint32_t gi, int lane) {
     stride = 32u;
-    row0 = g.row_begin + rb * ROWS_PER_CTA + gi * (32u * RI) + (uint32_t) lane;
+    row0 = block_row0(g, rb) + gi * (32u * RI) + (uint32_t) lane;
+    out0 = rb * (uint32_t) ROWS_PER_CTA + gi * (32u * RI) + (uint32_t) lane;
 #pragma unroll
     for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
   }
@@ -303,18 +316,22 @@ struct Rows<0> {
   float xn[RI];
   float eabs[RI];
   uint32_t row0;
+  uint32_t out0;
   uint32_t p[RI];
   uint32_t stride;
   __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * stride; }
+  __device__ __forceinline__ uint32_t out(int r) const { return out0 + (uint32_t) r * stride; }
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid, bool coherent = true) {
     stride = coherent ? 32u : (uint32_t) N_CONSUMERS;
-    row0 = g.row_begin + rb * ROWS_PER_CTA + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
+    row0 = block_row0(g, rb) + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
+    out0 = rb * (uint32_t) ROWS_PER_CTA + (row0 - block_row0(g, rb));
 #pragma unroll
     for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
   }
   __device__ __forceinline__ void load_group(const ScanGeom& g, uint32_t rb, uint32_t gi, int lane) {
     stride = 32u;
-    row0 = g.row_begin + rb * ROWS_PER_CTA + gi * (32u * RI) + (uint32_t) lane;
+    row0 = block_row0(g, rb) + gi * (32u * RI) + (uint32_t) lane;
+    out0 = rb * (uint32_t) ROWS_PER_CTA + gi * (32u * RI) + (uint32_t) lane;
 #pragma unroll
     for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
   }
@@ -551,8 +568,19 @@ struct PopsArgs {
   float rad2[32];           // ascending squared radii, padded with +inf
   float thr_fast;           // rad2[n_bins-1] (1 + e_rel): relative part of the filter margin (absolute part: Rows::eabs)
   float band[8];            // count mode: the part of the error band around rad2[b] that depends on the radius only
-  uint32_t* cnt;            // [n_bins][ld_cnt]: #{j != i : rad2[b-1] <= d2(i,j) < rad2[b]}, rows relative to row_begin
+  uint32_t* cnt;            // [n_bins][ld_cnt]: #{j != i : rad2[b-1] <= d2(i,j) < rad2[b]}, rows in out_index order
   size_t ld_cnt;
+  // bin mode (pops_bin_kernel): cell table over the fast squared distance s, built by api.cu (build_bin_table)
+  const float* lut;         // [lut_k] device: per cell the one squared radius B_k it can see with k in its low 5 mantissa bits
+                            //         (bin = k + (s >= entry)); cells that see none: +big | 0 when no radius lies below them,
+                            //         else -big | (k - 1)
+  int lut_k;                // cells, a power of two: cell = floor(sat(s * lut_scale) * (lut_k - 1)) (quarter-cell rounding)
+  float lut_scale;          // 1 / (span of the table in s units, a little more than r_max^2)
+  float lut_margin;         // the table decides only pairs whose error band is narrower than this (s units); others: handler
+  float band_max;           // radius part of the band half width for r_max (covers every radius of the pass) + the table's
+                            // own perturbation of the boundaries (32 ulp)
+  int dense_lanes;          // a 4x4 step is binned branch-free when at least this many lanes hold a candidate pair,
+                            // else candidate by candidate
 };
 
 __host__ __device__ inline size_t pops_smem_bytes(size_t ring_bytes, int n_bins) {
@@ -647,7 +675,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
         if (R.row(r) < g.row_end) {
           for (int b = 0; b < nb; ++b) {
             const uint32_t h = hist[b * ROWS_PER_CTA + r * N_CONSUMERS];
-            if (h) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + (R.row(r) - g.row_begin), h);
+            if (h) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + R.out(r), h);
           }
         }
       }
@@ -841,10 +869,393 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
           const uint32_t slot = (uint32_t) warp * (32 * RI) + (uint32_t) r * 32 + (uint32_t) lane;
-          const uint32_t row = g.row_begin + (uint32_t) m.row_block * ROWS_PER_CTA + slot;
+          const uint32_t row = block_row0(g, (uint32_t) m.row_block) + slot;
           const uint32_t c = cnt_s[b * ROWS_PER_CTA + slot];
-          if (row < g.row_end && c) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + (row - g.row_begin), c);
+          if (row < g.row_end && c) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + ((uint32_t) m.row_block * ROWS_PER_CTA + slot), c);
         }
+    }
+    cp.advance();
+  }
+  st.flush(g);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// populations, bin mode (long radius lists, D <= MAX_TEMPLATE_D): every pair of a step that holds candidates is binned
+// BRANCH-FREE through a cell table over the fast squared distance s = acc + |x'|^2:
+//     cell = floor(sat(s / span) * (K - 1))                      FMUL.SAT + FFMA (magic 2^21: the cell's byte offset
+//                                                                       sits in the mantissa) + 1 LOP3
+//     e    = table[cell]                                         1 LDS: the only radius boundary B_k the cell can see,
+//                                                                       k in its low 5 mantissa bits (a sentinel if none)
+//     bin  = k + (s >= e)                                        FSETP + select + shift-add
+//     hist[bin][row] += 1                                        LDS.U16 / IADD / STS.U16, lane-private bank
+//     band |= |s - e| < row band                                 FADD + FSETP
+// ~14 instructions per pair next to the D FFMAs, whatever the hit rate and the number of radii (the per-hit handler of
+// pops_kernel costs ~30 per HIT and the warp pays the maximum over its lanes: 12.9 % of the FFMA peak at 1M x 10, 20 radii).
+// Steps with few candidates (boundary tiles) are walked candidate by candidate with the same table.  Pairs inside the
+// rounding-error band of a boundary are re-decided with dist2_exact and the histogram is corrected.
+// Rows: the warp owns one 128-row group of the block = one tile of the layout, so its bounding box, centre and radius
+// are the tile's own header; tiles are pruned against the eight groups by the producer and against the warp's group
+// by the consumer with max(box gap, sphere gap) -- in 10 dimensions the boxes of two clusters overlap in most dims
+// while their spheres are far apart.
+// hist[b][row] counts rad2[b-1] <= d2 < rad2[b], the frame itself included (pops_finalize removes it).
+// ------------------------------------------------------------------------------------------------
+constexpr int BIN_STRIDE = N_CONSUMERS * RI * 2;      // bytes between the histogram rows of two bins (2048)
+constexpr int PGEO = 3 * MAX_TEMPLATE_D + 4;          // floats per group in the producer's geometry scratch
+
+__host__ __device__ inline size_t pops_bin_smem_bytes(size_t ring_bytes, int n_bins, int lut_k) {
+  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + (size_t) N_CONSUMER_WARPS * PGEO * 4 + (size_t) lut_k * 4 + 32 * 4 +
+         (size_t) (n_bins + 1) * BIN_STRIDE;
+}
+
+// lower bound (fast-value units) of the squared distance between a 128-row group and a tile from their boxes
+// (globally centred coordinates) and their spheres (centre + radius); geometry of the group: lo[D], hi[D], c[D], rad
+template <int D>
+__device__ __forceinline__ float group_tile_lb(const float* __restrict__ gg, const float (&tlo)[D], const float (&thi)[D],
+                                               const float (&tc)[D], float trad, float slack_len) {
+  float sb = 0.f, sc = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const float gap = fmaxf(fmaxf(gg[k] - thi[k], tlo[k] - gg[D + k]), 0.f);
+    sb = fmaf(gap, gap, sb);
+    const float dc = gg[2 * D + k] - tc[k];
+    sc = fmaf(dc, dc, sc);
+  }
+  const float gap = sqrtf(sc) * 0.99999f - (gg[3 * D] + trad) * 1.00001f - slack_len;
+  const float ss = gap > 0.f ? gap * gap : 0.f;
+  return fmaxf(sb, ss) * 0.999f;
+}
+
+// Producer of the bin kernel: like produce(), but a tile is streamed iff it comes within thr of at least one of the
+// (up to eight) 128-row groups of the block, by box and by sphere.  The groups' geometry is read from their tiles'
+// headers (the shard starts at a multiple of 128 rows: api.cu) into pgeo, private to the producer warp.
+template <int D>
+__device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& ring, float* __restrict__ pgeo) {
+  constexpr int TJ = TileW<D>::tj;
+  const int lane = threadIdx.x & 31;
+  Pipe<StagesOf<D>::n> pp;
+  const uint32_t total = g.n_row_blocks * g.n_col_items;
+  const uint32_t rec = (uint32_t) ((D + 1) * TJ + g.dp);
+  const float slack_len = sqrtf(g.prune_slack);
+  unsigned long long streamed = 0;
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(g.work_counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    uint32_t rb, ci;
+    item_coords(g, item, TJ, &rb, &ci);
+    const uint32_t t0 = ci * g.tiles_per_item;
+    const uint32_t t1 = min(t0 + g.tiles_per_item, g.n_col_tiles);
+    if (t0 >= t1) continue;
+    const uint32_t blk0 = block_row0(g, rb);
+    const uint32_t n_groups = (min(blk0 + (uint32_t) ROWS_PER_CTA, g.row_end) - blk0 + 32u * RI - 1) / (32u * RI);
+    __syncwarp();
+    for (uint32_t q = lane; q < n_groups * (3 * D + 1); q += 32) {
+      const uint32_t gi = q / (3 * D + 1), f = q % (3 * D + 1);
+      const float* hdr = g.cT + (size_t) (blk0 / TJ + gi) * rec + (size_t) (D + 1) * TJ;
+      float v;
+      if (f < (uint32_t) D) v = __ldg(hdr + D + 1 + f);                       // lo
+      else if (f < 2u * D) v = __ldg(hdr + D + 1 + f);                      // hi (header: lo[D] then hi[D])
+      else if (f < 3u * D) v = __ldg(hdr + (f - 2 * D)) - __ldg(g.centre + (f - 2 * D));     // centre, globally centred
+      else v = sqrtf(__ldg(hdr + D));                                       // radius about the centre
+      pgeo[gi * PGEO + f] = v;
+    }
+    __syncwarp();
+    bool first = true;
+    for (uint32_t base = t0; base < t1; base += 32) {
+      const uint32_t t = base + lane;
+      float lb = INFINITY;
+      if (t < t1) {
+        const float* hdr = g.cT + (size_t) t * rec + (size_t) (D + 1) * TJ;
+        float tlo[D], thi[D], tc[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          tc[k] = __ldg(hdr + k) - __ldg(g.centre + k);
+          tlo[k] = __ldg(hdr + D + 1 + k);
+          thi[k] = __ldg(hdr + 2 * D + 1 + k);
+        }
+        const float trad = sqrtf(__ldg(hdr + D));
+        for (uint32_t gi = 0; gi < n_groups; ++gi) lb = fminf(lb, group_tile_lb<D>(pgeo + gi * PGEO, tlo, thi, tc, trad, slack_len));
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, t < t1 && !(lb > g.prune_thr));     // NaN keeps
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        const uint32_t tt = base + (uint32_t) src;
+        mask &= mask - 1;
+        if (lane == 0) {
+          mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+          TileMeta m;
+          m.row_block = (int32_t) rb;
+          m.col0 = tt * TJ;
+          m.flags = first ? 1u : 0u;
+          m.aux = item;
+          ring.meta[pp.stage] = m;
+          mbar_arrive_expect_tx(&ring.full[pp.stage], rec * 4);
+          tma_load_1d(ring.tiles + pp.stage * ring.tile_floats, g.cT + (size_t) tt * rec, rec * 4, &ring.full[pp.stage]);
+        }
+        first = false;
+        ++streamed;
+        pp.advance();
+      }
+    }
+    if (!first) {
+      if (lane == 0) {                              // end-of-item marker
+        mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+        TileMeta m;
+        m.row_block = (int32_t) rb;
+        m.col0 = 0;
+        m.flags = 2u | 4u;
+        m.aux = item;
+        ring.meta[pp.stage] = m;
+        mbar_arrive(&ring.full[pp.stage]);
+      }
+      pp.advance();
+    }
+  }
+  if (lane == 0) {
+    mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+    ring.meta[pp.stage].row_block = -1;
+    mbar_arrive(&ring.full[pp.stage]);
+    if (g.stats && streamed) atomicAdd(g.stats + 2, streamed);
+  }
+}
+
+template <int D>
+__global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ PopsArgs a) {
+  static_assert(D >= 1 && D <= MAX_TEMPLATE_D, "bin mode: specialised dims");
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int TJ = TileW<D>::tj;
+  const ScanGeom& g = a.g;
+  SmemRing<D> ring(smem, D);
+  unsigned char* extra = smem + ((SmemRing<D>::bytes(D) + 15) & ~size_t(15));
+  float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
+  float* pgeo = reinterpret_cast<float*>(extra + SCRATCH_BYTES);
+  const float* lut = pgeo + N_CONSUMER_WARPS * PGEO;
+  float* rad2s = const_cast<float*>(lut) + a.lut_k;
+  unsigned char* hist = reinterpret_cast<unsigned char*>(rad2s + 32);       // [n_bins + 1][BIN_STRIDE]
+  ring.init();
+  for (int q = threadIdx.x; q < a.lut_k; q += CTA_THREADS) const_cast<float*>(lut)[q] = __ldg(a.lut + q);
+  if (threadIdx.x < 32) rad2s[threadIdx.x] = a.rad2[threadIdx.x];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == N_CONSUMER_WARPS) {
+    produce_groups<D>(g, ring, pgeo);
+    return;
+  }
+  const int nb = a.n_bins;
+  // this thread's counters: 16-bit, rows r and r^1 share a word, word index = bin * 512 + (r >> 1) * 256 + thread:
+  // bank = lane for every bin, so the 32 read-modify-writes of a warp never conflict
+  unsigned char* hb = hist + threadIdx.x * 4;
+  const uint32_t kmask4 = ((uint32_t) a.lut_k - 1u) << 2;
+  const float kscale = (float) (a.lut_k - 1);
+  // table entry of the cell of s: 2^21 + sat(s / span) (K - 1) has the cell number in mantissa bits 2.. (ulp 1/4), so
+  // masking the bit pattern yields the byte offset of the entry
+  auto entry = [&](float sv) -> float {
+    const float v = fmaf(__saturatef(sv * a.lut_scale), kscale, 2097152.f);
+    return *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(lut) + (__float_as_uint(v) & kmask4));
+  };
+  Rows<D> R;
+  float t[RI], bw[RI];
+  float glo = 0.f, ghi = 0.f, gc = 0.f, grad = 0.f;     // geometry of this warp's group: lane k holds dim k
+  bool gvalid = false, slow_unit = false;
+  const float slack_len = sqrtf(g.prune_slack);
+  Pipe<StagesOf<D>::n> cp;
+  SlowStats st;
+  uint32_t col0 = 0;
+  auto hrow = [&](int r) -> unsigned char* { return hb + (r >> 1) * (N_CONSUMERS * 4) + (r & 1) * 2; };
+  auto bump = [&](int r, int b, int delta) {
+    uint16_t* p = reinterpret_cast<uint16_t*>(hrow(r) + b * BIN_STRIDE);
+    *p = (uint16_t) (*p + delta);
+  };
+  // candidate-by-candidate path (sparse steps, and every step of a unit the table cannot serve)
+  auto hit = [&](int r, int jt, float accv) {
+    const uint32_t j = col0 + jt;
+    const uint32_t i = R.row(r);
+    float s = accv + sel4(R.xn, r);
+    if (i >= g.row_end) return;
+    ++st.slow;
+    int b;
+    bool inband;
+    if (!slow_unit) {
+      const float e = entry(s);
+      b = (int) (__float_as_uint(e) & 31u) + (s >= e ? 1 : 0);
+      inband = fabsf(s - e) < sel4(bw, r);
+    } else {
+      b = bin_of(rad2s, nb, s);
+      const float lo = b > 0 ? rad2s[b - 1] : -INFINITY;
+      const float hi = rad2s[b];
+      const float e = fmaf(g.e_rel, fabsf(s), sel4(R.eabs, r)) * 1.0001f;
+      inband = (s - lo < e) || (hi - s <= e);
+    }
+    if (inband) {
+      s = dist2_exact(g.xT, g.ld, D, i, j);
+      ++st.exact;
+      b = bin_of(rad2s, nb, s);
+    }
+    if (b < nb) bump(r, b, 1);
+  };
+  for (;;) {
+    mbar_wait(&ring.full[cp.stage], cp.phase);
+    const TileMeta m = ring.meta[cp.stage];
+    if (m.row_block < 0) break;
+    if (m.flags & 1u) {
+      R.load_group(g, (uint32_t) m.row_block, (uint32_t) warp, lane);
+      const uint32_t grow0 = block_row0(g, (uint32_t) m.row_block) + (uint32_t) warp * (32u * RI);
+      gvalid = grow0 < g.row_end;
+      if (gvalid) {
+        const float* hdr = g.cT + (size_t) (grow0 / TJ) * ((D + 1) * TJ + g.dp) + (size_t) (D + 1) * TJ;
+        const int k = lane & 15;
+        if (k < D) {
+          glo = __ldg(hdr + D + 1 + k);
+          ghi = __ldg(hdr + 2 * D + 1 + k);
+          gc = __ldg(hdr + k) - __ldg(g.centre + k);
+        }
+        grad = sqrtf(__ldg(hdr + D));
+      }
+      for (int b = 0; b <= nb; ++b) {
+        *reinterpret_cast<uint32_t*>(hb + b * BIN_STRIDE) = 0u;
+        *reinterpret_cast<uint32_t*>(hb + b * BIN_STRIDE + N_CONSUMERS * 4) = 0u;
+      }
+    }
+    col0 = m.col0;
+    if (!(m.flags & 4u) && gvalid) {
+      const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      const float* cen = tl + (D + 1) * TJ;
+      // does the tile come within r_max of this warp's group?  lanes 0..15: box gap per dim, lanes 16..31: centre distance per dim
+      bool reach;
+      {
+        const int k = lane & 15;
+        float v = 0.f;
+        if (k < D) {
+          if (lane < 16) {
+            const float gap = fmaxf(fmaxf(glo - cen[2 * D + 1 + k], cen[D + 1 + k] - ghi), 0.f);
+            v = gap * gap;
+          } else {
+            const float dc = gc - (cen[k] - __ldg(g.centre + k));
+            v = dc * dc;
+          }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float sb = __shfl_sync(0xffffffffu, v, 0), sc = __shfl_sync(0xffffffffu, v, 16);
+        const float gap = sqrtf(sc) * 0.99999f - (grad + sqrtf(cen[D])) * 1.00001f - slack_len;
+        const float ss = gap > 0.f ? gap * gap : 0.f;
+        reach = !(fmaxf(sb, ss) * 0.999f > g.prune_thr);          // NaN keeps
+      }
+      if (reach) {
+        ++st.wtiles;
+        R.retarget(g, cen);
+        bool wide = false;
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+          // every pair with exact d2 < r_max^2 has acc < t[r]  (thr_fast = r_max^2 (1 + e_rel), eabs: absolute error part)
+          t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));
+          // |s - e - (d2_exact - B_k)| < bw[r]: fast-path error (eabs + e_rel r^2), roundings of s, the table's perturbation of B_k
+          bw[r] = fmaf(1.01f, R.eabs[r], 2.4e-7f * R.xn[r]) + a.band_max;
+          wide |= !(bw[r] < a.lut_margin);
+        }
+        slow_unit = __any_sync(0xffffffffu, wide);
+#pragma unroll 1
+        for (int gcol = 0; gcol < TJ; gcol += CJ) {
+          float acc[RI][CJ];
+          {
+            const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + gcol);
+            const float4 y4 = *reinterpret_cast<const float4*>(tl + gcol);
+#pragma unroll
+            for (int r = 0; r < RI; ++r) {
+              acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
+              acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
+              acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
+              acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
+            }
+          }
+#pragma unroll
+          for (int k = 1; k < D; ++k) {
+            const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + gcol);
+#pragma unroll
+            for (int r = 0; r < RI; ++r) {
+              acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
+              acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
+              acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
+              acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
+            }
+          }
+          bool any = false;
+#pragma unroll
+          for (int r = 0; r < RI; ++r) {
+            const float mn = fminf(fminf(acc[r][0], acc[r][1]), fminf(acc[r][2], acc[r][3]));
+            any |= (mn < t[r]);
+          }
+          const uint32_t act = __ballot_sync(0xffffffffu, any);
+          if (act == 0u) continue;
+          if (__popc(act) >= a.dense_lanes && !slow_unit) {
+            // dense step: all 16 pairs of every lane through the table, no branches; misses land in the dump row nb
+            bool band = false;
+#pragma unroll
+            for (int c = 0; c < CJ; ++c) {
+              uint16_t* hp[RI];
+#pragma unroll
+              for (int r = 0; r < RI; ++r) {
+                const float s = acc[r][c] + R.xn[r];
+                const float e = entry(s);
+                const float dlt = s - e;
+                const uint32_t b = (__float_as_uint(e) & 31u) + (dlt >= 0.f ? 1u : 0u);
+                band |= fabsf(dlt) < bw[r];
+                hp[r] = reinterpret_cast<uint16_t*>(hrow(r) + b * BIN_STRIDE);
+              }
+              // the four counters belong to four different rows: distinct addresses, so load all, then store all
+              uint16_t h[RI];
+#pragma unroll
+              for (int r = 0; r < RI; ++r) h[r] = *hp[r];
+#pragma unroll
+              for (int r = 0; r < RI; ++r) *hp[r] = (uint16_t) (h[r] + 1);
+            }
+            if (band) {
+              // rare: some pair of this block is inside the error band of a boundary: re-decide those exactly and move
+              // their count to the right bin (one compact loop over the block parked in shared memory)
+#pragma unroll
+              for (int r = 0; r < RI; ++r)
+#pragma unroll
+                for (int c = 0; c < CJ; ++c) scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c];
+#pragma unroll 1
+              for (int p = 0; p < RI * CJ; ++p) {
+                const int r = p / CJ;
+                const float s = scratch[p * N_CONSUMERS] + sel4(R.xn, r);
+                const float e = entry(s);
+                const float dlt = s - e;
+                if (fabsf(dlt) < sel4(bw, r)) {
+                  const int bf = (int) (__float_as_uint(e) & 31u) + (dlt >= 0.f ? 1 : 0);
+                  ++st.slow;
+                  ++st.exact;
+                  const float d2 = dist2_exact(g.xT, g.ld, D, R.row(r), m.col0 + gcol + (p % CJ));
+                  const int be = (d2 == d2) ? bin_of(rad2s, nb, d2) : nb;        // NaN (padding) -> outside
+                  if (be != bf) {
+                    bump(r, bf, -1);
+                    bump(r, be, 1);
+                  }
+                }
+              }
+            }
+          } else if (any) {
+            walk_hits(scratch, acc, t, gcol, hit);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    if (m.flags & 2u) {
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        if (R.row(r) < g.row_end) {
+          for (int b = 0; b < nb; ++b) {
+            const uint32_t h = *reinterpret_cast<const uint16_t*>(hrow(r) + b * BIN_STRIDE);
+            if (h) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + R.out(r), h);
+          }
+        }
+      }
     }
     cp.advance();
   }
@@ -863,7 +1274,7 @@ struct NnArgs {
   float lo_bias;                // 0 when the float ranks are exact (lo_shift == 0), else 1 (equal coarse ranks stay candidates)
   uint32_t window;              // > 0: scan only the column tiles within `window` tiles of the row block's own position
                                 // (first pass: settles tight thresholds before the full scan); 0: all tiles
-  unsigned long long* key_nn;   // [row_end-row_begin] (d2 bits << 32 | original index), atomicMin'ed
+  unsigned long long* key_nn;   // [rows of the launch, out_index order] (d2 bits << 32 | original index), atomicMin'ed
   unsigned long long* key_hd;
 };
 
@@ -1038,8 +1449,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     // initial pruning threshold of an item: what the seeds and earlier items already found for the rows of the block
     produce<D>(g, ring, true, [&](uint32_t rb, uint32_t& lim0, uint32_t& lim1) {
       if (a.window) {
-        const uint32_t t_first = (g.row_begin + rb * ROWS_PER_CTA) / TJ;
-        const uint32_t t_last = (min(g.row_begin + (rb + 1) * ROWS_PER_CTA, g.row_end) - 1) / TJ;
+        const uint32_t t_first = block_row0(g, rb) / TJ;
+        const uint32_t t_last = (min(block_row0(g, rb) + (uint32_t) ROWS_PER_CTA, g.row_end) - 1) / TJ;
         lim0 = t_first > a.window ? t_first - a.window : 0u;
         lim1 = min(lim1, t_last + a.window + 1);
       }
@@ -1097,8 +1508,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
         uint32_t lo_i = 0;
         float lf = 0.f;
         if (R.row(r) < g.row_end) {
-          k0 = a.key_nn[R.row(r) - g.row_begin];
-          k1 = a.key_hd[R.row(r) - g.row_begin];
+          k0 = a.key_nn[R.out(r)];
+          k1 = a.key_hd[R.out(r)];
           lo_i = __ldg(a.lo + R.row(r));
           lf = __ldg(a.lof + R.row(r));
           v = fmaxf(v, key_d2(k0));
@@ -1216,10 +1627,10 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
         const uint32_t slot = (uint32_t) warp * (32u * RI) + (uint32_t) r * 32u + (uint32_t) lane;
-        const uint32_t row = g.row_begin + (uint32_t) m.row_block * ROWS_PER_CTA + slot;
+        const uint32_t row = block_row0(g, (uint32_t) m.row_block) + slot;
         if (row < g.row_end) {
-          atomicMin(a.key_nn + (row - g.row_begin), best[slot]);
-          atomicMin(a.key_hd + (row - g.row_begin), best[ROWS_PER_CTA + slot]);
+          atomicMin(a.key_nn + ((uint32_t) m.row_block * ROWS_PER_CTA + slot), best[slot]);
+          atomicMin(a.key_hd + ((uint32_t) m.row_block * ROWS_PER_CTA + slot), best[ROWS_PER_CTA + slot]);
         }
       }
       // what this group's rows still accept bounds every later item of the row block (positive floats order like their bits)
@@ -1274,7 +1685,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
   if (warp == N_CONSUMER_WARPS) {
     produce<D>(g, ring, false, [&](uint32_t rb, uint32_t&, uint32_t& lim1) {
       // only columns below the last row of the block can form an edge (j < i)
-      const uint32_t last_row = min(g.row_begin + (rb + 1) * ROWS_PER_CTA, g.row_end) - 1;
+      const uint32_t last_row = min(block_row0(g, rb) + (uint32_t) ROWS_PER_CTA, g.row_end) - 1;
       lim1 = min(lim1, last_row / TJ + 1);
     }, [&](uint32_t, int) { return g.prune_thr; });
     return;

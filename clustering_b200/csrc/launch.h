@@ -17,6 +17,8 @@ struct ScreenArgs;
   int occupancy_pops_d##D(int n_bins, int d);                                \
   cudaError_t launch_pops_count_d##D(const PopsArgs&, int grid, cudaStream_t st);  \
   int occupancy_pops_count_d##D(int n_bins, int d);                          \
+  cudaError_t launch_pops_bin_d##D(const PopsArgs&, int grid, cudaStream_t st);    \
+  int occupancy_pops_bin_d##D(int n_bins, int lut_k, int d);                 \
   int occupancy_nn_d##D(int d);                                              \
   cudaError_t launch_screen_d##D(const ScreenArgs&, int grid, cudaStream_t st); \
   int occupancy_screen_d##D(int d);

@@ -6,13 +6,15 @@ reference's Tools::read_coords result (tools.hxx:39-111).
 """
 import numpy as np
 
-# (n_rows, n_cols, radii, K, seed) of the BASELINE.json configs
+# (n_rows, n_cols, radii, K, seed) of the BASELINE.json configs; fe_radius_index: the radius whose populations give the
+# free energies the neighbour search runs on (C3: r = 1.0, median population ~700 of 1M -- the smallest radii leave
+# almost every frame alone, the largest make whole clusters tie)
 CONFIGS = {
-    "C1": dict(n=100_000, d=5, radii=[0.1, 0.2, 0.3, 0.4, 0.5], k=12, seed=1),
-    "C2": dict(n=1_000_000, d=5, radii=[0.3], k=12, seed=2),
-    "C3": dict(n=1_000_000, d=10, radii=[round(0.1 * i, 1) for i in range(1, 21)], k=12, seed=3),
-    "C4": dict(n=5_000_000, d=3, radii=[0.15], k=8, seed=4),
-    "C5": dict(n=500_000, d=128, radii=[1.0], k=16, seed=5),
+    "C1": dict(n=100_000, d=5, radii=[0.1, 0.2, 0.3, 0.4, 0.5], k=12, seed=1, fe_radius_index=2),
+    "C2": dict(n=1_000_000, d=5, radii=[0.3], k=12, seed=2, fe_radius_index=0),
+    "C3": dict(n=1_000_000, d=10, radii=[round(0.1 * i, 1) for i in range(1, 21)], k=12, seed=3, fe_radius_index=9),
+    "C4": dict(n=5_000_000, d=3, radii=[0.15], k=8, seed=4, fe_radius_index=0),
+    "C5": dict(n=500_000, d=128, radii=[1.0], k=16, seed=5, fe_radius_index=0),
 }
 
 

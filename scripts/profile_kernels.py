@@ -38,7 +38,7 @@ for it in range(reps):
     pp, t_pops = timed(lambda: s.populations(radii))
     st_p = s.stats(reset=True)
     pops = s.to_frame_order(pp)
-    fe = s.free_energies(pops[0].contiguous())
+    fe = s.free_energies(pops[cfg.get("fe_radius_index", 0)].contiguous())
     _, t_prep = timed(lambda: s.nn_prepare(fe))
     keys, t_nn = timed(lambda: s.nn_scan())
     st_n = s.stats(reset=True)
