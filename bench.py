@@ -1,19 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the `clustering density` hot path (BASELINE.json metric: density run wall-time & Gpair.dim/s).
+"""Benchmark of the `clustering density` hot path (BASELINE.json metric: density run wall-time & Gpair.dim/s, 1M frames,
+1/2/4/8 B200 vs OpenMP host).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C1|C3|C4|C5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C1|C2|C4|C5] [--impl ours|reference]
 
-One step = one full density pass over the workload: coordinate layout build, populations, free energies,
-nearest neighbours (+ nearest neighbour with lower free energy).  Default workload = BASELINE.json
-configs[1] (C2: 1M frames x 5 dims, radius 0.3, seed 2; synthetic "HP35-like" Gaussian mixture).
+One step = one full density run over the workload: coordinate layout build, populations for ALL radii of the workload,
+free energies, nearest neighbours (+ nearest neighbour with lower free energy) on the free energies of the workload's
+`fe_radius_index`.  Default workload = C3, the configuration BASELINE.json's north_star targets: 1M frames x 10 dims,
+the 20 radii 0.1 .. 2.0 (synthetic "HP35-like" Gaussian mixture, seed 3).  C4 adds the screening loop (all thresholds).
 
   value  whole-job Gpair.dim/s with the coordinates resident in HBM when the timed region starts
          (pair.dim = one (x_ik - x_jk)^2 term of the ordered N x N pair matrix; two pair scans per step)
-  e2e    same metric through the C ABI with HOST buffers (H2D/D2H inside the timed region)
-  N > 1  one process per GPU (torchrun), rows sharded, per-shard results assembled with NCCL all-gather
-         on the device; fixed total work => "strong" scaling
-  --impl reference   the reference's own OpenMP CPU implementation (oracle/_ref/libdcref.so, compiled from
-         the unmodified reference sources; else the C port in oracle/) on a bounded sample of the workload.
+  e2e    the same metric through the host-pointer C ABI (dcb200_density_run) with PINNED HOST buffers: the upload of
+         the coordinates and the download of every result are inside the timed region
+  N > 1  one process per GPU (torchrun), block-cyclic row shards, per-shard results assembled with ONE NCCL all-gather
+         per stage on the device; fixed total work => "strong" scaling.  Before the line is printed the sharded result
+         is compared with an unsharded run of rank 0 (checksum in the line).
+  --impl reference   the reference's own OpenMP CPU implementation (oracle/_ref/libdcref.so, compiled from the
+         unmodified reference sources; else the C port in oracle/) on a bounded sample of the workload.
 """
 import argparse
 import json
@@ -38,9 +42,9 @@ FLOP_EXECUTED_PER_PAIR_DIM = 2.0  # what the kernels issue: one FFMA per pair.di
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default="C3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override the frame count (debugging only; invalid as a bench line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -72,9 +76,11 @@ def ncu_traffic(kernel_name):
 
 def workload_label(name, cfg):
     """the same `config.workload` string in both arms"""
-    radii = ", ".join(f"{r:g}" for r in cfg["radii"])
-    return (f"{name}: clustering density, {cfg['n']} frames x {cfg['d']} dims, radius {radii}: "
-            "populations + free energies + nearest neighbours (-b)")
+    r = cfg["radii"]
+    radii = f"{len(r)} radii {r[0]:g} .. {r[-1]:g}" if len(r) > 3 else "radius " + ", ".join(f"{v:g}" for v in r)
+    tail = " + screening over all thresholds" if name == "C4" else ""
+    return (f"{name}: clustering density, {cfg['n']} frames x {cfg['d']} dims, {radii}: populations + free energies + "
+            f"nearest neighbours (-b) on the free energies of r = {r[cfg['fe_radius_index']]:g}{tail}")
 
 
 def pair_dims_per_step(n, d):
@@ -147,19 +153,19 @@ def cpu_impl():
     return "port", o, os.cpu_count()
 
 
-def cpu_step(kind, impl, x, radius):
-    """pops + FE + NN on the CPU; returns seconds."""
+def cpu_step(kind, impl, x, radii, fe_index):
+    """populations for all radii + free energies + neighbours on the CPU; returns seconds."""
     t0 = time.perf_counter()
-    pops = impl.populations(x, np.array([radius], np.float32))
-    fe = impl.free_energies(pops[0])
+    pops = impl.populations(x, np.asarray(radii, np.float32))
+    fe = impl.free_energies(pops[fe_index])
     impl.nearest_neighbors(x, fe)
     return time.perf_counter() - t0
 
 
-def cpu_sample_size(kind, impl, x_full, radius, target_s):
+def cpu_sample_size(kind, impl, x_full, radii, fe_index, target_s):
     """frames of the workload whose CPU step takes about target_s (brute-force NN is exactly quadratic)."""
-    n0 = min(8000, len(x_full))
-    t = cpu_step(kind, impl, x_full[:n0], radius)
+    n0 = min(6000, len(x_full))
+    t = cpu_step(kind, impl, x_full[:n0], radii, fe_index)
     n = int(n0 * (target_s / max(t, 1e-3)) ** 0.5)
     return max(2000, min(len(x_full), n))
 
@@ -173,14 +179,15 @@ def run_reference(args):
     kind, impl, cores = cpu_impl()
     total = args.steps + args.warmup
     target = min(4.0, 150.0 / max(total, 1))
-    ns = cpu_sample_size(kind, impl, x, cfg["radii"][0], target)
+    ns = cpu_sample_size(kind, impl, x, cfg["radii"], cfg["fe_radius_index"], target)
     xs = np.ascontiguousarray(x[:ns])
     for _ in range(args.warmup):
-        cpu_step(kind, impl, xs, cfg["radii"][0])
-    t = [cpu_step(kind, impl, xs, cfg["radii"][0]) for _ in range(args.steps)]
+        cpu_step(kind, impl, xs, cfg["radii"], cfg["fe_radius_index"])
+    t = [cpu_step(kind, impl, xs, cfg["radii"], cfg["fe_radius_index"]) for _ in range(args.steps)]
     sec = float(np.mean(t))
     val = pair_dims_per_step(ns, d) / sec / 1e9
-    sample = f"first {ns} frames of {args.workload} ({cfg['n']}x{d}), pops(r={cfg['radii'][0]})+FE+NN per step; pops is box-pruned on the CPU, pair.dims counted as the full N x N matrix"
+    sample = (f"first {ns} frames of {args.workload} ({cfg['n']}x{d}), populations ({len(cfg['radii'])} radii) + free energies + "
+              "neighbours per step; the CPU populations are box-pruned, pair.dims counted as the full N x N matrix")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -192,7 +199,7 @@ def run_reference(args):
     }))
 
 
-def reference_cuda_arm(x, radii, d, density):
+def reference_cuda_arm(x, radii, fe_index, d, density):
     """The reference's own CUDA path (unmodified .cu files built for sm_100a, oracle/_ref/libdcrefcuda.so) on a bounded sample of
     the workload, next to this library on the same sample: the "kernel to beat" of BASELINE.json's north_star.  Reported, never
     used as a parity oracle (its semantics differ from the CPU path: d2 <= r2, duplicates excluded)."""
@@ -203,22 +210,19 @@ def reference_cuda_arm(x, radii, d, density):
         if d > 12:
             return {"unavailable": f"the reference's population kernel needs 2*512*n_cols*4 B <= 48 KB of shared memory: n_cols <= 12, workload has {d}"}
         rc = RefCuda()
-        ns = min(len(x), 250_000)
+        ns = min(len(x), 200_000)
         xs = np.ascontiguousarray(x[:ns])
-        r1 = np.ascontiguousarray(radii[:1])
-        rc.populations(xs[:20000], r1)                       # warm-up (context, module load)
-        t0 = time.perf_counter(); pr = rc.populations(xs, r1); t_p = time.perf_counter() - t0
-        fe = density.calculate_free_energies(pr[0].astype(np.uint32))
+        rc.populations(xs[:20000], radii)                    # warm-up (context, module load)
+        t0 = time.perf_counter(); pr = rc.populations(xs, radii); t_p = time.perf_counter() - t0
+        fe = density.calculate_free_energies(pr[fe_index].astype(np.uint32))
         t0 = time.perf_counter(); rc.nearest_neighbors(xs, fe); t_n = time.perf_counter() - t0
-        density.calculate_populations(xs[:20000], r1)
-        t0 = time.perf_counter(); po = density.calculate_populations(xs, r1); t_po = time.perf_counter() - t0
-        t0 = time.perf_counter(); density.nearest_neighbors(xs, fe); t_no = time.perf_counter() - t0
-        return {"sample": f"first {ns} frames of the workload, radius {float(r1[0]):g}; host-pointer calls (H2D/D2H inside), wall clock",
+        density.density_run(xs[:20000], radii, fe_index)
+        t0 = time.perf_counter(); po = density.density_run(xs, radii, fe_index)["pops"]; t_o = time.perf_counter() - t0
+        return {"sample": f"first {ns} frames of the workload, all {len(radii)} radii; host-pointer calls (H2D/D2H inside), wall clock",
                 "populations_ms": t_p * 1e3, "nearest_neighbors_ms": t_n * 1e3,
                 "value": pair_dims_per_step(ns, d) / (t_p + t_n) / 1e9, "unit": UNIT,
-                "ours_same_sample": {"populations_ms": t_po * 1e3, "nearest_neighbors_ms": t_no * 1e3,
-                                     "value": pair_dims_per_step(ns, d) / (t_po + t_no) / 1e9},
-                "population_counts_differing": int(np.count_nonzero(pr[0] != po[0])),
+                "ours_same_sample": {"density_run_ms": t_o * 1e3, "value": pair_dims_per_step(ns, d) / t_o / 1e9},
+                "population_counts_differing": int(np.count_nonzero(pr.astype(np.uint32) != po)),
                 "note": "differences in counts come from the reference CUDA path's own rounding (sequential FMA) and '<=' test"}
     except Exception as ex:
         return {"unavailable": f"failed: {ex}"}
@@ -227,6 +231,18 @@ def reference_cuda_arm(x, radii, d, density):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def checksum(pops, nn):
+    """order-sensitive 64-bit checksums of the populations and of the four neighbour arrays (device tensors)."""
+    import torch
+    n = pops.shape[-1]
+    w = (torch.arange(n, device=pops.device, dtype=torch.int64) % 1000003) + 1
+    cp = int((pops.to(torch.int64) * w).sum().item())
+    cn = 0
+    for t in nn:
+        cn = (cn * 31 + int((t.view(torch.int32).to(torch.int64) * w).sum().item())) % (1 << 62)
+    return cp, cn
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -245,28 +261,28 @@ def run_ours(args):
     cfg, x = workload(args.workload, args.n)
     n, d = x.shape
     radii = np.asarray(cfg["radii"], np.float32)
-    r_fe = 0                                            # free energies / neighbours from the first radius
+    r_fe = cfg["fe_radius_index"]
+    screening_workload = args.workload == "C4"
     sess = Session(local)
     stream = sess.torch_stream()
 
-    from clustering_b200.dist import DensityPass, shard_bounds
-    b, e = shard_bounds(n, world, rank)
+    from clustering_b200.dist import DensityPass
     dpass = DensityPass(sess, n, radii)
 
     x_dev = torch.from_numpy(x).to(dev)                # resident in HBM before the timed region
     x_pin = torch.from_numpy(x).pin_memory()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > L2 (126 MB)
-    keys_loc = torch.zeros((2, n), dtype=torch.int64, device=dev) if world == 1 else None
     out_host = [torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory(),
                 torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory()]
     pops_host = torch.empty((radii.size, n), dtype=torch.int32).pin_memory()
     fe_host = torch.empty(n, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
 
-    def step(coords):
-        """one density pass; coords: device tensor (resident) or pinned host tensor (e2e)."""
-        with torch.cuda.stream(stream):
-            pops, fe, nn = dpass.run(coords if coords.is_cuda else coords.numpy(), r_fe)
-            if not coords.is_cuda:                       # e2e: results back in host memory
+    def step(coords, timed=False):
+        """one density pass; coords: device tensor (resident) or pinned host tensor (per-rank e2e at N > 1)."""
+        pops, fe, nn = dpass.run(coords if coords.is_cuda else coords.numpy(), r_fe, timed=timed)
+        if not coords.is_cuda:                           # e2e: results back in host memory (rank 0 keeps them)
+            with torch.cuda.stream(stream):
                 pops_host.copy_(pops, non_blocking=True)
                 fe_host.copy_(fe, non_blocking=True)
                 for h, t in zip(out_host, nn):
@@ -278,7 +294,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(coords, steps):
+    stage_acc = {}
+
+    def timed(coords, steps, stages=False):
         """per-step CUDA events on the session stream, L2 flushed between steps (outside the events)."""
         tot = 0.0
         for _ in range(steps):
@@ -287,10 +305,13 @@ def run_ours(args):
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            step(coords)
+            step(coords, timed=stages)
             e1.record(stream)
             e1.synchronize()
             tot += e0.elapsed_time(e1)
+            if stages:
+                for k, v in dpass.stage_ms().items():
+                    stage_acc[k] = stage_acc.get(k, 0.0) + v / steps
         t = torch.tensor([tot], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,19 +322,19 @@ def run_ours(args):
     if rank == 0:
         sampler.start()                                 # nvidia-smi needs ~1 s to deliver its first sample
     for _ in range(max(args.warmup, 3)):
-        step(x_dev)
+        last = step(x_dev)
     barrier()
     tensor_path = sess.gemm_info()[0]                   # 17 <= n_cols <= 256: the scans run on the tensor cores (tcgen05, TF32)
     peak_tflops = sess.tf32_peak(300.0) if tensor_path else sess.ffma_peak(300.0)
     s0 = sess.stats(reset=True)
     barrier()
-    ms = timed(x_dev, args.steps)
+    ms = timed(x_dev, args.steps, stages=True)
     barrier()
     s1 = sess.stats()
     # keep the load on until the sampler has seen it (short timed regions), then stop it
     t_end = time.time() + 1.5
     while time.time() < t_end:
-        step(x_dev)
+        last = step(x_dev)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     counts = torch.tensor([s1["launches"] - s0["launches"], s1["pairs_evaluated"], s1["pairs_scheduled"]], dtype=torch.int64, device=dev)
@@ -324,58 +345,145 @@ def run_ours(args):
     pd = pair_dims_per_step(n, d)
     value = pd / (ms * 1e-3) / 1e9
 
-    # ---- the two pair scans alone, for the roofline (the slower one is the dominant kernel) ---------
-    kms = None
-    if world == 1:
-        def time_scan(fn, reps=5):
-            fn()
-            sess.stats(reset=True)
-            kt = []
-            for _ in range(reps):
-                with torch.cuda.stream(stream):
-                    flush_buf.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                fn()
-                e1.record(stream)
-                e1.synchronize()
-                kt.append(e0.elapsed_time(e1))
-            return float(np.mean(kt)), sess.stats()["pairs_evaluated"] / float(reps)
+    # per-rank stage times (CUDA events inside the pass), min / max over ranks: names the limiter of the scaling curve
+    names = ["layout", "pops", "gather+fe+ranks", "nn", "gather+finish"]
+    mine = torch.tensor([stage_acc.get(k, 0.0) for k in names], dtype=torch.float64, device=dev)
+    lo, hi = mine.clone(), mine.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    stages = {k: {"min_ms": float(lo[i]), "max_ms": float(hi[i])} for i, k in enumerate(names)}
 
-        pops_loc = torch.zeros((radii.size, n), dtype=torch.int32, device=dev)
-        with torch.cuda.stream(stream):
-            fe_dev = sess.free_energies(sess.to_frame_order(sess.populations(radii, 0, n))[r_fe].contiguous())
-        sess.nn_prepare(fe_dev)
-        # nn_scan = seed kernel + block bounds + neighbourhood pass + full pass of nn_kernel (the last one is > 90 % of it)
+    # ---- parity of the sharded result: the gathered populations / neighbours == an unsharded scan of rank 0 -------------
+    parity = None
+    if world > 1:
+        cs = checksum(last[0], last[2])
+        if rank == 0:
+            from clustering_b200.dist import _OnSessionStream
+            with _OnSessionStream(sess):
+                sess.set_coords(x_dev)
+                full_p = sess.to_frame_order(sess.populations(radii, 0, n))
+                fe_full = sess.free_energies(full_p[r_fe].contiguous())
+                full_nn = sess.nearest_neighbors(fe_full)
+            torch.cuda.synchronize()
+            cs1 = checksum(full_p, full_nn)
+            same = bool(torch.equal(full_p, last[0])) and all(bool(torch.equal(a.view(torch.int32), b.view(torch.int32)))
+                                                              for a, b in zip(full_nn, last[2]))
+            parity = {"sharded_equals_unsharded": same, "pops_checksum": cs[0], "nn_checksum": cs[1],
+                      "unsharded_pops_checksum": cs1[0], "unsharded_nn_checksum": cs1[1]}
+        flag = torch.tensor([1 if (parity is None or parity["sharded_equals_unsharded"]) else 0], device=dev)
+        dist.broadcast(flag, 0)
+        if int(flag.item()) != 1:
+            raise SystemExit(f"bench.py: the sharded result on {world} GPUs differs from the unsharded scan: {parity}")
+    else:
+        cs = checksum(last[0], last[2])
+        parity = {"pops_checksum": cs[0], "nn_checksum": cs[1]}
+
+    # ---- the two pair scans alone on this rank's shard, for the roofline (the slower one is the dominant kernel) ---------
+    def time_scan(fn, reps=3):
+        fn()
+        sess.stats(reset=True)
+        kt = []
+        for _ in range(reps):
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            kt.append(e0.elapsed_time(e1))
+        return float(np.mean(kt)), sess.stats()["pairs_evaluated"] / float(reps)
+
+    barrier()
+    with torch.cuda.stream(stream):
+        sess.set_coords(x_dev)
+        sess.nn_prepare(last[1])
+    if world == 1:
+        keys_loc = torch.empty((2, n), dtype=torch.int64, device=dev)
+        pops_loc = torch.empty((radii.size, n), dtype=torch.int32, device=dev)
         nn_ms, nn_pairs = time_scan(lambda: sess.nn_scan(0, n, out=keys_loc))
         pops_ms, pops_pairs = time_scan(lambda: sess.populations(radii, 0, n, out=pops_loc))
-        scans = {"nn_kernel (neighbour scan)": (nn_ms, nn_pairs), "pops kernel (population scan)": (pops_ms, pops_pairs)}
-        kname = max(scans, key=lambda k: scans[k][0])
-        kms, k_pairs = scans[kname]
+    else:
+        nn_ms, nn_pairs = time_scan(lambda: sess.nn_scan_shard(rank, world, out=dpass.keys_loc))
+        pops_ms, pops_pairs = time_scan(lambda: sess.populations_shard(radii, rank, world, out=dpass.pops_loc))
+    scans = {"nn_kernel (neighbour scan)": (nn_ms, nn_pairs), "population kernel (multi-radius scan)": (pops_ms, pops_pairs)}
+    kname = max(scans, key=lambda k: scans[k][0])
+    kms, k_pairs = scans[kname]
+    barrier()
 
     # ---- end to end: host buffers through the C ABI ----------------------------------------------
+    screening_info = None
     if world == 1:
+        lib.set_gpus(1)                                  # the in-process path must use ONE GPU at N = 1
+        outs = dict(pops=pops_host.numpy().view(np.uint32), fe=fe_host.numpy(),
+                    nn=(out_host[0].numpy().view(np.uint32), out_host[1].numpy(), out_host[2].numpy().view(np.uint32), out_host[3].numpy()))
+        xp = x_pin.numpy()
+
         def e2e_step():
-            pops = density.calculate_populations(x, radii)
-            fe = density.calculate_free_energies(pops[r_fe])
-            density.nearest_neighbors(x, fe)
+            r = density.density_run(xp, radii, r_fe, neighbors=True, out=outs)
+            if screening_workload:
+                with density.ScreeningRun(r["fe"], r["nn"][1], xp) as run:
+                    t, t_to, k, lab = np.float32(0.1), float(r["fe"].max()), 0, None
+                    while (t < np.float32(t_to - 0.01 + 0.1)) and not (np.float32(t_to + 0.01 + 0.1) < t):
+                        lab = run.next(t)
+                        t = np.float32(t + np.float32(0.1))
+                        k += 1
+                return k, int(lab.max()), int((lab.astype(np.int64) * (np.arange(n) % 1000003 + 1)).sum())
+            return None
         e2e_step()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e2e_step()
+            info = e2e_step()
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-        h2d = 2 * x.nbytes + 4 * n + 4 * n                # coords for each of the two scans, pops, fe
-        d2h = radii.size * 4 * n + 4 * n + 2 * 8 * n + 4 * n   # pops, fe, neighbour keys, frame order
-        e2e_api = "host-pointer C ABI: dcb200_populations + dcb200_free_energies + dcb200_nearest_neighbors (wall clock)"
+        if info:
+            screening_info = {"thresholds": info[0], "clusters_at_last_threshold": info[1], "labels_checksum": info[2]}
+        h2d = x.nbytes + (x.nbytes if screening_workload else 0)
+        d2h = radii.size * 4 * n + 4 * n + 16 * n + (screening_info["thresholds"] * 4 * n if screening_info else 0)
+        e2e_api = ("host-pointer C ABI, pinned host buffers: dcb200_density_run (upload, populations of all radii, free energies, "
+                   "neighbours, downloads)" + (" + dcb200_screening_begin/next/end over all thresholds" if screening_workload else "") +
+                   "; wall clock around the calls")
+        cxx = None
     else:
         step(x_pin)
         e2e_ms = timed(x_pin, args.steps)
         h2d = x.nbytes
         d2h = radii.size * 4 * n + 4 * n + 16 * n
-        e2e_api = "session C ABI per rank with pinned host buffers: H2D coords, sharded scans, NCCL all-gather, D2H results (CUDA events, max over ranks)"
+        e2e_api = ("session C ABI per rank with pinned host buffers: H2D coords on every rank, block-cyclic sharded scans, NCCL all-gather, "
+                   "D2H results (CUDA events, max over ranks)")
+        # the C++ in-process path (what the `clustering` binary runs): one process, N GPUs, NCCL inside libdcb200.so
+        cxx = None
+        barrier()
+        if rank == 0:
+            try:
+                lib.set_gpus(world)
+                outs = dict(pops=pops_host.numpy().view(np.uint32), fe=fe_host.numpy(),
+                            nn=(out_host[0].numpy().view(np.uint32), out_host[1].numpy(), out_host[2].numpy().view(np.uint32), out_host[3].numpy()))
+                xp = x_pin.numpy()
+                density.density_run(xp, radii, r_fe, neighbors=True, out=outs)          # creates contexts + communicators
+                density.density_run(xp, radii, r_fe, neighbors=True, out=outs)
+                t0 = time.perf_counter()
+                reps = max(3, args.steps // 2)
+                for _ in range(reps):
+                    density.density_run(xp, radii, r_fe, neighbors=True, out=outs)
+                cms = (time.perf_counter() - t0) * 1e3 / reps
+                same = bool(np.array_equal(outs["pops"], last[0].cpu().numpy().view(np.uint32)) and
+                            np.array_equal(outs["nn"][0], last[2][0].cpu().numpy().view(np.uint32)) and
+                            np.array_equal(outs["nn"][3].view(np.uint32), last[2][3].cpu().numpy().view(np.uint32)))
+                cxx = {"ms_per_step": cms, "value": pd / (cms * 1e-3) / 1e9, "unit": UNIT, "equals_torchrun_result": same,
+                       "api": f"one process, {world} GPUs: dcb200_density_run (one H2D + NCCL broadcast, block-cyclic shards, ncclAllGather, one D2H)"}
+            except Exception as ex:
+                cxx = {"failed": str(ex)}
+        barrier()
     e2e_value = pd / (e2e_ms * 1e-3) / 1e9
+
+    # per-GPU roofline numbers of every rank (max kernel time decides the step)
+    roof = torch.tensor([kms, k_pairs, pops_ms, pops_pairs, nn_ms, nn_pairs], dtype=torch.float64, device=dev)
+    roofs = [torch.zeros_like(roof) for _ in range(world)] if world > 1 else [roof]
+    if world > 1:
+        dist.all_gather(roofs, roof)
 
     if rank == 0:
         line = {
@@ -383,55 +491,71 @@ def run_ours(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "tf32 filter + f32 exact recheck" if tensor_path else "f32", "data": "synthetic",
             "config": {"workload": workload_label(args.workload, cfg),
-                       "step": "layout build + populations + free energies + nearest neighbours (+ lower-free-energy neighbour)",
-                       "pair_dims_per_step": pd, "parallelism": f"rows sharded over {world} GPU(s), coords replicated, NCCL all-gather of populations and neighbour keys",
+                       "step": "layout build + populations (all radii) + free energies + nearest neighbours (+ lower-free-energy neighbour)",
+                       "pair_dims_per_step": pd,
+                       "parallelism": f"rows dealt block-cyclically (1024-row blocks) to {world} GPU(s), coords replicated, one NCCL all-gather "
+                                      "of the populations and one of the neighbour keys",
                        "l2": "flushed between timed steps (256 MiB write)", "seed": cfg["seed"],
                        "pairs_evaluated_frac": evaluated_frac},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "api": e2e_api},
             "gpu_launches": int(launches.item()),
+            "stages_ms": stages,
+            "parity": parity,
         }
-        if kms is not None:
-            pairs = float(n) * float(n)
-            achieved = FLOP_EXECUTED_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12
-            line["roofline"] = {
-                "bound": "tensor" if tensor_path else "fp32", "kernel": kname,
-                "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                "kernel_ms": kms,
-                "pairs_evaluated_per_launch": k_pairs, "pairs_evaluated_frac": k_pairs / pairs,
-                "evaluated_gpair_dim_per_s": k_pairs * d / (kms * 1e-3) / 1e9,
-                "effective_gpair_dim_per_s": pairs * d / (kms * 1e-3) / 1e9,
-                "algorithmic_3flop_tflops_on_evaluated_pairs": FLOP_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12,
-                "peak_source": ("tcgen05.mma kind::tf32 128x128x8 back to back on resident operands, measured in this run "
-                                "(dcb200_ctx_tf32_peak); MEASURED_PEAKS.json holds bf16 only (TF32 runs at half the bf16 rate)") if tensor_path else
-                               "FFMA-only microbenchmark in this run (dcb200_ctx_ffma_peak); MEASURED_PEAKS.json has no FP32 entry",
-                "traffic": ncu_traffic(("gscan_" + ("nn" if kname.startswith("nn") else "pops")) if tensor_path else kname),
-                "other_scans": {k: {"kernel_ms": v[0], "pairs_evaluated_frac": v[1] / pairs,
-                                    "achieved_tflops": FLOP_EXECUTED_PER_PAIR_DIM * v[1] * d / (v[0] * 1e-3) / 1e12}
-                                for k, v in scans.items() if k != kname},
-                "note": ("GEMM-form path (n_cols >= 17): the roofline is the tensor pipe (TF32). achieved = 2 flop per pair.dim x the pairs of "
-                         "the 128 x 128 tile pairs the kernel really multiplied; pruned tile pairs are not counted; the headline value "
-                         "counts the full N x N matrix") if tensor_path else
-                        "compute-bound path (SURVEY.md 8d): the roofline is the FP32 FFMA pipe, not HBM. achieved = 2 flop (one FFMA) per "
-                        "pair.dim x the pairs the kernel really evaluated = (warp, tile) scans x 128 rows x 128 columns; tiles out of reach "
-                        "of a row block / of a warp's rows are pruned and not counted; the headline value counts the full N x N matrix. "
-                        "traffic = dram bytes per launch from the committed ncu capture (profiles/), null if none",
-            }
+        if screening_info:
+            line["screening"] = screening_info
+        if cxx is not None:
+            line["cxx_inprocess"] = cxx
+        pairs = float(n) * float(n)
+        rows_frac = 1.0 / world
+        achieved = FLOP_EXECUTED_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12
+        line["roofline"] = {
+            "bound": "tensor" if tensor_path else "fp32", "kernel": kname + (f" (rank 0's shard of {world})" if world > 1 else ""),
+            "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+            "kernel_ms": kms,
+            "pairs_evaluated_per_launch": k_pairs, "pairs_evaluated_frac": k_pairs / (pairs * rows_frac),
+            "evaluated_gpair_dim_per_s": k_pairs * d / (kms * 1e-3) / 1e9,
+            "effective_gpair_dim_per_s": pairs * rows_frac * d / (kms * 1e-3) / 1e9,
+            "algorithmic_3flop_tflops_on_evaluated_pairs": FLOP_PER_PAIR_DIM * k_pairs * d / (kms * 1e-3) / 1e12,
+            "peak_source": ("tcgen05.mma kind::tf32 128x128x8 back to back on resident operands, measured in this run "
+                            "(dcb200_ctx_tf32_peak); MEASURED_PEAKS.json holds bf16 only (TF32 runs at half the bf16 rate)") if tensor_path else
+                           "FFMA-only microbenchmark in this run (dcb200_ctx_ffma_peak); MEASURED_PEAKS.json has no FP32 entry",
+            "traffic": ncu_traffic(("gscan_" + ("nn" if kname.startswith("nn") else "pops")) if tensor_path else kname),
+            "other_scans": {k: {"kernel_ms": v[0], "pairs_evaluated_frac": v[1] / (pairs * rows_frac),
+                                "achieved_tflops": FLOP_EXECUTED_PER_PAIR_DIM * v[1] * d / (v[0] * 1e-3) / 1e12}
+                            for k, v in scans.items() if k != kname},
+            "note": ("GEMM-form path (n_cols >= 17): the roofline is the tensor pipe (TF32). achieved = 2 flop per pair.dim x the pairs of "
+                     "the 128 x 128 tile pairs the kernel really multiplied; pruned tile pairs are not counted; the headline value "
+                     "counts the full N x N matrix") if tensor_path else
+                    "compute-bound path (SURVEY.md 8d): the roofline is the FP32 FFMA pipe, not HBM. achieved = 2 flop (one FFMA) per "
+                    "pair.dim x the pairs the kernel really evaluated = (warp, tile) scans x 128 rows x 128 columns; tiles out of reach "
+                    "of a row group are pruned and not counted; the headline value counts the full N x N matrix. "
+                    "traffic = dram bytes per launch from the committed ncu capture (profiles/), null if none",
+        }
+        if world > 1:
+            line["roofline"]["per_gpu"] = [
+                {"rank": g, "pops_ms": float(r[2]), "pops_tflops": FLOP_EXECUTED_PER_PAIR_DIM * float(r[3]) * d / (float(r[2]) * 1e-3) / 1e12,
+                 "nn_ms": float(r[4]), "nn_tflops": FLOP_EXECUTED_PER_PAIR_DIM * float(r[5]) * d / (float(r[4]) * 1e-3) / 1e12,
+                 "frac_of_peak_dominant": FLOP_EXECUTED_PER_PAIR_DIM * float(r[1]) * d / (float(r[0]) * 1e-3) / 1e12 / peak_tflops}
+                for g, r in enumerate(roofs)]
         if not args.no_cpu_baseline:
             try:
                 kind, impl, cores = cpu_impl()
-                ns = cpu_sample_size(kind, impl, x, float(radii[0]), 12.0)
-                sec = cpu_step(kind, impl, np.ascontiguousarray(x[:ns]), float(radii[0]))
+                ns = cpu_sample_size(kind, impl, x, radii, r_fe, 12.0)
+                sec = cpu_step(kind, impl, np.ascontiguousarray(x[:ns]), radii, r_fe)
                 line["cpu_baseline"] = {
                     "value": pair_dims_per_step(ns, d) / sec / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-                    "sample": f"first {ns} frames of the workload, one pops+FE+NN step in {sec:.1f} s (brute-force NN is quadratic; pops is box-pruned, counted as full N x N)"}
+                    "sample": f"first {ns} frames of the workload, one populations ({radii.size} radii) + free energies + neighbours step in {sec:.1f} s "
+                              "(brute-force NN is quadratic; the CPU populations are box-pruned, counted as full N x N)"}
             except Exception as ex:                       # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
         if not args.no_cpu_baseline and world == 1:
-            line["reference_cuda"] = reference_cuda_arm(x, radii, d, density)
+            line["reference_cuda"] = reference_cuda_arm(x, radii, r_fe, d, density)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

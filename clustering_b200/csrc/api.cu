@@ -75,6 +75,7 @@ struct Trace {
 namespace {
 
 constexpr int CENTRE_SAMPLES = 65536;
+constexpr int ORDER_MAX_DIMS = 12;      // dims that can enter the spatial ordering key (60 key bits are shared between them)
 
 // centre[k] / spread[k] = mean and standard deviation of a strided sample of the frames (any centre is
 // valid: it only tightens the error band of the fast path; the spread only scales the ordering key).
@@ -120,7 +121,8 @@ __global__ void spatial_keys_kernel(const float* __restrict__ coords, size_t n, 
                                     uint32_t* __restrict__ iota) {
   const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t q[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t q[ORDER_MAX_DIMS];
+  for (int k = 0; k < ORDER_MAX_DIMS; ++k) q[k] = 0;
   const float cells = (float) (1u << bits);
   for (int k = 0; k < m; ++k) {
     const float u = (coords[i * d + k] - centre[k]) / (8.0f * spread[k]) + 0.5f;
@@ -513,6 +515,7 @@ struct dcb200_ctx {
   unsigned long long* stats = nullptr;   // [0] slow pairs, [1] exact pairs, [2] tiles streamed
   float maxnorm2 = 0.f;
   bool nn_ready = false;
+  uint64_t layout_gen = 0;          // counts the layouts built on this context (sessions notice when theirs was replaced)
   uint64_t launches = 0;
   uint64_t pairs_scheduled = 0;     // pairs of the full row x column ranges of the scans since the last reset
   // GEMM-form (tcgen05) path for 17 <= d <= 256, spatial order only (gemm_kernels.cuh)
@@ -736,11 +739,21 @@ extern "C" int dcb200_ctx_create(int device, dcb200_ctx** out) {
   dcb200_ctx* c = new dcb200_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaMalloc(&c->scalars, 4 * sizeof(unsigned int)));
-  CK(cudaMalloc(&c->stats, 4 * sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(c->scalars, 0, 4 * sizeof(unsigned int), c->stream));
-  CK(cudaMemsetAsync(c->stats, 0, 4 * sizeof(unsigned long long), c->stream));
+  auto init = [&]() -> int {
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->scalars, 4 * sizeof(unsigned int)));
+    CK(cudaMalloc(&c->stats, 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->scalars, 0, 4 * sizeof(unsigned int), c->stream));
+    CK(cudaMemsetAsync(c->stats, 0, 4 * sizeof(unsigned long long), c->stream));
+    return 0;
+  };
+  if (const int rc = init()) {              // nothing of a half-built context survives a failure
+    if (c->scalars) cudaFree(c->scalars);
+    if (c->stats) cudaFree(c->stats);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return rc;
+  }
   *out = c;
   return 0;
 }
@@ -910,6 +923,7 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
   const size_t ld = (n + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN;
   c->n = n; c->d = d; c->ld = ld;
   c->nn_ready = false;
+  c->layout_gen += 1;
   c->spatial = !keep_order;
   CK(c->xT.reserve(d * ld));
   CK(c->cT.reserve((d + 1) * ld + ld / (d <= (size_t) MAX_TEMPLATE_D ? TileW<1>::tj : TileW<0>::tj) * ((3 * d + 1 + 3) / 4 * 4)));
@@ -922,7 +936,10 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
   centre_kernel<<<(unsigned int) d, 256, 0, c->stream>>>(dev_coords, n, (int) d, c->centre.p, c->centre.p + d);
   c->launches += 1;
   if (c->spatial) {
-    const int m = (int) std::min<size_t>(d, 6);
+    // dims that enter the key: all of them up to 8 (60 key bits: 7 bits each at 8 dims).  Measured at 1M x 10: ordering by
+    // 8 dims instead of 6 cuts the evaluated share of the pair matrix from 16.1 % to 13.5 % (populations 212 -> 189 ms);
+    // 10 dims gain nothing more and cost the neighbour search 8 %
+    const int m = (int) std::min<size_t>(d, (size_t) std::min(ORDER_MAX_DIMS, env_int("DCB200_ORDER_DIMS", 8)));
     const int bits = std::min(16, 60 / m);        // cells far smaller than a 128-frame tile even in the densest regions
     CK(c->skeys_a.reserve(n)); CK(c->skeys_b.reserve(n)); CK(c->iota.reserve(n));
     spatial_keys_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(dev_coords, n, (int) d, c->centre.p, c->centre.p + d, m, bits,
@@ -1196,6 +1213,8 @@ static int populations_impl(dcb200_ctx* c, const float* radii, size_t n_radii, s
     a.lut_k = 0;
     a.lut_scale = a.lut_margin = a.band_max = 0.f;
     a.dense_lanes = 0;
+    a.interleave = 0;
+    a.proj_prune = 0;
     for (int q = 0; q < 8; ++q) a.band[q] = 0.f;
     if (count_mode) {
       // radius-dependent part of the band: e_rel * r^2 (fast path) + roundings of s = acc + |x'|^2 and of s - r^2
@@ -1222,6 +1241,8 @@ static int populations_impl(dcb200_ctx* c, const float* radii, size_t n_radii, s
       // the table's entries may differ from the radii they stand for
       a.band_max = up((1.02 * (double) a.g.e_rel + 4.0 * ldexp(1.0, -24) + 32.0 * ldexp(1.0, -23)) * rmax2 + 1e-37);
       a.dense_lanes = env_int("DCB200_BIN_DENSE_LANES", 8);
+      a.interleave = env_int("DCB200_BIN_INTERLEAVE", 0);
+      a.proj_prune = a.interleave ? 0 : (env_int("DCB200_BIN_PROJ", 1) == 1 ? 1 : 0);
     }
     const bool counts_self = pm != HIST;           // count and bin mode count the frame itself through d2 = 0 < r^2
     CK(c->cnt.reserve((size_t) nb * ld_cnt));
@@ -1498,9 +1519,9 @@ extern "C" int dcb200_ctx_nn_scan_shard(dcb200_ctx* c, int shard, int n_shards, 
 }
 
 __global__ void nn_finish_shards_kernel(const unsigned long long* __restrict__ knn, const unsigned long long* __restrict__ khd,
-                                        const uint32_t* __restrict__ perm, size_t n, size_t cap, uint32_t n_shards, int cyclic,
-                                        uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2, uint32_t* __restrict__ hd_idx,
-                                        float* __restrict__ hd_d2) {
+                                        const uint32_t* __restrict__ perm, size_t n, size_t cap, size_t shard_stride, uint32_t n_shards,
+                                        int cyclic, uint32_t* __restrict__ nn_idx, float* __restrict__ nn_d2,
+                                        uint32_t* __restrict__ hd_idx, float* __restrict__ hd_d2) {
   const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   size_t shard, local;
@@ -1513,22 +1534,26 @@ __global__ void nn_finish_shards_kernel(const unsigned long long* __restrict__ k
     local = p % cap;
   }
   const size_t o = perm[p];
-  const unsigned long long a = knn[shard * cap + local], b = khd[shard * cap + local];
+  const unsigned long long a = knn[shard * shard_stride + local], b = khd[shard * shard_stride + local];
   nn_idx[o] = (uint32_t) a;
   nn_d2[o] = __uint_as_float((uint32_t) (a >> 32));
   hd_idx[o] = (uint32_t) b;
   hd_d2[o] = __uint_as_float((uint32_t) (b >> 32));
 }
-// gathered shard keys [n_shards][capacity] -> outputs in frame order
+// gathered shard keys -> outputs in frame order; shard s's keys start at dev_keys_*[s * shard_stride] (capacity for two
+// separately gathered arrays, 2 * capacity for one gathered [n_shards][2][capacity] block)
 extern "C" int dcb200_ctx_nn_finish_shards(dcb200_ctx* c, const uint64_t* dev_keys_nn, const uint64_t* dev_keys_hd, int n_shards,
-                                           uint32_t* dev_nn_idx, float* dev_nn_d2, uint32_t* dev_hd_idx, float* dev_hd_d2) {
-  if (!c || !dev_keys_nn || !dev_keys_hd || !dev_nn_idx || !dev_nn_d2 || !dev_hd_idx || !dev_hd_d2 || n_shards < 1)
+                                           size_t shard_stride, uint32_t* dev_nn_idx, float* dev_nn_d2, uint32_t* dev_hd_idx,
+                                           float* dev_hd_d2) {
+  if (!c || !dev_keys_nn || !dev_keys_hd || !dev_nn_idx || !dev_nn_d2 || !dev_hd_idx || !dev_hd_d2 || n_shards < 1 ||
+      shard_stride < dcb200_shard_capacity(c ? c->n : 0, n_shards))
     return fail("dcb200_ctx_nn_finish_shards: bad arguments");
   if (c->n == 0) return fail("dcb200_ctx_nn_finish_shards: no coordinates set");
   CK(cudaSetDevice(c->device));
   nn_finish_shards_kernel<<<blocks_for(c->n, 256), 256, 0, c->stream>>>(
       (const unsigned long long*) dev_keys_nn, (const unsigned long long*) dev_keys_hd, c->perm.p, c->n,
-      dcb200_shard_capacity(c->n, n_shards), (uint32_t) n_shards, c->gemm ? 0 : 1, dev_nn_idx, dev_nn_d2, dev_hd_idx, dev_hd_d2);
+      dcb200_shard_capacity(c->n, n_shards), shard_stride, (uint32_t) n_shards, c->gemm ? 0 : 1, dev_nn_idx, dev_nn_d2, dev_hd_idx,
+      dev_hd_d2);
   c->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -1679,13 +1704,23 @@ extern "C" int dcb200_ctx_ffma_peak(dcb200_ctx* c, double ms_target, double* tfl
 }
 
 // ------------------------------------------------------------------------------------------------
-// (1) host-pointer entry points: one worker thread per GPU, positions sharded, results scattered
-//     into the caller's arrays in frame order
+// (1) host-pointer entry points.  One GPU: everything stays on the device between upload and download.
+//     Several GPUs (replaces the per-GPU upload / download / host merge of density_clustering_cuda.cu:152-181, :286-328,
+//     :505-571): one worker thread per GPU, ONE host-to-device copy (to GPU 0) and an NCCL broadcast of the coordinates
+//     over NVLink, block-cyclic row shards, ncclAllGather of the shard results, frame-order assembly on the device, ONE
+//     download from GPU 0.  NCCL is bound at run time (nccl_dl.hpp); without it the shards are assembled through the host.
 // ------------------------------------------------------------------------------------------------
+#include <condition_variable>
+
+#include "nccl_dl.hpp"
+
 namespace {
 
 std::mutex g_pool_mutex;
 std::map<int, dcb200_ctx*> g_pool;     // one cached context per device (buffers are reused across calls)
+// The pooled contexts (buffers, stream, work counters) are shared by all callers of the host-pointer entry points: one
+// call at a time per process.  (The reference's path is not re-entrant either: SURVEY.md section 8b "Threading".)
+std::mutex g_call_mutex;
 
 int pooled_ctx(int device, dcb200_ctx** out) {
   std::lock_guard<std::mutex> lock(g_pool_mutex);
@@ -1724,12 +1759,335 @@ int on_gpus(int n_gpus, Fn&& fn) {
   return 0;
 }
 
-// shards are multiples of the row block so that no CTA straddles two devices
+// The worker threads agree on a status before every collective: a thread that failed must not leave the others waiting
+// inside NCCL.
+struct Rendezvous {
+  std::mutex m;
+  std::condition_variable cv;
+  int n, arrived = 0, gen = 0;
+  bool ok = true, result = true;
+  explicit Rendezvous(int n_) : n(n_) {}
+  bool all_ok(bool mine) {
+    std::unique_lock<std::mutex> lk(m);
+    ok = ok && mine;
+    if (++arrived == n) {
+      result = ok;
+      ok = true;
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+      return result;
+    }
+    const int my_gen = gen;
+    cv.wait(lk, [&] { return gen != my_gen; });
+    return result;
+  }
+};
+
+// the devices the host-pointer entry points shard over, with one NCCL communicator each (created once per device count)
+struct Gang {
+  int n = 0;
+  std::vector<dcb200_ctx*> ctx;
+  std::vector<ncclComm_t> comm;
+  bool nccl = false;
+  std::string why;                     // why NCCL is not in use
+};
+std::mutex g_gang_mutex;
+std::map<int, Gang*> g_gangs;
+
+int get_gang(int n_gpus, Gang** out) {
+  std::lock_guard<std::mutex> lock(g_gang_mutex);
+  auto it = g_gangs.find(n_gpus);
+  if (it != g_gangs.end()) {
+    *out = it->second;
+    return 0;
+  }
+  Gang* G = new Gang();
+  G->n = n_gpus;
+  G->ctx.resize(n_gpus, nullptr);
+  for (int g = 0; g < n_gpus; ++g) {
+    const int rc = pooled_ctx(g, &G->ctx[g]);
+    if (rc) {
+      delete G;
+      return rc;
+    }
+  }
+  const char* off = getenv("DCB200_NO_NCCL");
+  if (n_gpus > 1 && !(off && off[0] == '1')) {
+    NcclApi& api = nccl_api();
+    if (!api.ok) {
+      G->why = api.why;
+    } else {
+      std::vector<int> devs(n_gpus);
+      for (int g = 0; g < n_gpus; ++g) devs[g] = g;
+      G->comm.resize(n_gpus);
+      const ncclResult_t r = api.CommInitAll(G->comm.data(), n_gpus, devs.data());
+      if (r == ncclSuccess) G->nccl = true;
+      else G->why = std::string("ncclCommInitAll: ") + api.GetErrorString(r);
+    }
+    if (!G->nccl && getenv("DCB200_TRACE")) fprintf(stderr, "[dcb200] NCCL not in use (%s): shards are assembled through the host\n", G->why.c_str());
+  }
+  g_gangs[n_gpus] = G;
+  *out = G;
+  return 0;
+}
+
+#define NCK(call)                                                                                                   \
+  do {                                                                                                              \
+    ncclResult_t r__ = (call);                                                                                      \
+    if (r__ != ncclSuccess) return fail(std::string(#call) + ": " + nccl_api().GetErrorString(r__));                \
+  } while (0)
+
+// contiguous shards of the host-assembled fallback: multiples of the row block so that no CTA straddles two devices
 void shard(size_t n, int g, int n_gpus, size_t* b, size_t* e) {
   const size_t blocks = (n + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   const size_t per = (blocks + n_gpus - 1) / n_gpus * ROWS_PER_CTA;
   *b = std::min(n, per * g);
   *e = std::min(n, per * (g + 1));
+}
+
+int gpus_for_rows(size_t n_rows, int* n_gpus) {
+  CKI(gpus_to_use(n_gpus));
+  *n_gpus = (int) std::max<size_t>(1, std::min<size_t>((size_t) *n_gpus, (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
+  return 0;
+}
+
+// One density run on the gang: any of the three stages, results in the caller's host arrays (frame order).
+//   radii / pops        populations for n_radii radii (pops: [n_radii][n_rows]) -- skipped when n_radii == 0
+//   fe_all              optional: free energies for every radius, [n_radii][n_rows]
+//   fe_in               free energies to run the neighbour search on when there is no population stage (else NULL:
+//                       the free energies of radius fe_radius, also copied to fe_out when that is not NULL)
+//   nn_*                neighbour outputs; nn_idx == NULL skips the stage
+struct RunArgs {
+  const float* coords;
+  size_t n, d;
+  const float* radii;
+  size_t n_radii, fe_radius;
+  uint32_t* pops;
+  float* fe_all;
+  const float* fe_in;
+  float* fe_out;
+  uint32_t *nn_idx, *hd_idx;
+  float *nn_d2, *hd_d2;
+};
+
+int run_single(dcb200_ctx* c, const RunArgs& a, Trace& tr) {
+  const size_t n = a.n, R = a.n_radii;
+  const bool want_nn = a.nn_idx != nullptr;
+  CKI(dcb200_ctx_set_coords(c, a.coords, n, a.d));
+  tr.lap("upload+layout");
+  CK(c->io_u32.reserve(2 * std::max<size_t>(R, 1) * n + 2 * n));
+  CK(c->io_f32.reserve((R + 3) * n));
+  uint32_t *pos = c->io_u32.p, *frame = pos + std::max<size_t>(R, 1) * n, *d_ni = frame + std::max<size_t>(R, 1) * n, *d_hi = d_ni + n;
+  float *dfe = c->io_f32.p, *d_nd = dfe + n, *d_hd = d_nd + n, *dfe_all = d_hd + n;
+  if (R) {
+    CKI(dcb200_ctx_populations(c, a.radii, R, 0, n, pos));
+    CKI(dcb200_ctx_to_frame_order(c, pos, R, frame));
+    if (a.pops) CK(cudaMemcpyAsync(a.pops, frame, R * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (a.fe_all) {
+      for (size_t r = 0; r < R; ++r) CKI(dcb200_ctx_free_energies(c, frame + r * n, n, 0, dfe_all + r * n));
+      CK(cudaMemcpyAsync(a.fe_all, dfe_all, R * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (want_nn || a.fe_out) {
+      CKI(dcb200_ctx_free_energies(c, frame + a.fe_radius * n, n, 0, dfe));
+      if (a.fe_out) CK(cudaMemcpyAsync(a.fe_out, dfe, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (tr.on) { cudaStreamSynchronize(c->stream); tr.lap("populations"); }
+  } else if (want_nn) {
+    CK(cudaMemcpyAsync(dfe, a.fe_in, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (want_nn) {
+    CK(c->knn.reserve(n));
+    CK(c->khd.reserve(n));
+    CKI(dcb200_ctx_nn_prepare(c, dfe));
+    CKI(dcb200_ctx_nn_scan(c, 0, n, (uint64_t*) c->knn.p, (uint64_t*) c->khd.p));
+    CKI(dcb200_ctx_nn_finish(c, (const uint64_t*) c->knn.p, (const uint64_t*) c->khd.p, d_ni, d_nd, d_hi, d_hd));
+    CK(cudaMemcpyAsync(a.nn_idx, d_ni, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(a.nn_d2, d_nd, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(a.hd_idx, d_hi, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(a.hd_d2, d_hd, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  tr.lap("scan+download");
+  return 0;
+}
+
+// several GPUs with NCCL: see the header of this section
+int run_gang_nccl(Gang* G, const RunArgs& a) {
+  const size_t n = a.n, R = a.n_radii;
+  const bool want_nn = a.nn_idx != nullptr;
+  const size_t cap = dcb200_shard_capacity(n, G->n);
+  Rendezvous rv(G->n);
+  NcclApi& api = nccl_api();
+  return on_gpus(G->n, [&](int g, int W) -> int {
+    dcb200_ctx* c = G->ctx[g];
+    ncclComm_t comm = G->comm[g];
+    auto step = [&](int rc) -> int {          // agree before the next collective
+      if (!rv.all_ok(rc == 0)) return rc ? rc : fail("another GPU of the gang failed");
+      return 0;
+    };
+    auto prep = [&]() -> int {
+      CK(cudaSetDevice(c->device));
+      CK(c->stage.reserve(n * a.d));
+      if (g == 0) CK(cudaMemcpyAsync(c->stage.p, a.coords, n * a.d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      return 0;
+    };
+    CKI(step(prep()));
+    NCK(api.Broadcast(c->stage.p, c->stage.p, n * a.d, ncclFloat32, 0, comm, c->stream));
+    const size_t Rm = std::max<size_t>(R, 1);
+    auto layout = [&]() -> int {
+      CKI(build_layout(c, c->stage.p, n, a.d, false));
+      CK(c->io_u32.reserve(Rm * cap + (size_t) W * Rm * cap + Rm * n + 2 * n));
+      CK(c->io_f32.reserve((R + 3) * n));
+      return 0;
+    };
+    int rc = layout();
+    uint32_t *loc = c->io_u32.p, *all = loc + Rm * cap, *frame = all + (size_t) W * Rm * cap, *d_ni = frame + Rm * n, *d_hi = d_ni + n;
+    float *dfe = c->io_f32.p, *d_nd = dfe + n, *d_hd = d_nd + n, *dfe_all = d_hd + n;
+    if (R) {
+      if (!rc) rc = dcb200_ctx_populations_shard(c, a.radii, R, g, W, loc);
+      CKI(step(rc));
+      NCK(api.AllGather(loc, all, R * cap, ncclUint32, comm, c->stream));
+      auto after = [&]() -> int {
+        // every GPU needs the free energies of all frames for its shard of the neighbour search; only GPU 0 downloads
+        if (g == 0 || want_nn) CKI(dcb200_ctx_shards_to_frame_order(c, all, R, W, frame));
+        if (g == 0) {
+          if (a.pops) CK(cudaMemcpyAsync(a.pops, frame, R * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+          if (a.fe_all) {
+            for (size_t r = 0; r < R; ++r) CKI(dcb200_ctx_free_energies(c, frame + r * n, n, 0, dfe_all + r * n));
+            CK(cudaMemcpyAsync(a.fe_all, dfe_all, R * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+          }
+        }
+        if (want_nn || (g == 0 && a.fe_out)) CKI(dcb200_ctx_free_energies(c, frame + a.fe_radius * n, n, 0, dfe));
+        if (g == 0 && a.fe_out) CK(cudaMemcpyAsync(a.fe_out, dfe, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        return 0;
+      };
+      rc = after();
+    } else if (want_nn) {
+      if (!rc && g == 0) {
+        cudaError_t ce = cudaMemcpyAsync(dfe, a.fe_in, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+        if (ce != cudaSuccess) rc = fail(std::string("free energy upload: ") + cudaGetErrorString(ce));
+      }
+      CKI(step(rc));
+      NCK(api.Broadcast(dfe, dfe, n, ncclFloat32, 0, comm, c->stream));
+      rc = 0;
+    }
+    if (want_nn) {
+      auto scan = [&]() -> int {
+        CK(c->knn.reserve(cap + (size_t) W * cap));
+        CK(c->khd.reserve(cap + (size_t) W * cap));
+        CKI(dcb200_ctx_nn_prepare(c, dfe));
+        CKI(dcb200_ctx_nn_scan_shard(c, g, W, (uint64_t*) c->knn.p, (uint64_t*) c->khd.p));
+        return 0;
+      };
+      if (!rc) rc = scan();
+      CKI(step(rc));
+      NCK(api.GroupStart());
+      NCK(api.AllGather(c->knn.p, c->knn.p + cap, cap, ncclUint64, comm, c->stream));
+      NCK(api.AllGather(c->khd.p, c->khd.p + cap, cap, ncclUint64, comm, c->stream));
+      NCK(api.GroupEnd());
+      if (g == 0) {
+        CKI(dcb200_ctx_nn_finish_shards(c, (const uint64_t*) (c->knn.p + cap), (const uint64_t*) (c->khd.p + cap), W, cap, d_ni, d_nd, d_hi, d_hd));
+        CK(cudaMemcpyAsync(a.nn_idx, d_ni, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(a.nn_d2, d_nd, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(a.hd_idx, d_hi, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(a.hd_d2, d_hd, n * 4, cudaMemcpyDeviceToHost, c->stream));
+      }
+    } else if (rc) {
+      return rc;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  });
+}
+
+// several GPUs without NCCL: every GPU uploads the coordinates itself, contiguous shards, assembly on the host
+int run_gang_host(Gang* G, const RunArgs& a) {
+  const size_t n = a.n, R = a.n_radii;
+  const bool want_nn = a.nn_idx != nullptr;
+  std::vector<uint32_t> perm(n), tmp(R * n);
+  std::vector<float> fe_host;
+  const float* fe_nn = a.fe_in;
+  if (R) {
+    CKI(on_gpus(G->n, [&](int g, int W) -> int {
+      dcb200_ctx* c = G->ctx[g];
+      size_t b, e;
+      shard(n, g, W, &b, &e);
+      CKI(dcb200_ctx_set_coords(c, a.coords, n, a.d));     // same deterministic order on every device
+      if (e > b) {
+        const size_t rows = e - b;
+        CK(c->io_u32.reserve(R * rows));
+        CKI(dcb200_ctx_populations(c, a.radii, R, b, e, c->io_u32.p));
+        CK(cudaMemcpy2DAsync(tmp.data() + b, n * sizeof(uint32_t), c->io_u32.p, rows * sizeof(uint32_t), rows * sizeof(uint32_t), R,
+                             cudaMemcpyDeviceToHost, c->stream));
+      }
+      if (g == 0) CK(cudaMemcpyAsync(perm.data(), c->perm.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      return 0;
+    }));
+    std::vector<uint32_t> own;
+    uint32_t* pops = a.pops;
+    if (!pops) {
+      own.resize(R * n);
+      pops = own.data();
+    }
+    for (size_t r = 0; r < R; ++r)
+      for (size_t p = 0; p < n; ++p) pops[r * n + perm[p]] = tmp[r * n + p];
+    if (a.fe_all)
+      for (size_t r = 0; r < R; ++r) CKI(dcb200_free_energies(pops + r * n, n, a.fe_all + r * n));
+    if (want_nn || a.fe_out) {
+      fe_host.resize(n);
+      CKI(dcb200_free_energies(pops + a.fe_radius * n, n, fe_host.data()));
+      if (a.fe_out) memcpy(a.fe_out, fe_host.data(), n * sizeof(float));
+      fe_nn = fe_host.data();
+    }
+  }
+  if (!want_nn) return 0;
+  std::vector<unsigned long long> knn(n), khd(n);
+  CKI(on_gpus(G->n, [&](int g, int W) -> int {
+    dcb200_ctx* c = G->ctx[g];
+    size_t b, e;
+    shard(n, g, W, &b, &e);
+    if (!R) CKI(dcb200_ctx_set_coords(c, a.coords, n, a.d));
+    CK(c->io_f32.reserve(n));
+    CK(cudaMemcpyAsync(c->io_f32.p, fe_nn, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CKI(dcb200_ctx_nn_prepare(c, c->io_f32.p));
+    if (e > b) {
+      CK(c->knn.reserve(e - b));
+      CK(c->khd.reserve(e - b));
+      CKI(dcb200_ctx_nn_scan(c, b, e, (uint64_t*) c->knn.p, (uint64_t*) c->khd.p));
+      CK(cudaMemcpyAsync(knn.data() + b, c->knn.p, (e - b) * 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(khd.data() + b, c->khd.p, (e - b) * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (g == 0) CK(cudaMemcpyAsync(perm.data(), c->perm.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  }));
+  for (size_t p = 0; p < n; ++p) {
+    const size_t o = perm[p];
+    const uint32_t x = (uint32_t) (knn[p] >> 32), y = (uint32_t) (khd[p] >> 32);
+    a.nn_idx[o] = (uint32_t) knn[p];
+    memcpy(&a.nn_d2[o], &x, 4);
+    a.hd_idx[o] = (uint32_t) khd[p];
+    memcpy(&a.hd_d2[o], &y, 4);
+  }
+  return 0;
+}
+
+int run_density(const RunArgs& a, const char* what) {
+  if (a.n == 0 || a.d == 0) return fail(std::string(what) + ": empty coordinate array");
+  std::lock_guard<std::mutex> call(g_call_mutex);
+  int n_gpus = 0;
+  CKI(gpus_for_rows(a.n, &n_gpus));
+  Trace tr(what);
+  if (n_gpus == 1) {
+    dcb200_ctx* c = nullptr;
+    CKI(pooled_ctx(0, &c));
+    return run_single(c, a, tr);
+  }
+  Gang* G = nullptr;
+  CKI(get_gang(n_gpus, &G));
+  return G->nccl ? run_gang_nccl(G, a) : run_gang_host(G, a);
 }
 
 }  // namespace
@@ -1738,62 +2096,34 @@ extern "C" int dcb200_populations(const float* coords, size_t n_rows, size_t n_c
                                   uint32_t* pops) {
   if (!coords || !pops || (!radii && n_radii)) return fail("dcb200_populations: null argument");
   if (n_radii == 0) return 0;
-  int n_gpus = 0;
-  CKI(gpus_to_use(&n_gpus));
-  n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
-  Trace tr("populations");
-  if (n_gpus == 1) {                         // everything on the device, results land in frame order
-    dcb200_ctx* c = nullptr;
-    CKI(pooled_ctx(0, &c));
-    tr.lap("context");
-    CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
-    tr.lap("upload+layout");
-    CK(c->io_u32.reserve(2 * n_radii * n_rows));
-    uint32_t *dev = c->io_u32.p, *dev2 = dev + n_radii * n_rows;
-    tr.lap("buffers");
-    int rc = dcb200_ctx_populations(c, radii, n_radii, 0, n_rows, dev);
-    if (!rc) rc = dcb200_ctx_to_frame_order(c, dev, n_radii, dev2);
-    if (tr.on) { cudaStreamSynchronize(c->stream); tr.lap("scan"); }
-    if (!rc) {
-      cudaError_t ce = cudaMemcpyAsync(pops, dev2, n_radii * n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
-      if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
-      if (ce != cudaSuccess) rc = fail(std::string("populations download: ") + cudaGetErrorString(ce));
-    }
-    tr.lap("download");
-    return rc;
-  }
-  std::vector<uint32_t> tmp(n_radii * n_rows), perm(n_rows);
-  CKI(on_gpus(n_gpus, [&](int g, int G) -> int {
-    dcb200_ctx* c = nullptr;
-    CKI(pooled_ctx(g, &c));
-    size_t b, e;
-    shard(n_rows, g, G, &b, &e);
-    CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));     // same deterministic order on every device
-    int rc = 0;
-    cudaError_t ce = cudaSuccess;
-    if (e > b) {
-      const size_t rows = e - b;
-      CK(c->io_u32.reserve(n_radii * rows));
-      uint32_t* dev = c->io_u32.p;
-      rc = dcb200_ctx_populations(c, radii, n_radii, b, e, dev);
-      if (!rc)
-        ce = cudaMemcpy2DAsync(tmp.data() + b, n_rows * sizeof(uint32_t), dev, rows * sizeof(uint32_t), rows * sizeof(uint32_t),
-                               n_radii, cudaMemcpyDeviceToHost, c->stream);
-    }
-    if (!rc && ce == cudaSuccess && g == 0)
-      ce = cudaMemcpyAsync(perm.data(), c->perm.p, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
-    if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
-    if (ce != cudaSuccess) rc = fail(std::string("populations download: ") + cudaGetErrorString(ce));
-    return rc;
-  }));
-  for (size_t r = 0; r < n_radii; ++r)
-    for (size_t p = 0; p < n_rows; ++p) pops[r * n_rows + perm[p]] = tmp[r * n_rows + p];
-  return 0;
+  RunArgs a = {coords, n_rows, n_cols, radii, n_radii, 0, pops, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return run_density(a, "populations");
+}
+
+extern "C" int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size_t n_cols, const float* fe, uint32_t* nn_idx,
+                                        float* nn_d2, uint32_t* hd_idx, float* hd_d2) {
+  if (!coords || !fe || !nn_idx || !nn_d2 || !hd_idx || !hd_d2) return fail("dcb200_nearest_neighbors: null argument");
+  RunArgs a = {coords, n_rows, n_cols, nullptr, 0, 0, nullptr, nullptr, fe, nullptr, nn_idx, hd_idx, nn_d2, hd_d2};
+  return run_density(a, "nearest_neighbors");
+}
+
+// One density run without leaving the device(s) between the stages: ONE upload and ONE layout build serve the populations
+// of all radii, the free energies and the neighbour search (the separate entry points above upload and lay out the
+// coordinates once each, like the reference's CUDA functions do).
+extern "C" int dcb200_density_run(const float* coords, size_t n_rows, size_t n_cols, const float* radii, size_t n_radii,
+                                  size_t fe_radius, uint32_t* pops, float* fe_all, float* fe, uint32_t* nn_idx, float* nn_d2,
+                                  uint32_t* hd_idx, float* hd_d2) {
+  if (!coords || !radii || n_radii == 0) return fail("dcb200_density_run: needs coordinates and at least one radius");
+  if (fe_radius >= n_radii) return fail("dcb200_density_run: fe_radius out of range");
+  if (nn_idx && (!nn_d2 || !hd_idx || !hd_d2)) return fail("dcb200_density_run: the four neighbour outputs go together");
+  RunArgs a = {coords, n_rows, n_cols, radii, n_radii, fe_radius, pops, fe_all, nullptr, fe, nn_idx, hd_idx, nn_d2, hd_d2};
+  return run_density(a, "density_run");
 }
 
 extern "C" int dcb200_free_energies(const uint32_t* pops, size_t n, float* fe) {
   if (!pops || !fe) return fail("dcb200_free_energies: null argument");
   if (n == 0) return 0;
+  std::lock_guard<std::mutex> call(g_call_mutex);
   int n_gpus = 0;
   CKI(gpus_to_use(&n_gpus));
   dcb200_ctx* c = nullptr;
@@ -1803,137 +2133,203 @@ extern "C" int dcb200_free_energies(const uint32_t* pops, size_t n, float* fe) {
   CK(c->io_f32.reserve(n));
   uint32_t* dp = c->io_u32.p;
   float* df = c->io_f32.p;
-  int rc = 0;
-  cudaError_t ce = cudaMemcpyAsync(dp, pops, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-  if (ce == cudaSuccess) rc = dcb200_ctx_free_energies(c, dp, n, 0, df);
-  if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(fe, df, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-  if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
-  if (ce != cudaSuccess) rc = fail(std::string("free energies: ") + cudaGetErrorString(ce));
-  return rc;
-}
-
-extern "C" int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size_t n_cols, const float* fe, uint32_t* nn_idx,
-                                        float* nn_d2, uint32_t* hd_idx, float* hd_d2) {
-  if (!coords || !fe || !nn_idx || !nn_d2 || !hd_idx || !hd_d2) return fail("dcb200_nearest_neighbors: null argument");
-  int n_gpus = 0;
-  CKI(gpus_to_use(&n_gpus));
-  n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (n_rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
-  Trace tr("nearest_neighbors");
-  if (n_gpus == 1) {                         // everything on the device: scan, frame-order scatter, four downloads
-    dcb200_ctx* c = nullptr;
-    CKI(pooled_ctx(0, &c));
-    CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
-    tr.lap("upload+layout");
-    CK(c->io_f32.reserve(3 * n_rows));
-    CK(c->io_u32.reserve(2 * n_rows));
-    CK(c->knn.reserve(n_rows));
-    CK(c->khd.reserve(n_rows));
-    float *dfe = c->io_f32.p, *d_nd = dfe + n_rows, *d_hd = d_nd + n_rows;
-    uint32_t *d_ni = c->io_u32.p, *d_hi = d_ni + n_rows;
-    CK(cudaMemcpyAsync(dfe, fe, n_rows * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CKI(dcb200_ctx_nn_prepare(c, dfe));
-    if (tr.on) { cudaStreamSynchronize(c->stream); tr.lap("fe upload+ranks"); }
-    CKI(dcb200_ctx_nn_scan(c, 0, n_rows, (uint64_t*) c->knn.p, (uint64_t*) c->khd.p));
-    CKI(dcb200_ctx_nn_finish(c, (const uint64_t*) c->knn.p, (const uint64_t*) c->khd.p, d_ni, d_nd, d_hi, d_hd));
-    if (tr.on) { cudaStreamSynchronize(c->stream); tr.lap("scan"); }
-    CK(cudaMemcpyAsync(nn_idx, d_ni, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(nn_d2, d_nd, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(hd_idx, d_hi, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(hd_d2, d_hd, n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    tr.lap("download");
-    return 0;
-  }
-  std::vector<unsigned long long> knn(n_rows), khd(n_rows);
-  std::vector<uint32_t> perm(n_rows);
-  CKI(on_gpus(n_gpus, [&](int g, int G) -> int {
-    dcb200_ctx* c = nullptr;
-    CKI(pooled_ctx(g, &c));
-    size_t b, e;
-    shard(n_rows, g, G, &b, &e);
-    CKI(dcb200_ctx_set_coords(c, coords, n_rows, n_cols));
-    CK(c->io_f32.reserve(n_rows));
-    float* dfe = c->io_f32.p;
-    int rc = 0;
-    cudaError_t ce = cudaMemcpyAsync(dfe, fe, n_rows * sizeof(float), cudaMemcpyHostToDevice, c->stream);
-    if (ce == cudaSuccess) rc = dcb200_ctx_nn_prepare(c, dfe);
-    if (ce == cudaSuccess && !rc && e > b) {
-      ce = c->knn.reserve(e - b);
-      if (ce == cudaSuccess) ce = c->khd.reserve(e - b);
-      if (ce == cudaSuccess) rc = dcb200_ctx_nn_scan(c, b, e, (uint64_t*) c->knn.p, (uint64_t*) c->khd.p);
-      if (ce == cudaSuccess && !rc)
-        ce = cudaMemcpyAsync(knn.data() + b, c->knn.p, (e - b) * 8, cudaMemcpyDeviceToHost, c->stream);
-      if (ce == cudaSuccess && !rc)
-        ce = cudaMemcpyAsync(khd.data() + b, c->khd.p, (e - b) * 8, cudaMemcpyDeviceToHost, c->stream);
-    }
-    if (ce == cudaSuccess && !rc && g == 0)
-      ce = cudaMemcpyAsync(perm.data(), c->perm.p, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
-    if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
-    if (ce != cudaSuccess) rc = fail(std::string("nearest neighbours: ") + cudaGetErrorString(ce));
-    return rc;
-  }));
-  for (size_t p = 0; p < n_rows; ++p) {
-    const size_t o = perm[p];
-    const uint32_t a = (uint32_t) (knn[p] >> 32), b = (uint32_t) (khd[p] >> 32);
-    nn_idx[o] = (uint32_t) knn[p];
-    memcpy(&nn_d2[o], &a, 4);
-    hd_idx[o] = (uint32_t) khd[p];
-    memcpy(&hd_d2[o], &b, 4);
-  }
+  CK(cudaMemcpyAsync(dp, pops, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CKI(dcb200_ctx_free_energies(c, dp, n, 0, df));
+  CK(cudaMemcpyAsync(fe, df, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
+// ---- screening ----------------------------------------------------------------------------------
+// A screening session keeps the free-energy-sorted coordinates and the union-find forest on the device(s) between
+// thresholds: ONE upload and ONE layout build per run instead of one per threshold.
+struct dcb200_screen {
+  size_t n = 0, d = 0;
+  int n_gpus = 1;
+  Gang* gang = nullptr;
+  size_t m_done = 0;                      // sorted positions [0, m_done) are in the forest
+  std::vector<DevBuf<uint32_t>> comp;     // per GPU: forest [n] (+ scratch [n_gpus][n] for the gathered forests)
+  std::vector<float> sorted;              // host copy of the sorted coordinates: the per-GPU contexts are shared with the other
+  std::vector<uint64_t> gen;              // entry points; if one of them replaced the layout (gen), the session restores it
+};
+
+// (re)builds the session's layout on every GPU of its gang: one upload (+ NCCL broadcast), keep_order layout
+static int screen_upload(dcb200_screen* s) {
+  Gang* G = s->gang;
+  Rendezvous rv(G->n);
+  const size_t count = s->n * s->d;
+  return on_gpus(G->n, [&](int g, int W) -> int {
+    dcb200_ctx* c = G->ctx[g];
+    auto prep = [&]() -> int {
+      CK(cudaSetDevice(c->device));
+      CK(c->stage.reserve(count));
+      if (g == 0 || !G->nccl) CK(cudaMemcpyAsync(c->stage.p, s->sorted.data(), count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      return 0;
+    };
+    const int r0 = prep();
+    if (W > 1 && G->nccl) {
+      if (!rv.all_ok(r0 == 0)) return r0 ? r0 : fail("another GPU of the gang failed");
+      NCK(nccl_api().Broadcast(c->stage.p, c->stage.p, count, ncclFloat32, 0, G->comm[g], c->stream));
+    } else if (r0) {
+      return r0;
+    }
+    CKI(build_layout(c, c->stage.p, s->n, s->d, true));
+    s->gen[g] = c->layout_gen;
+    return 0;
+  });
+}
+
+extern "C" int dcb200_screen_begin(const float* sorted_coords, size_t n_sorted, size_t n_cols, dcb200_screen** out) {
+  if (!sorted_coords || !out) return fail("dcb200_screen_begin: null argument");
+  *out = nullptr;
+  if (n_sorted == 0 || n_cols == 0) return fail("dcb200_screen_begin: empty coordinate array");
+  std::lock_guard<std::mutex> call(g_call_mutex);
+  dcb200_screen* s = new dcb200_screen();
+  s->n = n_sorted;
+  s->d = n_cols;
+  int rc = gpus_for_rows(n_sorted, &s->n_gpus);
+  if (!rc) rc = get_gang(s->n_gpus, &s->gang);
+  if (rc) {
+    delete s;
+    return rc;
+  }
+  Gang* G = s->gang;
+  s->comp.resize(G->n);
+  s->gen.assign(G->n, 0);
+  s->sorted.assign(sorted_coords, sorted_coords + n_sorted * n_cols);
+  rc = screen_upload(s);
+  if (!rc)
+    rc = on_gpus(G->n, [&](int g, int W) -> int {
+      dcb200_ctx* c = G->ctx[g];
+      CK(cudaSetDevice(c->device));
+      CK(s->comp[g].reserve(n_sorted * (W > 1 ? (size_t) W + 1 : 1)));
+      iota_kernel<<<blocks_for(n_sorted, 256), 256, 0, c->stream>>>(s->comp[g].p, n_sorted);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(c->stream));
+      return 0;
+    });
+  if (rc) {
+    for (auto& b : s->comp) b.release();
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return 0;
+}
+
+// Extends the forest to the sorted positions [0, m_new) (edges: d2 < max_dist2 between a new row and any lower position)
+// and writes every position's representative (smallest sorted position of its cluster) to comp[0, m_new).
+// seed (optional, uint32 [m_done]): replaces the session's forest for the positions done so far (parents <= position).
+extern "C" int dcb200_screen_step(dcb200_screen* s, size_t m_new, float max_dist2, const uint32_t* seed, uint32_t* comp) {
+  if (!s || !comp) return fail("dcb200_screen_step: null argument");
+  if (m_new > s->n) return fail("dcb200_screen_step: m_new exceeds the session's frames");
+  if (m_new < s->m_done) return fail("dcb200_screen_step: thresholds must not decrease within a session");
+  std::lock_guard<std::mutex> call(g_call_mutex);
+  Gang* G = s->gang;
+  const size_t m_prev = s->m_done;
+  bool replaced = false;                  // another entry point used the shared contexts since the last step: restore the layout
+  for (int g = 0; g < G->n; ++g) replaced |= G->ctx[g]->layout_gen != s->gen[g];
+  if (replaced) CKI(screen_upload(s));
+  if (seed)
+    for (size_t p = 0; p < m_prev; ++p)
+      if (seed[p] > p) return fail("dcb200_screen_step: seed[p] must be <= p");
+  Rendezvous rv(G->n);
+  const bool nccl = G->n > 1 && G->nccl;
+  std::vector<std::vector<uint32_t>> parts(nccl ? 0 : G->n);
+  CKI(on_gpus(G->n, [&](int g, int W) -> int {
+    dcb200_ctx* c = G->ctx[g];
+    uint32_t* forest = s->comp[g].p;
+    auto scan = [&]() -> int {
+      CK(cudaSetDevice(c->device));
+      if (seed && m_prev) CK(cudaMemcpyAsync(forest, seed, m_prev * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      if (m_new > m_prev) {
+        // rows are dealt so that every GPU gets about the same number of pairs (row p has p candidates)
+        auto cut = [&](int q) -> size_t {
+          const double lo = (double) m_prev * m_prev, hi = (double) m_new * m_new;
+          return q >= W ? m_new : (size_t) sqrt(lo + (hi - lo) * q / W);
+        };
+        const size_t b = std::max(m_prev, cut(g)), e = std::max(b, cut(g + 1));
+        CKI(dcb200_ctx_screening_scan(c, m_prev, m_new, b, e, max_dist2, forest));
+      }
+      CKI(dcb200_ctx_screening_flatten(c, m_new, forest));
+      return 0;
+    };
+    const int r0 = scan();
+    if (W == 1) {
+      if (r0) return r0;
+      CK(cudaMemcpyAsync(comp, forest, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      return 0;
+    }
+    if (nccl) {
+      // ONE all-gather moves the per-GPU forests; every GPU unions them on the device, so all forests stay identical
+      if (!rv.all_ok(r0 == 0)) return r0 ? r0 : fail("another GPU of the gang failed");
+      uint32_t* all = forest + s->n;
+      NCK(nccl_api().AllGather(forest, all, m_new, ncclUint32, G->comm[g], c->stream));
+      for (int q = 0; q < W; ++q)
+        if (q != g) CKI(dcb200_ctx_screening_merge(c, m_new, forest, all + (size_t) q * m_new));
+      CKI(dcb200_ctx_screening_flatten(c, m_new, forest));
+      if (g == 0) CK(cudaMemcpyAsync(comp, forest, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      return 0;
+    }
+    if (r0) return r0;
+    parts[g].resize(m_new);
+    CK(cudaMemcpyAsync(parts[g].data(), forest, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  }));
+  if (G->n > 1 && !nccl) {
+    // merge the per-GPU forests on the host (roots are the smallest position of a component) and hand the result back
+    std::vector<uint32_t>& par = parts[0];
+    auto find = [&](uint32_t x) {
+      while (par[x] != x) { par[x] = par[par[x]]; x = par[x]; }
+      return x;
+    };
+    for (int g = 1; g < G->n; ++g)
+      for (size_t p = 0; p < m_new; ++p) {
+        uint32_t x = find((uint32_t) p), y = find(parts[g][p]);
+        if (x == y) continue;
+        if (x < y) std::swap(x, y);
+        par[x] = y;
+      }
+    for (size_t p = 0; p < m_new; ++p) comp[p] = find((uint32_t) p);
+    CKI(on_gpus(G->n, [&](int g, int) -> int {
+      dcb200_ctx* c = G->ctx[g];
+      CK(cudaSetDevice(c->device));
+      CK(cudaMemcpyAsync(s->comp[g].p, comp, m_new * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      return 0;
+    }));
+  }
+  s->m_done = m_new;
+  return 0;
+}
+
+extern "C" int dcb200_screen_end(dcb200_screen* s) {
+  if (!s) return 0;
+  std::lock_guard<std::mutex> call(g_call_mutex);
+  for (size_t g = 0; g < s->comp.size(); ++g) {
+    cudaSetDevice(s->gang->ctx[g]->device);
+    s->comp[g].release();
+  }
+  delete s;
+  return 0;
+}
+
+// stateless form: one session per call
 extern "C" int dcb200_screening_step(const float* sorted_coords, size_t n_cols, size_t m_prev, size_t m_new, float max_dist2,
                                      uint32_t* comp) {
   if (!sorted_coords || !comp) return fail("dcb200_screening_step: null argument");
   if (m_prev > m_new) return fail("dcb200_screening_step: m_prev > m_new");
   if (m_new == m_prev) return 0;
-  int n_gpus = 0;
-  CKI(gpus_to_use(&n_gpus));
-  n_gpus = (int) std::max<size_t>(1, std::min<size_t>(n_gpus, (m_new - m_prev + ROWS_PER_CTA - 1) / ROWS_PER_CTA));
   for (size_t p = 0; p < m_prev; ++p)
     if (comp[p] > p) return fail("dcb200_screening_step: comp[p] must be <= p");
-  for (size_t p = m_prev; p < m_new; ++p) comp[p] = (uint32_t) p;
-  std::vector<std::vector<uint32_t>> parts(n_gpus);
-  CKI(on_gpus(n_gpus, [&](int g, int G) -> int {
-    dcb200_ctx* c = nullptr;
-    CKI(pooled_ctx(g, &c));
-    CKI(dcb200_ctx_set_coords_ex(c, sorted_coords, m_new, n_cols, 0, 1));
-    // rows are sharded so that every GPU gets about the same number of pairs (row p has p candidates)
-    auto cut = [&](int q) -> size_t {
-      const double a = (double) m_prev * m_prev, b = (double) m_new * m_new;
-      return q >= G ? m_new : (size_t) sqrt(a + (b - a) * q / G);
-    };
-    const size_t b = std::max(m_prev, cut(g)), e = cut(g + 1);
-    CK(c->io_u32.reserve(m_new));
-    uint32_t* dev = c->io_u32.p;
-    int rc = 0;
-    cudaError_t ce = cudaMemcpyAsync(dev, comp, m_new * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-    if (ce == cudaSuccess) rc = dcb200_ctx_screening_scan(c, m_prev, m_new, b, e, max_dist2, dev);
-    if (ce == cudaSuccess && !rc) rc = dcb200_ctx_screening_flatten(c, m_new, dev);
-    parts[g].resize(m_new);
-    if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(parts[g].data(), dev, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
-    if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(c->stream);
-    if (ce != cudaSuccess) rc = fail(std::string("screening: ") + cudaGetErrorString(ce));
-    return rc;
-  }));
-  if (n_gpus == 1) {
-    memcpy(comp, parts[0].data(), m_new * sizeof(uint32_t));
-    return 0;
-  }
-  // merge the per-GPU forests (roots are the smallest position of a component)
-  std::vector<uint32_t>& par = parts[0];
-  auto find = [&](uint32_t x) {
-    while (par[x] != x) { par[x] = par[par[x]]; x = par[x]; }
-    return x;
-  };
-  for (int g = 1; g < n_gpus; ++g)
-    for (size_t p = 0; p < m_new; ++p) {
-      uint32_t a = find((uint32_t) p), b = find(parts[g][p]);
-      if (a == b) continue;
-      if (a < b) std::swap(a, b);
-      par[a] = b;
-    }
-  for (size_t p = 0; p < m_new; ++p) comp[p] = find((uint32_t) p);
-  return 0;
+  dcb200_screen* s = nullptr;
+  CKI(dcb200_screen_begin(sorted_coords, m_new, n_cols, &s));
+  s->m_done = m_prev;
+  std::vector<uint32_t> seed(comp, comp + m_prev);
+  const int rc = dcb200_screen_step(s, m_new, max_dist2, m_prev ? seed.data() : nullptr, comp);
+  dcb200_screen_end(s);
+  return rc;
 }

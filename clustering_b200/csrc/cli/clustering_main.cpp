@@ -259,6 +259,8 @@ int density_main(const Args& args, const std::string& header_comment) {
   const Coords coords = read_coords(args.str("file"));
   CommentsMap comments = default_comments();
   std::vector<float> free_energies;
+  Neighbours fused_nb;                 // neighbours computed together with the populations (single-radius runs)
+  bool have_fused_nb = false;
 
   if (args.count("input") && (args.count("free-energy") || args.count("nearest-neighbors"))) {
     std::cerr << "error: for input (-i) -D/-B should be used." << std::endl;
@@ -289,8 +291,11 @@ int density_main(const Args& args, const std::string& header_comment) {
       for (float r : radii) log << r << ", ";
       log << "\b\b  " << std::endl;
       log << "    using CUDA" << std::endl;
+      // one run on the device(s): the populations of all radii and, when wanted, their free energies (one upload, one layout)
       std::vector<uint32_t> pops(radii.size() * coords.n_rows);
-      if (dcb200_populations(coords.data.data(), coords.n_rows, coords.n_cols, radii.data(), radii.size(), pops.data()))
+      std::vector<float> fes(args.count("free-energy") ? radii.size() * coords.n_rows : 0);
+      if (dcb200_density_run(coords.data.data(), coords.n_rows, coords.n_cols, radii.data(), radii.size(), 0, pops.data(),
+                             fes.empty() ? nullptr : fes.data(), nullptr, nullptr, nullptr, nullptr, nullptr))
         die_cuda("populations");
       log << "    storing results" << std::endl;
       // the reference keeps the results in a map keyed by radius: one file per DISTINCT radius, ascending
@@ -303,10 +308,9 @@ int density_main(const Args& args, const std::string& header_comment) {
         const uint32_t* p = pops.data() + r * coords.n_rows;
         if (args.count("population"))
           write_pops(stringprintf((args.str("population") + "_%f").c_str(), radii[r]), p, coords.n_rows, header_comment, comments);
-        if (args.count("free-energy")) {
-          const std::vector<float> fe = free_energies_of(std::vector<uint32_t>(p, p + coords.n_rows));
-          write_fes(stringprintf((args.str("free-energy") + "_%f").c_str(), radii[r]), fe.data(), fe.size(), header_comment, comments);
-        }
+        if (args.count("free-energy"))
+          write_fes(stringprintf((args.str("free-energy") + "_%f").c_str(), radii[r]), fes.data() + r * coords.n_rows, coords.n_rows,
+                    header_comment, comments);
       }
     } else {
       float radius_lump = 1.0;
@@ -328,12 +332,27 @@ int density_main(const Args& args, const std::string& header_comment) {
       const float radius = args.count("radius") ? to_float(args.str("radius"), "radius") : radius_lump;
       log << "    using radius: " << radius << std::endl;
       comments["clustering_radius"] = radius;
-      const std::vector<uint32_t> pops = populations_single(coords, radius);
+      // when the neighbours are computed in this run as well, one density run serves all three stages (one upload, one
+      // layout build); the neighbour section below then finds them ready
+      const bool fuse_nn = !args.count("nearest-neighbors-input") && (args.count("nearest-neighbors") || args.count("output"));
+      std::vector<uint32_t> pops;
+      if (fuse_nn) {
+        pops.resize(coords.n_rows);
+        free_energies.resize(coords.n_rows);
+        fused_nb.nn_idx.resize(coords.n_rows); fused_nb.hd_idx.resize(coords.n_rows);
+        fused_nb.nn_d2.resize(coords.n_rows); fused_nb.hd_d2.resize(coords.n_rows);
+        if (dcb200_density_run(coords.data.data(), coords.n_rows, coords.n_cols, &radius, 1, 0, pops.data(), nullptr, free_energies.data(),
+                               fused_nb.nn_idx.data(), fused_nb.nn_d2.data(), fused_nb.hd_idx.data(), fused_nb.hd_d2.data()))
+          die_cuda("density run");
+        have_fused_nb = true;
+      } else {
+        pops = populations_single(coords, radius);
+      }
       if (args.count("population")) {
         log << "    storing population in: " << args.str("population") << std::endl;
         write_pops(args.str("population"), pops.data(), pops.size(), header_comment, comments);
       }
-      free_energies = free_energies_of(pops);
+      if (!fuse_nn) free_energies = free_energies_of(pops);
       if (args.count("free-energy")) {
         log << "    storing free energy in: " << args.str("free-energy") << std::endl;
         write_fes(args.str("free-energy"), free_energies.data(), free_energies.size(), header_comment, comments);
@@ -354,7 +373,8 @@ int density_main(const Args& args, const std::string& header_comment) {
       exit(EXIT_FAILURE);
     }
     log << "    calculating nearest neighbors" << std::endl;
-    nb = nearest_neighbours(coords, free_energies);
+    if (have_fused_nb) nb = std::move(fused_nb);
+    else nb = nearest_neighbours(coords, free_energies);
     if (comments["lumping_radius"] == 0.) {
       const double sigma2 = sigma2_of(nb.nn_d2);
       const float radius_lump = sqrt(4 * sigma2);
@@ -422,20 +442,23 @@ int density_main(const Args& args, const std::string& header_comment) {
       // the threshold compared with the free energies and the number printed into the file name
       const float t_to_low = t_to - t_step / 10.0f + t_step;
       const float t_to_high = t_to + t_step / 10.0f + t_step;
-      std::vector<uint32_t> clustering, next(coords.n_rows);
+      // one screening run for all thresholds: free energies sorted once, sorted coordinates resident on the device(s);
+      // the labels are those of the reference's call-per-threshold loop (density_clustering.cpp:806-816)
+      std::vector<uint32_t> clustering(coords.n_rows);
+      dcb200_screening_run* run = nullptr;
+      if (dcb200_screening_begin(free_energies.data(), nb.nn_d2.data(), coords.data.data(), coords.n_rows, coords.n_cols, &run))
+        die_cuda("screening");
       for (float t = t_from; (t < t_to_low) && !(t_to_high < t); t += t_step) {
-        if (dcb200_screening(free_energies.data(), nb.nn_d2.data(), t, coords.data.data(), coords.n_rows, coords.n_cols,
-                             clustering.empty() ? nullptr : clustering.data(), next.data()))
-          die_cuda("screening");
+        if (dcb200_screening_next(run, t, clustering.data())) die_cuda("screening");
         if (verbose) {
           size_t below = 0;
           for (float f : free_energies) below += f <= t;
           std::cout << "    " << std::setw(6) << stringprintf("%.2f", t) << " " << std::setw(9) << below << std::endl;
         }
-        clustering = next;
         write_clustered_trajectory(stringprintf((output_file + ".%0.2f").c_str(), t), clustering.data(), clustering.size(),
                                    header_comment, comments);
       }
+      dcb200_screening_end(run);
     } else {
       std::cerr << "error: one of -T/-i is needed to generate output." << std::endl;
       exit(EXIT_FAILURE);
@@ -518,5 +541,11 @@ int main(int argc, char* argv[]) {
   header << "\n#\n# Copyright (c) 2015-2019 Florian Sittel and Daniel Nagel\n"
          << "# please cite the corresponding paper, "
          << "see https://github.com/moldyn/clustering\n";
-  return density_main(args, header.str());
+  try {
+    return density_main(args, header.str());
+  } catch (const dcb_cli::IoError& e) {
+    // the reference's tools print the message and exit (tools.hxx:44-47, :236-243, tools.cpp:106-110)
+    std::cerr << e.what() << std::endl;
+    return EXIT_FAILURE;
+  }
 }

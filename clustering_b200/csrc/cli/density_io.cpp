@@ -23,10 +23,7 @@ CommentsMap default_comments() {
 
 static std::string slurp(const std::string& filename, const char* what_for) {
   FILE* f = fopen(filename.c_str(), "rb");
-  if (!f) {
-    std::cerr << "error: cannot open file '" << filename << "'" << what_for << std::endl;
-    exit(EXIT_FAILURE);
-  }
+  if (!f) throw IoError("error: cannot open file '" + filename + "'" + what_for);
   std::string buf;
   fseek(f, 0, SEEK_END);
   const long sz = ftell(f);
@@ -124,10 +121,7 @@ std::vector<float> read_single_column_float(const std::string& filename) {
   std::vector<float> out;
   const int kinds[1] = {1};
   scan_records(buf, kinds, 1, [&](const double* v) { out.push_back((float) v[0]); });
-  if (out.empty()) {
-    std::cerr << "error: opened empty file '" << filename << "'" << std::endl;
-    exit(EXIT_FAILURE);
-  }
+  if (out.empty()) throw IoError("error: opened empty file '" + filename + "'");
   return out;
 }
 
@@ -136,10 +130,7 @@ std::vector<std::size_t> read_single_column_size(const std::string& filename) {
   std::vector<std::size_t> out;
   const int kinds[1] = {0};
   scan_records(buf, kinds, 1, [&](const double* v) { out.push_back((std::size_t) v[0]); });
-  if (out.empty()) {
-    std::cerr << "error: opened empty file '" << filename << "'" << std::endl;
-    exit(EXIT_FAILURE);
-  }
+  if (out.empty()) throw IoError("error: opened empty file '" + filename + "'");
   return out;
 }
 
@@ -221,10 +212,7 @@ struct OutFile {
   std::string buf;
   explicit OutFile(const std::string& filename) {
     f = fopen(filename.c_str(), "wb");
-    if (!f) {
-      std::cerr << "error: cannot open file '" << filename << "' for writing." << std::endl;
-      exit(EXIT_FAILURE);
-    }
+    if (!f) throw IoError("error: cannot open file '" + filename + "' for writing.");
     buf.reserve(1 << 22);
   }
   void flush_if_big() {
@@ -304,72 +292,100 @@ void write_neighborhood(const std::string& filename, const uint32_t* nn_idx, con
 // ---- C ABI of the file formats (include/dcb200.h, section "file formats") -------------------------------------
 #include "../../../include/dcb200.h"
 
+extern "C" int dcb200_internal_fail(const char* msg);
+
 namespace {
 dcb_cli::CommentsMap map_of(const char* const* keys, const float* vals, size_t n) {
   dcb_cli::CommentsMap m;
   for (size_t i = 0; i < n; ++i) m[keys[i]] = vals[i];
   return m;
 }
+// runs fn; an I/O failure becomes an error status (message through dcb200_last_error), never an exit
+template <class Fn>
+int guarded(const char* what, Fn&& fn) {
+  try {
+    fn();
+    return 0;
+  } catch (const std::exception& e) {
+    return dcb200_internal_fail((std::string(what) + ": " + e.what()).c_str());
+  }
+}
 }  // namespace
+
+#define DCB_IO_NEED(cond, what) \
+  if (!(cond)) return dcb200_internal_fail(what ": null argument")
 
 extern "C" int dcb200_io_write_pops(const char* filename, const uint32_t* pops, size_t n, const char* header, const char* const* keys,
                                     const float* vals, size_t n_comments) {
-  dcb_cli::write_pops(filename, pops, n, header ? header : "", map_of(keys, vals, n_comments));
-  return 0;
+  DCB_IO_NEED(filename && (pops || !n) && ((keys && vals) || !n_comments), "dcb200_io_write_pops");
+  return guarded("dcb200_io_write_pops", [&] { dcb_cli::write_pops(filename, pops, n, header ? header : "", map_of(keys, vals, n_comments)); });
 }
 extern "C" int dcb200_io_write_fes(const char* filename, const float* fe, size_t n, const char* header, const char* const* keys,
                                    const float* vals, size_t n_comments) {
-  dcb_cli::write_fes(filename, fe, n, header ? header : "", map_of(keys, vals, n_comments));
-  return 0;
+  DCB_IO_NEED(filename && (fe || !n) && ((keys && vals) || !n_comments), "dcb200_io_write_fes");
+  return guarded("dcb200_io_write_fes", [&] { dcb_cli::write_fes(filename, fe, n, header ? header : "", map_of(keys, vals, n_comments)); });
 }
 extern "C" int dcb200_io_write_states(const char* filename, const uint32_t* states, size_t n, const char* header,
                                       const char* const* keys, const float* vals, size_t n_comments) {
-  dcb_cli::write_clustered_trajectory(filename, states, n, header ? header : "", map_of(keys, vals, n_comments));
-  return 0;
+  DCB_IO_NEED(filename && (states || !n) && ((keys && vals) || !n_comments), "dcb200_io_write_states");
+  return guarded("dcb200_io_write_states",
+                 [&] { dcb_cli::write_clustered_trajectory(filename, states, n, header ? header : "", map_of(keys, vals, n_comments)); });
 }
 extern "C" int dcb200_io_write_neighborhood(const char* filename, const uint32_t* nn_idx, const float* nn_d2, const uint32_t* hd_idx,
                                             const float* hd_d2, size_t n, const char* header, const char* const* keys,
                                             const float* vals, size_t n_comments) {
-  dcb_cli::write_neighborhood(filename, nn_idx, nn_d2, hd_idx, hd_d2, n, header ? header : "", map_of(keys, vals, n_comments));
-  return 0;
+  DCB_IO_NEED(filename && ((nn_idx && nn_d2 && hd_idx && hd_d2) || !n) && ((keys && vals) || !n_comments), "dcb200_io_write_neighborhood");
+  return guarded("dcb200_io_write_neighborhood", [&] {
+    dcb_cli::write_neighborhood(filename, nn_idx, nn_d2, hd_idx, hd_d2, n, header ? header : "", map_of(keys, vals, n_comments));
+  });
 }
 extern "C" int dcb200_io_read_coords(const char* filename, float* out, size_t capacity, size_t* n_rows, size_t* n_cols) {
-  const dcb_cli::Coords c = dcb_cli::read_coords(filename);
-  *n_rows = c.n_rows;
-  *n_cols = c.n_cols;
-  if (out) memcpy(out, c.data.data(), std::min(capacity, c.data.size()) * sizeof(float));
-  return 0;
+  DCB_IO_NEED(filename && n_rows && n_cols, "dcb200_io_read_coords");
+  return guarded("dcb200_io_read_coords", [&] {
+    const dcb_cli::Coords c = dcb_cli::read_coords(filename);
+    *n_rows = c.n_rows;
+    *n_cols = c.n_cols;
+    if (out) memcpy(out, c.data.data(), std::min(capacity, c.data.size()) * sizeof(float));
+  });
 }
 extern "C" int dcb200_io_read_column_float(const char* filename, float* out, size_t capacity, size_t* n) {
-  const std::vector<float> v = dcb_cli::read_single_column_float(filename);
-  *n = v.size();
-  if (out) memcpy(out, v.data(), std::min(capacity, v.size()) * sizeof(float));
-  return 0;
+  DCB_IO_NEED(filename && n, "dcb200_io_read_column_float");
+  return guarded("dcb200_io_read_column_float", [&] {
+    const std::vector<float> v = dcb_cli::read_single_column_float(filename);
+    *n = v.size();
+    if (out) memcpy(out, v.data(), std::min(capacity, v.size()) * sizeof(float));
+  });
 }
 extern "C" int dcb200_io_read_column_uint(const char* filename, uint32_t* out, size_t capacity, size_t* n) {
-  const std::vector<std::size_t> v = dcb_cli::read_single_column_size(filename);
-  *n = v.size();
-  if (out)
-    for (size_t i = 0; i < std::min(capacity, v.size()); ++i) out[i] = (uint32_t) v[i];
-  return 0;
+  DCB_IO_NEED(filename && n, "dcb200_io_read_column_uint");
+  return guarded("dcb200_io_read_column_uint", [&] {
+    const std::vector<std::size_t> v = dcb_cli::read_single_column_size(filename);
+    *n = v.size();
+    if (out)
+      for (size_t i = 0; i < std::min(capacity, v.size()); ++i) out[i] = (uint32_t) v[i];
+  });
 }
 extern "C" int dcb200_io_read_neighborhood(const char* filename, uint32_t* nn_idx, float* nn_d2, uint32_t* hd_idx, float* hd_d2,
                                            size_t capacity, size_t* n) {
-  std::vector<uint32_t> a, c;
-  std::vector<float> b, d;
-  dcb_cli::read_neighborhood(filename, a, b, c, d);
-  *n = a.size();
-  const size_t m = std::min(capacity, a.size());
-  if (nn_idx) memcpy(nn_idx, a.data(), m * 4);
-  if (nn_d2) memcpy(nn_d2, b.data(), m * 4);
-  if (hd_idx) memcpy(hd_idx, c.data(), m * 4);
-  if (hd_d2) memcpy(hd_d2, d.data(), m * 4);
-  return 0;
+  DCB_IO_NEED(filename && n, "dcb200_io_read_neighborhood");
+  return guarded("dcb200_io_read_neighborhood", [&] {
+    std::vector<uint32_t> a, c;
+    std::vector<float> b, d;
+    dcb_cli::read_neighborhood(filename, a, b, c, d);
+    *n = a.size();
+    const size_t m = std::min(capacity, a.size());
+    if (nn_idx) memcpy(nn_idx, a.data(), m * 4);
+    if (nn_d2) memcpy(nn_d2, b.data(), m * 4);
+    if (hd_idx) memcpy(hd_idx, c.data(), m * 4);
+    if (hd_d2) memcpy(hd_d2, d.data(), m * 4);
+  });
 }
 extern "C" int dcb200_io_read_comment(const char* filename, const char* key, float current, float* value) {
-  dcb_cli::CommentsMap m;
-  m[key] = current;
-  dcb_cli::read_comments(filename, m);
-  *value = m[key];
-  return 0;
+  DCB_IO_NEED(filename && key && value, "dcb200_io_read_comment");
+  return guarded("dcb200_io_read_comment", [&] {
+    dcb_cli::CommentsMap m;
+    m[key] = current;
+    dcb_cli::read_comments(filename, m);
+    *value = m[key];
+  });
 }

@@ -6,10 +6,18 @@
 #include <cstddef>
 #include <cstdint>
 #include <map>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
 namespace dcb_cli {
+
+// An unreadable / unwritable / empty file.  The `clustering` driver prints the message and exits like the reference's
+// tools do; the C ABI (dcb200_io_*) turns it into an error status + dcb200_last_error() -- a library must not end the
+// process that embeds it.
+struct IoError : std::runtime_error {
+  explicit IoError(const std::string& msg) : std::runtime_error(msg) {}
+};
 
 // "#@ key = value" parameters carried from file to file (reference: commentsMap, clustering.cpp:483-493)
 typedef std::map<std::string, float> CommentsMap;

@@ -20,7 +20,10 @@ constexpr int ROWS_PER_CTA = N_CONSUMERS * RI;   // 1024
 constexpr int LD_ALIGN = 256;                 // frame arrays are padded to a multiple of this (covers every tile width)
 // depth of the tile ring: deep for the register kernels (consumer warps that skip or finish a tile early run ahead
 // instead of idling), shallow for the run-time-D kernels whose tiles are large
-template <int D> struct StagesOf { static constexpr int n = D == 0 ? 3 : 6; };
+#ifndef DCB_STAGES
+#define DCB_STAGES 6
+#endif
+template <int D> struct StagesOf { static constexpr int n = D == 0 ? 3 : DCB_STAGES; };
 constexpr int MAX_BINS = 31;                  // distinct radii per population pass (table of 32 incl. +inf)
 constexpr int MAX_TEMPLATE_D = 16;            // dims held in registers by the specialised kernels
 
@@ -57,6 +60,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+// the same with a real pause between polls, for a warp that is usually far ahead of the ones it waits for (a producer whose
+// ring is full): ncu counted 5.6e9 poll iterations of the suspend-hinted loop per 258 ms launch, ~10 % of all instructions
+// issued, in the very scheduler slots the consumer warps of that SM sub-partition need
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) __nanosleep(400);
+}
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16 B aligned)
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

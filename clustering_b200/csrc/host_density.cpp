@@ -76,16 +76,23 @@ extern "C" int dcb200_sorted_cluster_names(const uint32_t* states, size_t n, uin
   return 0;
 }
 
-// One screening threshold = reference screening() (density_clustering_common.cpp:37-134) with
-// prepare_initial_clustering (:382-435), high_density_neighborhood (:292-332), lump_initial_clusters
-// (:506-555) and normalized_cluster_names (:437-456) of density_clustering.cpp.
+// Screening = reference screening() (density_clustering_common.cpp:37-134) with prepare_initial_clustering (:382-435),
+// high_density_neighborhood (:292-332), lump_initial_clusters (:506-555) and normalized_cluster_names (:437-456) of
+// density_clustering.cpp.
 //
-// Closed form used here: the clusters are the connected components of
-//   { sorted positions a, b < M : d2(a, b) < (float)(4 sigma2) },   M = #{fe <= threshold},
-// grown from the clusters of `initial` (frames that already carry a name are not expanded again, :98-99);
-// a component keeps the smallest initial name among its members, components without named members
-// are named max(initial)+1, +2, ... in the order of their first sorted member (:527-535), and finally
-// the names are renumbered 1..K in ascending order (:437-456).
+// Closed form.  With S = the free-energy-sorted frames, M = #{fe <= threshold}, cut = (float)(4 sigma2), "visited" = the sorted
+// positions below M that carry a name in `initial` (the reference never expands those, :98-99, :417-427):
+//   * the clusters are the connected components of { positions < M } under
+//       - same initial name  (frames that share a name are one cluster from the start), and
+//       - d2(a, b) < cut for an UNVISITED a and any b < M  (the neighbourhoods the reference scans);
+//   * a component keeps the smallest initial name among its members; components without named members get fresh names
+//     max(initial)+1, +2, ... in the order of their first sorted member (:527-535);
+//   * the names in use below the threshold are renumbered 1..K in ascending order (:437-456); frames above the threshold
+//     keep their (renumbered) initial name if it is still in use and become 0 otherwise.
+// The pair scan runs on the GPU(s) over the frames in the order [visited..., unvisited...] (both ascending): every edge has
+// an unvisited row and a column before it, which is what dcb200_screen_step scans.  When `initial` is the labelling of a
+// lower threshold of the same data (the reference's driver loop, density_clustering.cpp:806-816) the visited frames are a
+// prefix of S and this order is S itself.
 #include <chrono>
 #include <stdio.h>
 #include <stdlib.h>
@@ -101,58 +108,21 @@ struct Lap {          // DCB200_TRACE=1: wall-clock phases on stderr (diagnostic
     last = now;
   }
 };
-}  // namespace
 
-namespace {
-// The reference's driver calls screening() once per threshold with the same free energies (density_clustering.cpp:806-816)
-// and sorts them again every time (:401); at 5M frames that sort is 0.3 s per threshold, far more than the pair scan.
-// The order is therefore kept between calls, keyed by the CONTENT of the array (a 64-bit hash, ~2 ms): a changed input
-// simply misses.
-struct OrderCache {
-  std::mutex mu;
-  size_t n = 0;
-  uint64_t hash = 0;
-  std::vector<uint32_t> order;
-};
-OrderCache g_order_cache;
-
-uint64_t hash_floats(const float* v, size_t n) {
-  // 4 independent multiply-xor lanes over 64-bit words, folded at the end
-  uint64_t h[4] = {0x9e3779b97f4a7c15ull, 0xc2b2ae3d27d4eb4full, 0x165667b19e3779f9ull, 0x27d4eb2f165667c5ull};
-  const size_t words = n / 2;
-  const uint64_t* w = reinterpret_cast<const uint64_t*>(v);
-  size_t i = 0;
-  for (; i + 4 <= words; i += 4)
-    for (int q = 0; q < 4; ++q) {
-      uint64_t x;
-      memcpy(&x, w + i + q, 8);
-      h[q] = (h[q] ^ x) * 0x100000001b3ull;
-      h[q] ^= h[q] >> 29;
-    }
-  uint64_t r = h[0] ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7) ^ (uint64_t) n;
-  for (size_t k = i * 2; k < n; ++k) {
-    uint32_t x;
-    memcpy(&x, v + k, 4);
-    r = (r ^ x) * 0x100000001b3ull;
+size_t frames_below(const float* fe, const std::vector<uint32_t>& order, float threshold) {
+  // first_frame_above_threshold = upper_bound over the sorted free energies (:403-410)
+  size_t lo = 0, hi = order.size();
+  while (lo < hi) {
+    const size_t mid = (lo + hi) / 2;
+    if (threshold < fe[order[mid]]) hi = mid; else lo = mid + 1;
   }
-  return r;
+  return lo;
 }
 
-int cached_order(const float* fe, size_t n, std::vector<uint32_t>& out) {
-  const uint64_t h = hash_floats(fe, n);
-  std::lock_guard<std::mutex> lock(g_order_cache.mu);
-  if (g_order_cache.n != n || g_order_cache.hash != h || g_order_cache.order.size() != n) {
-    g_order_cache.order.resize(n);
-    const int rc = dcb200_sorted_free_energies(fe, n, g_order_cache.order.data());
-    if (rc) {
-      g_order_cache.n = 0;
-      return rc;
-    }
-    g_order_cache.n = n;
-    g_order_cache.hash = h;
-  }
-  out = g_order_cache.order;
-  return 0;
+void gather_rows(const float* coords, size_t n_cols, const uint32_t* frames, size_t m, float* out) {
+#pragma omp parallel for schedule(static)
+  for (long long p = 0; p < (long long) m; ++p)
+    memcpy(out + (size_t) p * n_cols, coords + (size_t) frames[p] * n_cols, n_cols * sizeof(float));
 }
 }  // namespace
 
@@ -161,72 +131,158 @@ extern "C" int dcb200_screening(const float* fe, const float* nn_d2, float thres
   if (!fe || !nn_d2 || !coords || !labels) return dcb200_internal_fail("dcb200_screening: null argument");
   if (n_rows == 0) return 0;
   Lap lap;
-  std::vector<uint32_t> order;
-  int rc = cached_order(fe, n_rows, order);
+  std::vector<uint32_t> order(n_rows);
+  int rc = dcb200_sorted_free_energies(fe, n_rows, order.data());
   if (rc) return rc;
   lap("order");
-  // first_frame_above_threshold = upper_bound over the sorted free energies (:403-410)
-  size_t lo = 0, hi = n_rows;
-  while (lo < hi) {
-    const size_t mid = (lo + hi) / 2;
-    if (threshold < fe[order[mid]]) hi = mid; else lo = mid + 1;
-  }
-  const size_t M = lo;
+  const size_t M = frames_below(fe, order, threshold);
   double sigma2 = 0.0;
   dcb200_sigma2(nn_d2, n_rows, &sigma2);
   const float max_dist2 = (float) (4 * sigma2);
 
-  // frames that already carry a name are "visited" (:417-427); they must be the first m_prev sorted frames
-  size_t m_prev = 0;
+  // scan order: visited positions first, then the unvisited ones (both ascending)
+  std::vector<uint32_t> pos;                     // scan position -> sorted position
+  pos.reserve(M);
   uint32_t max_name = 0;
+  size_t m_vis = 0;
   if (initial) {
     for (size_t i = 0; i < n_rows; ++i) max_name = std::max(max_name, initial[i]);
-    while (m_prev < M && initial[order[m_prev]] != 0) ++m_prev;
-    for (size_t p = m_prev; p < M; ++p)
-      if (initial[order[p]] != 0)
-        return dcb200_internal_fail(
-            "dcb200_screening: initial clusters are not a prefix of the free-energy order "
-            "(they must come from a screening at a lower threshold of the same data)");
+    for (size_t p = 0; p < M; ++p)
+      if (initial[order[p]] != 0) pos.push_back((uint32_t) p);
+    m_vis = pos.size();
+    for (size_t p = 0; p < M; ++p)
+      if (initial[order[p]] == 0) pos.push_back((uint32_t) p);
+  } else {
+    for (size_t p = 0; p < M; ++p) pos.push_back((uint32_t) p);
   }
   std::vector<uint32_t> comp(M);
   {
-    // representative of an initial cluster = its first sorted member
-    std::vector<uint32_t> first(max_name + 1, 0xffffffffu);
-    for (size_t p = 0; p < m_prev; ++p) {
-      uint32_t& f = first[initial[order[p]]];
-      if (f == 0xffffffffu) f = (uint32_t) p;
-      comp[p] = f;
+    // representative of an initial cluster = its first member in scan order
+    std::vector<uint32_t> first((size_t) max_name + 1, 0xffffffffu);
+    for (size_t q = 0; q < m_vis; ++q) {
+      uint32_t& f = first[initial[order[pos[q]]]];
+      if (f == 0xffffffffu) f = (uint32_t) q;
+      comp[q] = f;
     }
   }
-  if (M > m_prev) {
+  if (M > m_vis) {
+    std::vector<uint32_t> frames(M);
+    for (size_t q = 0; q < M; ++q) frames[q] = order[pos[q]];
     std::vector<float> sorted((size_t) M * n_cols);
-#pragma omp parallel for schedule(static)
-    for (long long p = 0; p < (long long) M; ++p)
-      memcpy(&sorted[(size_t) p * n_cols], coords + (size_t) order[p] * n_cols, n_cols * sizeof(float));
+    gather_rows(coords, n_cols, frames.data(), M, sorted.data());
     lap("prepare+gather");
-    rc = dcb200_screening_step(sorted.data(), n_cols, m_prev, M, max_dist2, comp.data());
+    rc = dcb200_screening_step(sorted.data(), n_cols, m_vis, M, max_dist2, comp.data());
     if (rc) return rc;
     lap("pair scan (GPU)");
   }
-  // name of a component: smallest initial name among its members, else a fresh name by first member
+  // name of a component: smallest initial name among its members, else a fresh name ordered by its first sorted member
+  // (its unvisited members are in ascending sorted order in the scan, so that member is the representative)
   const uint32_t none = 0xffffffffu;
   std::vector<uint32_t> name_of_rep(M, none);
-  for (size_t p = 0; p < m_prev; ++p) {
-    uint32_t& nm = name_of_rep[comp[p]];
-    nm = std::min(nm, initial[order[p]]);
+  for (size_t q = 0; q < m_vis; ++q) {
+    uint32_t& nm = name_of_rep[comp[q]];
+    nm = std::min(nm, initial[order[pos[q]]]);
   }
-  // ascending order of names: named components by name; fresh ones (all larger) by representative
-  std::vector<std::pair<uint64_t, uint32_t>> keys;
-  for (size_t p = 0; p < M; ++p)
-    if (comp[p] == p) {
-      const uint64_t k = name_of_rep[p] != none ? (uint64_t) name_of_rep[p] : ((uint64_t) 1 << 32) + p;
-      keys.push_back(std::make_pair(k, (uint32_t) p));
+  std::vector<std::pair<uint64_t, uint32_t>> keys;          // (old name, representative), ascending = the reference's renumbering
+  for (size_t q = 0; q < M; ++q)
+    if (comp[q] == q) {
+      const uint64_t k = name_of_rep[q] != none ? (uint64_t) name_of_rep[q] : ((uint64_t) 1 << 32) + pos[q];
+      keys.push_back(std::make_pair(k, (uint32_t) q));
     }
   std::sort(keys.begin(), keys.end());
   std::vector<uint32_t> final_name(M, 0);
-  for (size_t q = 0; q < keys.size(); ++q) final_name[keys[q].second] = (uint32_t) (q + 1);
-  memset(labels, 0, n_rows * sizeof(uint32_t));
-  for (size_t p = 0; p < M; ++p) labels[order[p]] = final_name[comp[p]];
+  for (size_t k = 0; k < keys.size(); ++k) final_name[keys[k].second] = (uint32_t) (k + 1);
+  if (initial) {
+    // frames above the threshold: their initial name, renumbered, if a cluster below the threshold still carries it
+    std::vector<uint32_t> renamed((size_t) max_name + 1, 0);
+    for (size_t k = 0; k < keys.size(); ++k)
+      if (keys[k].first <= max_name) renamed[keys[k].first] = (uint32_t) (k + 1);
+    for (size_t i = 0; i < n_rows; ++i) labels[i] = renamed[initial[i]];
+  } else {
+    memset(labels, 0, n_rows * sizeof(uint32_t));
+  }
+  for (size_t q = 0; q < M; ++q) labels[order[pos[q]]] = final_name[comp[q]];
   lap("names");
+  return 0;
+}
+
+// ---- a whole screening run: the thresholds of one `clustering density -T` call --------------------------------------
+// The reference's driver (density_clustering.cpp:806-816) calls screening() once per threshold with the previous labels;
+// every call sorts the free energies again (:401) and, on its CUDA path, uploads all coordinates again (cuda.cu:505-571).
+// A run does both ONCE: the free-energy order is kept, the sorted coordinates and the union-find forest stay on the
+// device(s) (dcb200_screen_*).  Labels are identical to the call-per-threshold form: with the previous labels as initial
+// clusters, named clusters keep their order and fresh ones follow, i.e. clusters are numbered by their first sorted member.
+struct dcb200_screening_run {
+  size_t n = 0, d = 0;
+  std::vector<float> fe;
+  std::vector<uint32_t> order;
+  float max_dist2 = 0.f;
+  dcb200_screen* scan = nullptr;
+  std::vector<uint32_t> comp;
+  size_t m_done = 0;
+  float last_threshold = 0.f;
+  bool any = false;
+};
+
+extern "C" int dcb200_screening_begin(const float* fe, const float* nn_d2, const float* coords, size_t n_rows, size_t n_cols,
+                                      dcb200_screening_run** out) {
+  if (!fe || !nn_d2 || !coords || !out) return dcb200_internal_fail("dcb200_screening_begin: null argument");
+  *out = nullptr;
+  if (n_rows == 0 || n_cols == 0) return dcb200_internal_fail("dcb200_screening_begin: empty input");
+  Lap lap;
+  dcb200_screening_run* r = new dcb200_screening_run();
+  r->n = n_rows;
+  r->d = n_cols;
+  r->fe.assign(fe, fe + n_rows);
+  r->order.resize(n_rows);
+  int rc = dcb200_sorted_free_energies(fe, n_rows, r->order.data());
+  double sigma2 = 0.0;
+  if (!rc) rc = dcb200_sigma2(nn_d2, n_rows, &sigma2);
+  r->max_dist2 = (float) (4 * sigma2);
+  lap("order");
+  if (!rc) {
+    std::vector<float> sorted(n_rows * n_cols);
+    gather_rows(coords, n_cols, r->order.data(), n_rows, sorted.data());
+    lap("gather");
+    rc = dcb200_screen_begin(sorted.data(), n_rows, n_cols, &r->scan);
+    lap("upload+layout");
+  }
+  if (rc) {
+    delete r;
+    return rc;
+  }
+  r->comp.resize(n_rows);
+  *out = r;
+  return 0;
+}
+
+extern "C" int dcb200_screening_next(dcb200_screening_run* r, float threshold, uint32_t* labels) {
+  if (!r || !labels) return dcb200_internal_fail("dcb200_screening_next: null argument");
+  if (r->any && threshold < r->last_threshold) return dcb200_internal_fail("dcb200_screening_next: thresholds must not decrease within a run");
+  Lap lap;
+  const size_t M = frames_below(r->fe.data(), r->order, threshold);
+  if (M > 0) {
+    const int rc = dcb200_screen_step(r->scan, M, r->max_dist2, nullptr, r->comp.data());
+    if (rc) return rc;
+  }
+  lap("pair scan (GPU)");
+  r->m_done = M;
+  r->last_threshold = threshold;
+  r->any = true;
+  // clusters numbered 1..K by ascending representative (= first sorted member)
+  std::vector<uint32_t> rank(M, 0);
+  uint32_t k = 0;
+  for (size_t p = 0; p < M; ++p)
+    if (r->comp[p] == p) rank[p] = ++k;
+  memset(labels, 0, r->n * sizeof(uint32_t));
+  for (size_t p = 0; p < M; ++p) labels[r->order[p]] = rank[r->comp[p]];
+  lap("names");
+  return 0;
+}
+
+extern "C" int dcb200_screening_end(dcb200_screening_run* r) {
+  if (!r) return 0;
+  dcb200_screen_end(r->scan);
+  delete r;
   return 0;
 }

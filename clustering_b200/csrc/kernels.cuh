@@ -581,6 +581,8 @@ struct PopsArgs {
                             // own perturbation of the boundaries (32 ulp)
   int dense_lanes;          // a 4x4 step is binned branch-free when at least this many lanes hold a candidate pair,
                             // else candidate by candidate
+  int interleave;           // diagnostics: rows interleaved over the block, every warp scans every streamed tile
+  int proj_prune;           // separating-axis test of (row group, tile) units along the line between their centres
 };
 
 __host__ __device__ inline size_t pops_smem_bytes(size_t ring_bytes, int n_bins) {
@@ -901,6 +903,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
 // hist[b][row] counts rad2[b-1] <= d2 < rad2[b], the frame itself included (pops_finalize removes it).
 // ------------------------------------------------------------------------------------------------
 constexpr int BIN_STRIDE = N_CONSUMERS * RI * 2;      // bytes between the histogram rows of two bins (2048)
+#ifndef DCB_BIN_COLS
+#define DCB_BIN_COLS 2                                // columns whose table lookups are in flight together (1, 2 or 4)
+#endif
 constexpr int PGEO = 3 * MAX_TEMPLATE_D + 4;          // floats per group in the producer's geometry scratch
 
 __host__ __device__ inline size_t pops_bin_smem_bytes(size_t ring_bytes, int n_bins, int lut_k) {
@@ -984,7 +989,7 @@ __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& r
         const uint32_t tt = base + (uint32_t) src;
         mask &= mask - 1;
         if (lane == 0) {
-          mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
+          mbar_wait_sleep(&ring.empty[pp.stage], pp.phase ^ 1);
           TileMeta m;
           m.row_block = (int32_t) rb;
           m.col0 = tt * TJ;
@@ -1101,10 +1106,11 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
     const TileMeta m = ring.meta[cp.stage];
     if (m.row_block < 0) break;
     if (m.flags & 1u) {
-      R.load_group(g, (uint32_t) m.row_block, (uint32_t) warp, lane);
+      if (a.interleave) R.load(g, (uint32_t) m.row_block, threadIdx.x, false);
+      else R.load_group(g, (uint32_t) m.row_block, (uint32_t) warp, lane);
       const uint32_t grow0 = block_row0(g, (uint32_t) m.row_block) + (uint32_t) warp * (32u * RI);
-      gvalid = grow0 < g.row_end;
-      if (gvalid) {
+      gvalid = grow0 < g.row_end || a.interleave;
+      if (gvalid && !a.interleave) {
         const float* hdr = g.cT + (size_t) (grow0 / TJ) * ((D + 1) * TJ + g.dp) + (size_t) (D + 1) * TJ;
         const int k = lane & 15;
         if (k < D) {
@@ -1124,8 +1130,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
       const float* cen = tl + (D + 1) * TJ;
       // does the tile come within r_max of this warp's group?  lanes 0..15: box gap per dim, lanes 16..31: centre distance per dim
-      bool reach;
-      {
+      bool reach = true;
+      if (!a.interleave) {
         const int k = lane & 15;
         float v = 0.f;
         if (k < D) {
@@ -1145,8 +1151,60 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
         reach = !(fmaxf(sb, ss) * 0.999f > g.prune_thr);          // NaN keeps
       }
       if (reach) {
-        ++st.wtiles;
         R.retarget(g, cen);
+        // Separating-axis test along the line from the tile's centre to the group's centre: the rows' smallest and the
+        // columns' largest projection onto it bound the distance of every pair from below.  In 10 dimensions the boxes and
+        // spheres of two neighbouring clusters overlap while their extents along the line between them do not
+        // (projection of a Gaussian blob: ~3 sigma, its radius: ~(sqrt(D) + 2) sigma).  ~130 instructions per unit.
+        if (a.proj_prune) {
+          float u[D];
+          float un = 0.f;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            // lane k (< 16) holds the group's centre in globally centred coordinates; the tile's is cen[k] - centre[k]
+            const float gck = __shfl_sync(0xffffffffu, gc, k);
+            u[k] = gck - (cen[k] - __ldg(g.centre + k));
+            un = fmaf(u[k], u[k], un);
+          }
+          const float inv = un > 0.f ? rsqrtf(un) : 0.f;
+          float pmin = INFINITY;
+#pragma unroll
+          for (int r = 0; r < RI; ++r) {
+            float pr = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) pr = fmaf(R.x[r][k], u[k], pr);
+            if (R.row(r) < g.row_end) pmin = fminf(pmin, pr);
+          }
+          float qmax = -INFINITY;
+          {
+            float q[CJ] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + 4 * lane);      // -2 y'
+              q[0] = fmaf(y4.x, u[k], q[0]);
+              q[1] = fmaf(y4.y, u[k], q[1]);
+              q[2] = fmaf(y4.z, u[k], q[2]);
+              q[3] = fmaf(y4.w, u[k], q[3]);
+            }
+            // padded columns hold y' = 0 (the tile's centre), inside the span of the real ones: harmless
+            qmax = -0.5f * fminf(fminf(q[0], q[1]), fminf(q[2], q[3]));
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+            qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+          }
+          // projections scaled by |u|: gap = (pmin - qmax) / |u|.  Rounding of the two D-term FFMA chains: D ulp of |x'||u| resp.
+          // |y'||u| with |x'| <= group radius + |u|, |y'| <= tile radius; slack_len covers the roundings of the centres
+          const float ulen = un * inv;
+          const float gap = (pmin - qmax) * inv;
+          const float slack = (float) D * 2e-7f * (grad + ulen + sqrtf(cen[D])) + slack_len;
+          const float lbp = gap * 0.99999f - slack;
+          if (lbp > 0.f && lbp * lbp * 0.999f > g.prune_thr) reach = false;
+        }
+      }
+      if (reach) {
+        ++st.wtiles;
         bool wide = false;
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
@@ -1193,24 +1251,32 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
           if (__popc(act) >= a.dense_lanes && !slow_unit) {
             // dense step: all 16 pairs of every lane through the table, no branches; misses land in the dump row nb
             bool band = false;
+            // two columns (eight independent lookup chains) at a time, then their read-modify-writes column by column:
+            // the four counters of a column belong to four different rows (distinct addresses: load all, then store all),
+            // while two columns of the same row may hit the same counter and must stay in order
 #pragma unroll
-            for (int c = 0; c < CJ; ++c) {
-              uint16_t* hp[RI];
+            for (int c0 = 0; c0 < CJ; c0 += DCB_BIN_COLS) {
+              uint16_t* hp[DCB_BIN_COLS][RI];
 #pragma unroll
-              for (int r = 0; r < RI; ++r) {
-                const float s = acc[r][c] + R.xn[r];
-                const float e = entry(s);
-                const float dlt = s - e;
-                const uint32_t b = (__float_as_uint(e) & 31u) + (dlt >= 0.f ? 1u : 0u);
-                band |= fabsf(dlt) < bw[r];
-                hp[r] = reinterpret_cast<uint16_t*>(hrow(r) + b * BIN_STRIDE);
+              for (int cc = 0; cc < DCB_BIN_COLS; ++cc)
+#pragma unroll
+                for (int r = 0; r < RI; ++r) {
+                  const float s = acc[r][c0 + cc] + R.xn[r];
+                  const float e = entry(s);
+                  const float dlt = s - e;
+                  // bin = k + (s >= e): k from the entry's low bits, the comparison from the sign of s - e
+                  const uint32_t b = (__float_as_uint(e) & 31u) + 1u - (__float_as_uint(dlt) >> 31);
+                  band |= fabsf(dlt) < bw[r];
+                  hp[cc][r] = reinterpret_cast<uint16_t*>(hrow(r) + b * BIN_STRIDE);
+                }
+#pragma unroll
+              for (int cc = 0; cc < DCB_BIN_COLS; ++cc) {
+                uint16_t h[RI];
+#pragma unroll
+                for (int r = 0; r < RI; ++r) h[r] = *hp[cc][r];
+#pragma unroll
+                for (int r = 0; r < RI; ++r) *hp[cc][r] = (uint16_t) (h[r] + 1);
               }
-              // the four counters belong to four different rows: distinct addresses, so load all, then store all
-              uint16_t h[RI];
-#pragma unroll
-              for (int r = 0; r < RI; ++r) h[r] = *hp[r];
-#pragma unroll
-              for (int r = 0; r < RI; ++r) *hp[r] = (uint16_t) (h[r] + 1);
             }
             if (band) {
               // rare: some pair of this block is inside the error band of a boundary: re-decide those exactly and move
@@ -1226,7 +1292,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
                 const float e = entry(s);
                 const float dlt = s - e;
                 if (fabsf(dlt) < sel4(bw, r)) {
-                  const int bf = (int) (__float_as_uint(e) & 31u) + (dlt >= 0.f ? 1 : 0);
+                  const int bf = (int) ((__float_as_uint(e) & 31u) + 1u - (__float_as_uint(dlt) >> 31));     // as counted above
                   ++st.slow;
                   ++st.exact;
                   const float d2 = dist2_exact(g.xT, g.ld, D, R.row(r), m.col0 + gcol + (p % CJ));

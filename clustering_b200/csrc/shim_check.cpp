@@ -1,8 +1,8 @@
-// Test driver of the C++ boundary (density_cuda.hpp): runs the reference-signature entry points on a
+// Test driver of the C++ boundary (include/dcb200/density_cuda.hpp): runs the reference-signature entry points on a
 // raw float32 coordinate file and dumps the results as raw arrays for tests/test_gpu_shim.py.
 //   shim_check <coords.f32> <n_rows> <n_cols> <out_prefix> <threshold_step> <radius> [radius ...]
 #define DCB200_STANDALONE_TYPES
-#include "density_cuda.hpp"
+#include "../../include/dcb200/density_cuda.hpp"
 
 #include <cstdio>
 #include <fstream>
@@ -60,6 +60,24 @@ int main(int argc, char** argv) {
   }
   dump(prefix + ".thr.f32", thresholds);
   dump(prefix + ".lab.u32", labels);
+  // ARBITRARY initial clusters (density_clustering.cpp:394-427 accepts any labelling): the labels of the middle threshold
+  // with every third named frame unassigned again and all names shifted, screened at the last threshold; this call does
+  // not continue the loop above, so it must not be served from its state
+  if (thresholds.size() >= 2) {
+    const std::size_t mid = thresholds.size() / 2;
+    std::vector<std::size_t> init(n);
+    std::vector<std::uint32_t> init_out(n), arb(n);
+    std::size_t named = 0;
+    for (std::size_t i = 0; i < n; ++i) {
+      const std::uint32_t l = labels[mid * n + i];
+      init[i] = l == 0 ? 0 : (++named % 3 == 0 ? 0 : l + 5);
+      init_out[i] = (std::uint32_t) init[i];
+    }
+    const std::vector<std::size_t> res = CU::screening(fe, std::get<0>(nh), thresholds.back(), coords.data(), n, d, init);
+    for (std::size_t i = 0; i < n; ++i) arb[i] = (std::uint32_t) res[i];
+    dump(prefix + ".arbinit.u32", init_out);
+    dump(prefix + ".arb.u32", arb);
+  }
   std::cout << "ok " << thresholds.size() << " thresholds" << std::endl;
   return 0;
 }

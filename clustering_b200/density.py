@@ -104,3 +104,61 @@ def screening_step(sorted_coords, m_prev, m_new, max_dist2, comp):
     lib.check(lib.load().dcb200_screening_step(sorted_coords, sorted_coords.shape[1], m_prev, m_new,
                                                 np.float32(max_dist2), comp))
     return comp
+
+
+def density_run(coords, radii, fe_radius_index=0, neighbors=True, all_free_energies=False, out=None):
+    """One density run through dcb200_density_run (one upload, one layout build): populations for all radii, the free
+    energies of radii[fe_radius_index] and the neighbour search on them.
+    -> dict(pops [R][n], fe [n], fe_all [R][n] or None, nn = (nn_idx, nn_d2, hd_idx, hd_d2) or None).
+    out: optional dict of preallocated arrays with the same keys (e.g. views of pinned memory)."""
+    coords = _coords(coords)
+    radii = np.ascontiguousarray(np.atleast_1d(radii), dtype=np.float32)
+    n, d = coords.shape
+    out = out or {}
+    pops = out.get("pops")
+    if pops is None:
+        pops = np.empty((radii.size, n), np.uint32)
+    fe = out.get("fe")
+    if fe is None:
+        fe = np.empty(n, np.float32)
+    fe_all = out.get("fe_all")
+    if fe_all is None and all_free_energies:
+        fe_all = np.empty((radii.size, n), np.float32)
+    nn = out.get("nn")
+    if nn is None and neighbors:
+        nn = (np.empty(n, np.uint32), np.empty(n, np.float32), np.empty(n, np.uint32), np.empty(n, np.float32))
+    p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    nnp = [p(a) for a in nn] if nn is not None else [None] * 4
+    lib.check(lib.load().dcb200_density_run(C.c_void_p(coords.ctypes.data), n, d, radii, radii.size, int(fe_radius_index), p(pops),
+                                            p(fe_all), p(fe), *nnp))
+    return dict(pops=pops, fe=fe, fe_all=fe_all, nn=nn)
+
+
+class ScreeningRun:
+    """All thresholds of one screening run (dcb200_screening_begin / _next / _end): the free energies are sorted once and
+    the sorted coordinates stay on the device(s); thresholds must not decrease."""
+
+    def __init__(self, free_energy, nn_d2, coords):
+        coords = _coords(coords)
+        self.n, d = coords.shape
+        fe = np.ascontiguousarray(free_energy, dtype=np.float32)
+        nn_d2 = np.ascontiguousarray(nn_d2, dtype=np.float32)
+        self.h = C.c_void_p()
+        lib.check(lib.load().dcb200_screening_begin(fe, nn_d2, coords, self.n, d, C.byref(self.h)))
+
+    def next(self, threshold):
+        labels = np.empty(self.n, np.uint32)
+        lib.check(lib.load().dcb200_screening_next(self.h, np.float32(threshold), labels))
+        return labels
+
+    def close(self):
+        if self.h:
+            lib.load().dcb200_screening_end(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -23,6 +23,10 @@ SYMBOLS = [
     "dcb200_ctx_free_energies", "dcb200_ctx_nn_prepare", "dcb200_ctx_nn_scan", "dcb200_ctx_nn_finish",
     "dcb200_ctx_screening_scan", "dcb200_ctx_screening_flatten", "dcb200_ctx_screening_merge", "dcb200_ctx_stats", "dcb200_ctx_ffma_peak",
     "dcb200_ctx_gemm_info", "dcb200_ctx_tf32_peak",
+    "dcb200_density_run", "dcb200_screen_begin", "dcb200_screen_step", "dcb200_screen_end",
+    "dcb200_screening_begin", "dcb200_screening_next", "dcb200_screening_end",
+    "dcb200_shard_capacity", "dcb200_ctx_shard_rows", "dcb200_ctx_populations_shard", "dcb200_ctx_nn_scan_shard",
+    "dcb200_ctx_shards_to_frame_order", "dcb200_ctx_nn_finish_shards",
 ]
 
 _f = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
@@ -80,6 +84,20 @@ def load():
     L.dcb200_ctx_ffma_peak.argtypes = [_p, C.c_double, C.POINTER(C.c_double)]
     L.dcb200_ctx_tf32_peak.argtypes = [_p, C.c_double, C.POINTER(C.c_double)]
     L.dcb200_ctx_gemm_info.argtypes = [_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    L.dcb200_density_run.argtypes = [_p, _sz, _sz, _f, _sz, _sz, _p, _p, _p, _p, _p, _p, _p]
+    L.dcb200_screen_begin.argtypes = [_f, _sz, _sz, C.POINTER(_p)]
+    L.dcb200_screen_step.argtypes = [_p, _sz, C.c_float, _p, _u32]
+    L.dcb200_screen_end.argtypes = [_p]
+    L.dcb200_screening_begin.argtypes = [_f, _f, _f, _sz, _sz, C.POINTER(_p)]
+    L.dcb200_screening_next.argtypes = [_p, C.c_float, _u32]
+    L.dcb200_screening_end.argtypes = [_p]
+    L.dcb200_shard_capacity.argtypes = [_sz, C.c_int]
+    L.dcb200_shard_capacity.restype = _sz
+    L.dcb200_ctx_shard_rows.argtypes = [_p, C.c_int, C.c_int, C.POINTER(_sz)]
+    L.dcb200_ctx_populations_shard.argtypes = [_p, _f, _sz, C.c_int, C.c_int, _p]
+    L.dcb200_ctx_nn_scan_shard.argtypes = [_p, C.c_int, C.c_int, _p, _p]
+    L.dcb200_ctx_shards_to_frame_order.argtypes = [_p, _p, _sz, C.c_int, _p]
+    L.dcb200_ctx_nn_finish_shards.argtypes = [_p, _p, _p, C.c_int, _sz, _p, _p, _p, _p]
     _lib = L
     return L
 

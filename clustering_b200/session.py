@@ -72,7 +72,8 @@ class Session:
         if isinstance(coords, torch.Tensor):
             assert coords.is_cuda and coords.dtype == torch.float32 and coords.is_contiguous()
             self.n, self.d = coords.shape
-            torch.cuda.current_stream(self.dev).synchronize()
+            # the tensor may have been produced on another stream: order the session stream after the caller's current one
+            self.torch_stream().wait_stream(torch.cuda.current_stream(self.dev))
             lib.check(self.L.dcb200_ctx_set_coords_ex(self.h, _ptr(coords), self.n, self.d, 1, int(keep_order)))
         else:
             coords = np.ascontiguousarray(coords, np.float32)
@@ -136,6 +137,52 @@ class Session:
         """fe: frame order -> (nn_idx, nn_d2, hd_idx, hd_d2) in frame order."""
         self.nn_prepare(fe)
         return self.nn_finish(self.nn_scan())
+
+    # ---- shards (block-cyclic dealing of the positions to the ranks of a multi-GPU run, include/dcb200.h)
+    def shard_capacity(self, n_shards):
+        return int(self.L.dcb200_shard_capacity(self.n, int(n_shards)))
+
+    def shard_rows(self, shard, n_shards):
+        r = C.c_size_t(0)
+        lib.check(self.L.dcb200_ctx_shard_rows(self.h, int(shard), int(n_shards), C.byref(r)))
+        return int(r.value)
+
+    def populations_shard(self, radii, shard, n_shards, out=None):
+        """-> int32 [n_radii][capacity] (the shard's rows first, the padding is not written).
+        (torch.empty, not zeros: a fill kernel on torch's stream would race with the library's own non-blocking stream)"""
+        radii = np.ascontiguousarray(np.atleast_1d(radii), np.float32)
+        if out is None:
+            out = torch.empty((radii.size, self.shard_capacity(n_shards)), dtype=torch.int32, device=self.dev)
+        lib.check(self.L.dcb200_ctx_populations_shard(self.h, radii, radii.size, int(shard), int(n_shards), _ptr(out)))
+        return out
+
+    def nn_scan_shard(self, shard, n_shards, out=None):
+        """-> int64 [2][capacity] neighbour keys of the shard's rows."""
+        if out is None:
+            out = torch.empty((2, self.shard_capacity(n_shards)), dtype=torch.int64, device=self.dev)
+        lib.check(self.L.dcb200_ctx_nn_scan_shard(self.h, int(shard), int(n_shards), _ptr(out[0]), _ptr(out[1])))
+        return out
+
+    def shards_to_frame_order(self, gathered, n_arrays, n_shards, out=None):
+        """gathered: 32-bit device tensor [n_shards][n_arrays][capacity] -> [n_arrays][n] in frame order."""
+        assert gathered.is_cuda and gathered.is_contiguous() and gathered.element_size() == 4
+        assert gathered.numel() == n_shards * n_arrays * self.shard_capacity(n_shards)
+        if out is None:
+            out = torch.empty((n_arrays, self.n), dtype=gathered.dtype, device=self.dev)
+        lib.check(self.L.dcb200_ctx_shards_to_frame_order(self.h, _ptr(gathered), int(n_arrays), int(n_shards), _ptr(out)))
+        return out
+
+    def nn_finish_shards(self, gathered, n_shards, out=None):
+        """gathered: int64 [n_shards][2][capacity] -> (nn_idx, nn_d2, hd_idx, hd_d2) in frame order."""
+        cap = self.shard_capacity(n_shards)
+        assert gathered.is_cuda and gathered.is_contiguous() and gathered.numel() == n_shards * 2 * cap
+        if out is None:
+            out = (torch.empty(self.n, dtype=torch.int32, device=self.dev), torch.empty(self.n, dtype=torch.float32, device=self.dev),
+                   torch.empty(self.n, dtype=torch.int32, device=self.dev), torch.empty(self.n, dtype=torch.float32, device=self.dev))
+        base = gathered.data_ptr()            # shard s: nn keys at [s][0], hd keys at [s][1] -> stride 2 * capacity, no copies
+        lib.check(self.L.dcb200_ctx_nn_finish_shards(self.h, C.c_void_p(base), C.c_void_p(base + 8 * cap), int(n_shards), 2 * cap,
+                                                     _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3])))
+        return out
 
     # ---- screening (coords must be the free-energy-sorted frames)
     def screening_scan(self, m_prev, m_new, max_dist2, comp, row_begin=0, row_end=None):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DCB200_VERSION 100
+#define DCB200_VERSION 200
 
 /* ---- process-wide ------------------------------------------------------------------------- */
 /* replaces Clustering::Density::CUDA::get_num_gpus (density_clustering_cuda.cu:32-43) */
@@ -65,13 +65,35 @@ int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size_t n_cols, 
  * The caller maps representatives to the reference's cluster numbers (1..K by ascending representative). */
 int dcb200_screening_step(const float* sorted_coords, size_t n_cols, size_t m_prev, size_t m_new, float max_dist2,
                           uint32_t* comp);
+/* The same pair scan as a session over ALL free-energy-sorted frames: the coordinates are uploaded and laid out ONCE
+ * (on every selected GPU; with several GPUs one host copy + an NCCL broadcast) and the union-find forest stays on the
+ * device(s) between thresholds.  dcb200_screen_step extends the forest from the positions done so far to [0, m_new)
+ * (m_new must not decrease) and writes every position's representative to comp[0, m_new); seed (or NULL) replaces the
+ * session's forest for the positions done so far (uint32 [positions done], seed[p] <= p).
+ * Sessions share the library's per-GPU contexts with the other host-pointer entry points: a call in between is allowed
+ * (the session notices that its layout was replaced and restores it from its host copy), it just costs an upload. */
+typedef struct dcb200_screen dcb200_screen;
+int dcb200_screen_begin(const float* sorted_coords, size_t n_sorted, size_t n_cols, dcb200_screen** session);
+int dcb200_screen_step(dcb200_screen* session, size_t m_new, float max_dist2, const uint32_t* seed, uint32_t* comp);
+int dcb200_screen_end(dcb200_screen* session);
+
+/* One density run without leaving the device(s) between its stages -- what `clustering density -r/-R ... -p -d -b` computes
+ * (density_clustering.cpp:596-735): populations for all radii, free energies, and the neighbour search on the free
+ * energies of radii[fe_radius], with ONE upload and ONE layout build (the separate entry points above upload and lay out
+ * the coordinates once each, like the reference's CUDA functions).  Outputs in frame order; optional ones may be NULL:
+ *   pops [n_radii][n_rows]; fe_all [n_radii][n_rows] (free energies of every radius); fe [n_rows] (of radii[fe_radius]);
+ *   nn_idx/nn_d2/hd_idx/hd_d2 [n_rows] (all four or none). */
+int dcb200_density_run(const float* coords, size_t n_rows, size_t n_cols, const float* radii, size_t n_radii, size_t fe_radius,
+                       uint32_t* pops, float* fe_all, float* fe, uint32_t* nn_idx, float* nn_d2, uint32_t* hd_idx,
+                       float* hd_d2);
 
 /* host-side bookkeeping of the screening (no pair work; kept bit-compatible with the reference's libstdc++ calls)
  *   dcb200_sorted_free_energies: order[k] = frame at sorted position k   (sorted_free_energies, density_clustering.cpp:214-228)
  *   dcb200_sigma2:               mean squared nearest-neighbour distance  (compute_sigma2, :334-343)
  *   dcb200_screening:            one free-energy threshold, = reference screening() (density_clustering_common.cpp:37-134);
- *                                initial: NULL or the labels of the previous (lower) threshold; labels: uint32 [n_rows], 0 = unassigned.
- *                                The pair scan inside runs on the GPU(s) through dcb200_screening_step.
+ *                                initial: NULL or ANY labelling of the frames (uint32 [n_rows], 0 = no cluster; typically the
+ *                                labels of a lower threshold, density_clustering.cpp:394-427); labels: uint32 [n_rows],
+ *                                0 = unassigned.  The pair scan inside runs on the GPU(s) through dcb200_screening_step.
  *   dcb200_assign_low_density_frames / dcb200_sorted_cluster_names: the microstate step after the screening
  *                                (`clustering density -i`): assign_low_density_frames (density_clustering.cpp:345-360) and
  *                                sorted_cluster_names (:458-493); uint32 [n_rows] in and out, 0 = no state */
@@ -82,13 +104,22 @@ int dcb200_sorted_cluster_names(const uint32_t* states, size_t n_rows, uint32_t*
 int dcb200_sigma2(const float* nn_d2, size_t n_rows, double* sigma2);
 int dcb200_screening(const float* fe, const float* nn_d2, float threshold, const float* coords, size_t n_rows,
                      size_t n_cols, const uint32_t* initial, uint32_t* labels);
+/* All thresholds of one `clustering density -T` run (the driver loop density_clustering.cpp:806-816, which calls
+ * screening() with the previous labels as initial clusters): the free energies are sorted ONCE and the sorted coordinates
+ * stay on the device(s).  Thresholds must not decrease; labels [n_rows] are identical to the call-per-threshold form. */
+typedef struct dcb200_screening_run dcb200_screening_run;
+int dcb200_screening_begin(const float* fe, const float* nn_d2, const float* coords, size_t n_rows, size_t n_cols,
+                           dcb200_screening_run** run);
+int dcb200_screening_next(dcb200_screening_run* run, float threshold, uint32_t* labels);
+int dcb200_screening_end(dcb200_screening_run* run);
 
 /* ---- file formats of `clustering density` ---------------------------------------------------------------
  * Byte-compatible with the reference's writers (src/tools.cpp:42-56, :64-70, :144-174, :267-277, tools.hxx:256-272) and
  * tolerant like its readers (tools.hxx:39-111, :229-253, tools.cpp:103-133, :229-265).  header: the "# ..." block every
  * file starts with (clustering.cpp:467-482); keys/vals: the "#@ key = value" parameters (zero values are not written).
- * Readers: pass out = NULL (or a small capacity) to query the size first.  I/O errors print a message and exit, exactly
- * like the reference's tools. */
+ * Readers: pass out = NULL (or a small capacity) to query the size first.  A file that cannot be opened (or holds no
+ * value) is an error status with the reference's message in dcb200_last_error(); only the `clustering` binary turns it
+ * into the reference's print-and-exit. */
 int dcb200_io_write_pops(const char* filename, const uint32_t* pops, size_t n, const char* header, const char* const* keys,
                          const float* vals, size_t n_comments);
 int dcb200_io_write_fes(const char* filename, const float* fe, size_t n, const char* header, const char* const* keys,
@@ -150,6 +181,32 @@ int dcb200_ctx_nn_scan(dcb200_ctx* ctx, size_t pos_begin, size_t pos_end, uint64
                        uint64_t* dev_keys_hd);
 int dcb200_ctx_nn_finish(dcb200_ctx* ctx, const uint64_t* dev_keys_nn, const uint64_t* dev_keys_hd,
                          uint32_t* dev_nn_idx, float* dev_nn_d2, uint32_t* dev_hd_idx, float* dev_hd_d2);
+
+/* ---- shards: the row split of the multi-GPU drivers (replaces the per-GPU row ranges of
+ * density_clustering_cuda.cu:152-181 and :286-328) ------------------------------------------------------------------
+ * The positions are dealt to n_shards shards in blocks of 1024 positions, block b going to shard b % n_shards
+ * (block-cyclic: the spatial order puts dense and sparse regions into long runs, so contiguous shards of equal length
+ * cost very different amounts).  A shard keeps its blocks in order; dcb200_shard_capacity is the common padded number
+ * of rows per shard, so that shard outputs [capacity]-strided concatenate with ONE all-gather:
+ *   dcb200_ctx_populations_shard   dev_pops: uint32 [n_radii][capacity]
+ *   dcb200_ctx_nn_scan_shard       dev_keys_*: uint64 [capacity]
+ *   dcb200_ctx_shards_to_frame_order   gathered uint32 [n_shards][n_arrays][capacity] -> [n_arrays][n_rows], frame order
+ *   dcb200_ctx_nn_finish_shards        gathered keys -> neighbour outputs in frame order; shard s's keys start at
+ *                                      dev_keys_*[s * shard_stride]: shard_stride = capacity for two separately gathered
+ *                                      arrays, 2 * capacity for ONE gathered [n_shards][2][capacity] block (nn, then hd)
+ * Every context (one per GPU, same coordinates) builds the same deterministic order, so shard s means the same rows
+ * everywhere.  Contexts on the GEMM-form path (17 <= n_cols <= 256) deal contiguous runs of `capacity` positions instead;
+ * the two assembling functions undo whichever dealing the context uses. */
+size_t dcb200_shard_capacity(size_t n_rows, int n_shards);
+int dcb200_ctx_shard_rows(dcb200_ctx* ctx, int shard, int n_shards, size_t* rows);
+int dcb200_ctx_populations_shard(dcb200_ctx* ctx, const float* radii, size_t n_radii, int shard, int n_shards,
+                                 uint32_t* dev_pops);
+int dcb200_ctx_nn_scan_shard(dcb200_ctx* ctx, int shard, int n_shards, uint64_t* dev_keys_nn, uint64_t* dev_keys_hd);
+int dcb200_ctx_shards_to_frame_order(dcb200_ctx* ctx, const uint32_t* dev_src, size_t n_arrays, int n_shards,
+                                     uint32_t* dev_dst);
+int dcb200_ctx_nn_finish_shards(dcb200_ctx* ctx, const uint64_t* dev_keys_nn, const uint64_t* dev_keys_hd, int n_shards,
+                                size_t shard_stride, uint32_t* dev_nn_idx, float* dev_nn_d2, uint32_t* dev_hd_idx,
+                                float* dev_hd_d2);
 
 /* screening on the device: the context's coordinates must be the free-energy-sorted frames, set with keep_order.
  * New rows [m_prev,m_new) restricted to [row_begin,row_end) are scanned against all lower positions;

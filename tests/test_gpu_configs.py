@@ -155,3 +155,183 @@ def test_population_kernels_agree(oracle, mode):
         else:
             os.environ["DCB200_POPS_MODE"] = old
     assert np.array_equal(want, got)
+
+
+# ---------------------------------------------------------------- sharded scans (D <= 16) ----------
+def _full_scan(sess, x, radii, fe_index):
+    import torch
+    n = len(x)
+    sess.set_coords(x)
+    pops_pos = sess.populations(radii, 0, n)
+    pops = sess.to_frame_order(pops_pos)
+    fe = sess.free_energies(pops[fe_index].contiguous())
+    sess.nn_prepare(fe)
+    keys = sess.nn_scan(0, n)
+    nn = sess.nn_finish(keys)
+    sess.sync()
+    return pops_pos, pops, fe, keys, nn
+
+
+@pytest.mark.parametrize("d,radii", [(5, [0.3]), (5, [0.1, 0.2, 0.3, 0.4, 0.5]), (10, [0.4, 0.7, 1.0, 1.3, 1.6, 2.0]), (16, [1.2, 2.0])])
+def test_position_range_shards_concatenate_to_the_full_scan(oracle, d, radii):
+    """dcb200_ctx_populations / dcb200_ctx_nn_scan over 2, 3 and 8 uneven position ranges -- starting on a tile, on a row
+    block, or anywhere (the count / table kernels need tile-aligned groups, other ranges fall back to the histogram
+    kernel) -- concatenated == the full scan == the oracle."""
+    import torch
+    from clustering_b200.session import Session
+    n = 21_500
+    x = gaussian_mixture(n, d, seed=7000 + d)
+    radii = np.asarray(radii, np.float32)
+    sess = Session(0)
+    pops_pos, pops, fe, keys, nn = _full_scan(sess, x, radii, 0)
+    want = oracle.populations(x, radii)
+    assert np.array_equal(pops.cpu().numpy().view(np.uint32), want)
+    fe_o = oracle.free_energies(want[0])
+    assert np.array_equal(bits(fe.cpu().numpy()), bits(fe_o))
+    nn_o = oracle.nearest_neighbors(x, fe_o)
+    assert same_neighbours(nn_o, tuple(t.cpu().numpy().view(np.uint32) if t.dtype == torch.int32 else t.cpu().numpy() for t in nn))
+    for cuts in ([0, 10_240, n], [0, 7_168, 14_000, n], [0, 1_024, 1_152, 5_000, 9_999, 10_000, 16_384, 21_499, n], [0, 333, n]):
+        parts_p = [sess.populations(radii, b, e) for b, e in zip(cuts[:-1], cuts[1:])]
+        parts_k = [sess.nn_scan(b, e) for b, e in zip(cuts[:-1], cuts[1:])]
+        sess.sync()
+        assert torch.equal(torch.cat(parts_p, dim=1), pops_pos), cuts
+        assert torch.equal(torch.cat(parts_k, dim=1), keys), cuts
+    sess.close()
+
+
+@pytest.mark.parametrize("d,radii,n", [(5, [0.3], 40_000), (10, [0.1 * i for i in range(1, 21)], 30_011), (3, [0.15, 0.3], 9_000)])
+def test_block_cyclic_shards_assemble_to_the_full_scan(oracle, d, radii, n):
+    """The shard entry points the one-process-per-GPU driver uses (dcb200_ctx_*_shard, blocks of 1024 positions dealt
+    round-robin) for 2, 3 and 8 emulated ranks on one device: gathered and assembled by the library's own kernels ==
+    the full scan == the oracle, in frame order."""
+    import torch
+    from clustering_b200.session import Session
+    x = gaussian_mixture(n, d, seed=7100 + d)
+    radii = np.asarray(radii, np.float32)
+    sess = Session(0)
+    _, pops, fe, _, nn = _full_scan(sess, x, radii, 0)
+    assert np.array_equal(pops.cpu().numpy().view(np.uint32), oracle.populations(x, radii))
+    for w in (2, 3, 8):
+        cap = sess.shard_capacity(w)
+        assert sum(sess.shard_rows(r, w) for r in range(w)) == n
+        # the library works on its own (non-blocking) stream: buffers are allocated up front (torch.empty launches nothing)
+        # and torch only looks at the results after sess.sync()
+        gp = torch.empty((w, len(radii), cap), dtype=torch.int32, device=sess.dev)            # what the all-gather delivers
+        gk = torch.empty((w, 2, cap), dtype=torch.int64, device=sess.dev)
+        for r in range(w):
+            sess.populations_shard(radii, r, w, out=gp[r])
+            sess.nn_scan_shard(r, w, out=gk[r])
+        got = sess.shards_to_frame_order(gp, len(radii), w)
+        got_nn = sess.nn_finish_shards(gk, w)
+        sess.sync()
+        assert torch.equal(got, pops), w
+        for a, b in zip(got_nn, nn):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), w
+    sess.close()
+
+
+def test_density_pass_from_the_default_stream(oracle):
+    """clustering_b200.dist.DensityPass and ScreeningPass driven from torch's default stream (the session stream is
+    non-blocking: the passes order themselves after the caller's stream and hand their results back to it)."""
+    import torch
+    from clustering_b200.dist import DensityPass, ScreeningPass
+    from clustering_b200.session import Session
+    n, d = 12_000, 4
+    x = gaussian_mixture(n, d, k=5, seed=7300)
+    radii = np.array([0.25, 0.4], np.float32)
+    sess = Session(0)
+    dp = DensityPass(sess, n, radii)
+    xd = torch.from_numpy(x).cuda() * 1.0                    # produced on the default stream, consumed by the session stream
+    pops, fe, nn = dp.run(xd, 1)
+    pops_h = pops.cpu().numpy().view(np.uint32)              # default-stream copies: must see the finished results
+    want = oracle.populations(x, radii)
+    assert np.array_equal(pops_h, want)
+    fe_o = oracle.free_energies(want[1])
+    assert np.array_equal(bits(fe.cpu().numpy()), bits(fe_o))
+    nn_o = oracle.nearest_neighbors(x, fe_o)
+    assert np.array_equal(nn[0].cpu().numpy().view(np.uint32), nn_o[0]) and np.array_equal(bits(nn[3].cpu().numpy()), bits(nn_o[3]))
+    # screening pass on the same data, two thresholds, comp initialised on the default stream
+    order = density.sorted_free_energies(fe_o)
+    xs = np.ascontiguousarray(x[order])
+    cut = np.float32(4.0 * density.compute_sigma2(nn_o[1]))
+    sp = ScreeningPass(sess, torch.from_numpy(xs).cuda())
+    comp = torch.arange(n, dtype=torch.int32, device="cuda")
+    prev_o, m_prev = None, 0
+    for t in (np.float32(0.8), np.float32(2.5)):
+        m_new = int(np.searchsorted(fe_o[order], t, side="right"))
+        sp.step(m_prev, m_new, float(cut), comp)
+        rep = comp[:m_new].cpu().numpy()
+        _, lab = np.unique(rep, return_inverse=True)
+        labels = np.zeros(n, np.uint32)
+        labels[order[:m_new]] = lab + 1
+        prev_o = oracle.screening(fe_o, nn_o[1], t, x, prev_o)
+        assert np.array_equal(labels, prev_o.astype(np.uint32)), float(t)
+        m_prev = m_new
+    sess.close()
+
+
+# ---------------------------------------------------------------- fused run, screening runs, arbitrary initial clusters ----
+def test_density_run_equals_the_separate_entry_points(oracle):
+    """dcb200_density_run (one upload, one layout build) == dcb200_populations + dcb200_free_energies +
+    dcb200_nearest_neighbors == the oracle, including the free energies of every radius."""
+    n, d = 30_000, 5
+    x = gaussian_mixture(n, d, seed=8100)
+    radii = np.array([0.2, 0.3, 0.45], np.float32)
+    r = density.density_run(x, radii, fe_radius_index=1, neighbors=True, all_free_energies=True)
+    want = oracle.populations(x, radii)
+    assert np.array_equal(r["pops"], want)
+    for k in range(len(radii)):
+        assert np.array_equal(bits(r["fe_all"][k]), bits(oracle.free_energies(want[k])))
+    fe = oracle.free_energies(want[1])
+    assert np.array_equal(bits(r["fe"]), bits(fe))
+    assert same_neighbours(oracle.nearest_neighbors(x, fe), r["nn"])
+    assert same_neighbours(density.nearest_neighbors(x, fe), r["nn"])
+    only = density.density_run(x, radii[:1], neighbors=False)
+    assert only["nn"] is None and np.array_equal(only["pops"][0], want[0])
+
+
+def test_screening_run_equals_call_per_threshold(oracle):
+    """All thresholds through ONE screening run (sorted once, coordinates resident) == one dcb200_screening call per
+    threshold with the previous labels == the oracle, at every threshold."""
+    x = gaussian_mixture(7000, 3, k=6, seed=8200)
+    x[15] = x[3]
+    fe = oracle.free_energies(oracle.populations(x, [0.3])[0])
+    _, nd, _, _ = oracle.nearest_neighbors(x, fe)
+    prev_o = prev_g = None
+    with density.ScreeningRun(fe, nd, x) as run:
+        t = np.float32(0.1)
+        while t < fe.max() + 0.2:
+            lo = oracle.screening(fe, nd, t, x, prev_o)
+            lr = run.next(t)
+            lg = density.screening(fe, nd, t, x, prev_g)
+            assert np.array_equal(lo.astype(np.uint32), lr), float(t)
+            assert np.array_equal(lr, lg), float(t)
+            prev_o, prev_g = lo, lg
+            t = np.float32(t + np.float32(0.35))
+        with pytest.raises(Exception):
+            run.next(np.float32(0.05))                     # thresholds must not decrease within a run
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_screening_accepts_arbitrary_initial_clusters(oracle, seed):
+    """initial_clusters that are NOT the labels of a lower threshold (density_clustering.cpp:394-427 takes any labelling):
+    random names with gaps on a random subset of the frames, some of them above the threshold, some clusters far apart
+    sharing a name -- labels must equal the oracle's literal restatement of the reference."""
+    rng = np.random.default_rng(seed)
+    n = 3000
+    x = gaussian_mixture(n, 3, k=5, seed=8300 + seed)
+    fe = oracle.free_energies(oracle.populations(x, [0.3])[0])
+    _, nd, _, _ = oracle.nearest_neighbors(x, fe)
+    init = np.zeros(n, np.uint32)
+    chosen = rng.choice(n, n // 3, replace=False)
+    init[chosen] = rng.choice(np.array([2, 3, 7, 11, 40], np.uint32), chosen.size)
+    for t in (np.float32(1.0), np.float32(2.5), np.float32(fe.max() + 1)):
+        want = oracle.screening(fe, nd, t, x, init.astype(np.uint64))
+        got = density.screening(fe, nd, t, x, init)
+        assert np.array_equal(got, want.astype(np.uint32)), float(t)
+    # a previous result with holes punched into it
+    base = density.screening(fe, nd, np.float32(1.5), x, None)
+    holes = base.copy()
+    holes[rng.choice(n, n // 5, replace=False)] = 0
+    want = oracle.screening(fe, nd, np.float32(2.0), x, holes.astype(np.uint64))
+    assert np.array_equal(density.screening(fe, nd, np.float32(2.0), x, holes), want.astype(np.uint32))

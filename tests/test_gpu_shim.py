@@ -1,4 +1,4 @@
-"""The C++ boundary (clustering_b200/csrc/density_cuda.hpp: the reference's own Clustering::Density::CUDA
+"""The C++ boundary (clustering_b200/include/dcb200/density_cuda.hpp: the reference's own Clustering::Density::CUDA
 signatures over libdcb200.so), driven through the compiled test driver and compared with the oracle."""
 import os
 import subprocess
@@ -39,6 +39,12 @@ def test_cpp_shim_matches_oracle(oracle, tmp_path):
     for k, t in enumerate(thr):
         prev = oracle.screening(fe, nd, t, x, prev)
         assert np.array_equal(lab[k], prev.astype(np.uint32)), k
+    # arbitrary initial clusters (not a prefix of the free-energy order, names with gaps)
+    init = np.fromfile(prefix + ".arbinit.u32", np.uint32)
+    arb = np.fromfile(prefix + ".arb.u32", np.uint32)
+    assert np.count_nonzero(init) > 0 and np.count_nonzero(init == 0) > 0
+    want = oracle.screening(fe, nd, thr[-1], x, init.astype(np.uint64))
+    assert np.array_equal(arb, want.astype(np.uint32))
 
 
 def test_cpp_shim_exits_like_the_reference_on_bad_input(tmp_path):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", lib.SO_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (dcb200_[a-z0-9_]+)", out))
     assert set(declared) <= exported
-    assert L.dcb200_version() == 100
+    assert L.dcb200_version() == 200
 
 
 def test_no_oracle_in_product():
@@ -68,7 +68,7 @@ def test_compute_fails_loudly_without_gpu():
 
 
 def test_shard_bounds_cover_everything():
-    from clustering_b200.dist import shard_bounds, shard_size
+    from clustering_b200.dist import shard_bounds, shard_positions, shard_size
     for n in (1, 1023, 1024, 1025, 100_000, 1_000_000, 5_000_001):
         for w in (1, 2, 3, 4, 8):
             prev = 0
@@ -79,26 +79,47 @@ def test_shard_bounds_cover_everything():
                 prev = e
             assert prev == n
             assert shard_size(n, w) * w >= n
+    # block-cyclic shards: a partition of the positions, every shard within the common capacity, and the library's
+    # own capacity formula agrees with the host-side one
+    from clustering_b200 import lib
+    L = lib.load()
+    for n in (1, 1023, 1024, 1025, 5000, 100_000):
+        for w in (1, 2, 3, 8):
+            seen = []
+            for r in range(w):
+                p = shard_positions(n, w, r)
+                assert len(p) <= shard_size(n, w)
+                seen += p
+            assert sorted(seen) == list(range(n))
+            assert L.dcb200_shard_capacity(n, w) == shard_size(n, w)
 
 
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, sys.argv[1])
 import torch, torch.distributed as dist
-from clustering_b200.dist import all_gather_positions, shard_bounds
+from clustering_b200.dist import gather_shards, shard_bounds, shard_positions, shard_size, shards_to_position_order
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
 w, r = dist.get_world_size(), dist.get_rank()
-for n in (5000, 1024, 3000):
+for n in (5000, 1024, 3000, 9001):
+    cap = shard_size(n, w)
+    want = torch.stack([torch.arange(n) * 3 + 1, -torch.arange(n)])
+    # block-cyclic shards (n_cols <= 16): what a rank computes for ITS positions, padded to the common capacity
+    pos = torch.tensor(shard_positions(n, w, r), dtype=torch.int64)
+    local = torch.full((2, cap), -7, dtype=torch.int64)
+    local[0, :len(pos)] = pos * 3 + 1
+    local[1, :len(pos)] = -pos
+    full = shards_to_position_order(gather_shards(local, w), n, cyclic=True)
+    assert full.shape == (2, n) and torch.equal(full, want), (n, r)
+    # contiguous shards (GEMM-form path)
     b, e = shard_bounds(n, w, r)
     pos = torch.arange(b, e, dtype=torch.int64)
-    local = torch.stack([pos * 3 + 1, -pos])                      # what a rank computes for its positions
-    full = all_gather_positions(local, n, w, r)
-    want = torch.stack([torch.arange(n) * 3 + 1, -torch.arange(n)])
-    assert full.shape == (2, n) and torch.equal(full, want), (n, r)
-    loc32 = (pos % 7).to(torch.int32).reshape(1, -1)
-    out = torch.empty((1, n), dtype=torch.int32)
-    all_gather_positions(loc32, n, w, r, out=out)
-    assert torch.equal(out[0], (torch.arange(n) % 7).to(torch.int32))
+    local = torch.full((2, cap), -7, dtype=torch.int64)
+    local[0, :e - b] = pos * 3 + 1
+    local[1, :e - b] = -pos
+    out = torch.empty((w, 2, cap), dtype=torch.int64)
+    full = shards_to_position_order(gather_shards(local, w, out=out), n, cyclic=False)
+    assert torch.equal(full, want), (n, r)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", r, "ok")
