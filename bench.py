@@ -256,8 +256,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")       # host-side barriers (an NCCL barrier spins ON the GPUs while it waits)
     cfg, x = workload(args.workload, args.n)
     n, d = x.shape
     radii = np.asarray(cfg["radii"], np.float32)
@@ -453,9 +455,11 @@ def run_ours(args):
         d2h = radii.size * 4 * n + 4 * n + 16 * n
         e2e_api = ("session C ABI per rank with pinned host buffers: H2D coords on every rank, block-cyclic sharded scans, NCCL all-gather, "
                    "D2H results (CUDA events, max over ranks)")
-        # the C++ in-process path (what the `clustering` binary runs): one process, N GPUs, NCCL inside libdcb200.so
+        # the C++ in-process path (what the `clustering` binary runs): one process, N GPUs, NCCL inside libdcb200.so.
+        # The other ranks wait on the HOST meanwhile, so that their GPUs are free for rank 0's worker threads.
         cxx = None
         barrier()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             try:
                 lib.set_gpus(world)
@@ -476,6 +480,7 @@ def run_ours(args):
                        "api": f"one process, {world} GPUs: dcb200_density_run (one H2D + NCCL broadcast, block-cyclic shards, ncclAllGather, one D2H)"}
             except Exception as ex:
                 cxx = {"failed": str(ex)}
+        dist.barrier(group=cpu_group)
         barrier()
     e2e_value = pd / (e2e_ms * 1e-3) / 1e9
 

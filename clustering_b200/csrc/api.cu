@@ -3,6 +3,7 @@
 #include "../../include/dcb200.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 #include <float.h>
 #include <math.h>
@@ -509,6 +510,7 @@ struct dcb200_ctx {
   DevBuf<uint32_t> cnt;
   DevBuf<float> lut;                // cell table of the bin-mode population kernel (one pass at a time)
   DevBuf<unsigned long long> knn, khd;
+  DevBuf<uint32_t> shard_tmp;       // compact rows of a GEMM-form shard before they are spread into the padded shard layout
   DevBuf<uint32_t> io_u32;          // host-pointer entry points: device-side staging of inputs / outputs
   DevBuf<float> io_f32;
   unsigned int* scalars = nullptr;  // [0] work counter, [1] max norm bits, [2] max pop
@@ -585,6 +587,7 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, size_t rb_
   g->dp = (int) ((3 * c->d + 1 + 3) / 4 * 4);
   g->centre = c->centre.p;
   g->prune_thr = INFINITY;
+  g->axis_prune = env_int("DCB200_AXIS_PRUNE", 1) == 1 ? 1 : 0;
   g->ld = c->ld;
   g->d = (int) c->d;
   g->n = (uint32_t) c->n;
@@ -766,7 +769,7 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   c->perm.release(); c->lo.release(); c->lof.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release(); c->skeys_a.release(); c->skeys_b.release();
   c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->lut.release(); c->knn.release(); c->khd.release();
-  c->io_u32.release(); c->io_f32.release();
+  c->io_u32.release(); c->io_f32.release(); c->shard_tmp.release();
   c->gT.release(); c->gnorm.release(); c->xR.release(); c->thdr.release(); c->lbmat.release(); c->lomin.release(); c->gthr.release();
   if (c->gcheck) cudaFree(c->gcheck);
   if (c->gprof) cudaFree(c->gprof);
@@ -1332,9 +1335,10 @@ extern "C" int dcb200_ctx_populations_shard(dcb200_ctx* c, const float* radii, s
     const size_t rows = e - b;
     if (rows == 0 || n_radii == 0) return 0;
     CK(cudaSetDevice(c->device));
-    CK(c->io_u32.reserve(n_radii * rows));
-    CKI(populations_impl(c, radii, n_radii, b, e, 1, rows, c->io_u32.p));
-    CK(cudaMemcpy2DAsync(dev_pops, cap * sizeof(uint32_t), c->io_u32.p, rows * sizeof(uint32_t), rows * sizeof(uint32_t), n_radii,
+    // (a buffer of its own: the caller's dev_pops may live in the context's io buffers)
+    CK(c->shard_tmp.reserve(n_radii * rows));
+    CKI(populations_impl(c, radii, n_radii, b, e, 1, rows, c->shard_tmp.p));
+    CK(cudaMemcpy2DAsync(dev_pops, cap * sizeof(uint32_t), c->shard_tmp.p, rows * sizeof(uint32_t), rows * sizeof(uint32_t), n_radii,
                          cudaMemcpyDeviceToDevice, c->stream));
     return 0;
   }
@@ -2141,19 +2145,120 @@ extern "C" int dcb200_free_energies(const uint32_t* pops, size_t n, float* fe) {
 }
 
 // ---- screening ----------------------------------------------------------------------------------
-// A screening session keeps the free-energy-sorted coordinates and the union-find forest on the device(s) between
-// thresholds: ONE upload and ONE layout build per run instead of one per threshold.
+// A screening session works on ALL free-energy-sorted frames at once.  At its first step it scans the frames -- laid out in
+// spatial order, so that tiles out of reach of the cut radius are never touched -- for every pair with d2 < cut (edge_kernel,
+// kernels.cuh; rows dealt block-cyclically to the GPUs of the gang) and sorts the edges by the sorted index of their later
+// frame.  A threshold then only unions the edges that became active since the previous one (lock-free union-find on GPU 0)
+// and downloads the representatives.  The reference scans (new frames) x (all lower frames) at every threshold
+// (density_clustering_common.cpp:98-123, density_clustering_cuda.cu:505-571): N^2/2 pairs per run; the edge list costs
+// about one population scan with r^2 = cut.
+namespace {
+
+__global__ void edge_union_kernel(const unsigned long long* __restrict__ edges, size_t e0, size_t e1, uint32_t* parent) {
+  const size_t q = e0 + (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= e1) return;
+  const unsigned long long e = edges[q];
+  uf_union(parent, (uint32_t) (e >> 32), (uint32_t) e);
+}
+// out[0] = number of edges (sorted by level) whose level (larger sorted index, high word) is below `limit`
+__global__ void edge_count_below_kernel(const unsigned long long* __restrict__ edges, size_t n_edges, uint32_t limit,
+                                        unsigned long long* __restrict__ out) {
+  size_t lo = 0, hi = n_edges;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if ((uint32_t) (edges[mid] >> 32) < limit) lo = mid + 1; else hi = mid;
+  }
+  out[0] = lo;
+}
+
+// cluster numbers on the device: clusters are numbered 1..K by ascending representative (= first sorted member)
+__global__ void root_flag_kernel(const uint32_t* __restrict__ forest, size_t m, uint32_t* __restrict__ flag) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < m) flag[p] = forest[p] == (uint32_t) p ? 1u : 0u;
+}
+// labels[order[p]] = number of p's cluster for p < m, 0 for the frames above the threshold (rank = exclusive sum of the flags)
+__global__ void label_scatter_kernel(const uint32_t* __restrict__ forest, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ order,
+                                     size_t m, size_t n, uint32_t* __restrict__ labels) {
+  const size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  labels[order[p]] = p < m ? rank[forest[p]] + 1u : 0u;
+}
+
+static cudaError_t launch_edge(int d, const EdgeArgs& a, int grid, cudaStream_t st) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) launch_edge_d##D(a, grid, st)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return cudaErrorInvalidValue;
+}
+static int occ_edge(int d) {
+  switch (d <= MAX_TEMPLATE_D ? d : 0) {
+#define FN(D) occupancy_edge_d##D(d)
+    DCB_FOR_EACH_D(DCB_DISPATCH)
+#undef FN
+  }
+  return 0;
+}
+
+// buf: [0] = counter, [1 ..] = edges.  Scans shard `shard` of `n_shards` (block-cyclic rows, upper triangle of the position
+// matrix) of the context's spatially ordered frames; grows the buffer and scans again if the edges did not fit.
+int edge_scan(dcb200_ctx* c, int shard, int n_shards, float cut, uint32_t level_min, DevBuf<unsigned long long>& buf,
+              unsigned long long* found) {
+  if (!c->spatial) return fail("dcb200: the edge scan needs the frames in spatial order");
+  CK(cudaSetDevice(c->device));
+  const size_t b = std::min(c->n, (size_t) shard * ROWS_PER_CTA);
+  *found = 0;
+  if (b >= c->n) return 0;
+  const size_t rows = launch_rows(b, c->n, (size_t) n_shards);
+  if (buf.cap < 2) CK(buf.reserve(std::max<size_t>(size_t(1) << 20, 24 * rows) + 1));
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    EdgeArgs a;
+    int grid = 0;
+    CKI(fill_geom(c, b, c->n, (size_t) n_shards, tile_width(c->d), occ_edge((int) c->d), 32u, &a.g, &grid));
+    a.cut = cut;
+    a.thr_fast = up((double) cut * (1.0 + 1.01 * (double) a.g.e_rel));
+    a.g.prune_thr = up((double) a.thr_fast * 1.0001 + 2.0 * (double) a.g.prune_slack);
+    a.rank = c->perm.p;                       // the coordinates came in free-energy order: position -> sorted index
+    a.level_min = level_min;
+    a.count = buf.p;
+    a.edges = buf.p + 1;
+    a.cap = buf.cap - 1;
+    CK(cudaMemsetAsync(buf.p, 0, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->scalars, 0, sizeof(unsigned int), c->stream));
+    CK(launch_edge((int) c->d, a, grid, c->stream));
+    c->launches += 1;
+    unsigned long long n_found = 0;
+    CK(cudaMemcpyAsync(&n_found, buf.p, sizeof(n_found), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *found = n_found;
+    if (n_found <= a.cap) return 0;
+    CK(buf.reserve((size_t) n_found + (size_t) (n_found / 16) + 2));          // now the count is known: scan once more
+  }
+  return fail("dcb200: the edge list kept growing between scans");
+}
+
+}  // namespace
+
 struct dcb200_screen {
   size_t n = 0, d = 0;
   int n_gpus = 1;
   Gang* gang = nullptr;
   size_t m_done = 0;                      // sorted positions [0, m_done) are in the forest
-  std::vector<DevBuf<uint32_t>> comp;     // per GPU: forest [n] (+ scratch [n_gpus][n] for the gathered forests)
   std::vector<float> sorted;              // host copy of the sorted coordinates: the per-GPU contexts are shared with the other
   std::vector<uint64_t> gen;              // entry points; if one of them replaced the layout (gen), the session restores it
+  // GPU 0: the forest and the edge list, sorted by level (= the larger sorted index of the pair)
+  DevBuf<uint32_t> forest;
+  DevBuf<unsigned long long> edges, edges_alt;
+  std::vector<DevBuf<unsigned long long>> part;      // per GPU: counter + the edges its rows found
+  size_t n_edges = 0, e_done = 0;
+  float cut = 0.f;
+  bool have_edges = false;
+  DevBuf<uint32_t> order, flag, rank, labels;        // naming on the device (dcb200_screen_labels)
+  bool have_order = false;
 };
 
-// (re)builds the session's layout on every GPU of its gang: one upload (+ NCCL broadcast), keep_order layout
+// (re)builds the session's layout on every GPU of its gang: one upload (+ NCCL broadcast), spatial order
 static int screen_upload(dcb200_screen* s) {
   Gang* G = s->gang;
   Rendezvous rv(G->n);
@@ -2173,16 +2278,55 @@ static int screen_upload(dcb200_screen* s) {
     } else if (r0) {
       return r0;
     }
-    CKI(build_layout(c, c->stage.p, s->n, s->d, true));
+    CKI(build_layout(c, c->stage.p, s->n, s->d, false));
     s->gen[g] = c->layout_gen;
     return 0;
   });
+}
+
+// all edges with level >= level_min of the session's frames, gathered on GPU 0 and sorted by level
+static int screen_build_edges(dcb200_screen* s, float cut, uint32_t level_min) {
+  Gang* G = s->gang;
+  bool replaced = false;                  // another entry point used the shared contexts in between: restore the layout
+  for (int g = 0; g < G->n; ++g) replaced |= G->ctx[g]->layout_gen != s->gen[g];
+  if (replaced) CKI(screen_upload(s));
+  std::vector<unsigned long long> found(G->n, 0);
+  CKI(on_gpus(G->n, [&](int g, int W) -> int { return edge_scan(G->ctx[g], g, W, cut, level_min, s->part[g], &found[g]); }));
+  size_t total = 0;
+  for (int g = 0; g < G->n; ++g) total += (size_t) found[g];
+  dcb200_ctx* c0 = G->ctx[0];
+  CK(cudaSetDevice(c0->device));
+  CK(s->edges.reserve(std::max<size_t>(total, 1)));
+  CK(s->edges_alt.reserve(std::max<size_t>(total, 1)));
+  size_t off = 0;
+  for (int g = 0; g < G->n; ++g) {
+    if (found[g] == 0) continue;
+    // peer copy: direct over NVLink where peer access is possible, staged by the driver otherwise
+    CK(cudaMemcpyPeerAsync(s->edges_alt.p + off, c0->device, s->part[g].p + 1, G->ctx[g]->device, (size_t) found[g] * sizeof(unsigned long long),
+                           c0->stream));
+    off += (size_t) found[g];
+  }
+  if (total) {
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, s->edges_alt.p, s->edges.p, (int) total, 32, 64, c0->stream));
+    CK(c0->cub_tmp.reserve(tmp_bytes));
+    CK(cub::DeviceRadixSort::SortKeys(c0->cub_tmp.p, tmp_bytes, s->edges_alt.p, s->edges.p, (int) total, 32, 64, c0->stream));
+    c0->launches += 4;
+  }
+  CK(cudaStreamSynchronize(c0->stream));
+  s->n_edges = total;
+  s->e_done = 0;
+  s->cut = cut;
+  s->have_edges = true;
+  if (getenv("DCB200_TRACE")) fprintf(stderr, "[dcb200] screening: %zu edges within the cut (%.1f per frame)\n", total, (double) total / (double) s->n);
+  return 0;
 }
 
 extern "C" int dcb200_screen_begin(const float* sorted_coords, size_t n_sorted, size_t n_cols, dcb200_screen** out) {
   if (!sorted_coords || !out) return fail("dcb200_screen_begin: null argument");
   *out = nullptr;
   if (n_sorted == 0 || n_cols == 0) return fail("dcb200_screen_begin: empty coordinate array");
+  if (n_sorted >= 0x7fffffffull) return fail("dcb200_screen_begin: too many frames");
   std::lock_guard<std::mutex> call(g_call_mutex);
   dcb200_screen* s = new dcb200_screen();
   s->n = n_sorted;
@@ -2194,124 +2338,135 @@ extern "C" int dcb200_screen_begin(const float* sorted_coords, size_t n_sorted, 
     return rc;
   }
   Gang* G = s->gang;
-  s->comp.resize(G->n);
+  s->part.resize(G->n);
   s->gen.assign(G->n, 0);
   s->sorted.assign(sorted_coords, sorted_coords + n_sorted * n_cols);
   rc = screen_upload(s);
-  if (!rc)
-    rc = on_gpus(G->n, [&](int g, int W) -> int {
-      dcb200_ctx* c = G->ctx[g];
+  if (!rc) {
+    dcb200_ctx* c = G->ctx[0];
+    auto forest = [&]() -> int {
       CK(cudaSetDevice(c->device));
-      CK(s->comp[g].reserve(n_sorted * (W > 1 ? (size_t) W + 1 : 1)));
-      iota_kernel<<<blocks_for(n_sorted, 256), 256, 0, c->stream>>>(s->comp[g].p, n_sorted);
+      CK(s->forest.reserve(n_sorted));
+      iota_kernel<<<blocks_for(n_sorted, 256), 256, 0, c->stream>>>(s->forest.p, n_sorted);
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(c->stream));
       return 0;
-    });
+    };
+    rc = forest();
+  }
   if (rc) {
-    for (auto& b : s->comp) b.release();
-    delete s;
+    dcb200_screen_end(s);
     return rc;
   }
   *out = s;
   return 0;
 }
 
-// Extends the forest to the sorted positions [0, m_new) (edges: d2 < max_dist2 between a new row and any lower position)
-// and writes every position's representative (smallest sorted position of its cluster) to comp[0, m_new).
-// seed (optional, uint32 [m_done]): replaces the session's forest for the positions done so far (parents <= position).
-extern "C" int dcb200_screen_step(dcb200_screen* s, size_t m_new, float max_dist2, const uint32_t* seed, uint32_t* comp) {
-  if (!s || !comp) return fail("dcb200_screen_step: null argument");
+// Extends the forest to the sorted positions [0, m_new) (edges: d2 < max_dist2 between a new frame and any lower position);
+// seed (optional, uint32 [m_done]) replaces the forest of the positions done so far.  The flattened forest stays on GPU 0.
+static int screen_advance(dcb200_screen* s, size_t m_new, float max_dist2, const uint32_t* seed) {
   if (m_new > s->n) return fail("dcb200_screen_step: m_new exceeds the session's frames");
   if (m_new < s->m_done) return fail("dcb200_screen_step: thresholds must not decrease within a session");
-  std::lock_guard<std::mutex> call(g_call_mutex);
-  Gang* G = s->gang;
   const size_t m_prev = s->m_done;
-  bool replaced = false;                  // another entry point used the shared contexts since the last step: restore the layout
-  for (int g = 0; g < G->n; ++g) replaced |= G->ctx[g]->layout_gen != s->gen[g];
-  if (replaced) CKI(screen_upload(s));
   if (seed)
     for (size_t p = 0; p < m_prev; ++p)
       if (seed[p] > p) return fail("dcb200_screen_step: seed[p] must be <= p");
-  Rendezvous rv(G->n);
-  const bool nccl = G->n > 1 && G->nccl;
-  std::vector<std::vector<uint32_t>> parts(nccl ? 0 : G->n);
-  CKI(on_gpus(G->n, [&](int g, int W) -> int {
-    dcb200_ctx* c = G->ctx[g];
-    uint32_t* forest = s->comp[g].p;
-    auto scan = [&]() -> int {
-      CK(cudaSetDevice(c->device));
-      if (seed && m_prev) CK(cudaMemcpyAsync(forest, seed, m_prev * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-      if (m_new > m_prev) {
-        // rows are dealt so that every GPU gets about the same number of pairs (row p has p candidates)
-        auto cut = [&](int q) -> size_t {
-          const double lo = (double) m_prev * m_prev, hi = (double) m_new * m_new;
-          return q >= W ? m_new : (size_t) sqrt(lo + (hi - lo) * q / W);
-        };
-        const size_t b = std::max(m_prev, cut(g)), e = std::max(b, cut(g + 1));
-        CKI(dcb200_ctx_screening_scan(c, m_prev, m_new, b, e, max_dist2, forest));
-      }
-      CKI(dcb200_ctx_screening_flatten(c, m_new, forest));
-      return 0;
-    };
-    const int r0 = scan();
-    if (W == 1) {
-      if (r0) return r0;
-      CK(cudaMemcpyAsync(comp, forest, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      return 0;
-    }
-    if (nccl) {
-      // ONE all-gather moves the per-GPU forests; every GPU unions them on the device, so all forests stay identical
-      if (!rv.all_ok(r0 == 0)) return r0 ? r0 : fail("another GPU of the gang failed");
-      uint32_t* all = forest + s->n;
-      NCK(nccl_api().AllGather(forest, all, m_new, ncclUint32, G->comm[g], c->stream));
-      for (int q = 0; q < W; ++q)
-        if (q != g) CKI(dcb200_ctx_screening_merge(c, m_new, forest, all + (size_t) q * m_new));
-      CKI(dcb200_ctx_screening_flatten(c, m_new, forest));
-      if (g == 0) CK(cudaMemcpyAsync(comp, forest, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      return 0;
-    }
-    if (r0) return r0;
-    parts[g].resize(m_new);
-    CK(cudaMemcpyAsync(parts[g].data(), forest, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  // the edge list is built at the first step (the cut is known only now); a different cut means a new list.  Edges between
+  // two frames that are settled already (both below m_prev) are never needed.
+  if (!s->have_edges || max_dist2 != s->cut) CKI(screen_build_edges(s, max_dist2, (uint32_t) m_prev));
+  dcb200_ctx* c = s->gang->ctx[0];
+  CK(cudaSetDevice(c->device));
+  if (seed && m_prev) CK(cudaMemcpyAsync(s->forest.p, seed, m_prev * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  // edges that become active: level in [m_prev, m_new)
+  unsigned long long e_new = 0;
+  {
+    unsigned long long* dcount = reinterpret_cast<unsigned long long*>(c->scalars + 2);   // transient scratch ([2], [3])
+    edge_count_below_kernel<<<1, 1, 0, c->stream>>>(s->edges.p, s->n_edges, (uint32_t) m_new, dcount);
+    CK(cudaMemcpyAsync(&e_new, dcount, sizeof(e_new), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    return 0;
-  }));
-  if (G->n > 1 && !nccl) {
-    // merge the per-GPU forests on the host (roots are the smallest position of a component) and hand the result back
-    std::vector<uint32_t>& par = parts[0];
-    auto find = [&](uint32_t x) {
-      while (par[x] != x) { par[x] = par[par[x]]; x = par[x]; }
-      return x;
-    };
-    for (int g = 1; g < G->n; ++g)
-      for (size_t p = 0; p < m_new; ++p) {
-        uint32_t x = find((uint32_t) p), y = find(parts[g][p]);
-        if (x == y) continue;
-        if (x < y) std::swap(x, y);
-        par[x] = y;
-      }
-    for (size_t p = 0; p < m_new; ++p) comp[p] = find((uint32_t) p);
-    CKI(on_gpus(G->n, [&](int g, int) -> int {
-      dcb200_ctx* c = G->ctx[g];
-      CK(cudaSetDevice(c->device));
-      CK(cudaMemcpyAsync(s->comp[g].p, comp, m_new * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      return 0;
-    }));
   }
+  if (e_new > s->e_done) {
+    const size_t cnt = (size_t) e_new - s->e_done;
+    edge_union_kernel<<<blocks_for(cnt, 256), 256, 0, c->stream>>>(s->edges.p, s->e_done, (size_t) e_new, s->forest.p);
+    c->launches += 1;
+  }
+  if (m_new) CKI(dcb200_ctx_screening_flatten(c, m_new, s->forest.p));
+  CK(cudaGetLastError());
+  s->e_done = std::max(s->e_done, (size_t) e_new);
   s->m_done = m_new;
+  return 0;
+}
+
+// ... and writes every position's representative (smallest sorted position of its cluster) to comp[0, m_new)
+extern "C" int dcb200_screen_step(dcb200_screen* s, size_t m_new, float max_dist2, const uint32_t* seed, uint32_t* comp) {
+  if (!s || !comp) return fail("dcb200_screen_step: null argument");
+  std::lock_guard<std::mutex> call(g_call_mutex);
+  CKI(screen_advance(s, m_new, max_dist2, seed));
+  dcb200_ctx* c = s->gang->ctx[0];
+  if (m_new) CK(cudaMemcpyAsync(comp, s->forest.p, m_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// order[p] = frame at sorted position p (all n_sorted of them): lets the session name the clusters on the device
+extern "C" int dcb200_screen_set_order(dcb200_screen* s, const uint32_t* order) {
+  if (!s || !order) return fail("dcb200_screen_set_order: null argument");
+  std::lock_guard<std::mutex> call(g_call_mutex);
+  dcb200_ctx* c = s->gang->ctx[0];
+  CK(cudaSetDevice(c->device));
+  CK(s->order.reserve(s->n));
+  CK(s->flag.reserve(s->n));
+  CK(s->rank.reserve(s->n));
+  CK(s->labels.reserve(s->n));
+  CK(cudaMemcpyAsync(s->order.p, order, s->n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  s->have_order = true;
+  return 0;
+}
+
+// One threshold with the naming on the device: labels [n_sorted] in FRAME order (through the order given to
+// dcb200_screen_set_order), clusters numbered 1..K by ascending representative, 0 above the threshold.
+extern "C" int dcb200_screen_labels(dcb200_screen* s, size_t m_new, float max_dist2, uint32_t* labels, uint32_t* n_clusters) {
+  if (!s || !labels) return fail("dcb200_screen_labels: null argument");
+  std::lock_guard<std::mutex> call(g_call_mutex);
+  if (!s->have_order) return fail("dcb200_screen_labels: call dcb200_screen_set_order first");
+  CKI(screen_advance(s, m_new, max_dist2, nullptr));
+  dcb200_ctx* c = s->gang->ctx[0];
+  uint32_t last[2] = {0, 0};
+  if (m_new) {
+    root_flag_kernel<<<blocks_for(m_new, 256), 256, 0, c->stream>>>(s->forest.p, m_new, s->flag.p);
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, s->flag.p, s->rank.p, (int) m_new, c->stream));
+    CK(c->cub_tmp.reserve(tmp_bytes));
+    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, s->flag.p, s->rank.p, (int) m_new, c->stream));
+    CK(cudaMemcpyAsync(&last[0], s->rank.p + (m_new - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&last[1], s->flag.p + (m_new - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  label_scatter_kernel<<<blocks_for(s->n, 256), 256, 0, c->stream>>>(s->forest.p, s->rank.p, s->order.p, m_new, s->n, s->labels.p);
+  c->launches += 4;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(labels, s->labels.p, s->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (n_clusters) *n_clusters = last[0] + last[1];
   return 0;
 }
 
 extern "C" int dcb200_screen_end(dcb200_screen* s) {
   if (!s) return 0;
   std::lock_guard<std::mutex> call(g_call_mutex);
-  for (size_t g = 0; g < s->comp.size(); ++g) {
-    cudaSetDevice(s->gang->ctx[g]->device);
-    s->comp[g].release();
+  if (s->gang) {
+    for (size_t g = 0; g < s->part.size(); ++g) {
+      cudaSetDevice(s->gang->ctx[g]->device);
+      s->part[g].release();
+    }
+    cudaSetDevice(s->gang->ctx[0]->device);
+    s->forest.release();
+    s->edges.release();
+    s->edges_alt.release();
+    s->order.release();
+    s->flag.release();
+    s->rank.release();
+    s->labels.release();
   }
   delete s;
   return 0;

@@ -445,6 +445,9 @@ int density_main(const Args& args, const std::string& header_comment) {
       // one screening run for all thresholds: free energies sorted once, sorted coordinates resident on the device(s);
       // the labels are those of the reference's call-per-threshold loop (density_clustering.cpp:806-816)
       std::vector<uint32_t> clustering(coords.n_rows);
+      const char* lb = getenv("DCB200_LABELS_BIN");
+      const bool labels_bin = lb && lb[0] == '1';
+      bool first_label_file = true;
       dcb200_screening_run* run = nullptr;
       if (dcb200_screening_begin(free_energies.data(), nb.nn_d2.data(), coords.data.data(), coords.n_rows, coords.n_cols, &run))
         die_cuda("screening");
@@ -455,8 +458,13 @@ int density_main(const Args& args, const std::string& header_comment) {
           for (float f : free_energies) below += f <= t;
           std::cout << "    " << std::setw(6) << stringprintf("%.2f", t) << " " << std::setw(9) << below << std::endl;
         }
-        write_clustered_trajectory(stringprintf((output_file + ".%0.2f").c_str(), t), clustering.data(), clustering.size(),
-                                   header_comment, comments);
+        const std::string label_file = stringprintf((output_file + ".%0.2f").c_str(), t);
+        write_clustered_trajectory(label_file, clustering.data(), clustering.size(), header_comment, comments);
+        // DCB200_LABELS_BIN=1: also keep the labels as raw uint32 in <out>.dcb200labels for `clustering network` (8f-4)
+        if (labels_bin) {
+          write_labels_record(label_file, clustering.data(), clustering.size(), first_label_file);
+          first_label_file = false;
+        }
       }
       dcb200_screening_end(run);
     } else {

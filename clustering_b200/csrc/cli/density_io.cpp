@@ -289,6 +289,84 @@ void write_neighborhood(const std::string& filename, const uint32_t* nn_idx, con
 
 }  // namespace dcb_cli
 
+// ---- binary side channel of the per-threshold label files ------------------------------------------
+// `clustering density -T` writes one N-line ASCII file per threshold (<out>.0.10, <out>.0.20, ...: 100+ files at 5M frames)
+// and `clustering network` reads them all back, one read_clustered_trajectory per file (network_builder.cpp:411-437): the
+// ASCII round trip is most of that mode's time.  The container <out>.dcb200labels keeps the same labels as raw uint32,
+// one record per file; a reader that finds a record for the file it was asked for -- and whose recorded ASCII size
+// still matches the file on disk -- takes the binary copy instead of parsing.  The ASCII files stay the format of record.
+namespace dcb_cli {
+namespace {
+const char LABELS_MAGIC[8] = {'D', 'C', 'B', '2', 'L', 'B', 'L', '1'};
+
+// "<base>.<int>.<2 digits>" (the reference's "%0.2f" suffix) -> "<base>.dcb200labels"; empty if the name has no such suffix
+std::string container_of(const std::string& filename) {
+  const size_t n = filename.size();
+  if (n < 5 || !isdigit((unsigned char) filename[n - 1]) || !isdigit((unsigned char) filename[n - 2]) || filename[n - 3] != '.') return "";
+  size_t p = n - 3;
+  size_t q = p;
+  while (q > 0 && isdigit((unsigned char) filename[q - 1])) --q;
+  if (q == p || q == 0 || filename[q - 1] != '.') return "";
+  return filename.substr(0, q - 1) + ".dcb200labels";
+}
+std::string leaf_of(const std::string& filename) {
+  const size_t s = filename.find_last_of('/');
+  return s == std::string::npos ? filename : filename.substr(s + 1);
+}
+long long file_size(const std::string& filename) {
+  FILE* f = fopen(filename.c_str(), "rb");
+  if (!f) return -1;
+  fseek(f, 0, SEEK_END);
+  const long long sz = ftell(f);
+  fclose(f);
+  return sz;
+}
+}  // namespace
+
+void write_labels_record(const std::string& text_file, const uint32_t* states, std::size_t n, bool truncate) {
+  const std::string container = container_of(text_file);
+  if (container.empty()) throw IoError("error: '" + text_file + "' does not end in a threshold suffix (.%0.2f): no label container for it");
+  const long long text_bytes = file_size(text_file);
+  if (text_bytes < 0) throw IoError("error: cannot open file '" + text_file + "'");
+  FILE* f = fopen(container.c_str(), truncate ? "wb" : "ab");
+  if (!f) throw IoError("error: cannot open file '" + container + "' for writing.");
+  const std::string leaf = leaf_of(text_file);
+  const uint64_t hdr[3] = {(uint64_t) leaf.size(), (uint64_t) n, (uint64_t) text_bytes};
+  bool ok = fwrite(LABELS_MAGIC, 1, 8, f) == 8 && fwrite(hdr, sizeof(uint64_t), 3, f) == 3 &&
+            fwrite(leaf.data(), 1, leaf.size(), f) == leaf.size() && fwrite(states, sizeof(uint32_t), n, f) == n;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) throw IoError("error: short write to '" + container + "'");
+}
+
+bool read_labels_record(const std::string& text_file, std::vector<uint32_t>& out) {
+  const std::string container = container_of(text_file);
+  if (container.empty()) return false;
+  FILE* f = fopen(container.c_str(), "rb");
+  if (!f) return false;
+  const std::string leaf = leaf_of(text_file);
+  const long long text_bytes = file_size(text_file);
+  bool found = false;
+  for (;;) {                                   // the last record of a name wins (a re-run appends)
+    char magic[8];
+    uint64_t hdr[3];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, LABELS_MAGIC, 8) != 0 || fread(hdr, sizeof(uint64_t), 3, f) != 3) break;
+    if (hdr[0] > 4096) break;
+    std::string name((size_t) hdr[0], '\0');
+    if (hdr[0] && fread(&name[0], 1, (size_t) hdr[0], f) != hdr[0]) break;
+    if (name == leaf && (long long) hdr[2] == text_bytes) {
+      std::vector<uint32_t> v((size_t) hdr[1]);
+      if (fread(v.data(), sizeof(uint32_t), v.size(), f) != v.size()) break;
+      out.swap(v);
+      found = true;
+    } else if (fseek(f, (long) (hdr[1] * sizeof(uint32_t)), SEEK_CUR) != 0) {
+      break;
+    }
+  }
+  fclose(f);
+  return found;
+}
+}  // namespace dcb_cli
+
 // ---- C ABI of the file formats (include/dcb200.h, section "file formats") -------------------------------------
 #include "../../../include/dcb200.h"
 
@@ -387,5 +465,25 @@ extern "C" int dcb200_io_read_comment(const char* filename, const char* key, flo
     m[key] = current;
     dcb_cli::read_comments(filename, m);
     *value = m[key];
+  });
+}
+
+// binary side channel of the per-threshold label files (see write_labels_record)
+extern "C" int dcb200_io_write_states_record(const char* text_filename, const uint32_t* states, size_t n, int truncate) {
+  DCB_IO_NEED(text_filename && (states || !n), "dcb200_io_write_states_record");
+  return guarded("dcb200_io_write_states_record", [&] { dcb_cli::write_labels_record(text_filename, states, n, truncate != 0); });
+}
+extern "C" int dcb200_io_read_states(const char* filename, uint32_t* out, size_t capacity, size_t* n, int* from_binary) {
+  DCB_IO_NEED(filename && n, "dcb200_io_read_states");
+  return guarded("dcb200_io_read_states", [&] {
+    std::vector<uint32_t> v;
+    const bool bin = dcb_cli::read_labels_record(filename, v);
+    if (!bin) {
+      const std::vector<std::size_t> t = dcb_cli::read_single_column_size(filename);
+      v.assign(t.begin(), t.end());
+    }
+    if (from_binary) *from_binary = bin ? 1 : 0;
+    *n = v.size();
+    if (out) memcpy(out, v.data(), std::min(capacity, v.size()) * sizeof(uint32_t));
   });
 }

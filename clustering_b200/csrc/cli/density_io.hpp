@@ -49,6 +49,12 @@ void write_clustered_trajectory(const std::string& filename, const uint32_t* tra
 void write_neighborhood(const std::string& filename, const uint32_t* nn_idx, const float* nn_d2, const uint32_t* hd_idx,
                         const float* hd_d2, std::size_t n, const std::string& header, const CommentsMap& comments);
 
+// binary side channel of the per-threshold label files: record of `text_file`'s labels in the container
+// <out>.dcb200labels next to it; read_labels_record is true when a record for the file exists AND the ASCII file on
+// disk still has the size it had when the record was written
+void write_labels_record(const std::string& text_file, const uint32_t* states, std::size_t n, bool truncate);
+bool read_labels_record(const std::string& text_file, std::vector<uint32_t>& out);
+
 std::string comments_block(const CommentsMap& comments);      // append_commentsMap
 std::string stringprintf(const char* fmt, double v);           // one float argument is all the driver needs
 

@@ -218,7 +218,6 @@ struct dcb200_screening_run {
   std::vector<uint32_t> order;
   float max_dist2 = 0.f;
   dcb200_screen* scan = nullptr;
-  std::vector<uint32_t> comp;
   size_t m_done = 0;
   float last_threshold = 0.f;
   bool any = false;
@@ -245,13 +244,13 @@ extern "C" int dcb200_screening_begin(const float* fe, const float* nn_d2, const
     gather_rows(coords, n_cols, r->order.data(), n_rows, sorted.data());
     lap("gather");
     rc = dcb200_screen_begin(sorted.data(), n_rows, n_cols, &r->scan);
+    if (!rc) rc = dcb200_screen_set_order(r->scan, r->order.data());
     lap("upload+layout");
   }
   if (rc) {
     delete r;
     return rc;
   }
-  r->comp.resize(n_rows);
   *out = r;
   return 0;
 }
@@ -261,22 +260,14 @@ extern "C" int dcb200_screening_next(dcb200_screening_run* r, float threshold, u
   if (r->any && threshold < r->last_threshold) return dcb200_internal_fail("dcb200_screening_next: thresholds must not decrease within a run");
   Lap lap;
   const size_t M = frames_below(r->fe.data(), r->order, threshold);
-  if (M > 0) {
-    const int rc = dcb200_screen_step(r->scan, M, r->max_dist2, nullptr, r->comp.data());
-    if (rc) return rc;
-  }
-  lap("pair scan (GPU)");
+  // the pair work, the union-find and the naming (clusters numbered 1..K by ascending representative = first sorted
+  // member) all happen on the device; one download brings the labels in frame order
+  const int rc = dcb200_screen_labels(r->scan, M, r->max_dist2, labels, nullptr);
+  if (rc) return rc;
+  lap("threshold (GPU)");
   r->m_done = M;
   r->last_threshold = threshold;
   r->any = true;
-  // clusters numbered 1..K by ascending representative (= first sorted member)
-  std::vector<uint32_t> rank(M, 0);
-  uint32_t k = 0;
-  for (size_t p = 0; p < M; ++p)
-    if (r->comp[p] == p) rank[p] = ++k;
-  memset(labels, 0, r->n * sizeof(uint32_t));
-  for (size_t p = 0; p < M; ++p) labels[r->order[p]] = rank[r->comp[p]];
-  lap("names");
   return 0;
 }
 

@@ -97,6 +97,21 @@ cudaError_t DCB_CAT(launch_screen_d, DCB_D)(const ScreenArgs& a, int grid, cudaS
   return cudaGetLastError();
 }
 
+cudaError_t DCB_CAT(launch_edge_d, DCB_D)(const EdgeArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = screen_smem_bytes(SmemRing<DCB_D>::bytes(a.g.d));
+  cudaError_t e = cudaFuncSetAttribute(edge_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  edge_kernel<DCB_D><<<grid, CTA_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+int DCB_CAT(occupancy_edge_d, DCB_D)(int d) {
+  int nb = 0;
+  const size_t smem = screen_smem_bytes(SmemRing<DCB_D>::bytes(d));
+  cudaFuncSetAttribute(edge_kernel<DCB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, edge_kernel<DCB_D>, CTA_THREADS, smem);
+  return nb;
+}
+
 int DCB_CAT(occupancy_pops_d, DCB_D)(int n_bins, int d) {
   int nb = 0;
   const size_t smem = pops_smem_bytes(SmemRing<DCB_D>::bytes(d), n_bins);

@@ -61,6 +61,7 @@ struct ScanGeom {
   float* blk_thr;                   // neighbour search only: [n_row_blocks][N_CONSUMER_WARPS] upper bounds (d2 units) of what the
                                     // rows of a block owned by one consumer warp still accept; lowered by atomicMin as items finish
   float prune_thr;                  // static pruning threshold (fast-value units); +inf disables pruning
+  int axis_prune;                   // (row group, tile) units of the count / neighbour kernels also pass a separating-axis test
 };
 
 // first row of row block rb of the launch, and the index of a row of that block in the launch's (compact) output arrays
@@ -433,6 +434,53 @@ __device__ __forceinline__ uint32_t groups_in_reach(const float* __restrict__ gb
   return __ballot_sync(0xffffffffu, !(s * 0.999f > thr_of_group)) & 0x11111111u;     // NaN keeps
 }
 
+// Separating-axis test of a (row group, tile) unit: a lower bound of the distance of every pair of the unit from the
+// extents of the rows and of the columns along ONE direction u (any direction gives a valid bound; the line between the
+// two centres is the one along which two separate blobs overlap least).  Rows: the thread's RI rows in tile-local
+// coordinates x' (Rows::retarget); columns: the tile's -2y' in shared memory (lane l looks at columns 4l .. 4l+3).
+// In 10 dimensions the boxes and spheres of two neighbouring clusters overlap while their extents along the line between
+// them do not (projection of a Gaussian blob: ~3 sigma, its radius: ~(sqrt(D) + 2) sigma).  ~130 instructions per unit.
+// Returns the bound on the DISTANCE (<= 0: none).  slack_len: rounding of the centres (globally centred coordinates).
+template <int D>
+__device__ __forceinline__ float axis_lower_bound(const ScanGeom& g, const Rows<D>& R, const float* __restrict__ tl, const float (&u)[D],
+                                                  float ymax, float slack_len, int lane) {
+  constexpr int TJ = TileW<D>::tj;
+  static_assert(TJ == 128, "one float4 of columns per lane");
+  float un = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) un = fmaf(u[k], u[k], un);
+  if (!(un > 0.f)) return 0.f;
+  const float inv = rsqrtf(un);
+  const float ulen = un * inv;
+  // rounding of a D-term FFMA chain over x'_k u_k: D ulp of |x'||u|, folded into the projections themselves
+  const float eps = (float) D * 2e-7f * ulen;
+  float pmin = INFINITY;
+#pragma unroll
+  for (int r = 0; r < RI; ++r) {
+    float pr = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) pr = fmaf(R.x[r][k], u[k], pr);
+    if (R.row(r) < g.row_end) pmin = fminf(pmin, pr - eps * sqrtf(R.xn[r]));
+  }
+  float q[CJ] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + 4 * lane);      // -2 y'
+    q[0] = fmaf(y4.x, u[k], q[0]);
+    q[1] = fmaf(y4.y, u[k], q[1]);
+    q[2] = fmaf(y4.z, u[k], q[2]);
+    q[3] = fmaf(y4.w, u[k], q[3]);
+  }
+  // padded columns hold y' = 0 (the tile's centre = the mean of its frames), inside the span of the real ones: harmless
+  float qmax = -0.5f * fminf(fminf(q[0], q[1]), fminf(q[2], q[3])) + eps * sqrtf(ymax);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+    qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+  }
+  return (pmin - qmax) * inv * 0.99999f - slack_len;
+}
+
 // register arrays must not be indexed dynamically (that would spill them to local memory)
 __device__ __forceinline__ float sel4(const float (&v)[RI], int r) {
   return r == 0 ? v[0] : r == 1 ? v[1] : r == 2 ? v[2] : v[3];
@@ -731,6 +779,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
   Rows<D> R;
   float wrow[RI];             // row part of the band half width: fast-path error bound + roundings of s and v
   uint32_t cnt[NB][RI];
+  const float slack_len = sqrtf(g.prune_slack);
   Pipe<StagesOf<D>::n> cp;
   SlowStats st;
   for (;;) {
@@ -762,9 +811,19 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) break;
         const uint32_t gi = __fns(reach, 0, (int) u + 1) >> 2;
-        ++st.wtiles;
         R.load_group(g, (uint32_t) m.row_block, gi, lane);
         R.retarget(g, tl + (D + 1) * TJ);
+        if (g.axis_prune) {
+          // separating-axis test along the line between the centre of the group's box and the tile's centre
+          const float* cen = tl + (D + 1) * TJ;
+          const float* blo = gbox + gi * 2 * GBOX_DIMS;
+          float ax[D];
+#pragma unroll
+          for (int k = 0; k < D; ++k) ax[k] = 0.5f * (blo[k] + blo[GBOX_DIMS + k]) - (cen[k] - __ldg(g.centre + k));
+          const float lbp = axis_lower_bound<D>(g, R, tl, ax, cen[D], slack_len, lane);
+          if (lbp > 0.f && lbp * lbp * 0.999f > g.prune_thr) continue;
+        }
+        ++st.wtiles;
         // |v - (d2_exact - r_b^2)| < wrow[r] + band[b]: fast-path error (eabs + e_rel r^2) + roundings of s and of v
 #pragma unroll
         for (int r = 0; r < RI; ++r) wrow[r] = fmaf(1.01f, R.eabs[r], 2.4e-7f * R.xn[r]);
@@ -1158,48 +1217,12 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
         // (projection of a Gaussian blob: ~3 sigma, its radius: ~(sqrt(D) + 2) sigma).  ~130 instructions per unit.
         if (a.proj_prune) {
           float u[D];
-          float un = 0.f;
 #pragma unroll
           for (int k = 0; k < D; ++k) {
             // lane k (< 16) holds the group's centre in globally centred coordinates; the tile's is cen[k] - centre[k]
-            const float gck = __shfl_sync(0xffffffffu, gc, k);
-            u[k] = gck - (cen[k] - __ldg(g.centre + k));
-            un = fmaf(u[k], u[k], un);
+            u[k] = __shfl_sync(0xffffffffu, gc, k) - (cen[k] - __ldg(g.centre + k));
           }
-          const float inv = un > 0.f ? rsqrtf(un) : 0.f;
-          float pmin = INFINITY;
-#pragma unroll
-          for (int r = 0; r < RI; ++r) {
-            float pr = 0.f;
-#pragma unroll
-            for (int k = 0; k < D; ++k) pr = fmaf(R.x[r][k], u[k], pr);
-            if (R.row(r) < g.row_end) pmin = fminf(pmin, pr);
-          }
-          float qmax = -INFINITY;
-          {
-            float q[CJ] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-              const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + 4 * lane);      // -2 y'
-              q[0] = fmaf(y4.x, u[k], q[0]);
-              q[1] = fmaf(y4.y, u[k], q[1]);
-              q[2] = fmaf(y4.z, u[k], q[2]);
-              q[3] = fmaf(y4.w, u[k], q[3]);
-            }
-            // padded columns hold y' = 0 (the tile's centre), inside the span of the real ones: harmless
-            qmax = -0.5f * fminf(fminf(q[0], q[1]), fminf(q[2], q[3]));
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
-            qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
-          }
-          // projections scaled by |u|: gap = (pmin - qmax) / |u|.  Rounding of the two D-term FFMA chains: D ulp of |x'||u| resp.
-          // |y'||u| with |x'| <= group radius + |u|, |y'| <= tile radius; slack_len covers the roundings of the centres
-          const float ulen = un * inv;
-          const float gap = (pmin - qmax) * inv;
-          const float slack = (float) D * 2e-7f * (grad + ulen + sqrtf(cen[D])) + slack_len;
-          const float lbp = gap * 0.99999f - slack;
+          const float lbp = axis_lower_bound<D>(g, R, tl, u, cen[D], slack_len, lane);
           if (lbp > 0.f && lbp * lbp * 0.999f > g.prune_thr) reach = false;
         }
       }
@@ -1529,6 +1552,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
   }
   Rows<D> R;
   NnFilter F;
+  const float slack_len = sqrtf(g.prune_slack);
   uint32_t col0 = 0, slot0 = 0;          // slot0: first slot of the group being worked on + lane
   Pipe<StagesOf<D>::n> cp;
   SlowStats st;
@@ -1621,9 +1645,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
       // peaks inter-cluster sized) lower-free-energy bound only if the tile holds a frame of lower rank than its largest
       // one at all.  The first warp to get here decides for everybody, so that unit numbers mean the same to all.
       uint32_t reach;
+      float lomin;
       {
         const float* lrow = cen + g.dp;
-        float lomin;
         if (TJ == 128) {
           const float4 q = *reinterpret_cast<const float4*>(lrow + 4 * lane);
           lomin = fminf(fminf(q.x, q.y), fminf(q.z, q.w));
@@ -1649,10 +1673,22 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) break;
         const uint32_t gi = __fns(reach, 0, (int) u + 1) >> 2;
-        ++st.wtiles;
         slot0 = gi * (32u * RI) + (uint32_t) lane;
         R.load_group(g, (uint32_t) m.row_block, gi, lane);
         R.retarget(g, cen);
+        if constexpr (D > 0) if (g.axis_prune) {
+          // separating-axis test along the line between the centre of the group's box and the tile's centre, against what
+          // the group's rows still accept (the bound of the moment: it may have tightened since the unit was listed)
+          float bound = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(gthr_nn + gi));
+          if (lomin < glor[gi]) bound = fmaxf(bound, __uint_as_float(*reinterpret_cast<volatile unsigned int*>(gthr_hd + gi)));
+          const float* blo = gbox + gi * 2 * GBOX_DIMS;
+          float ax[D ? D : 1];
+#pragma unroll
+          for (int k = 0; k < D; ++k) ax[k] = 0.5f * (blo[k] + blo[GBOX_DIMS + k]) - (cen[k] - __ldg(g.centre + k));
+          const float lbp = axis_lower_bound<D>(g, R, tl, ax, cen[D], slack_len, lane);
+          if (lbp > 0.f && lbp * lbp * 0.999f > bound) continue;
+        }
+        ++st.wtiles;
         // filter thresholds of this unit from the group's best keys so far (the error margin depends on the tile)
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
@@ -1787,6 +1823,105 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
     }
     col0 = m.col0;
     if (!(m.flags & 4u) && wb.reach(ring.tiles + cp.stage * ring.tile_floats + (d + 1) * TJ, lane, g.prune_thr)) {
+      const float* tl = ring.tiles + cp.stage * ring.tile_floats;
+      ++st.wtiles;
+      R.retarget(g, tl + (d + 1) * TJ);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));
+      scan_tile(g, tl, R, t, scratch, hit);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    cp.advance();
+  }
+  st.flush(g);
+}
+
+
+// ================================================================================================
+// screening as ONE neighbour-graph scan: all pairs {i, j} with d2 < cut of frames held in spatial order
+// ================================================================================================
+// The incremental scan above (screen_kernel) needs the frames in free-energy order, where tiles have no spatial
+// coherence: nothing is pruned and every threshold costs (new rows) x (all lower frames) -- N^2 / 2 pairs over a whole
+// screening run (ncu at 5M x 3: 50 ms per threshold at 49 % of the FFMA pipe, 3.1 s for 106 thresholds).  The clusters of
+// EVERY threshold follow from one list of edges instead: the pair {a, b} (free-energy-sorted indices, a > b) with
+// d2 < cut joins the graph exactly when frame a does, i.e. at the first threshold with more than a frames.  This kernel
+// scans the frames in the context's SPATIAL order (tiles pruned by the cut radius like a population scan, upper
+// triangle of the position matrix only) and emits (a << 32 | b) for every such pair; api.cu sorts the list by a and feeds
+// the union-find threshold by threshold.  rank[p] = free-energy-sorted index of the frame at position p.
+struct EdgeArgs {
+  ScanGeom g;
+  float cut;                      // (float)(4*sigma2); an edge needs d2 < cut (density_clustering.cpp:319)
+  float thr_fast;                 // cut (1 + e_rel)
+  const uint32_t* rank;           // [n] by position
+  uint32_t level_min;             // edges whose larger index is below this are not wanted (both ends settled already)
+  unsigned long long* edges;      // [cap]
+  unsigned long long cap;
+  unsigned long long* count;      // edges found; keeps counting past cap (api.cu then scans again with room for all)
+};
+
+template <int D>
+__global__ void DCB_LAUNCH_BOUNDS(D) edge_kernel(const __grid_constant__ EdgeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int TJ = TileW<D>::tj;
+  const ScanGeom& g = a.g;
+  const int d = D ? D : g.d;
+  SmemRing<D> ring(smem, d);
+  ring.init();
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == N_CONSUMER_WARPS) {
+    produce<D>(g, ring, false, [&](uint32_t rb, uint32_t& lim0, uint32_t&) {
+      // upper triangle of the position matrix: a pair is found from its lower position, so only tiles from the block's own on
+      lim0 = block_row0(g, rb) / TJ;
+    }, [&](uint32_t, int) { return g.prune_thr; });
+    return;
+  }
+  const int tid = threadIdx.x;
+  float* scratch = reinterpret_cast<float*>(smem + ((SmemRing<D>::bytes(d) + 15) & ~size_t(15))) + threadIdx.x;
+  Rows<D> R;
+  WarpBox<D> wb;
+  float t[RI];
+  Pipe<StagesOf<D>::n> cp;
+  SlowStats st;
+  uint32_t col0 = 0;
+  auto hit = [&](int r, int jt, float accv) {
+    const uint32_t j = col0 + jt;
+    const uint32_t i = R.row(r);
+    if (j <= i || j >= g.n || i >= g.row_end) return;
+    ++st.slow;
+    float s = accv + sel4(R.xn, r);
+    const float e = fmaf(g.e_rel, fabsf(s), sel4(R.eabs, r)) * 1.0001f;
+    if (fabsf(s - a.cut) <= e) {
+      s = dist2_exact(g.xT, g.ld, d, i, j);
+      ++st.exact;
+    }
+    if (!(s < a.cut)) return;
+    const uint32_t ri = __ldg(a.rank + i), rj = __ldg(a.rank + j);
+    const uint32_t hi = max(ri, rj), lo = min(ri, rj);
+    if (hi < a.level_min) return;
+    // the lanes that reach this point together reserve their slots with one atomic
+    const uint32_t peers = __activemask();
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(a.count, (unsigned long long) __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const unsigned long long slot = base + (unsigned long long) __popc(peers & ((1u << lane) - 1u));
+    if (slot < a.cap) a.edges[slot] = ((unsigned long long) hi << 32) | lo;
+  };
+  for (;;) {
+    mbar_wait(&ring.full[cp.stage], cp.phase);
+    const TileMeta m = ring.meta[cp.stage];
+    if (m.row_block < 0) break;
+    if (m.flags & 1u) {
+      R.load(g, (uint32_t) m.row_block, tid);
+      wb.compute(g, R, lane);
+    }
+    col0 = m.col0;
+    // tiles below the warp's own rows hold only lower positions: the other orientation finds those pairs
+    const bool ahead = m.col0 + (uint32_t) TJ > R.row0 - (uint32_t) lane;
+    if (!(m.flags & 4u) && ahead && wb.reach(ring.tiles + cp.stage * ring.tile_floats + (d + 1) * TJ, lane, g.prune_thr)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
       ++st.wtiles;
       R.retarget(g, tl + (d + 1) * TJ);

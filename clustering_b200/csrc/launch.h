@@ -8,6 +8,7 @@ namespace dcb {
 struct PopsArgs;
 struct NnArgs;
 struct ScreenArgs;
+struct EdgeArgs;
 
 #define DCB_FOR_EACH_D(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
@@ -21,7 +22,9 @@ struct ScreenArgs;
   int occupancy_pops_bin_d##D(int n_bins, int lut_k, int d);                 \
   int occupancy_nn_d##D(int d);                                              \
   cudaError_t launch_screen_d##D(const ScreenArgs&, int grid, cudaStream_t st); \
-  int occupancy_screen_d##D(int d);
+  int occupancy_screen_d##D(int d);                                          \
+  cudaError_t launch_edge_d##D(const EdgeArgs&, int grid, cudaStream_t st);  \
+  int occupancy_edge_d##D(int d);
 DCB_FOR_EACH_D(DCB_DECL)
 #undef DCB_DECL
 

@@ -26,6 +26,8 @@ def _L():
         L.dcb200_io_read_neighborhood.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                                   C.POINTER(C.c_size_t)]
         L.dcb200_io_read_comment.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.POINTER(C.c_float)]
+        L.dcb200_io_write_states_record.argtypes = [C.c_char_p, _u32, C.c_size_t, C.c_int]
+        L.dcb200_io_read_states.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         _bound = True
     return L
 
@@ -88,3 +90,19 @@ def read_comment(fname, key, current=0.0):
     v = C.c_float(0.0)
     lib.check(_L().dcb200_io_read_comment(fname.encode(), key.encode(), float(current), C.byref(v)))
     return v.value
+
+
+def write_states_record(text_fname, states, truncate=False):
+    """binary side channel of a per-threshold label file: record of text_fname's labels in <out>.dcb200labels."""
+    states = np.ascontiguousarray(states, np.uint32)
+    lib.check(_L().dcb200_io_write_states_record(text_fname.encode(), states, states.size, 1 if truncate else 0))
+
+
+def read_states(fname):
+    """-> (labels uint32 [n], from_binary): what read_clustered_trajectory returns for fname, from the binary container when
+    it holds a valid record for the file, else parsed from the ASCII file."""
+    n, b = C.c_size_t(0), C.c_int(0)
+    lib.check(_L().dcb200_io_read_states(fname.encode(), None, 0, C.byref(n), C.byref(b)))
+    out = np.empty(n.value, np.uint32)
+    lib.check(_L().dcb200_io_read_states(fname.encode(), out.ctypes.data, out.size, C.byref(n), C.byref(b)))
+    return out, bool(b.value)

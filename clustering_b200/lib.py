@@ -16,14 +16,14 @@ SYMBOLS = [
     "dcb200_assign_low_density_frames", "dcb200_sorted_cluster_names",
     "dcb200_io_write_pops", "dcb200_io_write_fes", "dcb200_io_write_states", "dcb200_io_write_neighborhood",
     "dcb200_io_read_coords", "dcb200_io_read_column_float", "dcb200_io_read_column_uint", "dcb200_io_read_neighborhood",
-    "dcb200_io_read_comment",
+    "dcb200_io_read_comment", "dcb200_io_write_states_record", "dcb200_io_read_states",
     "dcb200_ctx_create", "dcb200_ctx_destroy", "dcb200_ctx_stream", "dcb200_ctx_sync",
     "dcb200_ctx_set_coords", "dcb200_ctx_set_coords_device", "dcb200_ctx_set_coords_ex", "dcb200_ctx_order",
     "dcb200_ctx_to_frame_order", "dcb200_ctx_populations",
     "dcb200_ctx_free_energies", "dcb200_ctx_nn_prepare", "dcb200_ctx_nn_scan", "dcb200_ctx_nn_finish",
     "dcb200_ctx_screening_scan", "dcb200_ctx_screening_flatten", "dcb200_ctx_screening_merge", "dcb200_ctx_stats", "dcb200_ctx_ffma_peak",
     "dcb200_ctx_gemm_info", "dcb200_ctx_tf32_peak",
-    "dcb200_density_run", "dcb200_screen_begin", "dcb200_screen_step", "dcb200_screen_end",
+    "dcb200_density_run", "dcb200_screen_begin", "dcb200_screen_step", "dcb200_screen_end", "dcb200_screen_set_order", "dcb200_screen_labels",
     "dcb200_screening_begin", "dcb200_screening_next", "dcb200_screening_end",
     "dcb200_shard_capacity", "dcb200_ctx_shard_rows", "dcb200_ctx_populations_shard", "dcb200_ctx_nn_scan_shard",
     "dcb200_ctx_shards_to_frame_order", "dcb200_ctx_nn_finish_shards",

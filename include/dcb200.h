@@ -65,16 +65,24 @@ int dcb200_nearest_neighbors(const float* coords, size_t n_rows, size_t n_cols, 
  * The caller maps representatives to the reference's cluster numbers (1..K by ascending representative). */
 int dcb200_screening_step(const float* sorted_coords, size_t n_cols, size_t m_prev, size_t m_new, float max_dist2,
                           uint32_t* comp);
-/* The same pair scan as a session over ALL free-energy-sorted frames: the coordinates are uploaded and laid out ONCE
- * (on every selected GPU; with several GPUs one host copy + an NCCL broadcast) and the union-find forest stays on the
- * device(s) between thresholds.  dcb200_screen_step extends the forest from the positions done so far to [0, m_new)
- * (m_new must not decrease) and writes every position's representative to comp[0, m_new); seed (or NULL) replaces the
- * session's forest for the positions done so far (uint32 [positions done], seed[p] <= p).
+/* The same result as a session over ALL free-energy-sorted frames, by ONE neighbour-graph scan instead of one pair scan
+ * per threshold: at its first step the session scans the frames -- uploaded once, laid out in spatial order on every
+ * selected GPU, rows dealt block-cyclically -- for every pair with d2 < max_dist2 and sorts these edges by the sorted
+ * index of their later frame; a threshold then only unions the edges that became active since the previous one.  (The
+ * reference scans (new frames) x (all lower frames) at every threshold: N^2/2 pairs per run; the edge list costs about
+ * one population scan with r^2 = max_dist2.)  dcb200_screen_step extends the forest from the positions done so far to
+ * [0, m_new) (m_new must not decrease) and writes every position's representative to comp[0, m_new); seed (or NULL)
+ * replaces the session's forest for the positions done so far (uint32 [positions done], seed[p] <= p).
  * Sessions share the library's per-GPU contexts with the other host-pointer entry points: a call in between is allowed
  * (the session notices that its layout was replaced and restores it from its host copy), it just costs an upload. */
 typedef struct dcb200_screen dcb200_screen;
 int dcb200_screen_begin(const float* sorted_coords, size_t n_sorted, size_t n_cols, dcb200_screen** session);
 int dcb200_screen_step(dcb200_screen* session, size_t m_new, float max_dist2, const uint32_t* seed, uint32_t* comp);
+/* the same step with the cluster numbers made on the device: after dcb200_screen_set_order (order[p] = frame at sorted
+ * position p, uint32 [n_sorted]) dcb200_screen_labels writes the labels of ALL frames in FRAME order -- clusters numbered
+ * 1..K by ascending representative, 0 above the threshold -- and the number of clusters */
+int dcb200_screen_set_order(dcb200_screen* session, const uint32_t* order);
+int dcb200_screen_labels(dcb200_screen* session, size_t m_new, float max_dist2, uint32_t* labels, uint32_t* n_clusters);
 int dcb200_screen_end(dcb200_screen* session);
 
 /* One density run without leaving the device(s) between its stages -- what `clustering density -r/-R ... -p -d -b` computes
@@ -134,6 +142,16 @@ int dcb200_io_read_column_float(const char* filename, float* out, size_t capacit
 int dcb200_io_read_column_uint(const char* filename, uint32_t* out, size_t capacity, size_t* n);
 int dcb200_io_read_neighborhood(const char* filename, uint32_t* nn_idx, float* nn_d2, uint32_t* hd_idx, float* hd_d2,
                                 size_t capacity, size_t* n);
+/* Binary side channel of the per-threshold label files.  `clustering density -T` writes one N-line
+ * ASCII file per threshold and `clustering network` reads them all back (network_builder.cpp:411-437, one
+ * read_clustered_trajectory per file): the ASCII round trip dominates that mode.
+ *   dcb200_io_write_states_record: after the ASCII file <out>.<threshold> was written, stores its labels as raw uint32 in
+ *       the container <out>.dcb200labels (truncate != 0: start a new container);
+ *   dcb200_io_read_states: what read_clustered_trajectory returns for `filename`, taken from the container when it holds a
+ *       record for that file whose recorded ASCII size still matches the file on disk (*from_binary = 1), else parsed from
+ *       the ASCII file itself.  The ASCII files remain the format of record. */
+int dcb200_io_write_states_record(const char* text_filename, const uint32_t* states, size_t n, int truncate);
+int dcb200_io_read_states(const char* filename, uint32_t* out, size_t capacity, size_t* n, int* from_binary);
 /* value of "#@ key = ..." in the file (current: the value known so far, returned unchanged if the key is absent) */
 int dcb200_io_read_comment(const char* filename, const char* key, float current, float* value);
 

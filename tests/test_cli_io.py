@@ -158,3 +158,44 @@ def test_cli_argument_errors():
     assert r.returncode != 0 and "more than once" in r.stderr
     r = run_cli("density", "-f", "x", "--rad", "1")            # ambiguous abbreviation (radius / radii)
     assert r.returncode != 0 and "ambiguous" in r.stderr
+
+
+def test_label_side_channel_roundtrip(tmp_path):
+    """the binary container of the per-threshold label files.  A reader gets the labels from the container
+    only while the ASCII file it stands for is unchanged on disk; otherwise (no record, other size, other name pattern) it
+    parses the ASCII file -- the format of record -- like read_clustered_trajectory (network_builder.cpp:411-437)."""
+    from clustering_b200 import io
+    rng = np.random.default_rng(5)
+    base = str(tmp_path / "clust")
+    labels = {}
+    for k, t in enumerate((0.1, 0.2, 1.25)):
+        lab = rng.integers(0, 50, size=4000).astype(np.uint32)
+        fname = base + ".%0.2f" % t
+        io.write_states(fname, lab, "# header\n", {"screening_from": 0.1})
+        io.write_states_record(fname, lab, truncate=(k == 0))
+        labels[fname] = lab
+    assert os.path.exists(base + ".dcb200labels")
+    for fname, lab in labels.items():
+        got, from_bin = io.read_states(fname)
+        assert from_bin and np.array_equal(got, lab)
+        assert np.array_equal(io.read_column(fname, int), lab)            # the ASCII file says the same
+    # the ASCII file was rewritten by somebody else: the stale record must not be used
+    fname = base + ".0.20"
+    other = np.arange(3000, dtype=np.uint32)
+    io.write_states(fname, other, "# header\n", {})
+    got, from_bin = io.read_states(fname)
+    assert not from_bin and np.array_equal(got, other)
+    # a re-run appends a fresh record: the last one wins
+    io.write_states_record(fname, other)
+    got, from_bin = io.read_states(fname)
+    assert from_bin and np.array_equal(got, other)
+    # files without a threshold suffix have no container
+    plain = str(tmp_path / "states.dat")
+    io.write_states(plain, other, "", {})
+    got, from_bin = io.read_states(plain)
+    assert not from_bin and np.array_equal(got, other)
+    with pytest.raises(Exception):
+        io.write_states_record(plain, other)
+    # errors are statuses, not exits
+    with pytest.raises(Exception):
+        io.read_states(str(tmp_path / "missing.0.10"))

@@ -199,7 +199,8 @@ def test_position_range_shards_concatenate_to_the_full_scan(oracle, d, radii):
     sess.close()
 
 
-@pytest.mark.parametrize("d,radii,n", [(5, [0.3], 40_000), (10, [0.1 * i for i in range(1, 21)], 30_011), (3, [0.15, 0.3], 9_000)])
+@pytest.mark.parametrize("d,radii,n", [(5, [0.3], 40_000), (10, [0.1 * i for i in range(1, 21)], 30_011), (3, [0.15, 0.3], 9_000),
+                                       (20, [2.0, 2.6, 3.2], 5_000)])        # d = 20: GEMM-form path, contiguous shards
 def test_block_cyclic_shards_assemble_to_the_full_scan(oracle, d, radii, n):
     """The shard entry points the one-process-per-GPU driver uses (dcb200_ctx_*_shard, blocks of 1024 positions dealt
     round-robin) for 2, 3 and 8 emulated ranks on one device: gathered and assembled by the library's own kernels ==
