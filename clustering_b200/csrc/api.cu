@@ -2005,6 +2005,8 @@ int run_gang_nccl(Gang* G, const RunArgs& a) {
   });
 }
 
+int free_energies_host(const uint32_t* pops, size_t n, float* fe);   // below; the caller holds g_call_mutex
+
 // several GPUs without NCCL: every GPU uploads the coordinates itself, contiguous shards, assembly on the host
 int run_gang_host(Gang* G, const RunArgs& a) {
   const size_t n = a.n, R = a.n_radii;
@@ -2038,10 +2040,10 @@ int run_gang_host(Gang* G, const RunArgs& a) {
     for (size_t r = 0; r < R; ++r)
       for (size_t p = 0; p < n; ++p) pops[r * n + perm[p]] = tmp[r * n + p];
     if (a.fe_all)
-      for (size_t r = 0; r < R; ++r) CKI(dcb200_free_energies(pops + r * n, n, a.fe_all + r * n));
+      for (size_t r = 0; r < R; ++r) CKI(free_energies_host(pops + r * n, n, a.fe_all + r * n));
     if (want_nn || a.fe_out) {
       fe_host.resize(n);
-      CKI(dcb200_free_energies(pops + a.fe_radius * n, n, fe_host.data()));
+      CKI(free_energies_host(pops + a.fe_radius * n, n, fe_host.data()));
       if (a.fe_out) memcpy(a.fe_out, fe_host.data(), n * sizeof(float));
       fe_nn = fe_host.data();
     }
@@ -2128,6 +2130,12 @@ extern "C" int dcb200_free_energies(const uint32_t* pops, size_t n, float* fe) {
   if (!pops || !fe) return fail("dcb200_free_energies: null argument");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> call(g_call_mutex);
+  return free_energies_host(pops, n, fe);
+}
+
+namespace {
+// caller holds g_call_mutex
+int free_energies_host(const uint32_t* pops, size_t n, float* fe) {
   int n_gpus = 0;
   CKI(gpus_to_use(&n_gpus));
   dcb200_ctx* c = nullptr;
@@ -2143,6 +2151,7 @@ extern "C" int dcb200_free_energies(const uint32_t* pops, size_t n, float* fe) {
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
+}  // namespace
 
 // ---- screening ----------------------------------------------------------------------------------
 // A screening session works on ALL free-energy-sorted frames at once.  At its first step it scans the frames -- laid out in
@@ -2322,6 +2331,8 @@ static int screen_build_edges(dcb200_screen* s, float cut, uint32_t level_min) {
   return 0;
 }
 
+static void screen_free(dcb200_screen* s);   // caller holds g_call_mutex
+
 extern "C" int dcb200_screen_begin(const float* sorted_coords, size_t n_sorted, size_t n_cols, dcb200_screen** out) {
   if (!sorted_coords || !out) return fail("dcb200_screen_begin: null argument");
   *out = nullptr;
@@ -2355,7 +2366,7 @@ extern "C" int dcb200_screen_begin(const float* sorted_coords, size_t n_sorted, 
     rc = forest();
   }
   if (rc) {
-    dcb200_screen_end(s);
+    screen_free(s);
     return rc;
   }
   *out = s;
@@ -2454,6 +2465,12 @@ extern "C" int dcb200_screen_labels(dcb200_screen* s, size_t m_new, float max_di
 extern "C" int dcb200_screen_end(dcb200_screen* s) {
   if (!s) return 0;
   std::lock_guard<std::mutex> call(g_call_mutex);
+  screen_free(s);
+  return 0;
+}
+
+// caller holds g_call_mutex
+static void screen_free(dcb200_screen* s) {
   if (s->gang) {
     for (size_t g = 0; g < s->part.size(); ++g) {
       cudaSetDevice(s->gang->ctx[g]->device);
@@ -2469,7 +2486,6 @@ extern "C" int dcb200_screen_end(dcb200_screen* s) {
     s->labels.release();
   }
   delete s;
-  return 0;
 }
 
 // stateless form: one session per call
