@@ -599,8 +599,13 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, size_t rb_
   if (occupancy < 1) return fail("kernel does not fit on an SM (shared memory / registers)");
   *grid = c->sm_count * occupancy;
   // about 16 column items per row block: enough for load balance and for the column-step-major order
-  // (own neighbourhood first), few enough that the producers' per-item work stays negligible
-  tiles_per_item = std::min(std::max(tiles_per_item, (g->n_col_tiles + 15) / 16), max_tiles_per_item);
+  // (own neighbourhood first), few enough that the producers' per-item work stays negligible.  A shard of a multi-GPU
+  // run has 1/G of the row blocks: its column ranges shrink accordingly (down to the caller's minimum), so that the
+  // heavy items -- the few column ranges around a block's own position -- still come to several waves over the CTAs
+  // (C3 on 8 GPUs: 123 row blocks x 16 ranges left ~1.2 heavy items per CTA and the scan at 60 % of its one-GPU rate)
+  const uint32_t want_items = (uint32_t) *grid * (uint32_t) std::max(1, env_int("DCB200_ITEMS_PER_CTA", 48));
+  const uint32_t col_items = std::max(16u, (want_items + g->n_row_blocks - 1) / std::max(1u, g->n_row_blocks));
+  tiles_per_item = std::min(std::max(tiles_per_item, (g->n_col_tiles + col_items - 1) / col_items), max_tiles_per_item);
   g->tiles_per_item = std::max(1u, std::min(tiles_per_item, g->n_col_tiles));
   g->n_col_items = (g->n_col_tiles + g->tiles_per_item - 1) / g->tiles_per_item;
   if ((uint64_t) g->n_row_blocks * g->n_col_items >= 0x7fffffffull) return fail("too many work items");

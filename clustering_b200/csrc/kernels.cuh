@@ -268,60 +268,72 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
 //   x[r][k] = x_original - c_t[k],  xn[r] = |x'|^2,  eabs[r] = c_loc * (xn[r] + max|y'|^2 of the tile),
 // the absolute part of the fast path's rounding-error bound for this row against this tile.
 // The original coordinates are re-read from xT (coalesced, L1 resident after the first tile of an item).
+// register arrays must not be indexed dynamically (that would spill them to local memory)
+__device__ __forceinline__ float sel4(const float (&v)[RI], int r) {
+  return r == 0 ? v[0] : r == 1 ? v[1] : r == 2 ? v[2] : v[3];
+}
+__device__ __forceinline__ void put4(float (&v)[RI], int r, float x) {
+  if (r == 0) v[0] = x; else if (r == 1) v[1] = x; else if (r == 2) v[2] = x; else v[3] = x;
+}
+
+// Registers are the scarce resource of the specialised kernels (96 per thread at two CTAs per SM, 4 D of them row
+// operands): whatever can be recomputed in a few instructions outside the inner loop -- the clamped positions, the absolute
+// error part -- is a function, not a member, so that nothing of the inner loop's operands is spilled.
 template <int D>
 struct Rows {
   float x[RI][D];           // tile-local coordinates x'
   float xn[RI];             // |x'|^2
-  float eabs[RI];
+  float ymax;               // max |y'|^2 of the tile the rows are centred on
   uint32_t row0;
   uint32_t out0;            // index of row0 in the launch's output arrays (out_index)
-  uint32_t p[RI];           // clamped positions
   uint32_t stride;          // 32: the warp owns 128 consecutive rows; N_CONSUMERS: rows interleaved over the whole block
   __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * stride; }
   __device__ __forceinline__ uint32_t out(int r) const { return out0 + (uint32_t) r * stride; }
+  // clamped position: rows past the end read the last padded frame, their results are discarded
+  __device__ __forceinline__ uint32_t pos(const ScanGeom& g, int r) const { return min(row(r), (uint32_t) g.ld - 1u); }
+  // absolute part of the fast path's error bound of row r against the current tile
+  __device__ __forceinline__ float ea(const ScanGeom& g, int r) const { return g.c_loc * (sel4(xn, r) + ymax); }
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid, bool coherent = true) {
     stride = coherent ? 32u : (uint32_t) N_CONSUMERS;
     row0 = block_row0(g, rb) + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
     out0 = rb * (uint32_t) ROWS_PER_CTA + (row0 - block_row0(g, rb));
-#pragma unroll
-    for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);     // rows past the end: clamped, results discarded
   }
   // rows of row group gi (128 consecutive rows of the block), whichever warp works on them
   __device__ __forceinline__ void load_group(const ScanGeom& g, uint32_t rb, uint32_t gi, int lane) {
     stride = 32u;
     row0 = block_row0(g, rb) + gi * (32u * RI) + (uint32_t) lane;
     out0 = rb * (uint32_t) ROWS_PER_CTA + gi * (32u * RI) + (uint32_t) lane;
-#pragma unroll
-    for (int r = 0; r < RI; ++r) p[r] = (uint32_t) min((size_t) row(r), g.ld - 1);
   }
   __device__ __forceinline__ void retarget(const ScanGeom& g, const float* __restrict__ cen) {
     float c[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) c[k] = cen[k];
-    const float ymax = cen[D];
+    ymax = cen[D];
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
+      const uint32_t pr = pos(g, r);
       float s = 0.f;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
-        x[r][k] = __ldg(g.xT + (size_t) k * g.ld + p[r]) - c[k];
+        x[r][k] = __ldg(g.xT + (size_t) k * g.ld + pr) - c[k];
         s = fmaf(x[r][k], x[r][k], s);
       }
       xn[r] = s;
-      eabs[r] = g.c_loc * (s + ymax);
     }
   }
 };
 template <>
 struct Rows<0> {
   float xn[RI];
-  float eabs[RI];
+  float ymax;
   uint32_t row0;
   uint32_t out0;
   uint32_t p[RI];
   uint32_t stride;
   __device__ __forceinline__ uint32_t row(int r) const { return row0 + (uint32_t) r * stride; }
   __device__ __forceinline__ uint32_t out(int r) const { return out0 + (uint32_t) r * stride; }
+  __device__ __forceinline__ uint32_t pos(const ScanGeom&, int r) const { return p[r]; }
+  __device__ __forceinline__ float ea(const ScanGeom& g, int r) const { return g.c_loc * (sel4(xn, r) + ymax); }
   __device__ __forceinline__ void load(const ScanGeom& g, uint32_t rb, int tid, bool coherent = true) {
     stride = coherent ? 32u : (uint32_t) N_CONSUMERS;
     row0 = block_row0(g, rb) + (coherent ? (uint32_t) (tid >> 5) * (32u * RI) + (uint32_t) (tid & 31) : (uint32_t) tid);
@@ -348,12 +360,9 @@ struct Rows<0> {
         s[r] = fmaf(v, v, s[r]);
       }
     }
-    const float ymax = cen[g.d];
+    ymax = cen[g.d];
 #pragma unroll
-    for (int r = 0; r < RI; ++r) {
-      xn[r] = s[r];
-      eabs[r] = g.c_loc * (s[r] + ymax);
-    }
+    for (int r = 0; r < RI; ++r) xn[r] = s[r];
   }
 };
 
@@ -374,7 +383,7 @@ struct WarpBox {
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
         if (R.row(r) < g.row_end) {
-          const float v = __ldg(g.xT + (size_t) k * g.ld + R.p[r]) - ck;
+          const float v = __ldg(g.xT + (size_t) k * g.ld + R.pos(g, r)) - ck;
           lo = fminf(lo, v);
           hi = fmaxf(hi, v);
         }
@@ -481,13 +490,6 @@ __device__ __forceinline__ float axis_lower_bound(const ScanGeom& g, const Rows<
   return (pmin - qmax) * inv * 0.99999f - slack_len;
 }
 
-// register arrays must not be indexed dynamically (that would spill them to local memory)
-__device__ __forceinline__ float sel4(const float (&v)[RI], int r) {
-  return r == 0 ? v[0] : r == 1 ? v[1] : r == 2 ? v[2] : v[3];
-}
-__device__ __forceinline__ void put4(float (&v)[RI], int r, float x) {
-  if (r == 0) v[0] = x; else if (r == 1) v[1] = x; else if (r == 2) v[2] = x; else v[3] = x;
-}
 
 constexpr size_t SCRATCH_BYTES = (size_t) RI * CJ * N_CONSUMERS * 4;     // per-thread spill of one 4x4 block
 
@@ -687,7 +689,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
     int b = bin_of(rad2s, nb, s);
     const float lo = b > 0 ? rad2s[b - 1] : -INFINITY;
     const float hi = rad2s[b];
-    const float e = fmaf(g.e_rel, fabsf(s), sel4(R.eabs, r)) * 1.0001f;
+    const float e = fmaf(g.e_rel, fabsf(s), R.ea(g, r)) * 1.0001f;
     if ((s - lo < e) || (hi - s <= e)) {       // within the error band of a radius: decide exactly
       s = dist2_exact(g.xT, g.ld, d, i, j);
       ++st.exact;
@@ -714,7 +716,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
       R.retarget(g, tl + (d + 1) * TileW<D>::tj);
       // every pair with exact d2 < r_max^2 has acc < t[r]  (thr_fast = r_max^2 (1 + e_rel), eabs: absolute error part)
 #pragma unroll
-      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));
+      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.ea(g, r) - R.xn[r]));
       scan_tile(g, tl, R, t, scratch, hit);
     }
     __syncwarp();
@@ -826,7 +828,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
         ++st.wtiles;
         // |v - (d2_exact - r_b^2)| < wrow[r] + band[b]: fast-path error (eabs + e_rel r^2) + roundings of s and of v
 #pragma unroll
-        for (int r = 0; r < RI; ++r) wrow[r] = fmaf(1.01f, R.eabs[r], 2.4e-7f * R.xn[r]);
+        for (int r = 0; r < RI; ++r) wrow[r] = fmaf(1.01f, R.ea(g, r), 2.4e-7f * R.xn[r]);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
@@ -1121,7 +1123,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
     return *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(lut) + (__float_as_uint(v) & kmask4));
   };
   Rows<D> R;
-  float t[RI], bw[RI];
+  float thr_s = 0.f;          // every pair with exact d2 < r_max^2 has s = fl(acc + |x'|^2) < thr_s (one value per thread, see bwm)
+  float bwm = 0.f;            // band half width (s units): ONE value per thread, the widest of its rows (a wider band only
+                              // sends a few more pairs to the exact recheck), to keep the inner loop's registers for operands
   float glo = 0.f, ghi = 0.f, gc = 0.f, grad = 0.f;     // geometry of this warp's group: lane k holds dim k
   bool gvalid = false, slow_unit = false;
   const float slack_len = sqrtf(g.prune_slack);
@@ -1134,10 +1138,9 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
     *p = (uint16_t) (*p + delta);
   };
   // candidate-by-candidate path (sparse steps, and every step of a unit the table cannot serve)
-  auto hit = [&](int r, int jt, float accv) {
+  auto hit = [&](int r, int jt, float s) {
     const uint32_t j = col0 + jt;
     const uint32_t i = R.row(r);
-    float s = accv + sel4(R.xn, r);
     if (i >= g.row_end) return;
     ++st.slow;
     int b;
@@ -1145,12 +1148,12 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
     if (!slow_unit) {
       const float e = entry(s);
       b = (int) (__float_as_uint(e) & 31u) + (s >= e ? 1 : 0);
-      inband = fabsf(s - e) < sel4(bw, r);
+      inband = fabsf(s - e) < bwm;
     } else {
       b = bin_of(rad2s, nb, s);
       const float lo = b > 0 ? rad2s[b - 1] : -INFINITY;
       const float hi = rad2s[b];
-      const float e = fmaf(g.e_rel, fabsf(s), sel4(R.eabs, r)) * 1.0001f;
+      const float e = fmaf(g.e_rel, fabsf(s), R.ea(g, r)) * 1.0001f;
       inband = (s - lo < e) || (hi - s <= e);
     }
     if (inband) {
@@ -1228,16 +1231,18 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
       }
       if (reach) {
         ++st.wtiles;
-        bool wide = false;
+        bwm = 0.f;
+        float eam = 0.f;
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-          // every pair with exact d2 < r_max^2 has acc < t[r]  (thr_fast = r_max^2 (1 + e_rel), eabs: absolute error part)
-          t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));
-          // |s - e - (d2_exact - B_k)| < bw[r]: fast-path error (eabs + e_rel r^2), roundings of s, the table's perturbation of B_k
-          bw[r] = fmaf(1.01f, R.eabs[r], 2.4e-7f * R.xn[r]) + a.band_max;
-          wide |= !(bw[r] < a.lut_margin);
+          eam = fmaxf(eam, R.ea(g, r));
+          // |s - e - (d2_exact - B_k)| < bw: fast-path error (ea + e_rel r^2), roundings of s, the table's perturbation of B_k
+          bwm = fmaxf(bwm, fmaf(1.01f, R.ea(g, r), 2.4e-7f * R.xn[r]) + a.band_max);
         }
-        slow_unit = __any_sync(0xffffffffu, wide);
+        // exact d2 < r_max^2  =>  acc + |x'|^2 < thr_fast + ea in real arithmetic (thr_fast = r_max^2 (1 + e_rel)); the factor
+        // covers the rounding of the sum s and of the threshold itself
+        thr_s = next_up((a.thr_fast + eam) * 1.000001f);
+        slow_unit = __any_sync(0xffffffffu, !(bwm < a.lut_margin));
 #pragma unroll 1
         for (int gcol = 0; gcol < TJ; gcol += CJ) {
           float acc[RI][CJ];
@@ -1267,7 +1272,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
 #pragma unroll
           for (int r = 0; r < RI; ++r) {
             const float mn = fminf(fminf(acc[r][0], acc[r][1]), fminf(acc[r][2], acc[r][3]));
-            any |= (mn < t[r]);
+            any |= (mn + R.xn[r] < thr_s);
           }
           const uint32_t act = __ballot_sync(0xffffffffu, any);
           if (act == 0u) continue;
@@ -1289,7 +1294,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
                   const float dlt = s - e;
                   // bin = k + (s >= e): k from the entry's low bits, the comparison from the sign of s - e
                   const uint32_t b = (__float_as_uint(e) & 31u) + 1u - (__float_as_uint(dlt) >> 31);
-                  band |= fabsf(dlt) < bw[r];
+                  band |= fabsf(dlt) < bwm;
                   hp[cc][r] = reinterpret_cast<uint16_t*>(hrow(r) + b * BIN_STRIDE);
                 }
 #pragma unroll
@@ -1314,7 +1319,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
                 const float s = scratch[p * N_CONSUMERS] + sel4(R.xn, r);
                 const float e = entry(s);
                 const float dlt = s - e;
-                if (fabsf(dlt) < sel4(bw, r)) {
+                if (fabsf(dlt) < bwm) {
                   const int bf = (int) ((__float_as_uint(e) & 31u) + 1u - (__float_as_uint(dlt) >> 31));     // as counted above
                   ++st.slow;
                   ++st.exact;
@@ -1328,7 +1333,22 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
               }
             }
           } else if (any) {
-            walk_hits(scratch, acc, t, gcol, hit);
+            // sparse step: the block is parked in shared memory and this lane's candidates are walked one by one
+            uint32_t mask = 0;
+#pragma unroll
+            for (int r = 0; r < RI; ++r)
+#pragma unroll
+              for (int c = 0; c < CJ; ++c) {
+                const float sv = acc[r][c] + R.xn[r];
+                scratch[(r * CJ + c) * N_CONSUMERS] = sv;
+                mask |= (sv < thr_s) ? (1u << (r * CJ + c)) : 0u;
+              }
+#pragma unroll 1
+            while (mask) {
+              const int p = __ffs(mask) - 1;
+              mask &= mask - 1;
+              hit(p / CJ, gcol + (p % CJ), scratch[p * N_CONSUMERS]);
+            }
           }
         }
       }
@@ -1572,7 +1592,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     if (!(d2 < FLT_MAX)) return;
     const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | __ldg(a.perm + j);
     // another warp may be working on the same rows with another tile: the keys are only ever lowered, atomically
-    const float xnr = sel4(R.xn, r), ear = sel4(R.eabs, r);
+    const float xnr = sel4(R.xn, r), ear = R.ea(g, r);
     bool changed = false;
     if (key < atomicMin(best + slot, key)) {
       const float v = thr(d2, ear, xnr);
@@ -1694,10 +1714,10 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
         for (int r = 0; r < RI; ++r) {
           const uint32_t slot = slot0 + (uint32_t) r * 32u;
           F.lor[r] = lor_s[slot];
-          F.t_nn[r] = thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + slot)), R.eabs[r], R.xn[r]);
+          F.t_nn[r] = thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + slot)), R.ea(g, r), R.xn[r]);
           // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
           F.t_hd[r] = lo_s[slot] == 0 ? F.t_nn[r]
-                                      : thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + ROWS_PER_CTA + slot)), R.eabs[r], R.xn[r]);
+                                      : thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + ROWS_PER_CTA + slot)), R.ea(g, r), R.xn[r]);
           F.set_dl(r);
         }
         scan_tile_nn(g, tl, cen + g.dp, R, F, scratch, hit);
@@ -1806,7 +1826,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
     if (j >= i || i >= g.row_end) return;
     ++st.slow;
     float s = accv + sel4(R.xn, r);
-    const float e = fmaf(g.e_rel, fabsf(s), sel4(R.eabs, r)) * 1.0001f;
+    const float e = fmaf(g.e_rel, fabsf(s), R.ea(g, r)) * 1.0001f;
     if (fabsf(s - a.cut) <= e) {
       s = dist2_exact(g.xT, g.ld, d, i, j);
       ++st.exact;
@@ -1827,7 +1847,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
       ++st.wtiles;
       R.retarget(g, tl + (d + 1) * TJ);
 #pragma unroll
-      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));
+      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.ea(g, r) - R.xn[r]));
       scan_tile(g, tl, R, t, scratch, hit);
     }
     __syncwarp();
@@ -1892,7 +1912,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) edge_kernel(const __grid_constant__ EdgeArg
     if (j <= i || j >= g.n || i >= g.row_end) return;
     ++st.slow;
     float s = accv + sel4(R.xn, r);
-    const float e = fmaf(g.e_rel, fabsf(s), sel4(R.eabs, r)) * 1.0001f;
+    const float e = fmaf(g.e_rel, fabsf(s), R.ea(g, r)) * 1.0001f;
     if (fabsf(s - a.cut) <= e) {
       s = dist2_exact(g.xT, g.ld, d, i, j);
       ++st.exact;
@@ -1926,7 +1946,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) edge_kernel(const __grid_constant__ EdgeArg
       ++st.wtiles;
       R.retarget(g, tl + (d + 1) * TJ);
 #pragma unroll
-      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.eabs[r] - R.xn[r]));
+      for (int r = 0; r < RI; ++r) t[r] = next_up(next_up(a.thr_fast + R.ea(g, r) - R.xn[r]));
       scan_tile(g, tl, R, t, scratch, hit);
     }
     __syncwarp();
