@@ -155,4 +155,37 @@ struct Pipe {
   }
 };
 
+// Hand-back of ring stages from the consumer warps to the producer warp through the named barriers
+// STAGE_BARRIER0 + stage: every consumer warp arrives (bar.arrive, does not wait) when it is done with a stage, the
+// producer warp syncs on the barrier before it refills the stage.  A producer whose ring is full is parked by the
+// hardware and takes no issue slots: with mbarrier polling (try_wait with a suspend hint, or test_wait + nanosleep --
+// neither really sleeps) the waiting producers issued 14 % of all instructions of the C3 population scan
+// (profiles/ncu_summary_r02_c3.txt), in the scheduler slots of the consumer warps they wait for.
+// Whole warps execute these, converged.  Fill k (k = 0, 1, ...) uses stage k % NSTAGES and is handed back once; the
+// producer syncs before fill k >= NSTAGES and drains what is still out at the end, so every barrier completes.
+constexpr int STAGE_BARRIER0 = 2;             // 0: __syncthreads, 1: consumer_barrier
+__device__ __forceinline__ void stage_release(uint32_t stage) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(STAGE_BARRIER0 + stage), "n"(CTA_THREADS) : "memory");
+}
+template <int NSTAGES>
+struct FillPipe {
+  static_assert(STAGE_BARRIER0 + NSTAGES <= 16, "one named barrier per stage");
+  uint32_t stage = 0, fills = 0;
+  // wait until the consumers are done with the previous content of the current stage
+  __device__ __forceinline__ void acquire() const {
+    if (fills >= (uint32_t) NSTAGES) asm volatile("bar.sync %0, %1;" ::"r"(STAGE_BARRIER0 + stage), "n"(CTA_THREADS) : "memory");
+  }
+  __device__ __forceinline__ void advance() {
+    ++fills;
+    if (++stage == NSTAGES) stage = 0;
+  }
+  // after the end-of-stream marker (which the consumers do not hand back): collect the hand-backs still out
+  __device__ __forceinline__ void drain() {
+    for (int q = 0; q < NSTAGES - 1; ++q) {
+      advance();
+      acquire();
+    }
+  }
+};
+
 }  // namespace dcb

@@ -101,7 +101,7 @@ struct SmemRing {
   float* tiles;            // STAGES * ((d+1) * TJ + dp + xrows * TJ): column pack of the tile, its centre entry (tcen),
                            // then the optional extra row
   uint64_t* full;          // STAGES
-  uint64_t* empty;         // STAGES
+  uint64_t* empty;         // STAGES (unused: stages are handed back through named barriers, common.cuh: stage_release)
   TileMeta* meta;          // STAGES
   unsigned long long* wthr;   // N_CONSUMER_WARPS: (item << 32 | float bits) pruning threshold published per row group
   uint32_t* unext;         // STAGES: next (row group, tile) unit of the stage to hand out (dynamic kernels)
@@ -128,7 +128,6 @@ struct SmemRing {
     if (threadIdx.x == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], N_CONSUMER_WARPS);
       }
       for (int w = 0; w < N_CONSUMER_WARPS; ++w) wthr[w] = ~0ull;
       fence_mbar_init();
@@ -164,7 +163,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
   constexpr int TJ = TileW<D>::tj;
   constexpr int GPT = TJ / 64;                      // 64-frame bounding-box groups per tile
   const int lane = threadIdx.x & 31;
-  Pipe<StagesOf<D>::n> pp;
+  FillPipe<StagesOf<D>::n> pp;
   const int d = D ? D : g.d;
   const uint32_t total = g.n_row_blocks * g.n_col_items;
   unsigned long long streamed = 0;
@@ -215,10 +214,11 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
             // a value published for another item says nothing about this one
             thr = fmaxf(thr, (uint32_t) (v >> 32) == item ? __uint_as_float((uint32_t) v) : INFINITY);
           }
-          if (__shfl_sync(0xffffffffu, lb, src) > thr) continue;
+          // one lane decides for the warp: the stage hand-back below is a warp-wide barrier instruction
+          if (__shfl_sync(0xffffffffu, (int) (__shfl_sync(0xffffffffu, lb, src) > thr), 0)) continue;
         }
+        pp.acquire();
         if (lane == 0) {
-          mbar_wait_backoff(&ring.empty[pp.stage], pp.phase ^ 1);
           TileMeta m;
           m.row_block = (int32_t) rb;
           m.col0 = tt * TJ;
@@ -242,24 +242,30 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
         pp.advance();
       }
     }
-    if (!first && lane == 0) {                    // end-of-item marker
-      mbar_wait_backoff(&ring.empty[pp.stage], pp.phase ^ 1);
-      TileMeta m;
-      m.row_block = (int32_t) rb;
-      m.col0 = 0;
-      m.flags = 2u | 4u;
-      m.aux = item;
-      ring.meta[pp.stage] = m;
-      mbar_arrive(&ring.full[pp.stage]);
+    if (!first) {                                 // end-of-item marker
+      __syncwarp();
+      pp.acquire();
+      if (lane == 0) {
+        TileMeta m;
+        m.row_block = (int32_t) rb;
+        m.col0 = 0;
+        m.flags = 2u | 4u;
+        m.aux = item;
+        ring.meta[pp.stage] = m;
+        mbar_arrive(&ring.full[pp.stage]);
+      }
+      pp.advance();
     }
-    if (!first) pp.advance();
   }
+  __syncwarp();
+  pp.acquire();
   if (lane == 0) {
-    mbar_wait_backoff(&ring.empty[pp.stage], pp.phase ^ 1);
     ring.meta[pp.stage].row_block = -1;
     mbar_arrive(&ring.full[pp.stage]);
     if (g.stats && streamed) atomicAdd(g.stats + 2, streamed);
   }
+  __syncwarp();
+  pp.drain();
 }
 
 // Row operands of a consumer thread: rows row0 + 32 r, r = 0..RI-1, so that a warp owns 32*RI = 128 CONSECUTIVE rows of the
@@ -365,6 +371,81 @@ struct Rows<0> {
     for (int r = 0; r < RI; ++r) xn[r] = s[r];
   }
 };
+
+// The fast value of one RI x CJ block: acc[r][c] = |y'_c|^2 - 2 x'_r . y'_c for columns g .. g+CJ-1 of the tile at tl
+// (tlg = tl + g; dim-major rows of TJ floats, row D = |y'|^2): one broadcast LDS.128 per dim.
+// sm_100 has a packed FP32 FMA (fma.rn.f32x2, SASS FFMA2: two IEEE FMAs -- the same bits as two FFMAs -- whose second
+// source may be one scalar broadcast to both halves): rows r, r+1 share an instruction, the accumulators of the two rows
+// sit in an aligned register pair.  Same FMA-pipe time, half the issue slots (scripts/micro/ffma2.cu).
+#ifndef DCB_FFMA2
+#define DCB_FFMA2 1
+#endif
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+template <int D>
+__device__ __forceinline__ void fast_block(const float* __restrict__ tlg, const Rows<D>& R, float (&acc)[RI][CJ]) {
+  constexpr int TJ = TileW<D>::tj;
+#if DCB_FFMA2
+  static_assert(RI == 4 && CJ == 4, "row pairs (0,1) and (2,3)");
+  unsigned long long a2[RI / 2][CJ];
+  {
+    const float4 n4 = *reinterpret_cast<const float4*>(tlg + D * TJ);
+    const float4 y4 = *reinterpret_cast<const float4*>(tlg);
+    const float yc[CJ] = {y4.x, y4.y, y4.z, y4.w}, nc[CJ] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+    for (int h = 0; h < RI / 2; ++h)
+#pragma unroll
+      for (int c = 0; c < CJ; ++c) a2[h][c] = fma2(pack2(R.x[2 * h][0], R.x[2 * h + 1][0]), pack2(yc[c], yc[c]), pack2(nc[c], nc[c]));
+  }
+#pragma unroll
+  for (int k = 1; k < D; ++k) {
+    const float4 y4 = *reinterpret_cast<const float4*>(tlg + k * TJ);
+    const float yc[CJ] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+    for (int h = 0; h < RI / 2; ++h)
+#pragma unroll
+      for (int c = 0; c < CJ; ++c) a2[h][c] = fma2(pack2(R.x[2 * h][k], R.x[2 * h + 1][k]), pack2(yc[c], yc[c]), a2[h][c]);
+  }
+#pragma unroll
+  for (int h = 0; h < RI / 2; ++h)
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) unpack2(a2[h][c], acc[2 * h][c], acc[2 * h + 1][c]);
+#else
+  {
+    const float4 n4 = *reinterpret_cast<const float4*>(tlg + D * TJ);
+    const float4 y4 = *reinterpret_cast<const float4*>(tlg);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
+      acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
+      acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
+      acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
+    }
+  }
+#pragma unroll
+  for (int k = 1; k < D; ++k) {
+    const float4 y4 = *reinterpret_cast<const float4*>(tlg + k * TJ);
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
+      acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
+      acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
+      acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
+    }
+  }
+#endif
+}
 
 // Bounding box of the 128 rows a consumer warp owns (globally centred coordinates, the same arithmetic as the tile
 // boxes of api.cu: pack_tiles_kernel); lane k holds dimension k.  reach() is the warp-level version of the producer's
@@ -526,28 +607,7 @@ __device__ __forceinline__ void scan_tile(const ScanGeom&, const float* __restri
 #pragma unroll 1
   for (int g = 0; g < TJ; g += CJ) {
     float acc[RI][CJ];
-    {
-      const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + g);
-      const float4 y4 = *reinterpret_cast<const float4*>(tl + g);
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
-        acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
-        acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
-        acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
-      }
-    }
-#pragma unroll
-    for (int k = 1; k < D; ++k) {
-      const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + g);
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
-        acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
-        acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
-        acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
-      }
-    }
+    fast_block<D>(tl + g, R, acc);
     bool any = false;
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
@@ -720,7 +780,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_kernel(const __grid_constant__ PopsArg
       scan_tile(g, tl, R, t, scratch, hit);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    stage_release(cp.stage);
     if (m.flags & 2u) {
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
@@ -846,28 +906,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
 #pragma unroll 1
         for (int gcol = 0; gcol < TJ; gcol += CJ) {
           float acc[RI][CJ];
-          {
-            const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + gcol);
-            const float4 y4 = *reinterpret_cast<const float4*>(tl + gcol);
-#pragma unroll
-            for (int r = 0; r < RI; ++r) {
-              acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
-              acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
-              acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
-              acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
-            }
-          }
-#pragma unroll
-          for (int k = 1; k < D; ++k) {
-            const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + gcol);
-#pragma unroll
-            for (int r = 0; r < RI; ++r) {
-              acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
-              acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
-              acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
-              acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
-            }
-          }
+          fast_block<D>(tl + gcol, R, acc);
           bool band = false;
 #pragma unroll
           for (int r = 0; r < RI; ++r) {
@@ -923,7 +962,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    stage_release(cp.stage);
     if (m.flags & 2u) {
       // end of the item: every unit is done once all consumer warps are here; this warp writes group `warp` back
       consumer_barrier();
@@ -999,7 +1038,7 @@ template <int D>
 __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& ring, float* __restrict__ pgeo) {
   constexpr int TJ = TileW<D>::tj;
   const int lane = threadIdx.x & 31;
-  Pipe<StagesOf<D>::n> pp;
+  FillPipe<StagesOf<D>::n> pp;
   const uint32_t total = g.n_row_blocks * g.n_col_items;
   const uint32_t rec = (uint32_t) ((D + 1) * TJ + g.dp);
   const float slack_len = sqrtf(g.prune_slack);
@@ -1049,8 +1088,8 @@ __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& r
         const int src = __ffs(mask) - 1;
         const uint32_t tt = base + (uint32_t) src;
         mask &= mask - 1;
+        pp.acquire();
         if (lane == 0) {
-          mbar_wait_sleep(&ring.empty[pp.stage], pp.phase ^ 1);
           TileMeta m;
           m.row_block = (int32_t) rb;
           m.col0 = tt * TJ;
@@ -1066,8 +1105,9 @@ __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& r
       }
     }
     if (!first) {
+      __syncwarp();
+      pp.acquire();
       if (lane == 0) {                              // end-of-item marker
-        mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
         TileMeta m;
         m.row_block = (int32_t) rb;
         m.col0 = 0;
@@ -1079,12 +1119,15 @@ __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& r
       pp.advance();
     }
   }
+  __syncwarp();
+  pp.acquire();
   if (lane == 0) {
-    mbar_wait(&ring.empty[pp.stage], pp.phase ^ 1);
     ring.meta[pp.stage].row_block = -1;
     mbar_arrive(&ring.full[pp.stage]);
     if (g.stats && streamed) atomicAdd(g.stats + 2, streamed);
   }
+  __syncwarp();
+  pp.drain();
 }
 
 template <int D>
@@ -1246,28 +1289,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
 #pragma unroll 1
         for (int gcol = 0; gcol < TJ; gcol += CJ) {
           float acc[RI][CJ];
-          {
-            const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + gcol);
-            const float4 y4 = *reinterpret_cast<const float4*>(tl + gcol);
-#pragma unroll
-            for (int r = 0; r < RI; ++r) {
-              acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
-              acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
-              acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
-              acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
-            }
-          }
-#pragma unroll
-          for (int k = 1; k < D; ++k) {
-            const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + gcol);
-#pragma unroll
-            for (int r = 0; r < RI; ++r) {
-              acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
-              acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
-              acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
-              acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
-            }
-          }
+          fast_block<D>(tl + gcol, R, acc);
           bool any = false;
 #pragma unroll
           for (int r = 0; r < RI; ++r) {
@@ -1354,7 +1376,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    stage_release(cp.stage);
     if (m.flags & 2u) {
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
@@ -1443,28 +1465,7 @@ __device__ __forceinline__ void scan_tile_nn(const ScanGeom&, const float* __res
 #pragma unroll 1
   for (int g = 0; g < TJ; g += CJ) {
     float acc[RI][CJ];
-    {
-      const float4 n4 = *reinterpret_cast<const float4*>(tl + D * TJ + g);
-      const float4 y4 = *reinterpret_cast<const float4*>(tl + g);
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        acc[r][0] = fmaf(R.x[r][0], y4.x, n4.x);
-        acc[r][1] = fmaf(R.x[r][0], y4.y, n4.y);
-        acc[r][2] = fmaf(R.x[r][0], y4.z, n4.z);
-        acc[r][3] = fmaf(R.x[r][0], y4.w, n4.w);
-      }
-    }
-#pragma unroll
-    for (int k = 1; k < D; ++k) {
-      const float4 y4 = *reinterpret_cast<const float4*>(tl + k * TJ + g);
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        acc[r][0] = fmaf(R.x[r][k], y4.x, acc[r][0]);
-        acc[r][1] = fmaf(R.x[r][k], y4.y, acc[r][1]);
-        acc[r][2] = fmaf(R.x[r][k], y4.z, acc[r][2]);
-        acc[r][3] = fmaf(R.x[r][k], y4.w, acc[r][3]);
-      }
-    }
+    fast_block<D>(tl + g, R, acc);
     const float4 l4 = *reinterpret_cast<const float4*>(lrow + g);
     bool any = false;
 #pragma unroll
@@ -1742,7 +1743,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    stage_release(cp.stage);
     if (m.flags & 2u) {
       // end of the item: every unit is done once all consumer warps are here; this warp writes group `warp` back
       consumer_barrier();
@@ -1851,7 +1852,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) screen_kernel(const __grid_constant__ Scree
       scan_tile(g, tl, R, t, scratch, hit);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    stage_release(cp.stage);
     cp.advance();
   }
   st.flush(g);
@@ -1950,7 +1951,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) edge_kernel(const __grid_constant__ EdgeArg
       scan_tile(g, tl, R, t, scratch, hit);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[cp.stage]);
+    stage_release(cp.stage);
     cp.advance();
   }
   st.flush(g);
