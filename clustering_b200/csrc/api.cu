@@ -1221,7 +1221,7 @@ static int populations_impl(dcb200_ctx* c, const float* radii, size_t n_radii, s
     a.lut_k = 0;
     a.lut_scale = a.lut_margin = a.band_max = 0.f;
     a.dense_lanes = 0;
-    a.interleave = 0;
+    a.steal = 0;
     a.proj_prune = 0;
     for (int q = 0; q < 8; ++q) a.band[q] = 0.f;
     if (count_mode) {
@@ -1249,8 +1249,8 @@ static int populations_impl(dcb200_ctx* c, const float* radii, size_t n_radii, s
       // the table's entries may differ from the radii they stand for
       a.band_max = up((1.02 * (double) a.g.e_rel + 4.0 * ldexp(1.0, -24) + 32.0 * ldexp(1.0, -23)) * rmax2 + 1e-37);
       a.dense_lanes = env_int("DCB200_BIN_DENSE_LANES", 8);
-      a.interleave = env_int("DCB200_BIN_INTERLEAVE", 0);
-      a.proj_prune = a.interleave ? 0 : (env_int("DCB200_BIN_PROJ", 1) == 1 ? 1 : 0);
+      a.steal = env_int("DCB200_BIN_STEAL", 1) == 1 ? 1 : 0;
+      a.proj_prune = env_int("DCB200_BIN_PROJ", 1) == 1 ? 1 : 0;
     }
     const bool counts_self = pm != HIST;           // count and bin mode count the frame itself through d2 = 0 < r^2
     CK(c->cnt.reserve((size_t) nb * ld_cnt));

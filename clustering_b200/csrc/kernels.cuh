@@ -691,7 +691,7 @@ struct PopsArgs {
                             // own perturbation of the boundaries (32 ulp)
   int dense_lanes;          // a 4x4 step is binned branch-free when at least this many lanes hold a candidate pair,
                             // else candidate by candidate
-  int interleave;           // diagnostics: rows interleaved over the block, every warp scans every streamed tile
+  int steal;                // a warp whose own row group has nothing to do with a streamed tile takes over another group's unit
   int proj_prune;           // separating-axis test of (row group, tile) units along the line between their centres
 };
 
@@ -1070,7 +1070,7 @@ __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& r
     bool first = true;
     for (uint32_t base = t0; base < t1; base += 32) {
       const uint32_t t = base + lane;
-      float lb = INFINITY;
+      uint32_t units = 0;                           // bit gi: group gi of the block comes within r_max of tile t
       if (t < t1) {
         const float* hdr = g.cT + (size_t) t * rec + (size_t) (D + 1) * TJ;
         float tlo[D], thi[D], tc[D];
@@ -1081,21 +1081,24 @@ __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& r
           thi[k] = __ldg(hdr + 2 * D + 1 + k);
         }
         const float trad = sqrtf(__ldg(hdr + D));
-        for (uint32_t gi = 0; gi < n_groups; ++gi) lb = fminf(lb, group_tile_lb<D>(pgeo + gi * PGEO, tlo, thi, tc, trad, slack_len));
+        for (uint32_t gi = 0; gi < n_groups; ++gi)
+          if (!(group_tile_lb<D>(pgeo + gi * PGEO, tlo, thi, tc, trad, slack_len) > g.prune_thr)) units |= 1u << gi;     // NaN keeps
       }
-      uint32_t mask = __ballot_sync(0xffffffffu, t < t1 && !(lb > g.prune_thr));     // NaN keeps
+      uint32_t mask = __ballot_sync(0xffffffffu, units != 0u);
       while (mask) {
         const int src = __ffs(mask) - 1;
         const uint32_t tt = base + (uint32_t) src;
         mask &= mask - 1;
+        const uint32_t units_tt = __shfl_sync(0xffffffffu, units, src);
         pp.acquire();
         if (lane == 0) {
           TileMeta m;
           m.row_block = (int32_t) rb;
           m.col0 = tt * TJ;
-          m.flags = first ? 1u : 0u;
+          m.flags = (first ? 1u : 0u) | (units_tt << 8);      // bits 8..15: the (row group, tile) units of the stage
           m.aux = item;
           ring.meta[pp.stage] = m;
+          ring.umask[pp.stage] = 0u;                          // units claimed so far
           mbar_arrive_expect_tx(&ring.full[pp.stage], rec * 4);
           tma_load_1d(ring.tiles + pp.stage * ring.tile_floats, g.cT + (size_t) tt * rec, rec * 4, &ring.full[pp.stage]);
         }
@@ -1169,8 +1172,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
   float thr_s = 0.f;          // every pair with exact d2 < r_max^2 has s = fl(acc + |x'|^2) < thr_s (one value per thread, see bwm)
   float bwm = 0.f;            // band half width (s units): ONE value per thread, the widest of its rows (a wider band only
                               // sends a few more pairs to the exact recheck), to keep the inner loop's registers for operands
-  float glo = 0.f, ghi = 0.f, gc = 0.f, grad = 0.f;     // geometry of this warp's group: lane k holds dim k
-  bool gvalid = false, slow_unit = false;
+  bool slow_unit = false;
   const float slack_len = sqrtf(g.prune_slack);
   Pipe<StagesOf<D>::n> cp;
   SlowStats st;
@@ -1206,68 +1208,91 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
     }
     if (b < nb) bump(r, b, 1);
   };
+  // The histogram belongs to the WARP, not to a row group: it holds the counts of group `cur` of row block `cur_rb` and is
+  // added to the global counters (and cleared) when the warp turns to another group and at the end of every item.  So any
+  // warp may work on any group's (group, tile) unit: a warp whose own group has nothing to do with a streamed tile takes
+  // over a unit of another group instead of running into the end of the ring and waiting there -- a row block that
+  // straddles two clusters streams first the tiles only one half of its groups can reach, then those of the other half.
+  constexpr uint32_t NONE = 0xffffffffu;
+  uint32_t cur = NONE, cur_rb = 0;
+  auto flush_hist = [&]() {
+    if (cur == NONE) return;
+    const uint32_t row_a = block_row0(g, cur_rb) + cur * (32u * RI) + (uint32_t) lane;        // row r of the thread: row_a + 32 r
+    const size_t out_a = (size_t) cur_rb * ROWS_PER_CTA + cur * (32u * RI) + (uint32_t) lane;
+    for (int b = 0; b <= nb; ++b) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(hb + b * BIN_STRIDE + h2 * (N_CONSUMERS * 4));
+        const uint32_t v = *w;
+        if (v) {
+          *w = 0u;
+          if (b < nb) {
+            const uint32_t c0 = v & 0xffffu, c1 = v >> 16, r0 = 2u * h2;
+            if (c0 && row_a + 32u * r0 < g.row_end) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + out_a + 32u * r0, c0);
+            if (c1 && row_a + 32u * (r0 + 1u) < g.row_end) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + out_a + 32u * (r0 + 1u), c1);
+          }
+        }
+      }
+    }
+    cur = NONE;
+  };
+  for (int b = 0; b <= nb; ++b) {
+    *reinterpret_cast<uint32_t*>(hb + b * BIN_STRIDE) = 0u;
+    *reinterpret_cast<uint32_t*>(hb + b * BIN_STRIDE + N_CONSUMERS * 4) = 0u;
+  }
   for (;;) {
     mbar_wait(&ring.full[cp.stage], cp.phase);
     const TileMeta m = ring.meta[cp.stage];
     if (m.row_block < 0) break;
-    if (m.flags & 1u) {
-      if (a.interleave) R.load(g, (uint32_t) m.row_block, threadIdx.x, false);
-      else R.load_group(g, (uint32_t) m.row_block, (uint32_t) warp, lane);
-      const uint32_t grow0 = block_row0(g, (uint32_t) m.row_block) + (uint32_t) warp * (32u * RI);
-      gvalid = grow0 < g.row_end || a.interleave;
-      if (gvalid && !a.interleave) {
-        const float* hdr = g.cT + (size_t) (grow0 / TJ) * ((D + 1) * TJ + g.dp) + (size_t) (D + 1) * TJ;
-        const int k = lane & 15;
-        if (k < D) {
-          glo = __ldg(hdr + D + 1 + k);
-          ghi = __ldg(hdr + 2 * D + 1 + k);
-          gc = __ldg(hdr + k) - __ldg(g.centre + k);
-        }
-        grad = sqrtf(__ldg(hdr + D));
-      }
-      for (int b = 0; b <= nb; ++b) {
-        *reinterpret_cast<uint32_t*>(hb + b * BIN_STRIDE) = 0u;
-        *reinterpret_cast<uint32_t*>(hb + b * BIN_STRIDE + N_CONSUMERS * 4) = 0u;
-      }
-    }
     col0 = m.col0;
-    if (!(m.flags & 4u) && gvalid) {
+    if (!(m.flags & 4u)) {
       const float* tl = ring.tiles + cp.stage * ring.tile_floats;
       const float* cen = tl + (D + 1) * TJ;
-      // does the tile come within r_max of this warp's group?  lanes 0..15: box gap per dim, lanes 16..31: centre distance per dim
-      bool reach = true;
-      if (!a.interleave) {
-        const int k = lane & 15;
-        float v = 0.f;
-        if (k < D) {
-          if (lane < 16) {
-            const float gap = fmaxf(fmaxf(glo - cen[2 * D + 1 + k], cen[D + 1 + k] - ghi), 0.f);
-            v = gap * gap;
-          } else {
-            const float dc = gc - (cen[k] - __ldg(g.centre + k));
-            v = dc * dc;
+      // which unit of the stage is this warp's?  Its own group's, if that group reaches the tile (nobody else is left with
+      // it then); else ONE unit nobody has claimed yet, preferably of the group whose counts the histogram already holds
+      const uint32_t units = (m.flags >> 8) & 0xffu;
+      uint32_t pick = NONE;
+      if ((units >> warp) & 1u) {
+        uint32_t old = 0;
+        if (lane == 0) old = atomicOr(&ring.umask[cp.stage], 1u << warp);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (!((old >> warp) & 1u)) pick = (uint32_t) warp;
+      } else if (a.steal) {
+        uint32_t cand = units & ~*reinterpret_cast<volatile uint32_t*>(&ring.umask[cp.stage]);
+        cand = __shfl_sync(0xffffffffu, cand, 0);
+        while (cand) {
+          const uint32_t c = (cur != NONE && ((cand >> cur) & 1u)) ? cur : (uint32_t) __ffs(cand) - 1u;
+          uint32_t old = 0;
+          if (lane == 0) old = atomicOr(&ring.umask[cp.stage], 1u << c);
+          old = __shfl_sync(0xffffffffu, old, 0);
+          if (!((old >> c) & 1u)) {
+            pick = c;
+            break;
           }
+          cand &= ~(old | (1u << c));
         }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const float sb = __shfl_sync(0xffffffffu, v, 0), sc = __shfl_sync(0xffffffffu, v, 16);
-        const float gap = sqrtf(sc) * 0.99999f - (grad + sqrtf(cen[D])) * 1.00001f - slack_len;
-        const float ss = gap > 0.f ? gap * gap : 0.f;
-        reach = !(fmaxf(sb, ss) * 0.999f > g.prune_thr);          // NaN keeps
       }
+      bool reach = pick != NONE;
       if (reach) {
+        if (pick != cur || cur_rb != (uint32_t) m.row_block) {
+          flush_hist();
+          cur = pick;
+          cur_rb = (uint32_t) m.row_block;
+        }
+        R.load_group(g, (uint32_t) m.row_block, pick, lane);
         R.retarget(g, cen);
         // Separating-axis test along the line from the tile's centre to the group's centre: the rows' smallest and the
         // columns' largest projection onto it bound the distance of every pair from below.  In 10 dimensions the boxes and
         // spheres of two neighbouring clusters overlap while their extents along the line between them do not
         // (projection of a Gaussian blob: ~3 sigma, its radius: ~(sqrt(D) + 2) sigma).  ~130 instructions per unit.
         if (a.proj_prune) {
+          // the group's centre: header of the group's own tile (a group is one tile of the spatial order), globally centred
+          const float* hdr = g.cT + (size_t) ((block_row0(g, (uint32_t) m.row_block) + pick * (32u * RI)) / TJ) * ((D + 1) * TJ + g.dp) +
+                             (size_t) (D + 1) * TJ;
+          const float gck = lane < D ? __ldg(hdr + lane) - __ldg(g.centre + lane) : 0.f;
           float u[D];
 #pragma unroll
-          for (int k = 0; k < D; ++k) {
-            // lane k (< 16) holds the group's centre in globally centred coordinates; the tile's is cen[k] - centre[k]
-            u[k] = __shfl_sync(0xffffffffu, gc, k) - (cen[k] - __ldg(g.centre + k));
-          }
+          for (int k = 0; k < D; ++k) u[k] = __shfl_sync(0xffffffffu, gck, k) - (cen[k] - __ldg(g.centre + k));
           const float lbp = axis_lower_bound<D>(g, R, tl, u, cen[D], slack_len, lane);
           if (lbp > 0.f && lbp * lbp * 0.999f > g.prune_thr) reach = false;
         }
@@ -1377,17 +1402,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
     }
     __syncwarp();
     stage_release(cp.stage);
-    if (m.flags & 2u) {
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        if (R.row(r) < g.row_end) {
-          for (int b = 0; b < nb; ++b) {
-            const uint32_t h = *reinterpret_cast<const uint16_t*>(hrow(r) + b * BIN_STRIDE);
-            if (h) atomicAdd(a.cnt + (size_t) b * a.ld_cnt + R.out(r), h);
-          }
-        }
-      }
-    }
+    if (m.flags & 2u) flush_hist();               // end of the item
     cp.advance();
   }
   st.flush(g);
