@@ -603,7 +603,7 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, size_t rb_
   // run has 1/G of the row blocks: its column ranges shrink accordingly (down to the caller's minimum), so that the
   // heavy items -- the few column ranges around a block's own position -- still come to several waves over the CTAs
   // (C3 on 8 GPUs: 123 row blocks x 16 ranges left ~1.2 heavy items per CTA and the scan at 60 % of its one-GPU rate)
-  const uint32_t want_items = (uint32_t) *grid * (uint32_t) std::max(1, env_int("DCB200_ITEMS_PER_CTA", 48));
+  const uint32_t want_items = (uint32_t) *grid * (uint32_t) std::max(1, env_int("DCB200_ITEMS_PER_CTA", 192));
   const uint32_t col_items = std::max(16u, (want_items + g->n_row_blocks - 1) / std::max(1u, g->n_row_blocks));
   tiles_per_item = std::min(std::max(tiles_per_item, (g->n_col_tiles + col_items - 1) / col_items), max_tiles_per_item);
   g->tiles_per_item = std::max(1u, std::min(tiles_per_item, g->n_col_tiles));

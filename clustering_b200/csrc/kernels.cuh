@@ -1426,9 +1426,10 @@ struct NnArgs {
 
 __host__ __device__ inline size_t screen_smem_bytes(size_t ring_bytes) { return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES; }
 
+constexpr size_t NN_PARK_BYTES = (size_t) 2 * RI * N_CONSUMERS * 4;      // per thread: t_hd[RI], |x'|^2[RI] (NnFilter)
 __host__ __device__ inline size_t nn_smem_bytes(size_t ring_bytes) {
-  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + (size_t) 2 * ROWS_PER_CTA * 8 + (size_t) 2 * ROWS_PER_CTA * 4 + gbox_bytes() +
-         (size_t) 3 * N_CONSUMER_WARPS * 4;
+  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + NN_PARK_BYTES + (size_t) 2 * ROWS_PER_CTA * 8 + (size_t) 2 * ROWS_PER_CTA * 4 +
+         gbox_bytes() + (size_t) 3 * N_CONSUMER_WARPS * 4;
 }
 
 __device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as_float((uint32_t) (k >> 32)); }
@@ -1439,12 +1440,18 @@ __device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as
 // Both in one comparison with a per-pair threshold  te = t_nn[r] + cand * dl[r],  cand = sat(lor[r] - lo_c) in {0,1}
 // (one FADD.SAT + one FFMA + one FSETP per pair): frames that are close but have no lower free energy never
 // reach the slow path, however far the lower-free-energy neighbour of a density peak is.
+// The inner loop reads t_nn, dl and lor; what only the candidate handler and the unit's prologue / epilogue need -- t_hd and
+// the rows' |x'|^2 -- is parked in shared memory ([value][thread]: conflict-free), so that at D = 9, 10 (96 registers, 40 of
+// them row operands) the loop's operands are not spilled.
 struct NnFilter {
-  float t_nn[RI], t_hd[RI];
+  float t_nn[RI];
   float dl[RI];                 // min(t_hd - t_nn, 1e37), rounded up; 0 where t_nn is +inf
   float lor[RI];                // (float rank of the row) + lo_bias
+  float* park;                  // this thread's slots: t_hd[r] at park[r * N_CONSUMERS], |x'|^2 of row r at park[(RI + r) * N_CONSUMERS]
+  __device__ __forceinline__ float& t_hd(int r) { return park[r * N_CONSUMERS]; }
+  __device__ __forceinline__ float& xn(int r) { return park[(RI + r) * N_CONSUMERS]; }
   __device__ __forceinline__ void set_dl(int r) {
-    const float tn = sel4(t_nn, r), th = sel4(t_hd, r);
+    const float tn = sel4(t_nn, r), th = t_hd(r);
     float v = 0.f;
     if (tn < INFINITY) v = th < INFINITY ? fminf(next_up((th - tn) * 1.000001f), 1e37f) : 1e37f;
     put4(dl, r, fmaxf(v, 0.f));
@@ -1557,8 +1564,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
   float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
   // per row of the block (slot = group * 128 + r * 32 + lane): best[0][slot] = nearest-neighbour key, best[1][slot] =
   // nearest neighbour with lower free energy, lo_s = free-energy rank, lor_s = the same rank as the filter's float
-  unsigned long long* best = reinterpret_cast<unsigned long long*>(extra + SCRATCH_BYTES);
-  uint32_t* lo_s = reinterpret_cast<uint32_t*>(extra + SCRATCH_BYTES + (size_t) 2 * ROWS_PER_CTA * 8);
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(extra + SCRATCH_BYTES + NN_PARK_BYTES);
+  uint32_t* lo_s = reinterpret_cast<uint32_t*>(extra + SCRATCH_BYTES + NN_PARK_BYTES + (size_t) 2 * ROWS_PER_CTA * 8);
   float* lor_s = reinterpret_cast<float*>(lo_s + ROWS_PER_CTA);
   float* gbox = lor_s + ROWS_PER_CTA;
   // per row group (float bits, d2 units, pruning margins included): gthr_nn = what its rows still accept as nearest neighbour,
@@ -1588,6 +1595,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
   }
   Rows<D> R;
   NnFilter F;
+  F.park = reinterpret_cast<float*>(extra + SCRATCH_BYTES) + threadIdx.x;
   const float slack_len = sqrtf(g.prune_slack);
   uint32_t col0 = 0, slot0 = 0;          // slot0: first slot of the group being worked on + lane
   Pipe<StagesOf<D>::n> cp;
@@ -1599,7 +1607,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     const uint32_t i = R.row(r);
     ++st.slow;
     if (j == i || j >= g.n || i >= g.row_end) return;
-    const float tn = sel4(F.t_nn, r), th = sel4(F.t_hd, r);
+    const float tn = sel4(F.t_nn, r), th = F.t_hd(r);
     const uint32_t slot = slot0 + (uint32_t) r * 32u;
     const bool hd_cand = __ldg(a.lo + j) < lo_s[slot];
     if (!(accv < tn) && !(hd_cand && accv < th)) return;      // thresholds may have tightened since the block was filtered
@@ -1608,15 +1616,15 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     if (!(d2 < FLT_MAX)) return;
     const unsigned long long key = ((unsigned long long) __float_as_uint(d2) << 32) | __ldg(a.perm + j);
     // another warp may be working on the same rows with another tile: the keys are only ever lowered, atomically
-    const float xnr = sel4(R.xn, r), ear = R.ea(g, r);
+    const float xnr = F.xn(r), ear = g.c_loc * (xnr + R.ymax);
     bool changed = false;
     if (key < atomicMin(best + slot, key)) {
       const float v = thr(d2, ear, xnr);
       put4(F.t_nn, r, v);
-      if (lo_s[slot] == 0) put4(F.t_hd, r, v);
+      if (lo_s[slot] == 0) F.t_hd(r) = v;
       changed = true;
     }
-    if (hd_cand && key < atomicMin(best + ROWS_PER_CTA + slot, key)) { put4(F.t_hd, r, thr(d2, ear, xnr)); changed = true; }
+    if (hd_cand && key < atomicMin(best + ROWS_PER_CTA + slot, key)) { F.t_hd(r) = thr(d2, ear, xnr); changed = true; }
     if (changed) F.set_dl(r);
   };
   for (;;) {
@@ -1730,9 +1738,10 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
         for (int r = 0; r < RI; ++r) {
           const uint32_t slot = slot0 + (uint32_t) r * 32u;
           F.lor[r] = lor_s[slot];
+          F.xn(r) = R.xn[r];
           F.t_nn[r] = thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + slot)), R.ea(g, r), R.xn[r]);
           // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
-          F.t_hd[r] = lo_s[slot] == 0 ? F.t_nn[r]
+          F.t_hd(r) = lo_s[slot] == 0 ? F.t_nn[r]
                                       : thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + ROWS_PER_CTA + slot)), R.ea(g, r), R.xn[r]);
           F.set_dl(r);
         }
@@ -1743,8 +1752,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
 #pragma unroll
         for (int r = 0; r < RI; ++r)
           if (R.row(r) < g.row_end) {
-            v = fmaxf(v, (F.t_nn[r] + R.xn[r]) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
-            if (lo_s[slot0 + (uint32_t) r * 32u] != 0) vh = fmaxf(vh, (F.t_hd[r] + R.xn[r]) * 1.000001f + g.prune_slack);
+            v = fmaxf(v, (F.t_nn[r] + F.xn(r)) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
+            if (lo_s[slot0 + (uint32_t) r * 32u] != 0) vh = fmaxf(vh, (F.t_hd(r) + F.xn(r)) * 1.000001f + g.prune_slack);
           }
         if (!(v < INFINITY)) v = INFINITY;
         if (!(vh < INFINITY)) vh = INFINITY;
