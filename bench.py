@@ -60,18 +60,15 @@ def workload(name, n=None):
     return c, x
 
 
-def ncu_traffic(kernel_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, from profiles/ncu_traffic.json
-    (written by scripts/ncu_summary.py from an `ncu --set full` capture of this workload); None if not captured."""
+def ncu_traffic(workload_name, scan):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the workload's population ("pops") or neighbour ("nn")
+    scan kernel, from profiles/ncu_traffic.json (written by scripts/ncu_summary.py --traffic from an `ncu --set full`
+    capture of that workload at its full size); None if not captured."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            t = json.load(f)
-        for key, val in t.items():
-            if key in kernel_name:
-                return val
+            return json.load(f).get(workload_name, {}).get(scan)
     except Exception:
-        pass
-    return None
+        return None
 
 
 def workload_label(name, cfg):
@@ -421,6 +418,7 @@ def run_ours(args):
         outs = dict(pops=pops_host.numpy().view(np.uint32), fe=fe_host.numpy(),
                     nn=(out_host[0].numpy().view(np.uint32), out_host[1].numpy(), out_host[2].numpy().view(np.uint32), out_host[3].numpy()))
         xp = x_pin.numpy()
+        lab_host = torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32) if screening_workload else None
 
         def e2e_step():
             r = density.density_run(xp, radii, r_fe, neighbors=True, out=outs)
@@ -428,7 +426,7 @@ def run_ours(args):
                 with density.ScreeningRun(r["fe"], r["nn"][1], xp) as run:
                     t, t_to, k, lab = np.float32(0.1), float(r["fe"].max()), 0, None
                     while (t < np.float32(t_to - 0.01 + 0.1)) and not (np.float32(t_to + 0.01 + 0.1) < t):
-                        lab = run.next(t)
+                        lab = run.next(t, out=lab_host)
                         t = np.float32(t + np.float32(0.1))
                         k += 1
                 return k, int(lab.max()), int((lab.astype(np.int64) * (np.arange(n) % 1000003 + 1)).sum())
@@ -527,7 +525,7 @@ def run_ours(args):
             "peak_source": ("tcgen05.mma kind::tf32 128x128x8 back to back on resident operands, measured in this run "
                             "(dcb200_ctx_tf32_peak); MEASURED_PEAKS.json holds bf16 only (TF32 runs at half the bf16 rate)") if tensor_path else
                            "FFMA-only microbenchmark in this run (dcb200_ctx_ffma_peak); MEASURED_PEAKS.json has no FP32 entry",
-            "traffic": ncu_traffic(("gscan_" + ("nn" if kname.startswith("nn") else "pops")) if tensor_path else kname),
+            "traffic": ncu_traffic(args.workload, "nn" if kname.startswith("nn") else "pops") if args.n is None else None,
             "other_scans": {k: {"kernel_ms": v[0], "pairs_evaluated_frac": v[1] / (pairs * rows_frac),
                                 "achieved_tflops": FLOP_EXECUTED_PER_PAIR_DIM * v[1] * d / (v[0] * 1e-3) / 1e12}
                             for k, v in scans.items() if k != kname},

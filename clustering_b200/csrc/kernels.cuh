@@ -1426,7 +1426,7 @@ struct NnArgs {
 
 __host__ __device__ inline size_t screen_smem_bytes(size_t ring_bytes) { return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES; }
 
-constexpr size_t NN_PARK_BYTES = (size_t) 2 * RI * N_CONSUMERS * 4;      // per thread: t_hd[RI], |x'|^2[RI] (NnFilter)
+constexpr size_t NN_PARK_BYTES = (size_t) 5 * RI * N_CONSUMERS * 4;      // per thread: the parked values of NnFilter
 __host__ __device__ inline size_t nn_smem_bytes(size_t ring_bytes) {
   return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + NN_PARK_BYTES + (size_t) 2 * ROWS_PER_CTA * 8 + (size_t) 2 * ROWS_PER_CTA * 4 +
          gbox_bytes() + (size_t) 3 * N_CONSUMER_WARPS * 4;
@@ -1437,41 +1437,51 @@ __device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as
 // Filter state of the neighbour search.  A pair (row r, column c) is worth the exact evaluation iff
 //   acc < t_nn[r]                      (could beat or tie the nearest neighbour found so far), or
 //   acc < t_hd[r] and lo[c] < lo[r]    (could beat the nearest neighbour with lower free energy).
-// Both in one comparison with a per-pair threshold  te = t_nn[r] + cand * dl[r],  cand = sat(lor[r] - lo_c) in {0,1}
-// (one FADD.SAT + one FFMA + one FSETP per pair): frames that are close but have no lower free energy never
-// reach the slow path, however far the lower-free-energy neighbour of a density peak is.
-// The inner loop reads t_nn, dl and lor; what only the candidate handler and the unit's prologue / epilogue need -- t_hd and
-// the rows' |x'|^2 -- is parked in shared memory ([value][thread]: conflict-free), so that at D = 9, 10 (96 registers, 40 of
-// them row operands) the loop's operands are not spilled.
+// Two levels.  The inner loop only asks whether ANY pair of a row's CJ columns lies below tc[r] = max(t_nn[r], t_hd[r])
+// (a min tree over the accumulators: one instruction per pair on the ALU pipe, nothing on the FMA pipe the packed FMAs
+// saturate).  The few blocks that pass get the exact per-pair threshold  te = t_nn[r] + cand * dl[r],
+// cand = sat(lor[r] - lo_c) in {0,1}: frames that are close but have no lower free energy never reach the candidate
+// handler, however far the lower-free-energy neighbour of a density peak is.
+// Only tc lives in registers; everything the second level, the handler and the unit's prologue / epilogue need is parked in
+// shared memory ([value][thread]: conflict-free), so that at D = 9, 10 (96 registers, 40 of them row operands) none of the
+// loop's operands is spilled.
 struct NnFilter {
-  float t_nn[RI];
-  float dl[RI];                 // min(t_hd - t_nn, 1e37), rounded up; 0 where t_nn is +inf
-  float lor[RI];                // (float rank of the row) + lo_bias
-  float* park;                  // this thread's slots: t_hd[r] at park[r * N_CONSUMERS], |x'|^2 of row r at park[(RI + r) * N_CONSUMERS]
-  __device__ __forceinline__ float& t_hd(int r) { return park[r * N_CONSUMERS]; }
-  __device__ __forceinline__ float& xn(int r) { return park[(RI + r) * N_CONSUMERS]; }
-  __device__ __forceinline__ void set_dl(int r) {
-    const float tn = sel4(t_nn, r), th = t_hd(r);
+  float tc[RI];                 // max(t_nn, t_hd)
+  float* park;                  // this thread's slots, value v of row r at park[(v * RI + r) * N_CONSUMERS]
+  __device__ __forceinline__ float& t_nn(int r) { return park[r * N_CONSUMERS]; }
+  __device__ __forceinline__ float& t_hd(int r) { return park[(RI + r) * N_CONSUMERS]; }
+  __device__ __forceinline__ float& dl(int r) { return park[(2 * RI + r) * N_CONSUMERS]; }     // min(t_hd - t_nn, 1e37), rounded up; 0 where t_nn is +inf
+  __device__ __forceinline__ float& lor(int r) { return park[(3 * RI + r) * N_CONSUMERS]; }    // (float rank of the row) + lo_bias
+  __device__ __forceinline__ float& xn(int r) { return park[(4 * RI + r) * N_CONSUMERS]; }     // |x'|^2 of the row
+  // after t_nn(r) or t_hd(r) changed
+  __device__ __forceinline__ void update(int r) {
+    const float tn = t_nn(r), th = t_hd(r);
     float v = 0.f;
     if (tn < INFINITY) v = th < INFINITY ? fminf(next_up((th - tn) * 1.000001f), 1e37f) : 1e37f;
-    put4(dl, r, fmaxf(v, 0.f));
+    dl(r) = fmaxf(v, 0.f);
+    put4(tc, r, fmaxf(tn, th));
   }
 };
+constexpr int NN_PARK_VALUES = 5;
 
-// hits of one RI x CJ block under the per-pair thresholds; one compact copy of the handler (see walk_hits)
+// second level of the filter for one RI x CJ block that passed the first: the pairs below their exact per-pair threshold
+// go to the handler; one compact copy of it (see walk_hits).  lrow4: the free-energy ranks of the block's CJ columns.
 template <class Hit>
-__device__ __forceinline__ void walk_hits_nn(float* __restrict__ scratch, const float (&acc)[RI][CJ], const float4 l4, NnFilter& F, int jt0,
-                                             Hit& hit) {
+__device__ __forceinline__ void walk_hits_nn(float* __restrict__ scratch, const float (&acc)[RI][CJ], const float* __restrict__ lrow4, NnFilter& F,
+                                             int jt0, Hit& hit) {
   uint32_t mask = 0;
+  const float4 l4 = *reinterpret_cast<const float4*>(lrow4);
   const float lc[CJ] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-  for (int r = 0; r < RI; ++r)
+  for (int r = 0; r < RI; ++r) {
+    const float lor = F.lor(r), dl = F.dl(r), tn = F.t_nn(r);
 #pragma unroll
     for (int c = 0; c < CJ; ++c) {
       scratch[(r * CJ + c) * N_CONSUMERS] = acc[r][c];
-      const float te = fmaf(__saturatef(F.lor[r] - lc[c]), F.dl[r], F.t_nn[r]);
+      const float te = fmaf(__saturatef(lor - lc[c]), dl, tn);
       mask |= (acc[r][c] < te) ? (1u << (r * CJ + c)) : 0u;
     }
+  }
 #pragma unroll 1
   while (mask) {
     const int p = __ffs(mask) - 1;
@@ -1488,16 +1498,13 @@ __device__ __forceinline__ void scan_tile_nn(const ScanGeom&, const float* __res
   for (int g = 0; g < TJ; g += CJ) {
     float acc[RI][CJ];
     fast_block<D>(tl + g, R, acc);
-    const float4 l4 = *reinterpret_cast<const float4*>(lrow + g);
     bool any = false;
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
-      any |= acc[r][0] < fmaf(__saturatef(F.lor[r] - l4.x), F.dl[r], F.t_nn[r]);
-      any |= acc[r][1] < fmaf(__saturatef(F.lor[r] - l4.y), F.dl[r], F.t_nn[r]);
-      any |= acc[r][2] < fmaf(__saturatef(F.lor[r] - l4.z), F.dl[r], F.t_nn[r]);
-      any |= acc[r][3] < fmaf(__saturatef(F.lor[r] - l4.w), F.dl[r], F.t_nn[r]);
+      const float mn = fminf(fminf(acc[r][0], acc[r][1]), fminf(acc[r][2], acc[r][3]));
+      any |= mn < F.tc[r];
     }
-    if (any) walk_hits_nn(scratch, acc, l4, F, g, hit);
+    if (any) walk_hits_nn(scratch, acc, lrow + g, F, g, hit);
   }
 }
 
@@ -1539,16 +1546,13 @@ __device__ __forceinline__ void scan_tile_nn(const ScanGeom& gm, const float* __
     }
 #pragma unroll
     for (int c4 = 0; c4 < CG / CJ; ++c4) {
-      const float4 l4 = *reinterpret_cast<const float4*>(lrow + g + c4 * CJ);
       bool any = false;
 #pragma unroll
       for (int r = 0; r < RI; ++r) {
-        any |= acc[c4][r][0] < fmaf(__saturatef(F.lor[r] - l4.x), F.dl[r], F.t_nn[r]);
-        any |= acc[c4][r][1] < fmaf(__saturatef(F.lor[r] - l4.y), F.dl[r], F.t_nn[r]);
-        any |= acc[c4][r][2] < fmaf(__saturatef(F.lor[r] - l4.z), F.dl[r], F.t_nn[r]);
-        any |= acc[c4][r][3] < fmaf(__saturatef(F.lor[r] - l4.w), F.dl[r], F.t_nn[r]);
+        const float mn = fminf(fminf(acc[c4][r][0], acc[c4][r][1]), fminf(acc[c4][r][2], acc[c4][r][3]));
+        any |= mn < F.tc[r];
       }
-      if (any) walk_hits_nn(scratch, acc[c4], l4, F, g + c4 * CJ, hit);
+      if (any) walk_hits_nn(scratch, acc[c4], lrow + g + c4 * CJ, F, g + c4 * CJ, hit);
     }
   }
 }
@@ -1607,7 +1611,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     const uint32_t i = R.row(r);
     ++st.slow;
     if (j == i || j >= g.n || i >= g.row_end) return;
-    const float tn = sel4(F.t_nn, r), th = F.t_hd(r);
+    const float tn = F.t_nn(r), th = F.t_hd(r);
     const uint32_t slot = slot0 + (uint32_t) r * 32u;
     const bool hd_cand = __ldg(a.lo + j) < lo_s[slot];
     if (!(accv < tn) && !(hd_cand && accv < th)) return;      // thresholds may have tightened since the block was filtered
@@ -1620,12 +1624,12 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
     bool changed = false;
     if (key < atomicMin(best + slot, key)) {
       const float v = thr(d2, ear, xnr);
-      put4(F.t_nn, r, v);
+      F.t_nn(r) = v;
       if (lo_s[slot] == 0) F.t_hd(r) = v;
       changed = true;
     }
     if (hd_cand && key < atomicMin(best + ROWS_PER_CTA + slot, key)) { F.t_hd(r) = thr(d2, ear, xnr); changed = true; }
-    if (changed) F.set_dl(r);
+    if (changed) F.update(r);
   };
   for (;;) {
     mbar_wait(&ring.full[cp.stage], cp.phase);
@@ -1737,13 +1741,14 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
           const uint32_t slot = slot0 + (uint32_t) r * 32u;
-          F.lor[r] = lor_s[slot];
+          F.lor(r) = lor_s[slot];
           F.xn(r) = R.xn[r];
-          F.t_nn[r] = thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + slot)), R.ea(g, r), R.xn[r]);
+          const float tn = thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + slot)), R.ea(g, r), R.xn[r]);
+          F.t_nn(r) = tn;
           // a frame nobody has a lower free energy than has no such neighbour: do not let it hold the filter open
-          F.t_hd(r) = lo_s[slot] == 0 ? F.t_nn[r]
+          F.t_hd(r) = lo_s[slot] == 0 ? tn
                                       : thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + ROWS_PER_CTA + slot)), R.ea(g, r), R.xn[r]);
-          F.set_dl(r);
+          F.update(r);
         }
         scan_tile_nn(g, tl, cen + g.dp, R, F, scratch, hit);
         // what the group's rows still accept (d2 units, pruning margins included): for the warps' reach tests, for the
@@ -1752,7 +1757,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
 #pragma unroll
         for (int r = 0; r < RI; ++r)
           if (R.row(r) < g.row_end) {
-            v = fmaxf(v, (F.t_nn[r] + F.xn(r)) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
+            v = fmaxf(v, (F.t_nn(r) + F.xn(r)) * 1.000001f + g.prune_slack);     // fmaxf drops NaN
             if (lo_s[slot0 + (uint32_t) r * 32u] != 0) vh = fmaxf(vh, (F.t_hd(r) + F.xn(r)) * 1.000001f + g.prune_slack);
           }
         if (!(v < INFINITY)) v = INFINITY;

@@ -146,8 +146,12 @@ class ScreeningRun:
         self.h = C.c_void_p()
         lib.check(lib.load().dcb200_screening_begin(fe, nn_d2, coords, self.n, d, C.byref(self.h)))
 
-    def next(self, threshold):
-        labels = np.empty(self.n, np.uint32)
+    def next(self, threshold, out=None):
+        """labels (frame order) at `threshold`; out: optional uint32 [n] array to fill (e.g. pinned memory, reused over the
+        thresholds like the command-line driver reuses its label vector -- a fresh 20 MB array per call costs more in page
+        faults than the whole threshold on the device)."""
+        labels = np.empty(self.n, np.uint32) if out is None else out
+        assert labels.dtype == np.uint32 and labels.size == self.n and labels.flags["C_CONTIGUOUS"]
         lib.check(lib.load().dcb200_screening_next(self.h, np.float32(threshold), labels))
         return labels
 

@@ -33,7 +33,10 @@ for i, h in enumerate(hdr):
             pass
 
 if '--traffic' in sys.argv:
+    # python scripts/ncu_summary.py raw.csv --traffic profiles/ncu_traffic.json --workload C3 [--source "capture name"]
     out = sys.argv[sys.argv.index('--traffic') + 1]
+    wl = sys.argv[sys.argv.index('--workload') + 1]
+    src = sys.argv[sys.argv.index('--source') + 1] if '--source' in sys.argv else sys.argv[1]
 
     def to_bytes(v, unit):
         scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
@@ -42,11 +45,18 @@ if '--traffic' in sys.argv:
     traffic = {}
     for r in data:
         name = r[col['Kernel Name']]
-        key = 'nn_kernel' if 'nn_kernel' in name else 'pops' if 'pops' in name else name
+        key = 'nn' if 'nn_kernel' in name else 'pops' if 'pops' in name else None
+        if key is None:
+            continue
         b = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']]) + \
             to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
         ms = float(r[col['gpu__time_duration.sum']].replace(',', ''))
         if key not in traffic or ms > traffic[key][1]:        # the longest launch of a kernel = its main pass
             traffic[key] = (b, ms)
-    json.dump({k: v[0] for k, v in traffic.items()}, open(out, 'w'), indent=1)
-    print("traffic (dram bytes per launch) ->", out, {k: v[0] for k, v in traffic.items()})
+    try:
+        allw = json.load(open(out))
+    except Exception:
+        allw = {}
+    allw[wl] = dict({k: v[0] for k, v in traffic.items()}, source=src)
+    json.dump(allw, open(out, 'w'), indent=1)
+    print("traffic (dram bytes per launch) ->", out, allw[wl])
