@@ -48,9 +48,13 @@ if '--traffic' in sys.argv:
         key = 'nn' if 'nn_kernel' in name else 'pops' if 'pops' in name else None
         if key is None:
             continue
-        b = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']]) + \
-            to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
         ms = float(r[col['gpu__time_duration.sum']].replace(',', ''))
+        if 'dram__bytes_read.sum' in col:
+            b = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']]) + \
+                to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
+        else:       # section captures (no --set full): bytes per second over the launch duration
+            c = col['dram__bytes.sum.per_second']
+            b = to_bytes(r[c], units[c].split('/')[0]) * ms * 1e-3
         if key not in traffic or ms > traffic[key][1]:        # the longest launch of a kernel = its main pass
             traffic[key] = (b, ms)
     try:
