@@ -50,17 +50,22 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     # ---- multi-radius population kernel (C3)
     ins = instrs("_ZN3dcb15pops_bin_kernelILi10EEEvNS_8PopsArgsE")
-    k = densest(ins, r"^FFMA", 190)
-    votes = [q for q in range(k, len(ins)) if ins[q][1].startswith("VOTE.ANY")]
+    f2 = [q for q in range(len(ins)) if ins[q][1].startswith("FFMA2")]
+    k = f2[0] - 6
+    votes = [q for q in range(f2[-1], len(ins)) if ins[q][1].startswith("VOTE.ANY")]
     v = votes[0]
     ublk = [a for a, i in ins if "UBLKCP" in i]
     with open(os.path.join(ROOT, "profiles", "sass_r02_pops.txt"), "w") as f:
         f.write("pops_bin_kernel<10>: the multi-radius population scan of C3 (cuobjdump -sass clustering_b200/libdcb200.so, sm_100a)\n")
-        f.write(f"instructions: {len(ins)}; {count(ins, ['^FFMA', 'UBLKCP', 'SYNCS', r'^LDS', r'^STS', 'FMNMX3', 'LDL|STL'])}\n\n")
-        f.write("-- producer: ONE bulk copy (UBLKCP = cp.async.bulk, 1-D TMA) per column tile, completion counted on an mbarrier --\n")
+        f.write(f"instructions: {len(ins)}; {count(ins, ['^FFMA2', r'^FFMA ', 'UBLKCP', 'SYNCS', r'BAR\.', r'^LDS', r'^STS', 'FMNMX3', 'LDL|STL'])}\n\n")
+        f.write("-- producer: ONE bulk copy (UBLKCP = cp.async.bulk, 1-D TMA) per column tile, completion counted on an mbarrier;\n"
+                "   ring stages come back through named barriers (consumers BAR.ARV, producer BAR.SYNC) --\n")
         for a in ublk:
             f.write(excerpt(ins, a - 0x60, a + 0x20) + "\n")
-        f.write("\n-- step: one broadcast LDS.128 per dim + 16 FFMA (4 rows x 4 columns), candidate test (FMNMX / FMNMX3 + FSETP), warp vote --\n")
+        for a in [a for a, i in ins if i.startswith("BAR.ARV")][:1]:
+            f.write(excerpt(ins, a - 0x20, a + 0x10) + "\n")
+        f.write("\n-- step: one broadcast LDS.128 per dim + 8 FFMA2 (packed FP32 FMA: rows r, r+1 x one column, the column operand a broadcast scalar),\n"
+                "   candidate test (FMNMX / FMNMX3, FADD |x'|^2, FSETP), warp vote --\n")
         f.write(excerpt(ins, ins[k][0], ins[v][0] + 0x30) + "\n")
         f.write("\n-- dense step, first two columns (8 pairs): s = acc + |x'|^2 (FADD), cell (FMUL.SAT, FFMA + 2^21, LOP3), table entry (LDS),\n"
                 "   s - e (FADD), band (FSETP |.|), bin from the entry's low bits and the sign (LOP3, SHF, IADD3, LEA/IMAD), histogram LDS.U16 / add / STS.U16 --\n")
@@ -68,17 +73,18 @@ def main():
         f.write(excerpt(ins, ins[d0][0] - 0x40, ins[d0][0] + 0x5c0) + "\n")
     # ---- neighbour kernel (C3)
     ins = instrs("_ZN3dcb9nn_kernelILi10EEEvNS_6NnArgsE")
-    k = densest(ins, r"^FFMA", 190)
+    f2 = [q for q in range(len(ins)) if ins[q][1].startswith("FFMA2")]
+    k = f2[0] - 6
     sat = [q for q in range(k, len(ins)) if "FADD.SAT" in ins[q][1]]
     ublk = [a for a, i in ins if "UBLKCP" in i]
     with open(os.path.join(ROOT, "profiles", "sass_r02_nn.txt"), "w") as f:
         f.write("nn_kernel<10>: the neighbour scan of C3 (cuobjdump -sass clustering_b200/libdcb200.so, sm_100a)\n")
-        f.write(f"instructions: {len(ins)}; {count(ins, ['^FFMA', 'UBLKCP', 'SYNCS', r'^LDS', 'ATOM', 'FADD.SAT'])}\n\n")
+        f.write(f"instructions: {len(ins)}; {count(ins, ['^FFMA2', r'^FFMA ', 'UBLKCP', 'SYNCS', r'BAR\.', r'^LDS', 'ATOM', 'FADD.SAT', 'LDL|STL'])}\n\n")
         f.write("-- producer: bulk copies of the tile record and of the tile's free-energy ranks --\n")
         for a in ublk:
             f.write(excerpt(ins, a - 0x40, a + 0x20) + "\n")
-        f.write("\n-- step: LDS.128 + FFMA block, then the free-energy-aware filter per pair: FADD.SAT (rank difference -> {0,1}),\n"
-                "   FFMA (threshold = t_nn + cand * dl), FSETP --\n")
+        f.write("\n-- step: LDS.128 + FFMA2 block, first filter level (min tree FMNMX / FMNMX3 against max(t_nn, t_hd), FSETP, branch); then, for a\n"
+                "   block that passed, the free-energy-aware filter per pair: FADD.SAT (rank difference -> {0,1}), FFMA (t_nn + cand * dl), FSETP --\n")
         end = ins[sat[-1]][0] + 0x80 if sat else ins[k][0] + 0xe00
         f.write(excerpt(ins, ins[k][0], min(end, ins[k][0] + 0x1100)) + "\n")
     # ---- GEMM-form scans (C5)
