@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="override the frame count (debugging only; invalid as a bench line)")
+    ap.add_argument("--frames", dest="n", type=int, default=None,
+                    help="override the frame count (tests only; invalid as a bench line).  Not `--n`: torchrun's own parser rejects it as ambiguous")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

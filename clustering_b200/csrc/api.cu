@@ -2022,6 +2022,7 @@ int run_gang_host(Gang* G, const RunArgs& a) {
   if (R) {
     CKI(on_gpus(G->n, [&](int g, int W) -> int {
       dcb200_ctx* c = G->ctx[g];
+      CK(cudaSetDevice(c->device));                        // a fresh worker thread starts on device 0
       size_t b, e;
       shard(n, g, W, &b, &e);
       CKI(dcb200_ctx_set_coords(c, a.coords, n, a.d));     // same deterministic order on every device
@@ -2057,6 +2058,7 @@ int run_gang_host(Gang* G, const RunArgs& a) {
   std::vector<unsigned long long> knn(n), khd(n);
   CKI(on_gpus(G->n, [&](int g, int W) -> int {
     dcb200_ctx* c = G->ctx[g];
+    CK(cudaSetDevice(c->device));                          // this worker thread is not the one of the population stage
     size_t b, e;
     shard(n, g, W, &b, &e);
     if (!R) CKI(dcb200_ctx_set_coords(c, a.coords, n, a.d));
