@@ -390,6 +390,24 @@ __global__ void row_bbox_kernel(const float* __restrict__ bbox, int d, uint32_t 
   }
 }
 
+// sbbox[s] = union of the boxes of the 64-frame groups of super-tile s (SUPER_FRAMES consecutive positions): the coarse level
+// of the producers' tile pruning (one warp per super-tile)
+__global__ void super_bbox_kernel(const float* __restrict__ bbox, int d, uint32_t n_groups, uint32_t n_super, float* __restrict__ sbbox) {
+  const uint32_t sp = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (sp >= n_super) return;
+  const uint32_t g0 = sp * (SUPER_FRAMES / 64), g1 = min(g0 + SUPER_FRAMES / 64, n_groups);
+  for (int k = lane; k < d; k += 32) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (uint32_t q = g0; q < g1; ++q) {
+      lo = fminf(lo, bbox[(size_t) q * 2 * d + k]);          // fminf / fmaxf drop the NaN boxes of all-padding groups
+      hi = fmaxf(hi, bbox[(size_t) q * 2 * d + d + k]);
+    }
+    sbbox[(size_t) sp * 2 * d + k] = lo;
+    sbbox[(size_t) sp * 2 * d + d + k] = hi;
+  }
+}
+
 // blk_thr[rb][w] = bound (d2 units, with the pruning margins) of what the rows of block rb owned by consumer warp w
 // still accept after seeding: max over its rows of the seeded d2 (nearest / nearest with lower free energy)
 __global__ void nn_block_thr_kernel(const unsigned long long* __restrict__ key_nn, const unsigned long long* __restrict__ key_hd,
@@ -496,6 +514,7 @@ struct dcb200_ctx {
   bool spatial = false;             // frames are held in spatial (Hilbert curve) order; perm maps position -> frame
   DevBuf<float> xT, cT;             // [d][ld] original coords; tile-major column pack records (context order)
   DevBuf<float> bbox;               // [ld/64][2d]
+  DevBuf<float> sbbox;              // [ceil(ld/SUPER_FRAMES)][2d] boxes of the super-tiles (coarse pruning level)
   DevBuf<float> rbbox;              // [row blocks of the current launch][2d]
   DevBuf<float> blk_thr;            // [row blocks][N_CONSUMER_WARPS] neighbour search pruning bounds
   DevBuf<uint32_t> perm;            // [n] position -> frame (identity when !spatial)
@@ -584,6 +603,7 @@ static int fill_geom(dcb200_ctx* c, size_t row_begin, size_t row_end, size_t rb_
   g->xT = c->xT.p;
   g->cT = c->cT.p;
   g->bbox = c->bbox.p;
+  g->sbbox = env_int("DCB200_SUPER_PRUNE", 1) == 1 ? c->sbbox.p : nullptr;
   g->dp = (int) ((3 * c->d + 1 + 3) / 4 * 4);
   g->centre = c->centre.p;
   g->prune_thr = INFINITY;
@@ -770,7 +790,7 @@ extern "C" int dcb200_ctx_destroy(dcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->xT.release(); c->cT.release(); c->bbox.release(); c->rbbox.release(); c->blk_thr.release();
+  c->xT.release(); c->cT.release(); c->bbox.release(); c->sbbox.release(); c->rbbox.release(); c->blk_thr.release();
   c->perm.release(); c->lo.release(); c->lof.release(); c->keys_a.release(); c->keys_b.release(); c->iota.release(); c->skeys_a.release(); c->skeys_b.release();
   c->tmp_u32.release(); c->tmp2_u32.release();
   c->cub_tmp.release(); c->stage.release(); c->centre.release(); c->cnt.release(); c->lut.release(); c->knn.release(); c->khd.release();
@@ -961,7 +981,12 @@ static int build_layout(dcb200_ctx* c, const float* dev_coords, size_t n, size_t
   pack_tiles_kernel<<<(unsigned int) (ld / tj), tj, 0, c->stream>>>(dev_coords, n, (int) d, ld, dp, c->centre.p,
                                                                     c->spatial ? c->perm.p : nullptr, c->xT.p, c->cT.p, c->bbox.p,
                                                                     c->scalars + 1);
-  c->launches += 1;
+  {
+    const uint32_t n_super = (uint32_t) ((ld + SUPER_FRAMES - 1) / SUPER_FRAMES);
+    CK(c->sbbox.reserve((size_t) n_super * 2 * d));
+    super_bbox_kernel<<<blocks_for(n_super, 8), 256, 0, c->stream>>>(c->bbox.p, (int) d, (uint32_t) (ld / 64), n_super, c->sbbox.p);
+  }
+  c->launches += 2;
   CK(cudaGetLastError());
   c->gemm = gemm_eligible(n, d, c->spatial);
   c->lb_s0 = c->lb_s1 = 0;

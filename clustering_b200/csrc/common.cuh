@@ -17,6 +17,7 @@ constexpr int N_CONSUMER_WARPS = 8;
 constexpr int N_CONSUMERS = N_CONSUMER_WARPS * 32;
 constexpr int CTA_THREADS = N_CONSUMERS + 32; // + one producer warp (TMA issue)
 constexpr int ROWS_PER_CTA = N_CONSUMERS * RI;   // 1024
+constexpr int SUPER_FRAMES = 4096;            // frames per super-tile: the coarse level of the producers' tile pruning
 constexpr int LD_ALIGN = 256;                 // frame arrays are padded to a multiple of this (covers every tile width)
 // depth of the tile ring: deep for the register kernels (consumer warps that skip or finish a tile early run ahead
 // instead of idling), shallow for the run-time-D kernels whose tiles are large

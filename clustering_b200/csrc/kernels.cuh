@@ -57,6 +57,7 @@ struct ScanGeom {
   unsigned long long* stats;        // [0] pairs handed to the slow path, [1] pairs re-evaluated exactly,
                                     // [2] column tiles streamed, [3] (warp, tile) scans (x 32*RI rows x tile width = pairs evaluated)
   const float* bbox;                // [ld/64][2*d] bounding boxes (lo[d], hi[d]) of 64-frame groups, centred coords
+  const float* sbbox;               // [ceil(ld/SUPER_FRAMES)][2*d] boxes of the super-tiles, nullptr = no coarse level
   const float* rbbox;               // [n_row_blocks][2*d] bounding boxes of this launch's row blocks (api.cu: row_bbox_kernel)
   float* blk_thr;                   // neighbour search only: [n_row_blocks][N_CONSUMER_WARPS] upper bounds (d2 units) of what the
                                     // rows of a block owned by one consumer warp still accept; lowered by atomicMin as items finish
@@ -153,6 +154,28 @@ __device__ __forceinline__ void item_coords(const ScanGeom& g, uint32_t item, ui
   *ci = c;
 }
 
+// Coarse level of the producers' pruning.  The tile tests cost one round trip to L2 per 32 tiles, and a scan makes
+// N^2 / (1024 x 128) of them: at 5M frames that is 1.9e8 tests, ~54 000 cycles per work item in which the consumers of an
+// item with nothing in reach just wait.  Super-tiles (SUPER_FRAMES consecutive positions of the spatial order, boxes in
+// g.sbbox) are tested first, 32 per round trip: lane l of `super_mask` looks at super-tile s0 + l against the row block's
+// box (ring.rbb).  Bit l of the result: the super-tile may hold a column within thr of a row of the block.
+template <int D>
+__device__ __forceinline__ uint32_t super_mask(const ScanGeom& g, const float* __restrict__ rbb, uint32_t s0, uint32_t s_end, float thr, int lane) {
+  const int d = D ? D : g.d;
+  const uint32_t sp = s0 + (uint32_t) lane;
+  bool keep = false;
+  if (sp < s_end) {
+    const float* sb = g.sbbox + (size_t) sp * 2 * d;
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) {
+      const float gap = fmaxf(fmaxf(rbb[k] - __ldg(sb + d + k), __ldg(sb + k) - rbb[d + k]), 0.f);
+      acc = fmaf(gap, gap, acc);
+    }
+    keep = !(acc * 0.999f > thr);                   // NaN keeps
+  }
+  return __ballot_sync(0xffffffffu, keep);
+}
+
 // Producer warp: walks the work items, drops the column tiles whose bounding box is provably out of
 // reach of every row of the block (dynamic threshold published by the consumers, or the static one),
 // and streams the others with 1-D bulk TMA.  An item that streamed at least one tile is closed by a
@@ -186,10 +209,19 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
     const float thr0 = item_thr(rb, lane);
     __syncwarp();
     bool first = true;
-    for (uint32_t base = t0; base < t1; base += 32) {
+    constexpr uint32_t TPS = SUPER_FRAMES / TJ;     // tiles per super-tile
+    for (uint32_t s0 = t0 / TPS; s0 * TPS < t1; s0 += 32) {
+     const uint32_t s_end = (t1 + TPS - 1) / TPS;
+     uint32_t smask = g.sbbox ? super_mask<D>(g, ring.rbb, s0, s_end, thr0, lane) : 0xffffffffu;
+     while (smask) {
+      const uint32_t sp = s0 + (uint32_t) __ffs(smask) - 1u;
+      smask &= smask - 1;
+      if (sp >= s_end) break;
+      const uint32_t seg0 = max(t0, sp * TPS), seg1 = min(t1, (sp + 1) * TPS);
+    for (uint32_t base = seg0; base < seg1; base += 32) {
       const uint32_t t = base + lane;
       float lb = INFINITY;                          // lower bound of the fast value over (row block) x (tile t)
-      if (t < t1) {
+      if (t < seg1) {
         for (int q = 0; q < GPT; ++q) {
           const float* bb = g.bbox + (size_t) (t * GPT + q) * 2 * d;
           float s = 0.f;
@@ -201,7 +233,7 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
         }
         lb *= 0.999f;
       }
-      uint32_t mask = __ballot_sync(0xffffffffu, t < t1 && !(lb > thr0));     // NaN keeps
+      uint32_t mask = __ballot_sync(0xffffffffu, t < seg1 && !(lb > thr0));     // NaN keeps
       while (mask) {
         const int src = __ffs(mask) - 1;
         const uint32_t tt = base + (uint32_t) src;
@@ -241,6 +273,8 @@ __device__ __forceinline__ void produce(const ScanGeom& g, SmemRing<D>& ring, bo
         ++streamed;
         pp.advance();
       }
+    }
+     }
     }
     if (!first) {                                 // end-of-item marker
       __syncwarp();
@@ -1066,12 +1100,22 @@ __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& r
       else v = sqrtf(__ldg(hdr + D));                                       // radius about the centre
       pgeo[gi * PGEO + f] = v;
     }
+    for (int k = lane; k < 2 * D; k += 32) ring.rbb[k] = __ldg(g.rbbox + (size_t) rb * 2 * D + k);      // the block's box: coarse level
     __syncwarp();
     bool first = true;
-    for (uint32_t base = t0; base < t1; base += 32) {
+    constexpr uint32_t TPS = SUPER_FRAMES / TJ;     // tiles per super-tile
+    for (uint32_t s0 = t0 / TPS; s0 * TPS < t1; s0 += 32) {
+     const uint32_t s_end = (t1 + TPS - 1) / TPS;
+     uint32_t smask = g.sbbox ? super_mask<D>(g, ring.rbb, s0, s_end, g.prune_thr, lane) : 0xffffffffu;
+     while (smask) {
+      const uint32_t sp = s0 + (uint32_t) __ffs(smask) - 1u;
+      smask &= smask - 1;
+      if (sp >= s_end) break;
+      const uint32_t seg0 = max(t0, sp * TPS), seg1 = min(t1, (sp + 1) * TPS);
+    for (uint32_t base = seg0; base < seg1; base += 32) {
       const uint32_t t = base + lane;
       uint32_t units = 0;                           // bit gi: group gi of the block comes within r_max of tile t
-      if (t < t1) {
+      if (t < seg1) {
         const float* hdr = g.cT + (size_t) t * rec + (size_t) (D + 1) * TJ;
         float tlo[D], thi[D], tc[D];
 #pragma unroll
@@ -1106,6 +1150,8 @@ __device__ __forceinline__ void produce_groups(const ScanGeom& g, SmemRing<D>& r
         ++streamed;
         pp.advance();
       }
+    }
+     }
     }
     if (!first) {
       __syncwarp();
