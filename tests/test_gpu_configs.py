@@ -336,3 +336,39 @@ def test_screening_accepts_arbitrary_initial_clusters(oracle, seed):
     holes[rng.choice(n, n // 5, replace=False)] = 0
     want = oracle.screening(fe, nd, np.float32(2.0), x, holes.astype(np.uint64))
     assert np.array_equal(density.screening(fe, nd, np.float32(2.0), x, holes), want.astype(np.uint32))
+
+
+# ---------------------------------------------------------------- scheduling knobs ----------------
+@pytest.mark.parametrize("knobs", [
+    {"DCB200_ITEMS_PER_CTA": "1"},          # 16 column ranges per row block (round 1)
+    {"DCB200_ITEMS_PER_CTA": "4096"},       # the smallest ranges the kernels allow
+    {"DCB200_BIN_STEAL": "0"},              # warps only work on their own row group's units
+    {"DCB200_BIN_DENSE_LANES": "1"},        # every active step through the branch-free table path
+    {"DCB200_BIN_DENSE_LANES": "33"},       # every active step candidate by candidate
+    {"DCB200_SUPER_PRUNE": "0"},            # no coarse level in the producers' pruning
+    {"DCB200_AXIS_PRUNE": "2", "DCB200_BIN_PROJ": "2"},
+])
+def test_scheduling_knobs_never_change_results(oracle, knobs):
+    """How the pair matrix is cut into work items, which warp takes which unit, what is pruned at which level and which
+    path bins a step are scheduling decisions: populations, neighbours and screening labels must not depend on them."""
+    n, d = 9000, 10
+    x = gaussian_mixture(n, d, seed=8400)
+    radii = np.linspace(0.1, 2.0, 20, dtype=np.float32)
+    want = oracle.populations(x, radii)
+    fe = oracle.free_energies(want[9])
+    nn_want = oracle.nearest_neighbors(x, fe)
+    old = {k: os.environ.get(k) for k in knobs}
+    try:
+        os.environ.update(knobs)
+        r = density.density_run(x, radii, 9)
+        assert np.array_equal(r["pops"], want)
+        assert same_neighbours(nn_want, r["nn"])
+        assert np.array_equal(density.calculate_populations(x, radii[[3]]), want[[3]])        # count mode
+        lab = density.screening(fe, nn_want[1], np.float32(2.0), x, None)
+        assert np.array_equal(lab, oracle.screening(fe, nn_want[1], np.float32(2.0), x, None).astype(np.uint32))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

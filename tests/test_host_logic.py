@@ -148,3 +148,22 @@ def test_screening_row_cuts_balance_pairs():
         if m_new - m_prev > 100 * w:
             pairs = [sum(range(cuts[g], cuts[g + 1])) if m_new < 10000 else (cuts[g + 1] ** 2 - cuts[g] ** 2) / 2 for g in range(w)]
             assert max(pairs) < 1.2 * (sum(pairs) / w) + m_new
+
+
+def test_bench_reference_arm_under_torchrun():
+    """The driver launches both arms as `python -m torch.distributed.run ... bench.py --gpus N --steps K --warmup W [--impl reference]`:
+    torchrun's own parser must let every bench.py option through (it rejected `--n` as an ambiguous abbreviation of its own
+    options once), rank 0 alone prints the reference arm's line and the other rank exits 0 without work."""
+    import json
+    import subprocess
+    port = str(29800 + os.getpid() % 150)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", port, os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "1", "--warmup", "0", "--impl", "reference",
+           "--workload", "C1", "--frames", "3000"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "density_run_throughput" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
