@@ -281,8 +281,8 @@ def run_ours(args):
     def step(coords, timed=False):
         """one density pass; coords: device tensor (resident) or pinned host tensor (per-rank e2e at N > 1)."""
         pops, fe, nn = dpass.run(coords if coords.is_cuda else coords.numpy(), r_fe, timed=timed)
-        if not coords.is_cuda:                           # e2e: results back in host memory (rank 0 keeps them)
-            with torch.cuda.stream(stream):
+        if not coords.is_cuda and rank == 0:             # e2e: the results land in rank 0's host buffers (ONE download, like
+            with torch.cuda.stream(stream):              # the in-process path and the reference's single process)
                 pops_host.copy_(pops, non_blocking=True)
                 fe_host.copy_(fe, non_blocking=True)
                 for h, t in zip(out_host, nn):
@@ -452,8 +452,8 @@ def run_ours(args):
         e2e_ms = timed(x_pin, args.steps)
         h2d = x.nbytes
         d2h = radii.size * 4 * n + 4 * n + 16 * n
-        e2e_api = ("session C ABI per rank with pinned host buffers: H2D coords on every rank, block-cyclic sharded scans, NCCL all-gather, "
-                   "D2H results (CUDA events, max over ranks)")
+        e2e_api = ("session C ABI per rank with pinned host buffers: H2D of the coordinates on every rank (h2d_bytes_per_step is per rank), "
+                   "block-cyclic sharded scans, NCCL all-gathers, D2H of all results on rank 0 (CUDA events, max over ranks)")
         # the C++ in-process path (what the `clustering` binary runs): one process, N GPUs, NCCL inside libdcb200.so.
         # The other ranks wait on the HOST meanwhile, so that their GPUs are free for rank 0's worker threads.
         cxx = None
