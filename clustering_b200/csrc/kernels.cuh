@@ -1042,8 +1042,10 @@ constexpr int BIN_STRIDE = N_CONSUMERS * RI * 2;      // bytes between the histo
 #endif
 constexpr int PGEO = 3 * MAX_TEMPLATE_D + 4;          // floats per group in the producer's geometry scratch
 
+// the cell table is aligned to its own size (2 * lut_k * 4 bytes reserved), so that the address of an entry is
+// (cell bits & mask) | base: ONE LOP3 instead of an AND and an ADD per pair
 __host__ __device__ inline size_t pops_bin_smem_bytes(size_t ring_bytes, int n_bins, int lut_k) {
-  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + (size_t) N_CONSUMER_WARPS * PGEO * 4 + (size_t) lut_k * 4 + 32 * 4 +
+  return ((ring_bytes + 15) & ~size_t(15)) + SCRATCH_BYTES + (size_t) N_CONSUMER_WARPS * PGEO * 4 + (size_t) 2 * lut_k * 4 + 32 * 4 +
          (size_t) (n_bins + 1) * BIN_STRIDE;
 }
 
@@ -1189,8 +1191,11 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
   unsigned char* extra = smem + ((SmemRing<D>::bytes(D) + 15) & ~size_t(15));
   float* scratch = reinterpret_cast<float*>(extra) + threadIdx.x;
   float* pgeo = reinterpret_cast<float*>(extra + SCRATCH_BYTES);
-  const float* lut = pgeo + N_CONSUMER_WARPS * PGEO;
-  float* rad2s = const_cast<float*>(lut) + a.lut_k;
+  float* lut_region = pgeo + N_CONSUMER_WARPS * PGEO;                      // 2 * lut_k floats: room to align the table to its size
+  const uint32_t lut_bytes = (uint32_t) a.lut_k * 4u;
+  const uint32_t lut_sa = (smem_u32(lut_region) + lut_bytes - 1u) & ~(lut_bytes - 1u);      // shared-window address of the table
+  const float* lut = lut_region + (lut_sa - smem_u32(lut_region)) / 4u;
+  float* rad2s = lut_region + 2 * a.lut_k;
   unsigned char* hist = reinterpret_cast<unsigned char*>(rad2s + 32);       // [n_bins + 1][BIN_STRIDE]
   ring.init();
   for (int q = threadIdx.x; q < a.lut_k; q += CTA_THREADS) const_cast<float*>(lut)[q] = __ldg(a.lut + q);
@@ -1209,10 +1214,12 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
   const uint32_t kmask4 = ((uint32_t) a.lut_k - 1u) << 2;
   const float kscale = (float) (a.lut_k - 1);
   // table entry of the cell of s: 2^21 + sat(s / span) (K - 1) has the cell number in mantissa bits 2.. (ulp 1/4), so
-  // masking the bit pattern yields the byte offset of the entry
+  // masking the bit pattern yields the byte offset of the entry, OR-ing the (size-aligned) base its address: one LOP3
   auto entry = [&](float sv) -> float {
     const float v = fmaf(__saturatef(sv * a.lut_scale), kscale, 2097152.f);
-    return *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(lut) + (__float_as_uint(v) & kmask4));
+    float e;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"((__float_as_uint(v) & kmask4) | lut_sa));
+    return e;
   };
   Rows<D> R;
   float thr_s = 0.f;          // every pair with exact d2 < r_max^2 has s = fl(acc + |x'|^2) < thr_s (one value per thread, see bwm)
