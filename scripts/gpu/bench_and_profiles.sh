@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 2, call 6: bench lines of the round (C3 default with both baselines, reference arm, C2 / C4 / C5), the ncu launch
+# bench lines of the round (C3 default with both baselines, reference arm, C2 / C4 / C5), the ncu launch
 # list of the default bench command and the speed-of-light sections of the two C3 scan kernels at full size
 mkdir -p gpurun_out
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r02_c3.json 2> gpurun_out/bench_r02_c3.err; tail -c 300 gpurun_out/bench_r02_c3.err

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 2, call 8 (2 GPUs): host-assembly path after the device fix; the command-line binary on 2 GPUs against 1 GPU
+# host-assembly path after the device fix; the command-line binary on 2 GPUs against 1 GPU
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -12
 python - <<'PY'

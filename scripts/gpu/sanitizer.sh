@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 2, call 11: compute-sanitizer (memcheck, synccheck, racecheck) over a small pass through every FFMA scan kernel
+# compute-sanitizer (memcheck, synccheck, racecheck) over a small pass through every FFMA scan kernel
 mkdir -p gpurun_out
 for tool in memcheck synccheck racecheck; do
   echo "== $tool"
