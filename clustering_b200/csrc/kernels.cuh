@@ -1037,6 +1037,12 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_count_kernel(const __grid_constant__ P
 // hist[b][row] counts rad2[b-1] <= d2 < rad2[b], the frame itself included (pops_finalize removes it).
 // ------------------------------------------------------------------------------------------------
 constexpr int BIN_STRIDE = N_CONSUMERS * RI * 2;      // bytes between the histogram rows of two bins (2048)
+#ifndef DCB_BIN_WIDE_FROM
+#define DCB_BIN_WIDE_FROM 9                           // n_cols from which the unit is scanned 2 rows x 8 columns per step (99: never)
+#endif
+#ifndef DCB_BIN_WIDE_COLS
+#define DCB_BIN_WIDE_COLS 4                           // wide shape: columns whose lookups are in flight together (2, 4 or 8)
+#endif
 #ifndef DCB_BIN_COLS
 #define DCB_BIN_COLS 2                                // columns whose table lookups are in flight together (1, 2 or 4)
 #endif
@@ -1364,6 +1370,128 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
         // covers the rounding of the sum s and of the threshold itself
         thr_s = next_up((a.thr_fast + eam) * 1.000001f);
         slow_unit = __any_sync(0xffffffffu, !(bwm < a.lut_margin));
+        if constexpr (D >= DCB_BIN_WIDE_FROM) {
+          // Wide shape for the dims whose row operands crowd the register file (4 D of the 96 registers): the unit is scanned in
+          // two halves of TWO rows x EIGHT columns per step -- 2 D operand registers, the same 8 FFMA2 per dim and step (rows
+          // r, r+1 x one column each) with two broadcast LDS.128 -- so that the lookup chains of a dense step have registers
+          // to be in flight together.  Rows 2h, 2h+1 of the thread in half h: the same rows, histogram slots and results as
+          // the 4 x 4 shape.
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            float xw[2][D];
+            {
+              const uint32_t p0 = R.pos(g, 2 * h), p1 = R.pos(g, 2 * h + 1);
+#pragma unroll
+              for (int k = 0; k < D; ++k) {
+                xw[0][k] = __ldg(g.xT + (size_t) k * g.ld + p0) - cen[k];          // the arithmetic of Rows::retarget
+                xw[1][k] = __ldg(g.xT + (size_t) k * g.ld + p1) - cen[k];
+              }
+            }
+            const float xnw[2] = {h ? R.xn[2] : R.xn[0], h ? R.xn[3] : R.xn[1]};
+            unsigned char* hbh = hb + h * (N_CONSUMERS * 4);                        // rows 2h (low half word), 2h+1 (high)
+#pragma unroll 1
+            for (int gcol = 0; gcol < TJ; gcol += 8) {
+              float acc[2][8];
+              {
+                unsigned long long a2[8];
+                const float* tlg = tl + gcol;
+                {
+                  const float4 na = *reinterpret_cast<const float4*>(tlg + D * TJ), nb4 = *reinterpret_cast<const float4*>(tlg + D * TJ + 4);
+                  const float4 ya = *reinterpret_cast<const float4*>(tlg), yb = *reinterpret_cast<const float4*>(tlg + 4);
+                  const float yc[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+                  const float nc[8] = {na.x, na.y, na.z, na.w, nb4.x, nb4.y, nb4.z, nb4.w};
+                  const unsigned long long x2 = pack2(xw[0][0], xw[1][0]);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) a2[c] = fma2(x2, pack2(yc[c], yc[c]), pack2(nc[c], nc[c]));
+                }
+#pragma unroll
+                for (int k = 1; k < D; ++k) {
+                  const float4 ya = *reinterpret_cast<const float4*>(tlg + k * TJ), yb = *reinterpret_cast<const float4*>(tlg + k * TJ + 4);
+                  const float yc[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+                  const unsigned long long x2 = pack2(xw[0][k], xw[1][k]);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) a2[c] = fma2(x2, pack2(yc[c], yc[c]), a2[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) unpack2(a2[c], acc[0][c], acc[1][c]);
+              }
+              bool any = false;
+#pragma unroll
+              for (int r2 = 0; r2 < 2; ++r2) {
+                const float mn = fminf(fminf(fminf(acc[r2][0], acc[r2][1]), fminf(acc[r2][2], acc[r2][3])),
+                                       fminf(fminf(acc[r2][4], acc[r2][5]), fminf(acc[r2][6], acc[r2][7])));
+                any |= (mn + xnw[r2] < thr_s);
+              }
+              const uint32_t act = __ballot_sync(0xffffffffu, any);
+              if (act == 0u) continue;
+              if (__popc(act) >= a.dense_lanes && !slow_unit) {
+                bool band = false;
+#pragma unroll
+                for (int c0 = 0; c0 < 8; c0 += DCB_BIN_WIDE_COLS) {
+                  uint16_t* hp[DCB_BIN_WIDE_COLS][2];
+#pragma unroll
+                  for (int cc = 0; cc < DCB_BIN_WIDE_COLS; ++cc)
+#pragma unroll
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                      const float sv = acc[r2][c0 + cc] + xnw[r2];
+                      const float e = entry(sv);
+                      const float dlt = sv - e;
+                      const uint32_t b = (__float_as_uint(e) & 31u) + 1u - (__float_as_uint(dlt) >> 31);
+                      band |= fabsf(dlt) < bwm;
+                      hp[cc][r2] = reinterpret_cast<uint16_t*>(hbh + r2 * 2 + b * BIN_STRIDE);
+                    }
+                  // the two counters of a column belong to two different rows; columns of the same row stay in order
+#pragma unroll
+                  for (int cc = 0; cc < DCB_BIN_WIDE_COLS; ++cc) {
+                    const uint16_t h0 = *hp[cc][0], h1 = *hp[cc][1];
+                    *hp[cc][0] = (uint16_t) (h0 + 1);
+                    *hp[cc][1] = (uint16_t) (h1 + 1);
+                  }
+                }
+                if (band) {
+#pragma unroll
+                  for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) scratch[(r2 * 8 + c) * N_CONSUMERS] = acc[r2][c];
+#pragma unroll 1
+                  for (int p = 0; p < 16; ++p) {
+                    const int r2 = p >> 3, r = 2 * h + r2;
+                    const float sv = scratch[p * N_CONSUMERS] + (r2 ? xnw[1] : xnw[0]);
+                    const float e = entry(sv);
+                    const float dlt = sv - e;
+                    if (fabsf(dlt) < bwm) {
+                      const int bf = (int) ((__float_as_uint(e) & 31u) + 1u - (__float_as_uint(dlt) >> 31));     // as counted above
+                      ++st.slow;
+                      ++st.exact;
+                      const float d2 = dist2_exact(g.xT, g.ld, D, R.row(r), m.col0 + gcol + (p & 7));
+                      const int be = (d2 == d2) ? bin_of(rad2s, nb, d2) : nb;        // NaN (padding) -> outside
+                      if (be != bf) {
+                        bump(r, bf, -1);
+                        bump(r, be, 1);
+                      }
+                    }
+                  }
+                }
+              } else if (any) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float sv = acc[r2][c] + xnw[r2];
+                    scratch[(r2 * 8 + c) * N_CONSUMERS] = sv;
+                    mask |= (sv < thr_s) ? (1u << (r2 * 8 + c)) : 0u;
+                  }
+#pragma unroll 1
+                while (mask) {
+                  const int p = __ffs(mask) - 1;
+                  mask &= mask - 1;
+                  hit(2 * h + (p >> 3), gcol + (p & 7), scratch[p * N_CONSUMERS]);
+                }
+              }
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int gcol = 0; gcol < TJ; gcol += CJ) {
           float acc[RI][CJ];
@@ -1450,6 +1578,7 @@ __global__ void DCB_LAUNCH_BOUNDS(D) pops_bin_kernel(const __grid_constant__ Pop
               hit(p / CJ, gcol + (p % CJ), scratch[p * N_CONSUMERS]);
             }
           }
+        }
         }
       }
     }
