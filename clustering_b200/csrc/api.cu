@@ -1273,7 +1273,9 @@ static int populations_impl(dcb200_ctx* c, const float* radii, size_t n_radii, s
       // radius part of the band for r_max (e_rel r^2 + roundings of s and of s - e, as in count mode) + the 31 ulp by which
       // the table's entries may differ from the radii they stand for
       a.band_max = up((1.02 * (double) a.g.e_rel + 4.0 * ldexp(1.0, -24) + 32.0 * ldexp(1.0, -23)) * rmax2 + 1e-37);
-      a.dense_lanes = env_int("DCB200_BIN_DENSE_LANES", 8);
+      // a step is binned branch-free when this many lanes hold a candidate (C3: 4 / 8 / 16 lanes 126.5 / 127.5 / 131.5 ms with the
+      // 2 x 8 step shape of D >= 9; flat between 4 and 16 with the 4 x 4 shape)
+      a.dense_lanes = env_int("DCB200_BIN_DENSE_LANES", c->d >= 9 ? 4 : 8);
       a.steal = env_int("DCB200_BIN_STEAL", 1) == 1 ? 1 : 0;
       a.proj_prune = env_int("DCB200_BIN_PROJ", 1) == 1 ? 1 : 0;
     }
