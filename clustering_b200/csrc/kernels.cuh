@@ -1690,6 +1690,85 @@ __device__ __forceinline__ void scan_tile_nn(const ScanGeom&, const float* __res
   }
 }
 
+// Wide shape of the neighbour scan for the dims whose row operands crowd the register file (see pops_bin_kernel): the unit
+// is scanned in two halves of TWO rows x EIGHT columns per step -- 2 D operand registers, the same 8 FFMA2 per dim and step --
+// which leaves registers to keep the broadcast loads of the next dims in flight.  Rows 2h, 2h+1 of the thread in half h.
+#ifndef DCB_NN_WIDE_FROM
+#define DCB_NN_WIDE_FROM 9
+#endif
+template <int D, class Hit>
+__device__ __forceinline__ void scan_tile_nn_wide(const ScanGeom& g, const float* __restrict__ tl, const float* __restrict__ lrow, const Rows<D>& R,
+                                                  NnFilter& F, float* __restrict__ scratch, Hit& hit) {
+  constexpr int TJ = TileW<D>::tj;
+  const float* __restrict__ cen = tl + (D + 1) * TJ;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    float xw[2][D];
+    {
+      const uint32_t p0 = R.pos(g, 2 * h), p1 = R.pos(g, 2 * h + 1);
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        xw[0][k] = __ldg(g.xT + (size_t) k * g.ld + p0) - cen[k];          // the arithmetic of Rows::retarget
+        xw[1][k] = __ldg(g.xT + (size_t) k * g.ld + p1) - cen[k];
+      }
+    }
+#pragma unroll 1
+    for (int gc = 0; gc < TJ; gc += 8) {
+      float acc[2][8];
+      {
+        unsigned long long a2[8];
+        const float* tlg = tl + gc;
+        {
+          const float4 na = *reinterpret_cast<const float4*>(tlg + D * TJ), nb = *reinterpret_cast<const float4*>(tlg + D * TJ + 4);
+          const float4 ya = *reinterpret_cast<const float4*>(tlg), yb = *reinterpret_cast<const float4*>(tlg + 4);
+          const float yc[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+          const float nc[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+          const unsigned long long x2 = pack2(xw[0][0], xw[1][0]);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a2[c] = fma2(x2, pack2(yc[c], yc[c]), pack2(nc[c], nc[c]));
+        }
+#pragma unroll
+        for (int k = 1; k < D; ++k) {
+          const float4 ya = *reinterpret_cast<const float4*>(tlg + k * TJ), yb = *reinterpret_cast<const float4*>(tlg + k * TJ + 4);
+          const float yc[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+          const unsigned long long x2 = pack2(xw[0][k], xw[1][k]);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a2[c] = fma2(x2, pack2(yc[c], yc[c]), a2[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) unpack2(a2[c], acc[0][c], acc[1][c]);
+      }
+      // first level: any of a row's eight columns below tc?
+      const float tc0 = h ? F.tc[2] : F.tc[0], tc1 = h ? F.tc[3] : F.tc[1];
+      const float m0 = fminf(fminf(fminf(acc[0][0], acc[0][1]), fminf(acc[0][2], acc[0][3])), fminf(fminf(acc[0][4], acc[0][5]), fminf(acc[0][6], acc[0][7])));
+      const float m1 = fminf(fminf(fminf(acc[1][0], acc[1][1]), fminf(acc[1][2], acc[1][3])), fminf(fminf(acc[1][4], acc[1][5]), fminf(acc[1][6], acc[1][7])));
+      if (m0 < tc0 || m1 < tc1) {
+        // second level: exact per-pair thresholds, candidates to the handler (one compact loop)
+        uint32_t mask = 0;
+        const float4 la = *reinterpret_cast<const float4*>(lrow + gc), lb = *reinterpret_cast<const float4*>(lrow + gc + 4);
+        const float lc[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+          const int r = 2 * h + r2;
+          const float lor = F.lor(r), dl = F.dl(r), tn = F.t_nn(r);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            scratch[(r2 * 8 + c) * N_CONSUMERS] = acc[r2][c];
+            const float te = fmaf(__saturatef(lor - lc[c]), dl, tn);
+            mask |= (acc[r2][c] < te) ? (1u << (r2 * 8 + c)) : 0u;
+          }
+        }
+#pragma unroll 1
+        while (mask) {
+          const int p = __ffs(mask) - 1;
+          mask &= mask - 1;
+          hit(2 * h + (p >> 3), gc + (p & 7), scratch[p * N_CONSUMERS]);     // hit() re-checks against the thresholds of the moment
+        }
+      }
+    }
+  }
+}
+
 // run-time-D variant
 template <class Hit>
 __device__ __forceinline__ void scan_tile_nn(const ScanGeom& gm, const float* __restrict__ tl, const float* __restrict__ lrow, const Rows<0>& R,
@@ -1932,7 +2011,8 @@ __global__ void DCB_LAUNCH_BOUNDS(D) nn_kernel(const __grid_constant__ NnArgs a)
                                       : thr(key_d2(*reinterpret_cast<volatile unsigned long long*>(best + ROWS_PER_CTA + slot)), R.ea(g, r), R.xn[r]);
           F.update(r);
         }
-        scan_tile_nn(g, tl, cen + g.dp, R, F, scratch, hit);
+        if constexpr (D >= DCB_NN_WIDE_FROM) scan_tile_nn_wide<D>(g, tl, cen + g.dp, R, F, scratch, hit);
+        else scan_tile_nn(g, tl, cen + g.dp, R, F, scratch, hit);
         // what the group's rows still accept (d2 units, pruning margins included): for the warps' reach tests, for the
         // producer's dynamic pruning of this item, and (at the end of the item) for the later items of the row block
         float v = 0.f, vh = 0.f;
