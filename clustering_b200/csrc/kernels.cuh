@@ -1,22 +1,29 @@
 // The pair-scan kernels of the `clustering density` hot path, written for sm_100a:
 //
-//   pops_kernel<D>    multi-radius neighbourhood population count
-//                     (replaces reference density_clustering.cpp:126-195 / density_clustering_cuda_kernels.cu:9-56)
-//   nn_kernel<D>      nearest neighbour + nearest neighbour with lower free energy, fused
-//                     (replaces density_clustering.cpp:230-288 / density_clustering_cuda_kernels.cu:58-130)
-//   screen_kernel<D>  edge discovery + union-find of the free-energy screening
-//                     (replaces density_clustering_common.cpp:37-134 / density_clustering_cuda_kernels.cu:132-192)
+//   pops_count_kernel<D,NB>  neighbourhood populations for up to 3 distinct radii (branch-free sign-bit counting)
+//   pops_bin_kernel<D>       ... for 4 to 31 radii per pass: table-driven binning of the fast squared distance
+//   pops_kernel<D>           ... histogram fallback (radius lists no table can serve, shards off the 128-row grid)
+//                            (replace reference density_clustering.cpp:126-195 / density_clustering_cuda_kernels.cu:9-56)
+//   nn_kernel<D>             nearest neighbour + nearest neighbour with lower free energy, fused
+//                            (replaces density_clustering.cpp:230-288 / density_clustering_cuda_kernels.cu:58-130)
+//   edge_kernel<D>           all pairs within the screening cut of the spatially ordered frames: the neighbour graph from
+//                            which api.cu derives the clusters of EVERY threshold (union-find over the edges by level)
+//   screen_kernel<D>         edge discovery + union-find of ONE threshold on free-energy-sorted frames (session API)
+//                            (replace density_clustering_common.cpp:37-134 / density_clustering_cuda_kernels.cu:132-192)
 //
 // Common structure (not derived from the reference's kernels):
 //   * persistent CTAs, 8 consumer warps + 1 producer warp; work items (row block x column range) are
 //     handed out by an atomic counter, so dense and sparse regions balance dynamically;
-//   * the producer streams column tiles [D+1][TJ] (dim-major, 16 B aligned) into a 3-stage shared
-//     memory ring with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx); no __syncthreads in steady state;
-//   * every consumer thread keeps RI=4 rows in registers and sweeps CJ=4 columns per step with one
-//     broadcast LDS.128 per dim and RI*CJ FFMAs: acc = |y|^2 - 2 x.y (the column pack holds -2y and |y|^2
+//   * the producer prunes (super-tiles, then tiles, against the row block's / row groups' boxes and spheres) and streams
+//     the surviving column tiles [D+1][TJ] (dim-major, one contiguous record per tile) into a 6-stage shared memory ring
+//     with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx); stages come back through named barriers (bar.arrive /
+//     bar.sync), so a producer whose ring is full is parked; no __syncthreads in steady state;
+//   * every consumer thread keeps RI=4 rows in registers and sweeps CJ=4 columns per step with one broadcast LDS.128 per
+//     dim and RI*CJ/2 packed FMAs (FFMA2: rows r, r+1 x one broadcast column) -- for D >= 9 the table-driven and the
+//     neighbour kernel use 2 rows x 8 columns instead: acc = |y|^2 - 2 x.y (the column pack holds -2y and |y|^2
 //     of coordinates taken relative to the TILE's own centre; the rows are re-centred on that point at
 //     every tile, so operands are as small as the tile's neighbourhood and the rounding error of the
-//     expanded form stays ~1e-6 relative at the decision boundary), D FFMA + ~1 compare per pair;
+//     expanded form stays ~1e-6 relative at the decision boundary);
 //   * that fast value only *filters*: a pair is handed to the slow path when acc < t_row, where t_row
 //     carries a proven rounding-error margin.  The slow path decides with the squared distance
 //     evaluated in the exact rounding order of the reference's CPU build (dist2_exact) whenever the fast
