@@ -347,6 +347,8 @@ def test_screening_accepts_arbitrary_initial_clusters(oracle, seed):
     {"DCB200_BIN_DENSE_LANES": "33"},       # every active step candidate by candidate
     {"DCB200_SUPER_PRUNE": "0"},            # no coarse level in the producers' pruning
     {"DCB200_AXIS_PRUNE": "2", "DCB200_BIN_PROJ": "2"},
+    {"DCB200_NN_WINDOW": "1", "DCB200_NN_SEED_W": "1"},      # hardly any warm start of the neighbour thresholds
+    {"DCB200_NN_WINDOW": "64", "DCB200_NN_SEED_W": "16"},
 ])
 def test_scheduling_knobs_never_change_results(oracle, knobs):
     """How the pair matrix is cut into work items, which warp takes which unit, what is pruned at which level and which
